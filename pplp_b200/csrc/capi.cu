@@ -1,0 +1,658 @@
+// pplp_b200/csrc/capi.cu — the C ABI (include/pplp_b200.h) over the kernel launchers.  Host logic only: argument
+// checking, layout arithmetic, stream-ordered scratch, chunking, and the once-per-key sequential samplers.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+
+#include "../../include/pplp_b200.h"
+#include "bloom_host.hpp"
+#include "engine.hpp"
+
+using namespace pplp;
+
+struct pplp_ctx {
+    Engine eng;
+};
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string &msg) { g_err = msg; return code; }
+
+#define PPLP_TRY try {
+#define PPLP_CATCH                                                                          \
+    }                                                                                       \
+    catch (const CudaError &e) { return fail(PPLP_ECUDA, e.what()); }                       \
+    catch (const std::invalid_argument &e) { return fail(PPLP_EINVAL, e.what()); }          \
+    catch (const std::logic_error &e) { return fail(PPLP_ELOGIC, e.what()); }               \
+    catch (const std::bad_alloc &) { return fail(PPLP_ERUNTIME, "out of host memory"); }    \
+    catch (const std::exception &e) { return fail(PPLP_ERUNTIME, e.what()); }
+
+inline cudaStream_t S(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+Engine &dev_engine(pplp_ctx *ctx) {
+    if (!ctx) throw std::invalid_argument("pplp: null context");
+    if (!ctx->eng.host.ok) throw std::invalid_argument(std::string("pplp: encryption parameters are not set correctly: ") + ctx->eng.host.error_message);
+    if (ctx->eng.device < 0) throw CudaError("pplp: context has no CUDA device (there is no CPU fallback)");
+    PPLP_CUDA(cudaSetDevice(ctx->eng.device));
+    return ctx->eng;
+}
+size_t check_level(const Engine &E, size_t level) {
+    if (level >= E.host.levels.size()) throw std::invalid_argument("pplp: level out of range");
+    return E.host.levels[level].q.size();
+}
+Layout make_layout(int layout, size_t n, size_t k, size_t npoly, size_t nq) {
+    if (layout == PPLP_LAYOUT_SEAL) return Layout{npoly * k * n, k * n, n};
+    if (layout == PPLP_LAYOUT_LIMB_MAJOR) return Layout{n, nq * n, npoly * nq * n};
+    throw std::invalid_argument("pplp: unknown layout");
+}
+int to_int(size_t v, const char *what) {
+    if (v > 0x3fffffffu) throw std::invalid_argument(std::string("pplp: ") + what + " too large for one call");
+    return (int)v;
+}
+
+// Stream-ordered scratch: allocation and release are enqueued on the stream (no device-wide synchronisation); the
+// pool keeps the memory between calls.
+struct Scratch {
+    void *p = nullptr;
+    cudaStream_t st;
+    Scratch(size_t bytes, cudaStream_t s) : st(s) { PPLP_CUDA(cudaMallocAsync(&p, bytes ? bytes : 8, st)); }
+    ~Scratch() { if (p) cudaFreeAsync(p, st); }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+    Scratch(const Scratch &) = delete;
+    Scratch &operator=(const Scratch &) = delete;
+};
+
+// SEAL's Blake2xbPRNG on the host (key generation only): 4096-byte refills blake2xb(counter; key = seed).
+struct HostPrng {
+    u64 seed[8];
+    u64 counter = 0;
+    unsigned char buf[4096];
+    size_t head = 4096;
+    explicit HostPrng(const u64 *s) { std::memcpy(seed, s, 64); }
+    void refill() {
+        u64 root[8];
+        b2::xof_root(seed, counter++, root);
+        for (unsigned b = 0; b < 64; ++b) b2::xof_block(root, b, reinterpret_cast<u64 *>(buf + 64 * b));
+        head = 0;
+    }
+    void bytes(void *dst, size_t n) {
+        unsigned char *d = static_cast<unsigned char *>(dst);
+        while (n) {
+            if (head == 4096) refill();
+            size_t take = std::min(n, (size_t)4096 - head);
+            std::memcpy(d, buf + head, take);
+            head += take; d += take; n -= take;
+        }
+    }
+    u32 word() { u32 w; bytes(&w, 4); return w; }
+};
+// [SEAL] sample_poly_ternary draws std::uniform_int_distribution<uint64_t>(0,2) from a 32-bit generator.  With
+// libstdc++ (GCC >= 11) that is Lemire's multiply-shift: product = draw * 3, reject when the low half is below
+// 2^32 mod 3 = 1 (i.e. only draw == 0), result = high half.  Spelled out so it does not depend on the host library.
+void host_ternary(HostPrng &g, size_t n, signed char *out) {
+    for (size_t i = 0; i < n; ++i) {
+        u32 w;
+        do { w = g.word(); } while (w == 0);
+        out[i] = (signed char)((int)(((u64)w * 3) >> 32) - 1);
+    }
+}
+void host_cbd(HostPrng &g, size_t n, signed char *out) {
+    for (size_t i = 0; i < n; ++i) {
+        unsigned char x[6];
+        g.bytes(x, 6);
+        x[2] &= 0x1F; x[5] &= 0x1F;
+        out[i] = (signed char)(__builtin_popcount(x[0]) + __builtin_popcount(x[1]) + __builtin_popcount(x[2]) - __builtin_popcount(x[3]) -
+                               __builtin_popcount(x[4]) - __builtin_popcount(x[5]));
+    }
+}
+void host_uniform(HostPrng &g, const std::vector<u64> &q, size_t n, u64 *out) {
+    g.bytes(out, q.size() * n * 8);
+    for (size_t j = 0; j < q.size(); ++j) {
+        const u64 max_multiple = ~u64(0) - (~u64(0) % q[j]) - 1;
+        for (size_t i = 0; i < n; ++i) {
+            u64 r = out[j * n + i];
+            while (r >= max_multiple) g.bytes(&r, 8);
+            out[j * n + i] = r % q[j];
+        }
+    }
+}
+
+// Symmetric encryption of zero at the key level in NTT form ([SEAL] encrypt_zero_symmetric, is_ntt_form = true,
+// save_seed = false): c1 = a uniform (taken as NTT form), c0 = -(a s + e).  Optionally adds factor*s^2 on limb `digit`.
+void symmetric_zero_ntt(Engine &E, const u64 *seed, const u64 *d_sk, u64 *d_out /* [2][K][n] */, int digit, u64 factor, cudaStream_t st) {
+    const size_t n = E.host.n, K = E.host.K();
+    HostPrng bootstrap(seed);
+    u64 public_seed[8];
+    bootstrap.bytes(public_seed, 64);
+    HostPrng ct_prng(public_seed);
+    std::vector<u64> a(K * n);
+    host_uniform(ct_prng, E.host.q, n, a.data());
+    std::vector<signed char> e(n);
+    host_cbd(bootstrap, n, e.data());
+    Scratch d_e(n, st), d_en(K * n * 8, st);
+    PPLP_CUDA(cudaMemcpyAsync(d_out + K * n, a.data(), K * n * 8, cudaMemcpyHostToDevice, st));
+    PPLP_CUDA(cudaMemcpyAsync(d_e.p, e.data(), n, cudaMemcpyHostToDevice, st));
+    launch_expand_small(E, d_e.as<signed char>(), d_en.as<u64>(), st);
+    launch_ntt(E, d_en.as<u64>(), E.seal_layout(0, 1), 1, 1, E.qmap(0), false, st);
+    launch_pk_combine(E, d_out + K * n, d_sk, d_en.as<u64>(), d_out, digit, factor, st);
+    PPLP_CUDA(cudaStreamSynchronize(st));   // host staging vectors die here
+}
+
+__global__ void proximity_plain_kernel(const u64 *__restrict__ xa, const u64 *__restrict__ ya, int nq, u64 t, u64 *__restrict__ plain, int *flags) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const u64 x = xa[q], y = ya[q];
+    const u64 u = x * x + y * y, x2 = x << 1, y2 = y << 1;   // src/client.cc:64,111-113
+    plain[3 * q] = u; plain[3 * q + 1] = x2; plain[3 * q + 2] = y2;
+    if (flags && (u >= t || x2 >= t || y2 >= t)) atomicOr(&flags[q], 2);   // SEAL: "plain is not valid for encryption parameters"
+}
+__global__ void gather_u64_kernel(const u64 *__restrict__ src, const int *__restrict__ idx, int stride, int col, int n, u64 *__restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[(idx ? idx[i] : 0) * stride + col];
+}
+
+}  // namespace
+
+void Engine::upload_tables(int dev) {
+    device = dev;
+    PPLP_CUDA(cudaSetDevice(dev));
+    cudaDeviceProp prop;
+    PPLP_CUDA(cudaGetDeviceProperties(&prop, dev));
+    sm_count = prop.multiProcessorCount;
+    h_mods.resize(host.tables.size());
+    for (size_t i = 0; i < host.tables.size(); ++i) {
+        const HostTable &T = host.tables[i];
+        DevMod &m = h_mods[i];
+        m.m = make_mod(T.q);
+        m.fwd = upload(T.fwd.data(), T.fwd.size());
+        m.inv = upload(T.inv.data(), T.inv.size());
+        m.n_inv = T.n_inv;
+        m.inv1_n_inv = T.inv1_n_inv;
+    }
+    d_mods = upload(h_mods.data(), h_mods.size());
+    std::vector<DevLevel> lv(host.levels.size());
+    for (size_t i = 0; i < lv.size(); ++i) lv[i] = host.levels[i].dev;
+    d_levels = upload(lv.data(), lv.size());
+    // keep scratch in the stream-ordered pool instead of returning it to the driver after every call
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+}
+
+extern "C" {
+
+const char *pplp_last_error(void) { return g_err.c_str(); }
+const char *pplp_version(void) { return "pplp_b200 0.1 (sm_100a)"; }
+
+size_t pplp_bfv_default(size_t n, uint64_t *out, size_t cap) {
+    std::vector<u64> v = bfv_default_moduli(n);
+    if (v.size() > cap) return 0;
+    std::copy(v.begin(), v.end(), out);
+    return v.size();
+}
+uint64_t pplp_plain_batching(size_t n, int bits) {
+    try {
+        if (bits < 2 || bits > 60 || n < 2 || (n & (n - 1))) return 0;
+        return hm::primes_below(2 * (u64)n, bits, 1)[0];
+    } catch (...) { return 0; }
+}
+
+int pplp_ctx_create(size_t n, const uint64_t *q, size_t K, uint64_t t, int device, int enforce_security, pplp_ctx **out) {
+    PPLP_TRY
+    if (!out) throw std::invalid_argument("pplp: null output");
+    *out = nullptr;
+    std::unique_ptr<pplp_ctx> c(new pplp_ctx);
+    std::vector<u64> qv(q, q + K);
+    c->eng.host.build(n, qv, t, enforce_security != 0);
+    if (c->eng.host.ok && device >= 0) c->eng.upload_tables(device);
+    *out = c.release();
+    return PPLP_OK;
+    PPLP_CATCH
+}
+void pplp_ctx_destroy(pplp_ctx *ctx) {
+    if (!ctx) return;
+    if (ctx->eng.device >= 0) cudaSetDevice(ctx->eng.device);
+    delete ctx;
+}
+int pplp_ctx_ok(const pplp_ctx *ctx) { return ctx && ctx->eng.host.ok ? 1 : 0; }
+const char *pplp_ctx_error_name(const pplp_ctx *ctx) { return ctx ? ctx->eng.host.error_name.c_str() : "null"; }
+const char *pplp_ctx_error_message(const pplp_ctx *ctx) { return ctx ? ctx->eng.host.error_message.c_str() : "null context"; }
+int pplp_ctx_device(const pplp_ctx *ctx) { return ctx ? ctx->eng.device : -1; }
+size_t pplp_ctx_poly_degree(const pplp_ctx *ctx) { return ctx ? ctx->eng.host.n : 0; }
+uint64_t pplp_ctx_plain_modulus(const pplp_ctx *ctx) { return ctx ? ctx->eng.host.t : 0; }
+size_t pplp_ctx_num_levels(const pplp_ctx *ctx) { return ctx ? ctx->eng.host.levels.size() : 0; }
+size_t pplp_ctx_first_level(const pplp_ctx *ctx) { return ctx ? ctx->eng.host.first_level() : 0; }
+size_t pplp_ctx_level_limbs(const pplp_ctx *ctx, size_t level) { return (ctx && level < ctx->eng.host.levels.size()) ? ctx->eng.host.levels[level].q.size() : 0; }
+int pplp_ctx_level_bits(const pplp_ctx *ctx, size_t level) { return (ctx && level < ctx->eng.host.levels.size()) ? ctx->eng.host.levels[level].total_bits : 0; }
+int pplp_ctx_parms_id(const pplp_ctx *ctx, size_t level, uint64_t out[4]) {
+    if (!ctx || level >= ctx->eng.host.levels.size()) return fail(PPLP_EINVAL, "pplp: level out of range");
+    std::copy(ctx->eng.host.levels[level].id.begin(), ctx->eng.host.levels[level].id.end(), out);
+    return PPLP_OK;
+}
+int pplp_ctx_find_level(const pplp_ctx *ctx, const uint64_t id[4]) {
+    if (!ctx) return -1;
+    ParmsId p = {id[0], id[1], id[2], id[3]};
+    return ctx->eng.host.find_level(p);
+}
+int pplp_ctx_level_info(const pplp_ctx *ctx, size_t level, size_t limb, uint64_t out[8]) {
+    if (!ctx || level >= ctx->eng.host.levels.size() || limb >= ctx->eng.host.levels[level].q.size()) return fail(PPLP_EINVAL, "pplp: level/limb out of range");
+    const HostLevel &L = ctx->eng.host.levels[level];
+    out[0] = L.q[limb]; out[1] = ctx->eng.host.tables[limb].psi; out[2] = L.dev.delta[limb]; out[3] = L.dev.q_mod_t;
+    out[4] = L.dev.t_threshold; out[5] = L.dev.neg_t[limb]; out[6] = L.gamma; out[7] = L.m_sk;
+    return PPLP_OK;
+}
+int pplp_ctx_batching(const pplp_ctx *ctx) { return ctx && ctx->eng.host.batching ? 1 : 0; }
+
+// ---- memory ----
+int pplp_dev_alloc(pplp_ctx *ctx, size_t bytes, void **out) {
+    PPLP_TRY
+    dev_engine(ctx);
+    PPLP_CUDA(cudaMalloc(out, bytes ? bytes : 8));
+    return PPLP_OK;
+    PPLP_CATCH
+}
+int pplp_dev_free(pplp_ctx *ctx, void *ptr) {
+    PPLP_TRY
+    dev_engine(ctx);
+    PPLP_CUDA(cudaFree(ptr));
+    return PPLP_OK;
+    PPLP_CATCH
+}
+int pplp_dev_memset(pplp_ctx *ctx, void *d_ptr, int value, size_t bytes, void *stream) {
+    PPLP_TRY
+    dev_engine(ctx);
+    PPLP_CUDA(cudaMemsetAsync(d_ptr, value, bytes, S(stream)));
+    return PPLP_OK;
+    PPLP_CATCH
+}
+int pplp_h2d(pplp_ctx *ctx, void *d_dst, const void *h_src, size_t bytes, void *stream) {
+    PPLP_TRY
+    dev_engine(ctx);
+    PPLP_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, S(stream)));
+    return PPLP_OK;
+    PPLP_CATCH
+}
+int pplp_d2h(pplp_ctx *ctx, void *h_dst, const void *d_src, size_t bytes, void *stream) {
+    PPLP_TRY
+    dev_engine(ctx);
+    PPLP_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, S(stream)));
+    return PPLP_OK;
+    PPLP_CATCH
+}
+int pplp_d2d(pplp_ctx *ctx, void *d_dst, const void *d_src, size_t bytes, void *stream) {
+    PPLP_TRY
+    dev_engine(ctx);
+    PPLP_CUDA(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, S(stream)));
+    return PPLP_OK;
+    PPLP_CATCH
+}
+int pplp_sync(pplp_ctx *ctx, void *stream) {
+    PPLP_TRY
+    dev_engine(ctx);
+    PPLP_CUDA(cudaStreamSynchronize(S(stream)));
+    return PPLP_OK;
+    PPLP_CATCH
+}
+int pplp_host_alloc(size_t bytes, void **out) {
+    PPLP_TRY
+    PPLP_CUDA(cudaMallocHost(out, bytes ? bytes : 8));
+    return PPLP_OK;
+    PPLP_CATCH
+}
+int pplp_host_free(void *ptr) {
+    PPLP_TRY
+    PPLP_CUDA(cudaFreeHost(ptr));
+    return PPLP_OK;
+    PPLP_CATCH
+}
+
+// ---- keys ----
+int pplp_keygen(pplp_ctx *ctx, const uint64_t seed[8], uint64_t *d_sk, uint64_t *d_pk, void *stream) {
+    PPLP_TRY
+    Engine &E = dev_engine(ctx);
+    cudaStream_t st = S(stream);
+    const size_t n = E.host.n;
+    {   // secret key: ternary, then NTT at the key level ([SEAL] KeyGenerator::generate_sk)
+        HostPrng g(seed);
+        std::vector<signed char> s(n);
+        host_ternary(g, n, s.data());
+        Scratch d_s(n, st);
+        PPLP_CUDA(cudaMemcpyAsync(d_s.p, s.data(), n, cudaMemcpyHostToDevice, st));
+        launch_expand_small(E, d_s.as<signed char>(), d_sk, st);
+        launch_ntt(E, d_sk, E.seal_layout(0, 1), 1, 1, E.qmap(0), false, st);
+        PPLP_CUDA(cudaStreamSynchronize(st));
+    }
+    if (d_pk) symmetric_zero_ntt(E, seed, d_sk, d_pk, -1, 0, st);
+    return PPLP_OK;
+    PPLP_CATCH
+}
+int pplp_relin_keygen(pplp_ctx *ctx, const uint64_t *seeds, const uint64_t *d_sk, uint64_t *d_rk, void *stream) {
+    PPLP_TRY
+    Engine &E = dev_engine(ctx);
+    if (E.host.levels.size() < 2) throw std::logic_error("keyswitching is not supported by the context");
+    const size_t n = E.host.n, K = E.host.K(), nd = E.host.levels[1].q.size();
+    const u64 P = E.host.q[K - 1];
+    for (size_t i = 0; i < nd; ++i) symmetric_zero_ntt(E, seeds + 8 * i, d_sk, d_rk + i * 2 * K * n, (int)i, P % E.host.q[i], S(stream));
+    return PPLP_OK;
+    PPLP_CATCH
+}
+
+// ---- encryption / decryption ----
+int pplp_encrypt(pplp_ctx *ctx, const uint64_t *d_pk, const uint64_t *d_seeds, const uint64_t *d_plain, size_t plain_count, size_t plain_stride,
+                 uint64_t *d_out, int layout, size_t nct, void *stream) {
+    PPLP_TRY
+    Engine &E = dev_engine(ctx);
+    if (plain_count > E.host.n) throw std::invalid_argument("plain is not valid for encryption parameters");
+    if (nct == 0) return PPLP_OK;
+    const size_t first = E.host.first_level(), k = E.host.levels[first].q.size();
+    const int nc = to_int(nct, "ciphertext count");
+    cudaStream_t st = S(stream);
+    Scratch ws(encrypt_tmp_words(E, nc) * 8, st), flag(sizeof(int), st);
+    PPLP_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), st));
+    launch_encrypt(E, d_pk, d_seeds, d_plain, plain_count, plain_stride, ws.as<u64>(), d_out, make_layout(layout, E.host.n, k, 2, nct), nc, flag.as<int>(), st);
+    return PPLP_OK;
+    PPLP_CATCH
+}
+int pplp_decrypt(pplp_ctx *ctx, size_t level, const uint64_t *d_ct, int layout, size_t nq, size_t size, const uint64_t *d_sk, uint64_t *d_plain,
+                 size_t plain_stride, size_t ncoeff, void *stream) {
+    PPLP_TRY
+    Engine &E = dev_engine(ctx);
+    const size_t k = check_level(E, level);
+    if (size < 2 || size > 3) throw std::invalid_argument("encrypted is not valid for encryption parameters");
+    if (ncoeff == 0 || ncoeff > E.host.n) throw std::invalid_argument("pplp: ncoeff must be in 1..N");
+    if (nq == 0) return PPLP_OK;
+    const int nqi = to_int(nq, "query count");
+    cudaStream_t st = S(stream);
+    Scratch tmp(decrypt_tmp_words(E, level, nqi, (int)size) * 8, st);
+    launch_decrypt(E, level, d_ct, make_layout(layout, E.host.n, k, size, nq), nqi, (int)size, d_sk, tmp.as<u64>(), d_plain, plain_stride, (int)ncoeff, st);
+    return PPLP_OK;
+    PPLP_CATCH
+}
+
+// ---- evaluator ----
+static int add_sub_common(pplp_ctx *ctx, size_t level, uint64_t *d_a, const uint64_t *d_b, int layout, size_t nq, size_t npoly, int mode, void *stream) {
+    PPLP_TRY
+    Engine &E = dev_engine(ctx);
+    const size_t k = check_level(E, level);
+    launch_add_sub(E, level, d_a, d_b, make_layout(layout, E.host.n, k, npoly, nq), to_int(nq, "query count"), (int)npoly, mode == 1, mode == 2, S(stream));
+    return PPLP_OK;
+    PPLP_CATCH
+}
+int pplp_add(pplp_ctx *ctx, size_t level, uint64_t *d_a, const uint64_t *d_b, int layout, size_t nq, size_t npoly, void *stream) {
+    return add_sub_common(ctx, level, d_a, d_b, layout, nq, npoly, 0, stream);
+}
+int pplp_sub(pplp_ctx *ctx, size_t level, uint64_t *d_a, const uint64_t *d_b, int layout, size_t nq, size_t npoly, void *stream) {
+    return add_sub_common(ctx, level, d_a, d_b, layout, nq, npoly, 1, stream);
+}
+int pplp_negate(pplp_ctx *ctx, size_t level, uint64_t *d_a, const uint64_t *d_b, int layout, size_t nq, size_t npoly, void *stream) {
+    return add_sub_common(ctx, level, d_a, d_b, layout, nq, npoly, 2, stream);
+}
+static int add_plain_common(pplp_ctx *ctx, size_t level, uint64_t *d_ct, int layout, size_t nq, size_t npoly, const uint64_t *d_plain, size_t count,
+                            size_t plain_stride, bool subtract, void *stream) {
+    PPLP_TRY
+    Engine &E = dev_engine(ctx);
+    const size_t k = check_level(E, level);
+    if (count > E.host.n) throw std::invalid_argument("plain is not valid for encryption parameters");
+    launch_add_plain(E, level, d_ct, make_layout(layout, E.host.n, k, npoly, nq), to_int(nq, "query count"), d_plain, count, plain_stride, subtract, S(stream));
+    return PPLP_OK;
+    PPLP_CATCH
+}
+int pplp_add_plain(pplp_ctx *ctx, size_t level, uint64_t *d_ct, int layout, size_t nq, size_t npoly, const uint64_t *d_plain, size_t count,
+                   size_t plain_stride, void *stream) {
+    return add_plain_common(ctx, level, d_ct, layout, nq, npoly, d_plain, count, plain_stride, false, stream);
+}
+int pplp_sub_plain(pplp_ctx *ctx, size_t level, uint64_t *d_ct, int layout, size_t nq, size_t npoly, const uint64_t *d_plain, size_t count,
+                   size_t plain_stride, void *stream) {
+    return add_plain_common(ctx, level, d_ct, layout, nq, npoly, d_plain, count, plain_stride, true, stream);
+}
+int pplp_multiply_plain_mono(pplp_ctx *ctx, size_t level, uint64_t *d_ct, int layout, size_t nq, size_t npoly, const uint64_t *d_scalar,
+                             size_t scalar_stride, size_t exponent, void *stream) {
+    PPLP_TRY
+    Engine &E = dev_engine(ctx);
+    const size_t k = check_level(E, level), n = E.host.n;
+    if (exponent >= n) throw std::invalid_argument("plain is not valid for encryption parameters");
+    if (nq == 0 || npoly == 0) return PPLP_OK;
+    cudaStream_t st = S(stream);
+    const Layout lay = make_layout(layout, n, k, npoly, nq);
+    if (exponent == 0) {
+        launch_mul_mono(E, level, d_ct, d_ct, lay, to_int(nq, "query count"), (int)npoly, d_scalar, scalar_stride, 0, st);
+    } else {   // the negacyclic shift permutes coefficients: go through a copy
+        const size_t words = nq * npoly * k * n;
+        Scratch tmp(words * 8, st);
+        PPLP_CUDA(cudaMemcpyAsync(tmp.p, d_ct, words * 8, cudaMemcpyDeviceToDevice, st));
+        launch_mul_mono(E, level, tmp.as<u64>(), d_ct, lay, to_int(nq, "query count"), (int)npoly, d_scalar, scalar_stride, exponent, st);
+    }
+    return PPLP_OK;
+    PPLP_CATCH
+}
+int pplp_multiply_plain_poly(pplp_ctx *ctx, size_t level, uint64_t *d_ct, int layout, size_t nq, size_t npoly, const uint64_t *d_plain, size_t count,
+                             void *stream) {
+    PPLP_TRY
+    Engine &E = dev_engine(ctx);
+    const size_t k = check_level(E, level), n = E.host.n;
+    if (count > n) throw std::invalid_argument("plain is not valid for encryption parameters");
+    if (nq == 0 || npoly == 0) return PPLP_OK;
+    cudaStream_t st = S(stream);
+    const Layout lay = make_layout(layout, n, k, npoly, nq);
+    const RowMap map = E.qmap(level);
+    Scratch pl(k * n * 8, st);
+    launch_lift_plain(E, level, d_plain, count, pl.as<u64>(), st);
+    launch_ntt(E, pl.as<u64>(), Layout{0, 0, n}, 1, 1, map, false, st);
+    const Layout pl_lay{0, 0, n};   // broadcast over queries and polynomials
+    if (E.host.logn <= 14) {
+        launch_polymul(E, d_ct, lay, pl.as<u64>(), pl_lay, nullptr, lay, d_ct, lay, to_int(nq, "query count"), (int)npoly, map, st);
+    } else {
+        launch_ntt(E, d_ct, lay, to_int(nq, "query count"), (int)npoly, map, false, st);
+        launch_dyadic(E, d_ct, lay, pl.as<u64>(), pl_lay, (int)nq, (int)npoly, map, st);
+        launch_ntt(E, d_ct, lay, (int)nq, (int)npoly, map, true, st);
+    }
+    return PPLP_OK;
+    PPLP_CATCH
+}
+int pplp_circuit_a(pplp_ctx *ctx, size_t level, const uint64_t *d_c0, const uint64_t *d_c1, const uint64_t *d_c2, uint64_t *d_out, int layout,
+                   size_t nq, const uint64_t *d_xb, const uint64_t *d_yb, const uint64_t *d_r, const uint64_t *d_s, int *d_flags, void *stream) {
+    PPLP_TRY
+    Engine &E = dev_engine(ctx);
+    const size_t k = check_level(E, level);
+    if (nq == 0) return PPLP_OK;
+    const int nqi = to_int(nq, "query count");
+    cudaStream_t st = S(stream);
+    Scratch sc(circuit_a_scratch_words(E, level, nqi) * 8, st);
+    if (d_flags) PPLP_CUDA(cudaMemsetAsync(d_flags, 0, nq * sizeof(int), st));
+    launch_circuit_a(E, level, d_c0, d_c1, d_c2, d_out, make_layout(layout, E.host.n, k, 2, nq), nqi, d_xb, d_yb, d_r, d_s, sc.as<u64>(), d_flags, st);
+    return PPLP_OK;
+    PPLP_CATCH
+}
+
+int pplp_circuit_a_host(pplp_ctx *ctx, size_t level, const uint64_t *h_c0, const uint64_t *h_c1, const uint64_t *h_c2, uint64_t *h_out, size_t nq,
+                        const uint64_t *h_xb, const uint64_t *h_yb, const uint64_t *h_r, const uint64_t *h_s, int *h_flags, size_t chunk) {
+    PPLP_TRY
+    Engine &E = dev_engine(ctx);
+    const size_t k = check_level(E, level), n = E.host.n;
+    if (nq == 0) return PPLP_OK;
+    if (chunk == 0) chunk = 256;
+    chunk = std::min(chunk, nq);
+    const size_t ctw = 2 * k * n;   // words per ciphertext
+    constexpr int NB = 3;           // slabs in flight: copy-in, compute, copy-out overlap
+    struct Slab { cudaStream_t st; u64 *c[3]; u64 *out; u64 *sc; u64 *par; int *flags; };
+    Slab sl[NB];
+    std::vector<void *> owned;
+    auto dalloc = [&](size_t bytes) { void *p; PPLP_CUDA(cudaMalloc(&p, bytes)); owned.push_back(p); return p; };
+    struct Cleanup {
+        std::vector<void *> &o; Slab *s; int nb;
+        ~Cleanup() { for (int i = 0; i < nb; ++i) if (s[i].st) cudaStreamDestroy(s[i].st); for (void *p : o) cudaFree(p); }
+    } cleanup{owned, sl, NB};
+    for (auto &s : sl) s.st = nullptr;
+    for (auto &s : sl) {
+        PPLP_CUDA(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+        for (int i = 0; i < 3; ++i) s.c[i] = (u64 *)dalloc(chunk * ctw * 8);
+        s.out = s.c[0];   // in place on c0
+        s.sc = (u64 *)dalloc(circuit_a_scratch_words(E, level, (int)chunk) * 8);
+        s.par = (u64 *)dalloc(chunk * 4 * 8);
+        s.flags = (int *)dalloc(chunk * sizeof(int));
+    }
+    const Layout lay = make_layout(PPLP_LAYOUT_SEAL, n, k, 2, chunk);
+    size_t done = 0;
+    for (int it = 0; done < nq; ++it) {
+        Slab &s = sl[it % NB];
+        const size_t c = std::min(chunk, nq - done);
+        const u64 *src[3] = {h_c0, h_c1, h_c2};
+        for (int i = 0; i < 3; ++i) PPLP_CUDA(cudaMemcpyAsync(s.c[i], src[i] + done * ctw, c * ctw * 8, cudaMemcpyHostToDevice, s.st));
+        const u64 *par[4] = {h_xb, h_yb, h_r, h_s};
+        for (int i = 0; i < 4; ++i) PPLP_CUDA(cudaMemcpyAsync(s.par + i * chunk, par[i] + done, c * 8, cudaMemcpyHostToDevice, s.st));
+        if (h_flags) PPLP_CUDA(cudaMemsetAsync(s.flags, 0, c * sizeof(int), s.st));
+        launch_circuit_a(E, level, s.c[0], s.c[1], s.c[2], s.out, lay, (int)c, s.par, s.par + chunk, s.par + 2 * chunk, s.par + 3 * chunk, s.sc,
+                         h_flags ? s.flags : nullptr, s.st);
+        PPLP_CUDA(cudaMemcpyAsync(h_out + done * ctw, s.out, c * ctw * 8, cudaMemcpyDeviceToHost, s.st));
+        if (h_flags) PPLP_CUDA(cudaMemcpyAsync(h_flags + done, s.flags, c * sizeof(int), cudaMemcpyDeviceToHost, s.st));
+        done += c;
+    }
+    for (auto &s : sl) PPLP_CUDA(cudaStreamSynchronize(s.st));
+    return PPLP_OK;
+    PPLP_CATCH
+}
+
+int pplp_ntt(pplp_ctx *ctx, size_t level, int base, uint64_t *d_data, int layout, size_t nq, size_t npoly, int inverse, void *stream) {
+    PPLP_TRY
+    Engine &E = dev_engine(ctx);
+    check_level(E, level);
+    if (base != 0 && base != 1) throw std::invalid_argument("pplp: base must be 0 (q) or 1 (Bsk)");
+    const RowMap map = base == 0 ? E.qmap(level) : E.bskmap(level);
+    launch_ntt(E, d_data, make_layout(layout, E.host.n, (size_t)map.nlimbs, npoly, nq), to_int(nq, "query count"), (int)npoly, map, inverse != 0, S(stream));
+    return PPLP_OK;
+    PPLP_CATCH
+}
+
+// ---- Bloom filter ----
+int pplp_bloom_params(uint64_t projected_elements, double fpp, uint64_t random_seed, uint32_t *k_out, uint64_t *m_bits_out, uint64_t *seed_out,
+                      uint32_t *salts) {
+    PPLP_TRY
+    bloomh::Params P;
+    if (!bloomh::make_params(projected_elements, fpp, random_seed, P)) throw std::invalid_argument("pplp: invalid Bloom filter parameters");
+    *k_out = P.k; *m_bits_out = P.m_bits; *seed_out = P.seed;
+    std::copy(P.salts.begin(), P.salts.end(), salts);
+    return PPLP_OK;
+    PPLP_CATCH
+}
+size_t pplp_bloom_table_stride(uint64_t m_bits) { return bloom_table_stride(m_bits); }
+int pplp_bloom_build(pplp_ctx *ctx, uint8_t *d_tables, uint64_t m_bits, const uint32_t *d_salts, uint32_t k, const uint64_t *d_rsw, size_t nf,
+                     uint64_t count, void *stream) {
+    PPLP_TRY
+    Engine &E = dev_engine(ctx);
+    if (m_bits == 0 || m_bits % 8 || k == 0 || k > 128) throw std::invalid_argument("pplp: invalid Bloom filter geometry");
+    launch_bloom_build(E, d_tables, m_bits, d_salts, (int)k, d_rsw, to_int(nf, "filter count"), count, S(stream));
+    return PPLP_OK;
+    PPLP_CATCH
+}
+int pplp_bloom_query(pplp_ctx *ctx, const uint8_t *d_tables, uint64_t m_bits, const uint32_t *d_salts, uint32_t k, const uint64_t *d_bd, size_t bd_stride,
+                     const uint64_t *d_rsw, const int *d_fidx, size_t nq, uint8_t *d_verdict, void *stream) {
+    PPLP_TRY
+    Engine &E = dev_engine(ctx);
+    if (m_bits == 0 || m_bits % 8 || k == 0 || k > 128) throw std::invalid_argument("pplp: invalid Bloom filter geometry");
+    launch_bloom_query(E, d_tables, m_bits, d_salts, (int)k, d_bd, bd_stride, d_rsw, d_fidx, to_int(nq, "query count"), d_verdict, S(stream));
+    return PPLP_OK;
+    PPLP_CATCH
+}
+int pplp_bloom_insert_keys(pplp_ctx *ctx, uint8_t *d_table, uint64_t m_bits, const uint32_t *d_salts, uint32_t k, const uint64_t *d_keys, size_t nkeys,
+                           void *stream) {
+    PPLP_TRY
+    Engine &E = dev_engine(ctx);
+    launch_bloom_insert_keys(E, d_table, m_bits, d_salts, (int)k, d_keys, to_int(nkeys, "key count"), S(stream));
+    return PPLP_OK;
+    PPLP_CATCH
+}
+int pplp_bloom_contains_keys(pplp_ctx *ctx, const uint8_t *d_table, uint64_t m_bits, const uint32_t *d_salts, uint32_t k, const uint64_t *d_keys,
+                             size_t nkeys, uint8_t *d_verdict, void *stream) {
+    PPLP_TRY
+    Engine &E = dev_engine(ctx);
+    launch_bloom_contains_keys(E, d_table, m_bits, d_salts, (int)k, d_keys, to_int(nkeys, "key count"), d_verdict, S(stream));
+    return PPLP_OK;
+    PPLP_CATCH
+}
+
+// ---- protocol ----
+int pplp_proximity_batch(pplp_ctx *ctx, const uint64_t *d_pk, const uint64_t *d_sk, size_t nq, const uint64_t *d_xa, const uint64_t *d_ya,
+                         const uint64_t *d_xb, const uint64_t *d_yb, const uint64_t *d_rsw, const int *d_fidx, const uint64_t *d_seeds,
+                         const uint8_t *d_tables, uint64_t m_bits, const uint32_t *d_salts, uint32_t k, uint64_t *d_blind, uint8_t *d_verdict,
+                         int *d_flags, size_t chunk, void *stream) {
+    PPLP_TRY
+    Engine &E = dev_engine(ctx);
+    if (nq == 0) return PPLP_OK;
+    to_int(nq, "query count");
+    const size_t level = E.host.first_level(), kk = E.host.levels[level].q.size(), n = E.host.n;
+    if (chunk == 0) chunk = 1024;
+    chunk = std::min(chunk, nq);
+    cudaStream_t st = S(stream);
+    const size_t ctw = 2 * kk * n;
+    const int C = (int)chunk;
+    // per chunk: ciphertext q*3+i is encryption i of query q, so (c0,c1,c2) of one query are adjacent and Circuit A
+    // sees three interleaved batches with query stride 3*ctw
+    Scratch cts(chunk * 3 * ctw * 8, st), ws(encrypt_tmp_words(E, 3 * C) * 8, st), plain(chunk * 3 * 8, st), sc(circuit_a_scratch_words(E, level, C) * 8, st),
+        dtmp(decrypt_tmp_words(E, level, C, 2) * 8, st), rs(chunk * 2 * 8, st), err(sizeof(int), st);
+    PPLP_CUDA(cudaMemsetAsync(err.p, 0, sizeof(int), st));
+    if (d_flags) PPLP_CUDA(cudaMemsetAsync(d_flags, 0, nq * sizeof(int), st));
+    const Layout enc_lay = make_layout(PPLP_LAYOUT_SEAL, n, kk, 2, 3 * chunk);
+    const Layout q_lay{3 * ctw, kk * n, n};
+    for (size_t done = 0; done < nq; done += chunk) {
+        const int c = (int)std::min(chunk, nq - done);
+        proximity_plain_kernel<<<(c + 255) / 256, 256, 0, st>>>(d_xa + done, d_ya + done, c, E.host.t, plain.as<u64>(), d_flags ? d_flags + done : nullptr);
+        launch_encrypt(E, d_pk, d_seeds + done * 3 * 8, plain.as<u64>(), 1, 1, ws.as<u64>(), cts.as<u64>(), enc_lay, 3 * c, err.as<int>(), st);
+        gather_u64_kernel<<<(c + 255) / 256, 256, 0, st>>>(d_rsw, d_fidx ? d_fidx + done : nullptr, 3, 0, c, rs.as<u64>());
+        gather_u64_kernel<<<(c + 255) / 256, 256, 0, st>>>(d_rsw, d_fidx ? d_fidx + done : nullptr, 3, 1, c, rs.as<u64>() + chunk);
+        u64 *base = cts.as<u64>();
+        launch_circuit_a(E, level, base, base + ctw, base + 2 * ctw, base, q_lay, c, d_xb + done, d_yb + done, rs.as<u64>(), rs.as<u64>() + chunk, sc.as<u64>(),
+                         d_flags ? d_flags + done : nullptr, st);
+        launch_decrypt(E, level, base, q_lay, c, 2, d_sk, dtmp.as<u64>(), d_blind + done, 1, 1, st);
+        if (d_tables && d_verdict)
+            launch_bloom_query(E, d_tables, m_bits, d_salts, (int)k, d_blind + done, 1, d_rsw, d_fidx ? d_fidx + done : nullptr, c, d_verdict + done, st);
+    }
+    return PPLP_OK;
+    PPLP_CATCH
+}
+
+int pplp_proximity_batch_host(pplp_ctx *ctx, const uint64_t *d_pk, const uint64_t *d_sk, size_t nq, const uint64_t *h_xa, const uint64_t *h_ya,
+                              const uint64_t *h_xb, const uint64_t *h_yb, const uint64_t *d_rsw, const int *h_fidx, const uint64_t *h_seeds,
+                              const uint8_t *d_tables, uint64_t m_bits, const uint32_t *d_salts, uint32_t k, uint64_t *h_blind, uint8_t *h_verdict,
+                              int *h_flags, size_t chunk) {
+    PPLP_TRY
+    Engine &E = dev_engine(ctx);
+    if (nq == 0) return PPLP_OK;
+    cudaStream_t st;
+    PPLP_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    struct Guard { cudaStream_t s; ~Guard() { cudaStreamDestroy(s); } } guard{st};
+    int rc;
+    {
+        Scratch in(nq * 4 * 8, st), seeds(nq * 3 * 64, st), fidx(nq * sizeof(int), st), blind(nq * 8, st), verdict(nq, st), flags(nq * sizeof(int), st);
+        u64 *d_in = in.as<u64>();
+        const u64 *src[4] = {h_xa, h_ya, h_xb, h_yb};
+        for (int i = 0; i < 4; ++i) PPLP_CUDA(cudaMemcpyAsync(d_in + i * nq, src[i], nq * 8, cudaMemcpyHostToDevice, st));
+        PPLP_CUDA(cudaMemcpyAsync(seeds.p, h_seeds, nq * 3 * 64, cudaMemcpyHostToDevice, st));
+        if (h_fidx) PPLP_CUDA(cudaMemcpyAsync(fidx.p, h_fidx, nq * sizeof(int), cudaMemcpyHostToDevice, st));
+        PPLP_CUDA(cudaMemsetAsync(verdict.p, 0, nq, st));
+        rc = pplp_proximity_batch(ctx, d_pk, d_sk, nq, d_in, d_in + nq, d_in + 2 * nq, d_in + 3 * nq, d_rsw, h_fidx ? fidx.as<int>() : nullptr, seeds.as<u64>(),
+                                  d_tables, m_bits, d_salts, k, blind.as<u64>(), verdict.as<uint8_t>(), flags.as<int>(), chunk, st);
+        if (rc == PPLP_OK) {
+            PPLP_CUDA(cudaMemcpyAsync(h_blind, blind.p, nq * 8, cudaMemcpyDeviceToHost, st));
+            if (h_verdict) PPLP_CUDA(cudaMemcpyAsync(h_verdict, verdict.p, nq, cudaMemcpyDeviceToHost, st));
+            if (h_flags) PPLP_CUDA(cudaMemcpyAsync(h_flags, flags.p, nq * sizeof(int), cudaMemcpyDeviceToHost, st));
+        }
+    }
+    PPLP_CUDA(cudaStreamSynchronize(st));
+    return rc;
+    PPLP_CATCH
+}
+
+int pplp_prng_stream(pplp_ctx *ctx, const uint64_t *d_seeds, size_t nstreams, size_t nrefill, uint64_t *d_out, void *stream) {
+    PPLP_TRY
+    Engine &E = dev_engine(ctx);
+    launch_prng_stream(E, d_seeds, to_int(nstreams, "stream count"), to_int(nrefill, "refill count"), d_out, S(stream));
+    return PPLP_OK;
+    PPLP_CATCH
+}
+
+}  // extern "C"

@@ -1,0 +1,438 @@
+// pplp_b200/csrc/crypto.cu — client-side BFV kernels: randomness (BLAKE2Xb PRNG + samplers), public-key encryption,
+// decryption (dot product with the secret key + BEHZ scale-and-round) and the device half of key generation.
+//
+// Reference call sites: Encryptor::encrypt src/client.cc:111-113, src/demo.cc:138-140; Decryptor::decrypt
+// src/client.cc:151, src/demo.cc:164; KeyGenerator src/demo.cc:81-85, src/client.cc:103-106.
+// [SEAL] encryptor.cpp, decryptor.cpp, keygenerator.cpp, util/rlwe.cpp, util/rns.cpp, randomgen.cpp, util/blake2xb.c.
+//
+// Encryption of one ciphertext (K key-level limbs, k = K-1 data limbs):
+//   prng_stream_kernel     BLAKE2Xb stream of the ciphertext's own PRNG: every 64-byte block is one independent
+//                          compression of the refill's root hash, so the stream is generated 64 B per thread
+//   sample_encrypt_kernel  u <- ternary (libstdc++ uniform_int_distribution<u64>(0,2) over 32-bit draws, i.e.
+//                          Lemire's method: only a zero draw is rejected), e0, e1 <- centred binomial (6 bytes each);
+//                          stream order u, e0, e1 as in encrypt_zero_asymmetric
+//   encrypt_limb_kernel    per (ciphertext, limb): U = NTT(u); for p in {0,1}: T_p = INTT(U (.) pk_p) + e_p.
+//                          One forward transform feeds both inverse transforms; nothing NTT-form touches HBM.
+//   modswitch_kernel       divide_and_round_q_last (drop the special prime) fused with the scaling-variant plaintext
+//                          addition c0 += round(Q m / t): the only cross-limb step.
+#include "blake2.cuh"
+#include "engine.hpp"
+#include "ntt.cuh"
+
+namespace pplp {
+
+typedef unsigned __int128 u128;
+
+// ---- PRNG stream ---------------------------------------------------------------------------------------------------
+constexpr int kRefillBytes = 4096;       // [SEAL] UniformRandomGenerator buffer size
+constexpr int kRefillsPerCta = 32;
+
+__global__ void __launch_bounds__(256) prng_stream_kernel(const u64 *__restrict__ seeds, int nrefill, u64 *__restrict__ stream) {
+    __shared__ u64 roots[kRefillsPerCta][8];
+    const int ct = blockIdx.y;
+    const int refill0 = blockIdx.x * kRefillsPerCta;
+    const u64 *seed = seeds + (size_t)ct * 8;
+    if (threadIdx.x < kRefillsPerCta && refill0 + threadIdx.x < nrefill) {
+        u64 s[8], root[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s[i] = seed[i];
+        b2::xof_root(s, (u64)(refill0 + threadIdx.x), root);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) roots[threadIdx.x][i] = root[i];
+    }
+    __syncthreads();
+    u64 *dst = stream + (size_t)ct * nrefill * (kRefillBytes / 8);
+    for (int idx = threadIdx.x; idx < kRefillsPerCta * 64; idx += 256) {
+        const int r = idx >> 6, b = idx & 63;
+        if (refill0 + r >= nrefill) break;
+        u64 root[8], out[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) root[i] = roots[r][i];
+        b2::xof_block(root, (unsigned)b, out);
+        ulonglong2 *o = reinterpret_cast<ulonglong2 *>(dst + ((size_t)(refill0 + r) * 64 + b) * 8);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = make_ulonglong2(out[2 * i], out[2 * i + 1]);
+    }
+}
+
+int encrypt_stream_refills(int n) { return (16 * n + kRefillBytes - 1) / kRefillBytes + 1; }  // + 1024 spare draws for rejections
+
+// ---- samplers ------------------------------------------------------------------------------------------------------
+// One CTA per ciphertext.  noise: int8 [nct][3][n] = u, e0, e1.  errflag set if the spare refill was exhausted.
+__global__ void __launch_bounds__(1024) sample_encrypt_kernel(const u64 *__restrict__ stream, int nrefill, int n, signed char *__restrict__ noise, int *errflag) {
+    __shared__ int warp_sums[32];
+    __shared__ int s_base, s_end_word;
+    const int ct = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned *words = reinterpret_cast<const unsigned *>(stream + (size_t)ct * nrefill * (kRefillBytes / 8));
+    const int total_words = nrefill * (kRefillBytes / 4);
+    signed char *u = noise + (size_t)ct * 3 * n;
+    if (tid == 0) { s_base = 0; s_end_word = -1; }
+    __syncthreads();
+    // ternary: accepted draw a sits at the a-th non-zero 32-bit word
+    for (int pos = 0; pos < total_words; pos += 1024) {
+        const int base = s_base;
+        if (base >= n) break;
+        const int wi = pos + tid;
+        const unsigned w = wi < total_words ? words[wi] : 0u;
+        const int flag = (wi < total_words && w != 0u) ? 1 : 0;
+        const unsigned ball = __ballot_sync(0xffffffffu, flag);
+        const int in_warp = __popc(ball & ((1u << lane) - 1u));
+        if (lane == 0) warp_sums[warp] = __popc(ball);
+        __syncthreads();
+        int before = 0;
+        for (int v = 0; v < warp; ++v) before += warp_sums[v];
+        const int a = base + before + in_warp;
+        if (flag && a < n) {
+            const unsigned r = (unsigned)(((u64)w * 3ull) >> 32);   // Lemire: high half of the 64-bit product
+            u[a] = (signed char)((int)r - 1);
+            if (a == n - 1) s_end_word = wi + 1;
+        }
+        __syncthreads();
+        if (tid == 1023) s_base = base + before + in_warp + flag;
+        __syncthreads();
+    }
+    const int end_word = s_end_word;
+    if (end_word < 0 || (size_t)end_word * 4 + (size_t)12 * n > (size_t)total_words * 4) {
+        if (tid == 0) atomicExch(errflag, 1);
+        return;
+    }
+    // centred binomial: 6 bytes per sample, x2 and x5 masked to 5 bits  ([SEAL] util/rlwe.cpp sample_poly_cbd)
+    const unsigned short *h = reinterpret_cast<const unsigned short *>(words + end_word);
+    for (int i = tid; i < 2 * n; i += 1024) {
+        const unsigned w0 = h[3 * i], w1 = h[3 * i + 1], w2 = h[3 * i + 2];
+        const int v = __popc(w0) + __popc(w1 & 0x1Fu) - __popc(w1 >> 8) - __popc(w2 & 0xFFu) - __popc((w2 >> 8) & 0x1Fu);
+        u[n + i] = (signed char)v;
+    }
+}
+
+// ---- encryption ----------------------------------------------------------------------------------------------------
+struct EncLimbArgs {
+    const signed char *noise;   // [nct][3][n]
+    const u64 *pk;              // [2][K][n] NTT form
+    u64 *tmp;                   // [nct][2][K][n]
+    int K, n;
+    const DevMod *mods;
+};
+
+template <int LOGM>
+__global__ void __launch_bounds__(NttShape<LOGM>::T) encrypt_limb_kernel(const EncLimbArgs a) {
+    using S = NttShape<LOGM>;
+    extern __shared__ __align__(16) u64 sm[];
+    const int tid = threadIdx.x;
+    const int ct = blockIdx.x / a.K, j = blockIdx.x % a.K;   // limbs of one ciphertext adjacent: noise stays in L2/L1
+    const DevMod &md = a.mods[j];
+    const Mod mod = md.m;
+    const u64 q = mod.q;
+    const signed char *nz = a.noise + (size_t)ct * 3 * a.n;
+
+    u64 x[16], uu[16];
+    CoarsePass<LOGM>::for_each(tid, [&](int r, int i) {
+        const int v = nz[i];
+        x[r] = v < 0 ? q - 1 : (u64)v;
+    });
+    block_ntt_forward<LOGM>(x, sm, tid, md.fwd, 0, 0, q);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) uu[r] = canon4(x[r], q);
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        const u64 *pk = a.pk + ((size_t)p * a.K + j) * a.n + 16 * tid;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const ulonglong2 bv = __ldg(reinterpret_cast<const ulonglong2 *>(pk + 2 * c));
+            x[2 * c] = mul_mod(uu[2 * c], bv.x, mod);
+            x[2 * c + 1] = mul_mod(uu[2 * c + 1], bv.y, mod);
+        }
+        __syncthreads();
+        block_ntt_inverse<LOGM, true>(x, sm, tid, md.inv, 0, 0, q, md.n_inv, md.inv1_n_inv);
+        u64 *out = a.tmp + (((size_t)ct * 2 + p) * a.K + j) * a.n;
+        const signed char *e = nz + (size_t)(1 + p) * a.n;
+        CoarsePass<LOGM>::for_each(tid, [&](int r, int i) {
+            const int v = e[i];
+            const u64 ev = v < 0 ? q - (u64)(-v) : (u64)v;
+            out[i] = add_mod(csub(x[r], q), ev, q);
+        });
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ u64 dev_scaled_plain(const DevLevel &L, u64 m, int j) {
+    const u128 numer = (u128)m * L.q_mod_t + L.t_threshold;
+    const u64 fix = (u64)(numer / L.t);
+    const Mod &mq = L.q[j];
+    return add_mod(mul_mod(barrett64(m, mq), L.delta[j], mq), barrett64(fix, mq), mq.q);
+}
+
+// tmp [nct][2][K][n] at key level -> out (data level, k = K-1 limbs), c0 += round(Q m/t).   KL = key level constants,
+// DL = data level constants.  grid.y = ct*2 + p.
+__global__ void __launch_bounds__(256) modswitch_kernel(const DevLevel *KLp, const DevLevel *DLp, const u64 *__restrict__ tmp, u64 *__restrict__ out, Layout lay,
+                                                        const u64 *__restrict__ plain, int plain_count, size_t plain_stride) {
+    const DevLevel &KL = *KLp;
+    const DevLevel &DL = *DLp;
+    const int K = KL.k, k = K - 1, n = KL.n;
+    const int ct = blockIdx.y >> 1, p = blockIdx.y & 1;
+    const u64 P = KL.q[K - 1].q, half = KL.half_last;
+    const u64 *src = tmp + ((size_t)ct * 2 + p) * K * n;
+    u64 *dst = out + ct * lay.sq + p * lay.sp;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const u64 last = add_mod(src[(size_t)(K - 1) * n + i], half, P);
+        const bool has_plain = (p == 0 && i < plain_count);
+        const u64 m = has_plain ? plain[ct * plain_stride + i] : 0;
+        for (int j = 0; j < k; ++j) {
+            const Mod &mq = KL.q[j];
+            const u64 corr = sub_mod(barrett64(last, mq), KL.half_last_mod[j], mq.q);
+            u64 v = mul_shoup(sub_mod(src[(size_t)j * n + i], corr, mq.q), KL.inv_last[j], mq.q);
+            if (has_plain) v = add_mod(v, dev_scaled_plain(DL, m, j), mq.q);
+            dst[j * lay.sl + i] = v;
+        }
+    }
+}
+
+// single-prime chain (K == 1): no modulus switching, tmp is already the ciphertext
+__global__ void __launch_bounds__(256) copy_addplain_kernel(const DevLevel *DLp, const u64 *__restrict__ tmp, u64 *__restrict__ out, Layout lay,
+                                                            const u64 *__restrict__ plain, int plain_count, size_t plain_stride) {
+    const DevLevel &DL = *DLp;
+    const int k = DL.k, n = DL.n;
+    const int ct = blockIdx.y >> 1, p = blockIdx.y & 1;
+    const u64 *src = tmp + ((size_t)ct * 2 + p) * k * n;
+    u64 *dst = out + ct * lay.sq + p * lay.sp;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const bool has_plain = (p == 0 && i < plain_count);
+        const u64 m = has_plain ? plain[ct * plain_stride + i] : 0;
+        for (int j = 0; j < k; ++j) {
+            u64 v = src[(size_t)j * n + i];
+            if (has_plain) v = add_mod(v, dev_scaled_plain(DL, m, j), DL.q[j].q);
+            dst[j * lay.sl + i] = v;
+        }
+    }
+}
+
+// generic (unfused) pieces used when N does not fit one CTA (N = 32768)
+__global__ void expand_noise_kernel(const DevMod *mods, const signed char *__restrict__ noise, int which, u64 *__restrict__ out, size_t out_ct_stride, int K, int n) {
+    const int ct = blockIdx.z, j = blockIdx.y;
+    const u64 q = mods[j].m.q;
+    const signed char *src = noise + ((size_t)ct * 3 + which) * n;
+    u64 *dst = out + ct * out_ct_stride + (size_t)j * n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int v = src[i];
+        dst[i] = v < 0 ? q - (u64)(-v) : (u64)v;
+    }
+}
+__global__ void mul_pk_kernel(const DevMod *mods, const u64 *__restrict__ u_ntt, const u64 *__restrict__ pk, u64 *__restrict__ tmp, int K, int n) {
+    const int ct = blockIdx.z, j = blockIdx.y;
+    const Mod mq = mods[j].m;
+    const u64 *uu = u_ntt + ((size_t)ct * K + j) * n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const u64 v = uu[i];
+        tmp[(((size_t)ct * 2 + 0) * K + j) * n + i] = mul_mod(v, pk[((size_t)0 * K + j) * n + i], mq);
+        tmp[(((size_t)ct * 2 + 1) * K + j) * n + i] = mul_mod(v, pk[((size_t)1 * K + j) * n + i], mq);
+    }
+}
+__global__ void add_noise_kernel(const DevMod *mods, const signed char *__restrict__ noise, u64 *__restrict__ tmp, int K, int n) {
+    const int ct = blockIdx.z >> 1, p = blockIdx.z & 1, j = blockIdx.y;
+    const u64 q = mods[j].m.q;
+    const signed char *e = noise + ((size_t)ct * 3 + 1 + p) * n;
+    u64 *dst = tmp + (((size_t)ct * 2 + p) * K + j) * n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int v = e[i];
+        dst[i] = add_mod(dst[i], v < 0 ? q - (u64)(-v) : (u64)v, q);
+    }
+}
+
+size_t encrypt_tmp_words(const Engine &E, int nct) {
+    const size_t n = E.host.n, K = E.host.K();
+    const size_t stream = (size_t)nct * encrypt_stream_refills((int)n) * (kRefillBytes / 8);
+    const size_t noise = ((size_t)nct * 3 * n + 7) / 8 + 2;
+    const size_t tmp = (size_t)nct * 2 * K * n;
+    const size_t extra = E.host.logn == 15 ? (size_t)nct * K * n : 0;
+    return stream + noise + tmp + extra + 8;
+}
+
+template <int LOGM> static void run_encrypt_limb(const EncLimbArgs &a, int nct, cudaStream_t st) {
+    static bool done[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int bytes = NttShape<LOGM>::SMEM_WORDS * 8;
+    if (!done[dev]) { PPLP_CUDA(cudaFuncSetAttribute(encrypt_limb_kernel<LOGM>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)); done[dev] = true; }
+    encrypt_limb_kernel<LOGM><<<nct * a.K, NttShape<LOGM>::T, bytes, st>>>(a);
+}
+
+void launch_encrypt(const Engine &E, const u64 *pk, const u64 *seeds, const u64 *plain, size_t plain_count, size_t plain_stride, u64 *ws, u64 *out,
+                    Layout out_lay, int nct, int *errflag, cudaStream_t st) {
+    E.require_device();
+    if (nct == 0) return;
+    const int n = (int)E.host.n, K = (int)E.host.K();
+    const int nrefill = encrypt_stream_refills(n);
+    u64 *stream = ws;
+    signed char *noise = reinterpret_cast<signed char *>(stream + (size_t)nct * nrefill * (kRefillBytes / 8));
+    u64 *tmp = reinterpret_cast<u64 *>(noise) + ((size_t)nct * 3 * n + 7) / 8 + 2;
+    u64 *extra = tmp + (size_t)nct * 2 * K * n;
+    dim3 gs((nrefill + kRefillsPerCta - 1) / kRefillsPerCta, nct);
+    prng_stream_kernel<<<gs, 256, 0, st>>>(seeds, nrefill, stream);
+    sample_encrypt_kernel<<<nct, 1024, 0, st>>>(stream, nrefill, n, noise, errflag);
+    EncLimbArgs a{noise, pk, tmp, K, n, E.d_mods};
+    switch (E.host.logn) {
+    case 10: run_encrypt_limb<10>(a, nct, st); break;
+    case 11: run_encrypt_limb<11>(a, nct, st); break;
+    case 12: run_encrypt_limb<12>(a, nct, st); break;
+    case 13: run_encrypt_limb<13>(a, nct, st); break;
+    case 14: run_encrypt_limb<14>(a, nct, st); break;
+    case 15: {
+        RowMap map = E.qmap(0);
+        dim3 g((n + 1023) / 1024, K, nct);
+        expand_noise_kernel<<<g, 256, 0, st>>>(E.d_mods, noise, 0, extra, (size_t)K * n, K, n);
+        launch_ntt(E, extra, Layout{(size_t)K * n, 0, (size_t)n}, nct, 1, map, false, st);
+        mul_pk_kernel<<<g, 256, 0, st>>>(E.d_mods, extra, pk, tmp, K, n);
+        launch_ntt(E, tmp, Layout{(size_t)2 * K * n, (size_t)K * n, (size_t)n}, nct, 2, map, true, st);
+        dim3 g2((n + 1023) / 1024, K, nct * 2);
+        add_noise_kernel<<<g2, 256, 0, st>>>(E.d_mods, noise, tmp, K, n);
+        break;
+    }
+    default: throw std::invalid_argument("pplp: encryption kernels support poly_modulus_degree 1024..32768");
+    }
+    dim3 gm((n + 255) / 256, nct * 2);
+    const size_t first = E.host.first_level();
+    if (K > 1) modswitch_kernel<<<gm, 256, 0, st>>>(E.d_levels, E.d_levels + first, tmp, out, out_lay, plain, (int)plain_count, plain_stride);
+    else copy_addplain_kernel<<<gm, 256, 0, st>>>(E.d_levels, tmp, out, out_lay, plain, (int)plain_count, plain_stride);
+    PPLP_CUDA(cudaGetLastError());
+}
+
+// ---- decryption ----------------------------------------------------------------------------------------------------
+// x [nq][k][n] (= c0 + c1 s (+ c2 s^2), canonical) -> m [nq][ncoeff]   ([SEAL] RNSTool::decrypt_scale_and_round)
+__global__ void __launch_bounds__(256) scale_round_kernel(const DevLevel *Lp, const u64 *__restrict__ x, u64 *__restrict__ plain, size_t plain_stride, int ncoeff) {
+    const DevLevel &L = *Lp;
+    const int k = L.k, n = L.n;
+    const int qi = blockIdx.y;
+    const u64 t = L.t, gamma = L.gamma.q, gamma_half = gamma >> 1;
+    const u64 *src = x + (size_t)qi * k * n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ncoeff; i += gridDim.x * blockDim.x) {
+        U128 at{0, 0}, ag{0, 0};
+        for (int j = 0; j < k; ++j) {
+            const u64 q = L.q[j].q;
+            const u64 y = mul_shoup(src[(size_t)j * n + i], L.t_gamma[j], q);
+            const u64 z = mul_shoup(y, L.inv_punct[j], q);
+            mac128(at, z, L.punct_mod_t[j]);       // k * 2^60 * 2^61 < 2^128
+            mac128(ag, z, L.punct_mod_gamma[j]);
+        }
+        const u64 yt = mul_mod(barrett128(at.lo, at.hi, L.tmod), L.neg_inv_q_mod_t, L.tmod);
+        const u64 yg = mul_mod(barrett128(ag.lo, ag.hi, L.gamma), L.neg_inv_q_mod_gamma, L.gamma);
+        u64 r;
+        if (yg > gamma_half) r = add_mod(yt, barrett64(gamma - yg, L.tmod), t);
+        else r = sub_mod(yt, barrett64(yg, L.tmod), t);
+        if (r) r = mul_mod(r, L.inv_gamma_mod_t, L.tmod);
+        plain[qi * plain_stride + i] = r;
+    }
+}
+
+// acc += NTT(c2) (.) s^2 : only for size-3 inputs (not on the reference path); unfused.
+__global__ void dot3_kernel(const DevMod *mods, const u64 *__restrict__ c1n, const u64 *__restrict__ c2n, const u64 *__restrict__ sk, u64 *__restrict__ acc, int k, int n) {
+    const int qi = blockIdx.z, j = blockIdx.y;
+    const Mod mq = mods[j].m;
+    const size_t off = ((size_t)qi * k + j) * n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const u64 s = sk[(size_t)j * n + i];
+        const u64 s2 = mul_mod(s, s, mq);
+        acc[off + i] = add_mod(mul_mod(c1n[off + i], s, mq), mul_mod(c2n[off + i], s2, mq), mq.q);
+    }
+}
+__global__ void gather_rows_kernel(const u64 *__restrict__ src, Layout lay, int p, u64 *__restrict__ dst, int k, int n) {
+    const int qi = blockIdx.z, j = blockIdx.y;
+    const u64 *s = src + qi * lay.sq + p * lay.sp + j * lay.sl;
+    u64 *d = dst + ((size_t)qi * k + j) * n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) d[i] = s[i];
+}
+__global__ void add_rows_kernel(const DevMod *mods, u64 *__restrict__ acc, const u64 *__restrict__ src, Layout lay, int p, int k, int n) {
+    const int qi = blockIdx.z, j = blockIdx.y;
+    const u64 q = mods[j].m.q;
+    const u64 *s = src + qi * lay.sq + p * lay.sp + j * lay.sl;
+    u64 *d = acc + ((size_t)qi * k + j) * n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) d[i] = add_mod(d[i], s[i], q);
+}
+
+size_t decrypt_tmp_words(const Engine &E, size_t level, int nq, int size) {
+    const size_t k = E.host.levels[level].q.size(), n = E.host.n;
+    const bool generic = size > 2 || E.host.logn == 15;
+    return (size_t)nq * k * n * (generic ? 3 : 1);
+}
+
+void launch_decrypt(const Engine &E, size_t level, const u64 *ct, Layout lay, int nq, int size, const u64 *sk, u64 *tmp, u64 *plain_out, size_t plain_stride,
+                    int ncoeff, cudaStream_t st) {
+    E.require_device();
+    if (nq == 0) return;
+    const int k = (int)E.host.levels[level].q.size(), n = (int)E.host.n;
+    RowMap map = E.qmap(level);
+    const Layout tl{(size_t)k * n, 0, (size_t)n};
+    if (size == 2 && E.host.logn <= 14) {
+        // x = INTT(NTT(c1) (.) s) + c0 in one kernel
+        Layout a_lay = lay, c_lay = lay;
+        launch_polymul(E, ct + lay.sp, a_lay, sk, Layout{0, 0, (size_t)n}, ct, c_lay, tmp, tl, nq, 1, map, st);
+    } else {
+        u64 *c1n = tmp + (size_t)nq * k * n, *c2n = c1n + (size_t)nq * k * n;
+        dim3 g((n + 1023) / 1024, k, nq);
+        gather_rows_kernel<<<g, 256, 0, st>>>(ct, lay, 1, c1n, k, n);
+        launch_ntt(E, c1n, tl, nq, 1, map, false, st);
+        if (size == 3) {
+            gather_rows_kernel<<<g, 256, 0, st>>>(ct, lay, 2, c2n, k, n);
+            launch_ntt(E, c2n, tl, nq, 1, map, false, st);
+            dot3_kernel<<<g, 256, 0, st>>>(E.d_mods, c1n, c2n, sk, tmp, k, n);
+        } else if (size == 2) {
+            PPLP_CUDA(cudaMemcpyAsync(tmp, c1n, (size_t)nq * k * n * 8, cudaMemcpyDeviceToDevice, st));
+            launch_dyadic(E, tmp, tl, sk, Layout{0, 0, (size_t)n}, nq, 1, map, st);
+        } else {
+            throw std::invalid_argument("pplp: decrypt supports ciphertexts of size 2 or 3");
+        }
+        launch_ntt(E, tmp, tl, nq, 1, map, true, st);
+        add_rows_kernel<<<g, 256, 0, st>>>(E.d_mods, tmp, ct, lay, 0, k, n);
+    }
+    dim3 gs((ncoeff + 255) / 256, nq);
+    scale_round_kernel<<<gs, 256, 0, st>>>(E.d_levels + level, tmp, plain_out, plain_stride, ncoeff);
+    PPLP_CUDA(cudaGetLastError());
+}
+
+// ---- key generation (device half) ----------------------------------------------------------------------------------
+// small signed values [n] -> residues [K][n]
+__global__ void expand_small_kernel(const DevMod *mods, const signed char *__restrict__ src, u64 *__restrict__ out, int n) {
+    const int j = blockIdx.y;
+    const u64 q = mods[j].m.q;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int v = src[i];
+        out[(size_t)j * n + i] = v < 0 ? q - (u64)(-v) : (u64)v;
+    }
+}
+// pk0 = -(a (.) s + e), everything NTT form; optional extra term (P mod q_i) s^2 on limb `digit` (relin keys)
+__global__ void pk_combine_kernel(const DevMod *mods, const u64 *__restrict__ a, const u64 *__restrict__ s, const u64 *__restrict__ e, u64 *__restrict__ c0, int n,
+                                  int digit, u64 factor) {
+    const int j = blockIdx.y;
+    const Mod mq = mods[j].m;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const size_t o = (size_t)j * n + i;
+        const u64 sv = s[o];
+        u64 v = neg_mod(add_mod(e[o], mul_mod(sv, a[o], mq), mq.q), mq.q);
+        if (j == digit) v = add_mod(v, mul_mod(mul_mod(sv, sv, mq), factor, mq), mq.q);
+        c0[o] = v;
+    }
+}
+
+void launch_expand_small(const Engine &E, const signed char *d_small, u64 *out, cudaStream_t st) {
+    E.require_device();
+    const int n = (int)E.host.n, K = (int)E.host.K();
+    dim3 g((n + 1023) / 1024, K);
+    expand_small_kernel<<<g, 256, 0, st>>>(E.d_mods, d_small, out, n);
+    PPLP_CUDA(cudaGetLastError());
+}
+void launch_pk_combine(const Engine &E, const u64 *a, const u64 *s, const u64 *e_ntt, u64 *c0, int digit, u64 factor, cudaStream_t st) {
+    E.require_device();
+    const int n = (int)E.host.n, K = (int)E.host.K();
+    dim3 g((n + 1023) / 1024, K);
+    pk_combine_kernel<<<g, 256, 0, st>>>(E.d_mods, a, s, e_ntt, c0, n, digit, factor);
+    PPLP_CUDA(cudaGetLastError());
+}
+
+// raw PRNG stream for tests and for host-driven samplers: out [nrefill*4096 bytes]
+void launch_prng_stream(const Engine &E, const u64 *d_seed, int nstreams, int nrefill, u64 *out, cudaStream_t st) {
+    E.require_device();
+    dim3 gs((nrefill + kRefillsPerCta - 1) / kRefillsPerCta, nstreams);
+    prng_stream_kernel<<<gs, 256, 0, st>>>(d_seed, nrefill, out);
+    PPLP_CUDA(cudaGetLastError());
+}
+
+}  // namespace pplp

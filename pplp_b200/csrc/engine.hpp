@@ -1,0 +1,92 @@
+// pplp_b200/csrc/engine.hpp — the device-side context (tables in HBM) and the launch interface of every kernel file.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "context.hpp"
+
+namespace pplp {
+
+struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
+#define PPLP_CUDA(expr)                                                                                          \
+    do {                                                                                                         \
+        cudaError_t e__ = (expr);                                                                                \
+        if (e__ != cudaSuccess) throw ::pplp::CudaError(std::string(#expr) + ": " + cudaGetErrorString(e__));    \
+    } while (0)
+
+struct Engine {
+    HostContext host;
+    int device = -1;                 // -1: host-only context (no kernels may be launched)
+    int sm_count = 148;
+    DevMod *d_mods = nullptr;        // [tables.size()]
+    DevLevel *d_levels = nullptr;    // [levels.size()]
+    std::vector<void *> owned;       // device allocations freed with the engine
+    std::vector<DevMod> h_mods;
+
+    void require_device() const { if (device < 0) throw std::logic_error("pplp: context was created without a CUDA device"); }
+    template <class T> T *upload(const T *src, size_t count) {
+        T *d = nullptr;
+        PPLP_CUDA(cudaMalloc(&d, count * sizeof(T)));
+        owned.push_back(d);
+        PPLP_CUDA(cudaMemcpy(d, src, count * sizeof(T), cudaMemcpyHostToDevice));
+        return d;
+    }
+    void upload_tables(int dev);
+    ~Engine() { for (void *p : owned) cudaFree(p); }
+
+    RowMap qmap(size_t level) const { RowMap m; m.nlimbs = (int)host.levels[level].q.size(); for (int j = 0; j < m.nlimbs; ++j) m.mod_id[j] = j; return m; }
+    RowMap bskmap(size_t level) const { RowMap m; const DevLevel &D = host.levels[level].dev; m.nlimbs = D.nBsk; for (int j = 0; j < m.nlimbs; ++j) m.mod_id[j] = D.bsk_mod_id[j]; return m; }
+    Layout seal_layout(size_t level, size_t npoly) const { size_t k = host.levels[level].q.size(); return Layout{npoly * k * host.n, k * host.n, host.n}; }
+};
+
+// ---- ntt.cu ----
+// In-place transform of every (query, poly, limb) row of a batch.  `map` gives the modulus of each limb.
+void launch_ntt(const Engine &E, u64 *data, Layout lay, int nq, int npoly, const RowMap &map, bool inverse, cudaStream_t st);
+// out = INTT(NTT(a) (.) b_ntt) [+ c]   row-wise; b is broadcast over queries when b_lay.sq == 0.
+void launch_polymul(const Engine &E, const u64 *a, Layout a_lay, const u64 *b_ntt, Layout b_lay, const u64 *c, Layout c_lay, u64 *out, Layout out_lay,
+                    int nq, int npoly, const RowMap &map, cudaStream_t st);
+
+// ---- eval.cu ----
+void launch_circuit_a(const Engine &E, size_t level, const u64 *c0, const u64 *c1, const u64 *c2, u64 *out, Layout lay, int nq,
+                      const u64 *xb, const u64 *yb, const u64 *r, const u64 *s, u64 *scratch /* nq*k*8 u64 */, int *flags, cudaStream_t st);
+size_t circuit_a_scratch_words(const Engine &E, size_t level, int nq);
+// a <- a +/- b (elementwise, canonical)
+void launch_add_sub(const Engine &E, size_t level, u64 *a, const u64 *b, Layout lay, int nq, int npoly, bool subtract, bool negate_b_only, cudaStream_t st);
+// c0 +/-= round(Q*m/t) for plaintext coefficients m[0..count) (same plaintext for every query when m_stride == 0)
+void launch_add_plain(const Engine &E, size_t level, u64 *ct, Layout lay, int nq, const u64 *plain, size_t count, size_t m_stride, bool subtract, cudaStream_t st);
+// every coefficient of every poly *= lift(m) (monomial x^exponent multiply, negacyclic shift)
+void launch_mul_mono(const Engine &E, size_t level, const u64 *in, u64 *out, Layout lay, int nq, int npoly, const u64 *scalar /* per query */, size_t scalar_stride,
+                     size_t exponent, cudaStream_t st);
+// lift plaintext coefficients into RNS rows: out[j][i] = lift(m_i) mod q_j
+void launch_lift_plain(const Engine &E, size_t level, const u64 *plain, size_t count, u64 *out /* [k][n] */, cudaStream_t st);
+void launch_dyadic(const Engine &E, u64 *a, Layout a_lay, const u64 *b, Layout b_lay, int nq, int npoly, const RowMap &map, cudaStream_t st);
+int launch_is_zero(const Engine &E, const u64 *p, size_t words, int *d_flag, cudaStream_t st);  // returns 1 if all zero (synchronises)
+
+// ---- crypto.cu ----
+// Fresh BFV public-key encryptions.  seeds: [nct][8] (one BLAKE2Xb PRNG per ciphertext, counter 0); plain: [nct][plain_stride]
+// coefficients (plain_count used); ws: encrypt_tmp_words() scratch; out: ciphertext batch at the first data level.
+void launch_encrypt(const Engine &E, const u64 *pk, const u64 *seeds, const u64 *plain, size_t plain_count, size_t plain_stride, u64 *ws, u64 *out,
+                    Layout out_lay, int nct, int *errflag, cudaStream_t st);
+size_t encrypt_tmp_words(const Engine &E, int nct);
+int encrypt_stream_refills(int n);
+// Decrypt: x = INTT(NTT(c1) (.) s) + c0 (+ c2 s^2 when size 3), then BEHZ scale-and-round to Z_t.  plain_out [nq][plain_stride].
+void launch_decrypt(const Engine &E, size_t level, const u64 *ct, Layout lay, int nq, int size, const u64 *sk /* [K][n] NTT */, u64 *tmp, u64 *plain_out,
+                    size_t plain_stride, int ncoeff /* leading coefficients to produce per query */, cudaStream_t st);
+size_t decrypt_tmp_words(const Engine &E, size_t level, int nq, int size);
+// key generation pieces (sampling is sequential rejection logic and runs on the host once per key; the transforms run here)
+void launch_expand_small(const Engine &E, const signed char *d_small /* [n] */, u64 *out /* [K][n] */, cudaStream_t st);
+void launch_pk_combine(const Engine &E, const u64 *a, const u64 *s, const u64 *e_ntt, u64 *c0, int digit /* -1: none */, u64 factor, cudaStream_t st);
+void launch_prng_stream(const Engine &E, const u64 *d_seed, int nstreams, int nrefill, u64 *out, cudaStream_t st);
+
+// ---- bloom.cu ----
+size_t bloom_table_stride(u64 m_bits);   // bytes between consecutive filters' tables (m/8 rounded up to 16)
+void launch_bloom_build(const Engine &E, unsigned char *tables, u64 m_bits, const u32 *salts, int k, const u64 *rsw /* [nf][3] */, int nf, u64 count, cudaStream_t st);
+void launch_bloom_query(const Engine &E, const unsigned char *tables, u64 m_bits, const u32 *salts, int k, const u64 *bd, size_t bd_stride, const u64 *rsw,
+                        const int *fidx, int nq, unsigned char *verdict, cudaStream_t st);
+void launch_bloom_insert_keys(const Engine &E, unsigned char *table, u64 m_bits, const u32 *salts, int k, const u64 *keys, int nkeys, cudaStream_t st);
+void launch_bloom_contains_keys(const Engine &E, const unsigned char *table, u64 m_bits, const u32 *salts, int k, const u64 *keys, int nkeys, unsigned char *verdict,
+                                cudaStream_t st);
+
+}  // namespace pplp

@@ -1,0 +1,236 @@
+// pplp_b200/csrc/eval.cu — coefficient-wise evaluator kernels: the reference's server-side evaluation ("Circuit A")
+// fused into one streaming pass, plus the individual Evaluator primitives the SEAL-facing shim maps onto.
+//
+// Reference path (src/server.cc:127-133, src/demo.cc:154-160, src/test/test_server.cc:150-167 "d_homoCalc"):
+//     add_plain_inplace(c0, z); multiply_plain_inplace(c1, xb); multiply_plain_inplace(c2, yb);
+//     add_inplace(c1, c2); sub_inplace(c0, c1); multiply_plain_inplace(c0, s); add_plain_inplace(c0, s*r)
+// All plaintexts are constants, so SEAL takes the monomial fast path ([SEAL] evaluator.cpp multiply_plain_normal,
+// util/polyarithsmallmod.cpp negacyclic_multiply_poly_mono_coeffmod) and the scaling-variant add touches only
+// coefficient 0 of polynomial 0 ([SEAL] util/scalingvariant.cpp).  Every step leaves canonical residues and Z_q is a
+// ring, so the seven calls equal, bit for bit, per query / poly p / limb j / coefficient n:
+//     out = S_j * (c0 + [p=0,n=0] Z_j - XB_j*c1 - YB_j*c2) + [p=0,n=0] SR_j   (mod q_j)
+// with XB_j = lift(xb) mod q_j, ..., Z_j = round(Q z/t) mod q_j, SR_j = round(Q (s r mod 2^64)/t) mod q_j.
+//
+// circuit_a_kernel is the hot kernel of the headline metric: 3 ciphertexts in, 1 out, 64*k*N bytes per query, three
+// Shoup multiplications per coefficient — HBM-bound.  128-bit streaming loads/stores (L1 no-allocate: each byte is
+// touched once), 4 independent 16-byte accesses per input stream in flight per thread.
+#include "engine.hpp"
+
+namespace pplp {
+
+typedef unsigned __int128 u128;
+
+__device__ __forceinline__ u64 dev_lift(const DevLevel &L, u64 m, int j) {
+    const u64 r = barrett64(m, L.q[j]);
+    return m >= L.t_threshold ? add_mod(r, L.neg_t[j], L.q[j].q) : r;
+}
+// round(Q*m/t) mod q_j for ANY 64-bit m:  (m * floor(Q/t) + floor((m*(Q mod t) + floor((t+1)/2)) / t)) mod q_j
+__device__ __forceinline__ u64 dev_scaled(const DevLevel &L, u64 m, int j) {
+    const u128 numer = (u128)m * L.q_mod_t + L.t_threshold;
+    const u64 fix = (u64)(numer / L.t);
+    const Mod &mq = L.q[j];
+    return add_mod(mul_mod(barrett64(m, mq), L.delta[j], mq), barrett64(fix, mq), mq.q);
+}
+__device__ __forceinline__ u64 dev_shoup_quotient(u64 w, u64 q) { return (u64)(((u128)w << 64) / q); }
+
+// scratch row per (query, limb): {XB.w, XB.wq, YB.w, YB.wq, S.w, S.wq, Z, SR}
+constexpr int kScalarWords = 8;
+
+__global__ void circuit_a_prepare_kernel(const DevLevel *Lp, int nq, const u64 *xb, const u64 *yb, const u64 *r, const u64 *s, u64 *scratch, int *flags) {
+    const DevLevel &L = *Lp;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nq * L.k) return;
+    const int qi = idx / L.k, j = idx % L.k;
+    const u64 q = L.q[j].q;
+    const u64 vxb = xb[qi], vyb = yb[qi], vs = s[qi], vr = r[qi];
+    const u64 z = vxb * vxb + vyb * vyb;  // uint64 arithmetic, as the reference computes it (src/server.cc:55)
+    const u64 sr = vs * vr;               // src/server.cc:133
+    u64 *o = scratch + (size_t)idx * kScalarWords;
+    const u64 a = dev_lift(L, vxb, j), b = dev_lift(L, vyb, j), c = dev_lift(L, vs, j);
+    o[0] = a; o[1] = dev_shoup_quotient(a, q);
+    o[2] = b; o[3] = dev_shoup_quotient(b, q);
+    o[4] = c; o[5] = dev_shoup_quotient(c, q);
+    o[6] = dev_scaled(L, z, j);
+    o[7] = dev_scaled(L, sr, j);
+    // SEAL throws logic_error("result ciphertext is transparent") when a multiplier plaintext is zero; a batch flags it.
+    if (flags && j == 0 && (vxb == 0 || vyb == 0 || vs == 0)) atomicOr(&flags[qi], 1);   // caller zeroes flags
+}
+
+constexpr int kCaThreads = 256;
+constexpr int kCaUnroll = 4;
+constexpr int kCaSeg = kCaThreads * 2 * kCaUnroll;  // coefficients per CTA
+
+__global__ void __launch_bounds__(kCaThreads) circuit_a_kernel(const DevLevel *Lp, const u64 *__restrict__ c0, const u64 *__restrict__ c1,
+                                                               const u64 *__restrict__ c2, u64 *__restrict__ out, Layout lay, int nq, int n,
+                                                               const u64 *__restrict__ scratch) {
+    const DevLevel &L = *Lp;
+    const int segs = n / kCaSeg > 0 ? n / kCaSeg : 1;
+    const int seg = blockIdx.x % segs;
+    int row = blockIdx.x / segs;
+    const int qi = row % nq; row /= nq;
+    const int p = row & 1;
+    const int j = row >> 1;
+    const u64 q = L.q[j].q, two_q = q << 1, four_q = q << 2;
+    const u64 *sc = scratch + ((size_t)qi * L.k + j) * kScalarWords;
+    const u64 xbw = sc[0], xbq = sc[1], ybw = sc[2], ybq = sc[3], sw = sc[4], sq = sc[5];
+    const size_t base = qi * lay.sq + p * lay.sp + j * lay.sl;
+    const int first = seg * kCaSeg + 2 * threadIdx.x;
+    ulonglong2 a[kCaUnroll], b[kCaUnroll], c[kCaUnroll];
+#pragma unroll
+    for (int u = 0; u < kCaUnroll; ++u) {
+        const int i = first + u * 2 * kCaThreads;
+        if (i < n) { a[u] = ldg_stream(c0 + base + i); b[u] = ldg_stream(c1 + base + i); c[u] = ldg_stream(c2 + base + i); }
+    }
+#pragma unroll
+    for (int u = 0; u < kCaUnroll; ++u) {
+        const int i = first + u * 2 * kCaThreads;
+        if (i >= n) continue;
+        u64 vx = a[u].x + four_q - mul_shoup_lazy(b[u].x, xbw, xbq, q) - mul_shoup_lazy(c[u].x, ybw, ybq, q);
+        u64 vy = a[u].y + four_q - mul_shoup_lazy(b[u].y, xbw, xbq, q) - mul_shoup_lazy(c[u].y, ybw, ybq, q);
+        const bool head = (p == 0 && i == 0);
+        if (head) vx += sc[6];
+        u64 rx = mul_shoup_lazy(vx, sw, sq, q), ry = mul_shoup_lazy(vy, sw, sq, q);
+        if (head) rx += sc[7];
+        rx = rx >= two_q ? rx - two_q : rx;
+        ulonglong2 o;
+        o.x = csub(rx, q);
+        o.y = csub(ry, q);
+        stg_stream(out + base + i, o);
+    }
+}
+
+size_t circuit_a_scratch_words(const Engine &E, size_t level, int nq) { return (size_t)nq * E.host.levels[level].q.size() * kScalarWords; }
+
+void launch_circuit_a(const Engine &E, size_t level, const u64 *c0, const u64 *c1, const u64 *c2, u64 *out, Layout lay, int nq, const u64 *xb,
+                      const u64 *yb, const u64 *r, const u64 *s, u64 *scratch, int *flags, cudaStream_t st) {
+    E.require_device();
+    if (nq == 0) return;
+    const int k = (int)E.host.levels[level].q.size(), n = (int)E.host.n;
+    const DevLevel *L = E.d_levels + level;
+    circuit_a_prepare_kernel<<<(nq * k + 127) / 128, 128, 0, st>>>(L, nq, xb, yb, r, s, scratch, flags);
+    const int segs = n / kCaSeg > 0 ? n / kCaSeg : 1;
+    const long long ctas = (long long)nq * 2 * k * segs;
+    if (ctas > 0x7fffffffLL) throw std::invalid_argument("pplp: batch too large for one launch");
+    circuit_a_kernel<<<(unsigned)ctas, kCaThreads, 0, st>>>(L, c0, c1, c2, out, lay, nq, n, scratch);
+    PPLP_CUDA(cudaGetLastError());
+}
+
+// ---- individual primitives (SEAL-facing shim; batch-of-nq views) ---------------------------------------------------
+__global__ void add_sub_kernel(const DevLevel *Lp, u64 *a, const u64 *b, Layout lay, int nq, int npoly, int n, int mode) {
+    const DevLevel &L = *Lp;
+    int row = blockIdx.y;
+    const int qi = row % nq; row /= nq;
+    const int p = row % npoly, j = row / npoly;
+    const u64 q = L.q[j].q;
+    const size_t base = qi * lay.sq + p * lay.sp + j * lay.sl;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const u64 y = b[base + i];
+        if (mode == 0) a[base + i] = add_mod(a[base + i], y, q);
+        else if (mode == 1) a[base + i] = sub_mod(a[base + i], y, q);
+        else a[base + i] = neg_mod(y, q);  // a <- -b (sub_inplace when the left operand is shorter)
+    }
+}
+void launch_add_sub(const Engine &E, size_t level, u64 *a, const u64 *b, Layout lay, int nq, int npoly, bool subtract, bool negate_b_only, cudaStream_t st) {
+    E.require_device();
+    const int k = (int)E.host.levels[level].q.size(), n = (int)E.host.n;
+    if (nq * npoly == 0) return;
+    dim3 grid((n + 1023) / 1024, nq * npoly * k);
+    add_sub_kernel<<<grid, 256, 0, st>>>(E.d_levels + level, a, b, lay, nq, npoly, n, negate_b_only ? 2 : (subtract ? 1 : 0));
+    PPLP_CUDA(cudaGetLastError());
+}
+
+// c0[j][i] +/-= round(Q m_i / t) mod q_j   ([SEAL] multiply_add/sub_plain_with_scaling_variant)
+__global__ void add_plain_kernel(const DevLevel *Lp, u64 *ct, Layout lay, int nq, const u64 *plain, int count, size_t m_stride, int subtract) {
+    const DevLevel &L = *Lp;
+    const int total = nq * L.k * count;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int i = idx % count;
+        const int j = (idx / count) % L.k;
+        const int qi = idx / (count * L.k);
+        const u64 v = dev_scaled(L, plain[qi * m_stride + i], j);
+        u64 *x = ct + qi * lay.sq + j * lay.sl + i;
+        *x = subtract ? sub_mod(*x, v, L.q[j].q) : add_mod(*x, v, L.q[j].q);
+    }
+}
+void launch_add_plain(const Engine &E, size_t level, u64 *ct, Layout lay, int nq, const u64 *plain, size_t count, size_t m_stride, bool subtract, cudaStream_t st) {
+    E.require_device();
+    const int k = (int)E.host.levels[level].q.size();
+    const long long total = (long long)nq * k * (long long)count;
+    if (total == 0) return;
+    const int blocks = (int)std::min<long long>((total + 127) / 128, 4096);
+    add_plain_kernel<<<blocks, 128, 0, st>>>(E.d_levels + level, ct, lay, nq, plain, (int)count, m_stride, subtract ? 1 : 0);
+    PPLP_CUDA(cudaGetLastError());
+}
+
+// out[idx] = +/- in[i] * lift(m) with idx = (i + exponent) mod N, sign flipped on wrap   (monomial multiply_plain)
+__global__ void mul_mono_kernel(const DevLevel *Lp, const u64 *in, u64 *out, Layout lay, int nq, int npoly, int n, const u64 *scalar, size_t scalar_stride, int exponent) {
+    const DevLevel &L = *Lp;
+    int row = blockIdx.y;
+    const int qi = row % nq; row /= nq;
+    const int p = row % npoly, j = row / npoly;
+    const Mod mq = L.q[j];
+    const u64 w = dev_lift(L, scalar[qi * scalar_stride], j);
+    const size_t base = qi * lay.sq + p * lay.sp + j * lay.sl;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const u64 v = mul_mod(in[base + i], w, mq);
+        const int raw = i + exponent, dst = raw & (n - 1);
+        out[base + dst] = ((raw & n) && v) ? mq.q - v : v;
+    }
+}
+void launch_mul_mono(const Engine &E, size_t level, const u64 *in, u64 *out, Layout lay, int nq, int npoly, const u64 *scalar, size_t scalar_stride, size_t exponent, cudaStream_t st) {
+    E.require_device();
+    const int k = (int)E.host.levels[level].q.size(), n = (int)E.host.n;
+    if (nq * npoly == 0) return;
+    if (in == out && exponent != 0) throw std::invalid_argument("pplp: shifted monomial multiply must be out of place");
+    dim3 grid((n + 1023) / 1024, nq * npoly * k);
+    mul_mono_kernel<<<grid, 256, 0, st>>>(E.d_levels + level, in, out, lay, nq, npoly, n, scalar, scalar_stride, (int)exponent);
+    PPLP_CUDA(cudaGetLastError());
+}
+
+__global__ void lift_plain_kernel(const DevLevel *Lp, const u64 *plain, int count, u64 *out, int n) {
+    const DevLevel &L = *Lp;
+    const int j = blockIdx.y;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[(size_t)j * n + i] = i < count ? dev_lift(L, plain[i], j) : 0;
+}
+void launch_lift_plain(const Engine &E, size_t level, const u64 *plain, size_t count, u64 *out, cudaStream_t st) {
+    E.require_device();
+    const int k = (int)E.host.levels[level].q.size(), n = (int)E.host.n;
+    dim3 grid((n + 255) / 256, k);
+    lift_plain_kernel<<<grid, 256, 0, st>>>(E.d_levels + level, plain, (int)count, out, n);
+    PPLP_CUDA(cudaGetLastError());
+}
+
+__global__ void dyadic_kernel(const DevMod *mods, RowMap map, u64 *a, Layout a_lay, const u64 *b, Layout b_lay, int nq, int npoly, int n) {
+    int row = blockIdx.y;
+    const int qi = row % nq; row /= nq;
+    const int p = row % npoly, j = row / npoly;
+    const Mod mq = mods[map.mod_id[j]].m;
+    u64 *pa = a + qi * a_lay.sq + p * a_lay.sp + j * a_lay.sl;
+    const u64 *pb = b + qi * b_lay.sq + p * b_lay.sp + j * b_lay.sl;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) pa[i] = mul_mod(pa[i], pb[i], mq);
+}
+void launch_dyadic(const Engine &E, u64 *a, Layout a_lay, const u64 *b, Layout b_lay, int nq, int npoly, const RowMap &map, cudaStream_t st) {
+    E.require_device();
+    const int n = (int)E.host.n;
+    if (nq * npoly == 0) return;
+    dim3 grid((n + 1023) / 1024, nq * npoly * map.nlimbs);
+    dyadic_kernel<<<grid, 256, 0, st>>>(E.d_mods, map, a, a_lay, b, b_lay, nq, npoly, n);
+    PPLP_CUDA(cudaGetLastError());
+}
+
+__global__ void is_zero_kernel(const u64 *p, size_t words, int *flag) {
+    int nz = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < words; i += (size_t)gridDim.x * blockDim.x) nz |= p[i] != 0;
+    if (__syncthreads_or(nz) && threadIdx.x == 0) atomicOr(flag, 1);
+}
+int launch_is_zero(const Engine &E, const u64 *p, size_t words, int *d_flag, cudaStream_t st) {
+    E.require_device();
+    PPLP_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
+    if (words) is_zero_kernel<<<(unsigned)std::min<size_t>((words + 1023) / 1024, 1024), 256, 0, st>>>(p, words, d_flag);
+    int h = 0;
+    PPLP_CUDA(cudaMemcpyAsync(&h, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PPLP_CUDA(cudaStreamSynchronize(st));
+    return h == 0;
+}
+
+}  // namespace pplp

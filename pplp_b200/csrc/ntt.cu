@@ -1,0 +1,239 @@
+// pplp_b200/csrc/ntt.cu — batched forward / inverse negacyclic NTT kernels and the fused NTT-domain product.
+//
+// Kernels (one CTA = one RNS-limb polynomial of one query; grid = rows of the batch, limb-major so that CTAs that
+// share a twiddle table are co-resident and the table stays in L2):
+//   ntt_forward_kernel<LOGM>   global -> regs (coalesced) -> radix-16 passes -> smem -> coalesced stores
+//   ntt_inverse_kernel<LOGM>   the mirror image, N^-1 folded into the last stage
+//   polymul_kernel<LOGM>       out = INTT(NTT(a) (.) b) [+ c]: the dyadic product happens in registers between the
+//                              two transforms (fine layout of the forward == fine layout of the inverse), so the
+//                              NTT-form intermediate never touches HBM  (decrypt: c1*s + c0; multiply_plain generic)
+//   stage0 kernels             N = 32768 does not fit one CTA (256 KiB > 227 KiB smem): the first (last) butterfly stage
+//                              runs as a streaming pass over HBM and the two 16384-point halves go through the CTA kernel.
+// Algorithmic HBM bytes: 16*N per limb transform (read + write); polymul: 8*N*(2 + has_c) + b (L2-resident when
+// broadcast).  Roofline note in DESIGN.md: ~6.5*N Shoup butterflies per transform make these kernels integer-pipe bound.
+#include "engine.hpp"
+#include "ntt.cuh"
+
+namespace pplp {
+
+struct NttArgs {
+    u64 *data;
+    Layout lay;
+    int nq, npoly;
+    int stage_base;      // 0, or 1 when the block is half of a 32768-point transform
+    RowMap map;
+    const DevMod *mods;
+};
+
+__device__ __forceinline__ void decode_row(int row, int nq, int npoly, int &qi, int &p, int &j) {
+    qi = row % nq; row /= nq;
+    p = row % npoly;
+    j = row / npoly;
+}
+
+template <int LOGM>
+__global__ void __launch_bounds__(NttShape<LOGM>::T) ntt_forward_kernel(const NttArgs a) {
+    using S = NttShape<LOGM>;
+    extern __shared__ __align__(16) u64 sm[];
+    const int tid = threadIdx.x;
+    const int nblk = 1 << a.stage_base;
+    const int blk = blockIdx.x % nblk;
+    int qi, p, j;
+    decode_row(blockIdx.x / nblk, a.nq, a.npoly, qi, p, j);
+    const DevMod &md = a.mods[a.map.mod_id[j]];
+    const u64 q = md.m.q;
+    u64 *ptr = a.data + qi * a.lay.sq + p * a.lay.sp + j * a.lay.sl + (size_t)blk * S::M;
+
+    u64 x[16];
+    CoarsePass<LOGM>::for_each(tid, [&](int r, int i) { x[r] = ptr[i]; });
+    block_ntt_forward<LOGM>(x, sm, tid, md.fwd, a.stage_base, blk, q);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) x[r] = canon4(x[r], q);
+    __syncthreads();
+    FinePass<LOGM>::store_smem(x, sm, tid);
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+        const int i = tid + c * S::T;
+        ptr[i] = sm[smem_slot(i)];
+    }
+}
+
+template <int LOGM>
+__global__ void __launch_bounds__(NttShape<LOGM>::T) ntt_inverse_kernel(const NttArgs a) {
+    using S = NttShape<LOGM>;
+    extern __shared__ __align__(16) u64 sm[];
+    const int tid = threadIdx.x;
+    const int nblk = 1 << a.stage_base;
+    const int blk = blockIdx.x % nblk;
+    int qi, p, j;
+    decode_row(blockIdx.x / nblk, a.nq, a.npoly, qi, p, j);
+    const DevMod &md = a.mods[a.map.mod_id[j]];
+    const u64 q = md.m.q;
+    u64 *ptr = a.data + qi * a.lay.sq + p * a.lay.sp + j * a.lay.sl + (size_t)blk * S::M;
+
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+        const int i = tid + c * S::T;
+        sm[smem_slot(i)] = ptr[i];
+    }
+    __syncthreads();
+    u64 x[16];
+    FinePass<LOGM>::load_smem(x, sm, tid);
+    __syncthreads();
+    if (a.stage_base == 0) {
+        block_ntt_inverse<LOGM, true>(x, sm, tid, md.inv, 0, 0, q, md.n_inv, md.inv1_n_inv);
+        CoarsePass<LOGM>::for_each(tid, [&](int r, int i) { ptr[i] = csub(x[r], q); });
+    } else {
+        block_ntt_inverse<LOGM, false>(x, sm, tid, md.inv, a.stage_base, blk, q, md.n_inv, md.inv1_n_inv);
+        CoarsePass<LOGM>::for_each(tid, [&](int r, int i) { ptr[i] = x[r]; });  // lazily in [0,2q); stage-0 pass canonicalises
+    }
+}
+
+// Streaming butterfly stage 0 for N = 2*M (gap N/2, single twiddle fwd[1]).  Output lazily < 4q (forward) / canonical (inverse).
+__global__ void ntt_stage0_forward_kernel(const NttArgs a, int half_n) {
+    int qi, p, j;
+    decode_row(blockIdx.y, a.nq, a.npoly, qi, p, j);
+    const DevMod &md = a.mods[a.map.mod_id[j]];
+    const u64 q = md.m.q, two_q = q << 1;
+    u64 *ptr = a.data + qi * a.lay.sq + p * a.lay.sp + j * a.lay.sl;
+    const ShoupW w = ld_twiddle(md.fwd + 1);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < half_n; i += gridDim.x * blockDim.x) {
+        u64 x = ptr[i], y = ptr[i + half_n];
+        ct_butterfly(x, y, w, q, two_q);
+        ptr[i] = x; ptr[i + half_n] = y;
+    }
+}
+__global__ void ntt_stage0_inverse_kernel(const NttArgs a, int half_n) {
+    int qi, p, j;
+    decode_row(blockIdx.y, a.nq, a.npoly, qi, p, j);
+    const DevMod &md = a.mods[a.map.mod_id[j]];
+    const u64 q = md.m.q, two_q = q << 1;
+    u64 *ptr = a.data + qi * a.lay.sq + p * a.lay.sp + j * a.lay.sl;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < half_n; i += gridDim.x * blockDim.x) {
+        u64 x = ptr[i], y = ptr[i + half_n];   // in [0,2q)
+        u64 s = x + y, d = x - y + two_q;
+        ptr[i] = csub(mul_shoup_lazy(s, md.n_inv.w, md.n_inv.wq, q), q);
+        ptr[i + half_n] = csub(mul_shoup_lazy(d, md.inv1_n_inv.w, md.inv1_n_inv.wq, q), q);
+    }
+}
+
+// ---- fused product ------------------------------------------------------------------------------------------------
+struct PolymulArgs {
+    const u64 *a; Layout a_lay;
+    const u64 *b; Layout b_lay;     // NTT form
+    const u64 *c; Layout c_lay;     // optional addend (coefficient form), nullptr to skip
+    u64 *out; Layout out_lay;
+    int nq, npoly;
+    RowMap map;
+    const DevMod *mods;
+};
+
+template <int LOGM>
+__global__ void __launch_bounds__(NttShape<LOGM>::T) polymul_kernel(const PolymulArgs a) {
+    using S = NttShape<LOGM>;
+    extern __shared__ __align__(16) u64 sm[];
+    const int tid = threadIdx.x;
+    int qi, p, j;
+    decode_row(blockIdx.x, a.nq, a.npoly, qi, p, j);
+    const DevMod &md = a.mods[a.map.mod_id[j]];
+    const Mod mod = md.m;
+    const u64 q = mod.q;
+    const u64 *pa = a.a + qi * a.a_lay.sq + p * a.a_lay.sp + j * a.a_lay.sl;
+    const u64 *pb = a.b + qi * a.b_lay.sq + p * a.b_lay.sp + j * a.b_lay.sl;
+    u64 *po = a.out + qi * a.out_lay.sq + p * a.out_lay.sp + j * a.out_lay.sl;
+
+    u64 x[16];
+    CoarsePass<LOGM>::for_each(tid, [&](int r, int i) { x[r] = pa[i]; });
+    block_ntt_forward<LOGM>(x, sm, tid, md.fwd, 0, 0, q);
+    // dyadic product in the fine layout: thread owns coefficients 16*tid .. 16*tid+15 of the NTT-form operand
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const ulonglong2 bv = __ldg(reinterpret_cast<const ulonglong2 *>(pb + 16 * tid + 2 * c));
+        x[2 * c] = mul_mod(canon4(x[2 * c], q), bv.x, mod);
+        x[2 * c + 1] = mul_mod(canon4(x[2 * c + 1], q), bv.y, mod);
+    }
+    __syncthreads();   // all threads are past their last smem read of the forward transform
+    block_ntt_inverse<LOGM, true>(x, sm, tid, md.inv, 0, 0, q, md.n_inv, md.inv1_n_inv);
+    if (a.c) {
+        const u64 *pc = a.c + qi * a.c_lay.sq + p * a.c_lay.sp + j * a.c_lay.sl;
+        CoarsePass<LOGM>::for_each(tid, [&](int r, int i) { po[i] = add_mod(csub(x[r], q), pc[i], q); });
+    } else {
+        CoarsePass<LOGM>::for_each(tid, [&](int r, int i) { po[i] = csub(x[r], q); });
+    }
+}
+
+// ---- launchers -----------------------------------------------------------------------------------------------------
+template <int LOGM> static void set_smem_attr_once() {
+    static bool done[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (done[dev]) return;
+    const int bytes = NttShape<LOGM>::SMEM_WORDS * 8;
+    PPLP_CUDA(cudaFuncSetAttribute(ntt_forward_kernel<LOGM>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    PPLP_CUDA(cudaFuncSetAttribute(ntt_inverse_kernel<LOGM>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    PPLP_CUDA(cudaFuncSetAttribute(polymul_kernel<LOGM>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    done[dev] = true;
+}
+
+template <int LOGM> static void run_block_ntt(const NttArgs &a, int rows, bool inverse, cudaStream_t st) {
+    set_smem_attr_once<LOGM>();
+    const int bytes = NttShape<LOGM>::SMEM_WORDS * 8;
+    const int grid = rows << a.stage_base;
+    if (inverse) ntt_inverse_kernel<LOGM><<<grid, NttShape<LOGM>::T, bytes, st>>>(a);
+    else ntt_forward_kernel<LOGM><<<grid, NttShape<LOGM>::T, bytes, st>>>(a);
+}
+
+void launch_ntt(const Engine &E, u64 *data, Layout lay, int nq, int npoly, const RowMap &map, bool inverse, cudaStream_t st) {
+    E.require_device();
+    const int rows = nq * npoly * map.nlimbs;
+    if (rows == 0) return;
+    NttArgs a{data, lay, nq, npoly, 0, map, E.d_mods};
+    const int logn = E.host.logn;
+    switch (logn) {
+    case 10: run_block_ntt<10>(a, rows, inverse, st); break;
+    case 11: run_block_ntt<11>(a, rows, inverse, st); break;
+    case 12: run_block_ntt<12>(a, rows, inverse, st); break;
+    case 13: run_block_ntt<13>(a, rows, inverse, st); break;
+    case 14: run_block_ntt<14>(a, rows, inverse, st); break;
+    case 15: {
+        const int half_n = 1 << 14;
+        dim3 g0(32, rows);
+        a.stage_base = 1;
+        if (!inverse) {
+            ntt_stage0_forward_kernel<<<g0, 512, 0, st>>>(a, half_n);
+            run_block_ntt<14>(a, rows, false, st);
+        } else {
+            run_block_ntt<14>(a, rows, true, st);
+            ntt_stage0_inverse_kernel<<<g0, 512, 0, st>>>(a, half_n);
+        }
+        break;
+    }
+    default: throw std::invalid_argument("pplp: NTT kernels support poly_modulus_degree 1024..32768");
+    }
+    PPLP_CUDA(cudaGetLastError());
+}
+
+template <int LOGM> static void run_polymul(const PolymulArgs &a, int rows, cudaStream_t st) {
+    set_smem_attr_once<LOGM>();
+    polymul_kernel<LOGM><<<rows, NttShape<LOGM>::T, NttShape<LOGM>::SMEM_WORDS * 8, st>>>(a);
+}
+
+void launch_polymul(const Engine &E, const u64 *a, Layout a_lay, const u64 *b_ntt, Layout b_lay, const u64 *c, Layout c_lay, u64 *out, Layout out_lay,
+                    int nq, int npoly, const RowMap &map, cudaStream_t st) {
+    E.require_device();
+    const int rows = nq * npoly * map.nlimbs;
+    if (rows == 0) return;
+    PolymulArgs pa{a, a_lay, b_ntt, b_lay, c, c_lay, out, out_lay, nq, npoly, map, E.d_mods};
+    switch (E.host.logn) {
+    case 10: run_polymul<10>(pa, rows, st); break;
+    case 11: run_polymul<11>(pa, rows, st); break;
+    case 12: run_polymul<12>(pa, rows, st); break;
+    case 13: run_polymul<13>(pa, rows, st); break;
+    case 14: run_polymul<14>(pa, rows, st); break;
+    default: throw std::invalid_argument("pplp: fused polymul supports poly_modulus_degree 1024..16384");
+    }
+    PPLP_CUDA(cudaGetLastError());
+}
+
+}  // namespace pplp

@@ -1,0 +1,215 @@
+// pplp_b200/csrc/ntt.cuh — in-CTA negacyclic NTT building blocks (device functions).
+//
+// What it computes.  Forward: out[j] = sum_i a_i psi^(i*(2*bitrev(j)+1)) mod q — Cooley–Tukey with bit-reversed output,
+// the function of SEAL's ntt_negacyclic_harvey ([SEAL] util/ntt.cpp, util/dwthandler.h transform_to_rev).  Inverse:
+// Gentleman–Sande with N^-1 folded into the last stage (transform_from_rev).  Results are canonical, hence identical
+// to SEAL's whatever the butterfly schedule.  Used by: encrypt (src/client.cc:111-113), decrypt (src/client.cc:151),
+// and the north-star square / relinearise / generic multiply_plain paths.
+//
+// How (B200).  One CTA owns one polynomial of M = 2^LOGM coefficients.  Each thread keeps 16 coefficients in
+// registers and runs radix-16 passes (4 butterfly stages each, 32 independent Shoup butterflies per thread per
+// pass) — the kernel is bound by the integer (IMAD) pipe, not HBM, so the design minimises instructions per
+// butterfly and keeps 16-way ILP per thread.  Between passes the CTA transposes through shared memory (padded by
+// one word per 16 so the stride-G accesses of every pass are bank-conflict-free).  A pass is in place: a thread writes the slots it read, so one __syncthreads per pass.
+// Twiddles (w, w' = floor(w 2^64/q)) are fetched as one 128-bit read-only load from the L2-resident table.
+#pragma once
+#include "devstructs.h"
+
+namespace pplp {
+
+template <int LOGM> struct NttShape {
+    static constexpr int M = 1 << LOGM;
+    static constexpr int E = 16;              // coefficients per thread
+    static constexpr int T = M / E;           // threads per CTA
+    static constexpr int R0 = (LOGM % 4 == 0) ? 4 : (LOGM % 4);   // radix of the coarse (large-gap) pass
+    static constexpr int NFULL = (LOGM - R0) / 4;                 // radix-16 passes after it
+    static constexpr int SMEM_WORDS = M + (M >> 4);
+};
+
+// One pad word per 16: with 8-byte words (16 banks of 8 B) every access pattern used below — contiguous lanes, stride-16
+// lanes (LG = 4 passes) and 16-consecutive-per-thread (fine layout) — hits each bank at most twice per warp, the minimum.
+__device__ __forceinline__ int smem_slot(int i) { return i + (i >> 4); }
+
+// Harvey lazy butterflies.  Forward keeps values in [0,4q); inverse in [0,2q).
+__device__ __forceinline__ void ct_butterfly(u64 &x, u64 &y, const ShoupW w, const u64 q, const u64 two_q) {
+    u64 u = x >= two_q ? x - two_q : x;
+    u64 v = mul_shoup_lazy(y, w.w, w.wq, q);
+    x = u + v;
+    y = u - v + two_q;
+}
+__device__ __forceinline__ void gs_butterfly(u64 &x, u64 &y, const ShoupW w, const u64 q, const u64 two_q) {
+    u64 s = x + y;
+    u64 d = x - y + two_q;
+    x = s >= two_q ? s - two_q : s;
+    y = mul_shoup_lazy(d, w.w, w.wq, q);
+}
+
+__device__ __forceinline__ ShoupW ld_twiddle(const ShoupW *p) {
+    ShoupW r;
+    const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(p));
+    r.w = v.x; r.wq = v.y;
+    return r;
+}
+
+// Geometry of pass (S0,R) of a 2^LOGM block: thread `tid` owns NU = 16>>R radix-2^R butterflies; butterfly u covers
+// indices  (hi << (LG+R)) + (e << LG) + lo,  e = 0..2^R-1,  where c = tid + u*T, lo = c & (G-1), hi = c >> LG,
+// G = 2^LG = M >> (S0+R) is the smallest gap of the pass.
+template <int LOGM, int S0, int R> struct Pass {
+    static constexpr int LG = LOGM - S0 - R;
+    static constexpr int G = 1 << LG;
+    static constexpr int NU = 16 >> R;
+    static constexpr int RR = 1 << R;
+    static constexpr int T = NttShape<LOGM>::T;
+    __device__ static __forceinline__ int index(int tid, int u, int e) {
+        const int c = tid + u * T;
+        return ((c >> LG) << (LG + R)) + (e << LG) + (c & (G - 1));
+    }
+    __device__ static __forceinline__ int hi(int tid, int u) { return (tid + u * T) >> LG; }
+
+    template <class F> __device__ static __forceinline__ void for_each(int tid, F f) {
+#pragma unroll
+        for (int u = 0; u < NU; ++u)
+#pragma unroll
+            for (int e = 0; e < RR; ++e) f(u * RR + e, index(tid, u, e));
+    }
+    __device__ static __forceinline__ void load_smem(u64 (&x)[16], const u64 *sm, int tid) {
+        for_each(tid, [&](int r, int i) { x[r] = sm[smem_slot(i)]; });
+    }
+    __device__ static __forceinline__ void store_smem(const u64 (&x)[16], u64 *sm, int tid) {
+        for_each(tid, [&](int r, int i) { sm[smem_slot(i)] = x[r]; });
+    }
+
+    // One butterfly stage V (local) of radix-2^R butterfly u.  Everything but tid-derived values is a compile-time constant.
+    template <int V, bool INVERSE, bool FOLD_SCALE>
+    __device__ static __forceinline__ void stage(u64 (&x)[16], int u, int h, const ShoupW *__restrict__ tw, int stage_base, int blk, u64 q, u64 two_q,
+                                                 ShoupW n_inv, ShoupW inv1_n_inv) {
+        constexpr int HALF = 1 << (R - 1 - V);
+        const int tbase = (1 << (stage_base + S0 + V)) + (blk << (S0 + V)) + (h << V);
+        if constexpr (INVERSE && FOLD_SCALE && V == 0) {
+#pragma unroll
+            for (int i = 0; i < HALF; ++i) {
+                u64 &a = x[u * RR + i], &b = x[u * RR + i + HALF];
+                const u64 s = a + b, d = a - b + two_q;
+                a = mul_shoup_lazy(s, n_inv.w, n_inv.wq, q);          // Shoup accepts any 64-bit input
+                b = mul_shoup_lazy(d, inv1_n_inv.w, inv1_n_inv.wq, q);
+            }
+        } else {
+#pragma unroll
+            for (int g = 0; g < (1 << V); ++g) {
+                const ShoupW w = ld_twiddle(tw + tbase + g);
+#pragma unroll
+                for (int i = 0; i < HALF; ++i) {
+                    if constexpr (INVERSE) gs_butterfly(x[u * RR + g * 2 * HALF + i], x[u * RR + g * 2 * HALF + i + HALF], w, q, two_q);
+                    else ct_butterfly(x[u * RR + g * 2 * HALF + i], x[u * RR + g * 2 * HALF + i + HALF], w, q, two_q);
+                }
+            }
+        }
+    }
+
+    // Forward stages S0 .. S0+R-1 (global stage = stage_base + local stage; blk = index of this block among the
+    // 2^stage_base sub-transforms when M < N).
+    __device__ static __forceinline__ void forward(u64 (&x)[16], int tid, const ShoupW *__restrict__ tw, int stage_base, int blk, u64 q, u64 two_q) {
+        const ShoupW z{0, 0};
+#pragma unroll
+        for (int u = 0; u < NU; ++u) {
+            const int h = hi(tid, u);
+            stage<0, false, false>(x, u, h, tw, stage_base, blk, q, two_q, z, z);
+            if constexpr (R >= 2) stage<(R >= 2 ? 1 : 0), false, false>(x, u, h, tw, stage_base, blk, q, two_q, z, z);
+            if constexpr (R >= 3) stage<(R >= 3 ? 2 : 0), false, false>(x, u, h, tw, stage_base, blk, q, two_q, z, z);
+            if constexpr (R >= 4) stage<(R >= 4 ? 3 : 0), false, false>(x, u, h, tw, stage_base, blk, q, two_q, z, z);
+        }
+    }
+    // Inverse stages S0+R-1 .. S0.  When FOLD_SCALE (only legal for S0 == 0 and stage_base == 0) the last stage
+    // multiplies by N^-1:  x = (u+v) N^-1,  y = (u-v) (inv[1] N^-1).
+    template <bool FOLD_SCALE>
+    __device__ static __forceinline__ void inverse(u64 (&x)[16], int tid, const ShoupW *__restrict__ tw, int stage_base, int blk, u64 q, u64 two_q,
+                                                   ShoupW n_inv, ShoupW inv1_n_inv) {
+#pragma unroll
+        for (int u = 0; u < NU; ++u) {
+            const int h = hi(tid, u);
+            if constexpr (R >= 4) stage<(R >= 4 ? 3 : 0), true, FOLD_SCALE>(x, u, h, tw, stage_base, blk, q, two_q, n_inv, inv1_n_inv);
+            if constexpr (R >= 3) stage<(R >= 3 ? 2 : 0), true, FOLD_SCALE>(x, u, h, tw, stage_base, blk, q, two_q, n_inv, inv1_n_inv);
+            if constexpr (R >= 2) stage<(R >= 2 ? 1 : 0), true, FOLD_SCALE>(x, u, h, tw, stage_base, blk, q, two_q, n_inv, inv1_n_inv);
+            stage<0, true, FOLD_SCALE>(x, u, h, tw, stage_base, blk, q, two_q, n_inv, inv1_n_inv);
+        }
+    }
+};
+
+// ---- whole-block transforms -------------------------------------------------------------------------------------
+// Register layouts at the two ends:
+//   "coarse" layout = Pass<LOGM,0,R0>            (what a coalesced global access gives: consecutive threads, consecutive words)
+//   "fine"   layout = Pass<LOGM,LOGM-4,4>        (16 consecutive coefficients per thread)
+template <int LOGM> using CoarsePass = Pass<LOGM, 0, NttShape<LOGM>::R0>;
+template <int LOGM> using FinePass = Pass<LOGM, LOGM - 4, 4>;
+
+template <int LOGM, int P> struct FullPassAt {  // P-th radix-16 pass after the coarse one (P = 0..NFULL-1)
+    using type = Pass<LOGM, NttShape<LOGM>::R0 + 4 * P, 4>;
+};
+
+// Forward: x holds the block in coarse layout, values < 4q (any value < 2^62 that is congruent is fine for x-side,
+// y-side inputs may be any 64-bit).  On return x holds the transform in fine layout, lazily in [0,4q).
+template <int LOGM>
+__device__ __forceinline__ void block_ntt_forward(u64 (&x)[16], u64 *sm, int tid, const ShoupW *__restrict__ tw, int stage_base, int blk, u64 q) {
+    using S = NttShape<LOGM>;
+    const u64 two_q = q << 1;
+    CoarsePass<LOGM>::forward(x, tid, tw, stage_base, blk, q, two_q);
+    CoarsePass<LOGM>::store_smem(x, sm, tid);
+    __syncthreads();
+    if constexpr (S::NFULL >= 1) {
+        using P0 = typename FullPassAt<LOGM, 0>::type;
+        P0::load_smem(x, sm, tid);
+        P0::forward(x, tid, tw, stage_base, blk, q, two_q);
+        if constexpr (S::NFULL > 1) { P0::store_smem(x, sm, tid); __syncthreads(); }
+    }
+    if constexpr (S::NFULL >= 2) {
+        using P1 = typename FullPassAt<LOGM, 1>::type;
+        P1::load_smem(x, sm, tid);
+        P1::forward(x, tid, tw, stage_base, blk, q, two_q);
+        if constexpr (S::NFULL > 2) { P1::store_smem(x, sm, tid); __syncthreads(); }
+    }
+    if constexpr (S::NFULL >= 3) {
+        using P2 = typename FullPassAt<LOGM, 2>::type;
+        P2::load_smem(x, sm, tid);
+        P2::forward(x, tid, tw, stage_base, blk, q, two_q);
+    }
+}
+
+// Inverse: x holds the block in fine layout with values in [0,2q).  On return x holds the result in coarse layout,
+// lazily in [0,2q), scaled by N^-1 when FOLD_SCALE.
+template <int LOGM, bool FOLD_SCALE>
+__device__ __forceinline__ void block_ntt_inverse(u64 (&x)[16], u64 *sm, int tid, const ShoupW *__restrict__ tw, int stage_base, int blk, u64 q,
+                                                  ShoupW n_inv, ShoupW inv1_n_inv) {
+    using S = NttShape<LOGM>;
+    const u64 two_q = q << 1;
+    if constexpr (S::NFULL >= 3) {
+        using P2 = typename FullPassAt<LOGM, 2>::type;
+        P2::template inverse<false>(x, tid, tw, stage_base, blk, q, two_q, n_inv, inv1_n_inv);
+        P2::store_smem(x, sm, tid);
+        __syncthreads();
+    }
+    if constexpr (S::NFULL >= 2) {
+        using P1 = typename FullPassAt<LOGM, 1>::type;
+        if constexpr (S::NFULL > 2) P1::load_smem(x, sm, tid);
+        P1::template inverse<false>(x, tid, tw, stage_base, blk, q, two_q, n_inv, inv1_n_inv);
+        P1::store_smem(x, sm, tid);
+        __syncthreads();
+    }
+    if constexpr (S::NFULL >= 1) {
+        using P0 = typename FullPassAt<LOGM, 0>::type;
+        if constexpr (S::NFULL > 1) P0::load_smem(x, sm, tid);
+        P0::template inverse<false>(x, tid, tw, stage_base, blk, q, two_q, n_inv, inv1_n_inv);
+        P0::store_smem(x, sm, tid);
+        __syncthreads();
+    }
+    CoarsePass<LOGM>::load_smem(x, sm, tid);
+    CoarsePass<LOGM>::template inverse<FOLD_SCALE>(x, tid, tw, stage_base, blk, q, two_q, n_inv, inv1_n_inv);
+}
+
+// [0,4q) -> [0,q)
+__device__ __forceinline__ u64 canon4(u64 v, u64 q) {
+    const u64 two_q = q << 1;
+    v = v >= two_q ? v - two_q : v;
+    return v >= q ? v - q : v;
+}
+
+}  // namespace pplp

@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the pplp hot path on B200 (contract: see the task's bench section).
+
+Metric   proximity queries/s: the reference's server-side encrypted squared-distance evaluation with random blinding
+         ("Circuit A", /root/reference src/server.cc:127-133) at BFV N=8192, BFVDefault coefficient modulus (k=4 data
+         limbs), t=2^56, batched over independent client queries.  BASELINE.json configs[1].
+Step     one pass of the fused evaluation kernel over one batch of Q synthetic queries per GPU (3 ciphertexts in,
+         1 out, 64*k*N = 2 MiB of HBM traffic per query).  Inputs are uniform residues generated on the device (for
+         timing they are indistinguishable from ciphertexts); a parity subset of REAL encryptions is evaluated and
+         checked against the oracle before the clock starts.
+value    whole-job queries/s with inputs resident in HBM (max over ranks, CUDA events).
+e2e      the same evaluation through the C-ABI host entry (pplp_circuit_a_host): ciphertexts in page-locked HOST
+         memory, H2D + kernel + D2H inside the timed region.
+extras   protocol (encrypt x3 -> Circuit A -> decrypt -> Bloom verdict, host coordinates in, verdicts out) and the NTT
+         GB/s microbenchmark, so the other kernels have a measured number too.
+--impl reference   times the CPU restatement of the reference path (oracle/) on the box's host cores, same config.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N = 8192
+T = 1 << 56
+METRIC = "proximity_queries_per_sec"
+UNIT = "queries/s"
+WORKLOAD = "circuitA_bfv_n8192_k4_t2^56_batched"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--queries", type=int, default=8192, help="queries per GPU per step (resident run)")
+    ap.add_argument("--e2e-queries", type=int, default=1024, help="queries per GPU per step (host-buffer run)")
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the CPU baseline sample (0 = calibrate to ~10 s)")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) >= 7:
+                self.rows.append((time.time(), parts))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [p for (ts, p) in self.rows if t0 - 0.05 <= ts <= t1 + 0.15] or [p for (_, p) in self.rows]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[0]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for i, nm in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
+        pw = [float(r[2]) for r in rows if r[2].replace(".", "", 1).isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons, "samples": len(rows), "power_w_max": max(pw) if pw else None}
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def seed8(x):
+    return np.array([(x * 0x9E3779B97F4A7C15 + i * 0xD1B54A32D192ED03) & 0xFFFFFFFFFFFFFFFF for i in range(8)], dtype=np.uint64)
+
+
+def synth_host_batch(q, nq, seed):
+    """[nq][2][k][N] uniform residues + per-query plaintext constants (host, numpy)."""
+    rng = np.random.default_rng(seed)
+    k = len(q)
+    c = []
+    for _ in range(3):
+        a = np.empty((nq, 2, k, N), dtype=np.uint64)
+        for j in range(k):
+            a[:, :, j, :] = rng.integers(0, q[j], size=(nq, 2, N), dtype=np.uint64)
+        c.append(a)
+    xb = rng.integers(1, 1 << 27, nq, dtype=np.uint64)
+    yb = rng.integers(1, 1 << 27, nq, dtype=np.uint64)
+    r = rng.integers(0, 1 << 32, nq, dtype=np.uint64)
+    s = rng.integers(1, 1 << 32, nq, dtype=np.uint64)
+    return c, xb, yb, r, s
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_circuit_a_rate(steps, warmup, sample, threads):
+    """CPU restatement of the reference path (oracle/, 'port'): Circuit A over `sample` host-resident queries per step."""
+    from tests import oracle_lib
+    orc = oracle_lib.load()
+    q = orc.bfv_default(N)
+    octx = orc.context(N, q, T, seed=seed8(1))
+    k = octx.k
+    if sample <= 0:   # calibrate: ~10 s of CPU work in total over the timed steps
+        c, xb, yb, r, s = synth_host_batch(q[:k], 16, 3)
+        t0 = time.perf_counter()
+        octx.circuit_a_batch(c[0], c[1], c[2], xb, yb, r, s, nthreads=min(threads, 16))
+        per_q_cpu = (time.perf_counter() - t0) * min(threads, 16) / 16
+        sample = int(max(threads, min(4096, 10.0 / max(per_q_cpu, 1e-6) / max(steps, 1))))
+        sample = max(threads, (sample // threads) * threads)
+    c, xb, yb, r, s = synth_host_batch(q[:k], sample, 4)
+    for _ in range(warmup):
+        octx.circuit_a_batch(c[0], c[1], c[2], xb, yb, r, s, nthreads=threads)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        octx.circuit_a_batch(c[0], c[1], c[2], xb, yb, r, s, nthreads=threads)
+    dt = time.perf_counter() - t0
+    return sample * steps / dt, dt / steps, sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = host_threads()
+    rate, per_step, sample = cpu_circuit_a_rate(args.steps, args.warmup, args.cpu_sample, threads)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "queries_per_step": sample, "poly_modulus_degree": N, "limbs": 4, "plain_modulus": "2^56"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{sample} queries/step x {args.steps} steps, SEAL-4.1-equivalent CPU restatement (oracle/), {threads} host threads"},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def parity_gate(engine, ctx):
+    """Real encryptions through the timed entry point must equal the oracle bit for bit before any timing counts."""
+    from tests import oracle_lib
+    orc = oracle_lib.load()
+    octx = orc.context(N, ctx.q, T, seed=seed8(7))
+    osk, opk = octx.keygen()
+    nq = 4
+    rng = np.random.default_rng(5)
+    xa = rng.integers(0, 1 << 27, nq, dtype=np.uint64); ya = rng.integers(0, 1 << 27, nq, dtype=np.uint64)
+    xb = rng.integers(1, 1 << 27, nq, dtype=np.uint64); yb = rng.integers(1, 1 << 27, nq, dtype=np.uint64)
+    r = rng.integers(0, 1 << 32, nq, dtype=np.uint64); s = rng.integers(1, 1 << 32, nq, dtype=np.uint64)
+    vals = [xa * xa + ya * ya, xa << np.uint64(1), ya << np.uint64(1)]
+    cts = [np.stack([octx.encrypt(opk, [int(v[i])], seed=seed8(50 + 3 * i + j)) for i in range(nq)]) for j, v in enumerate(vals)]
+    ref = octx.circuit_a_batch(cts[0], cts[1], cts[2], xb, yb, r, s, nthreads=2)
+    lm = [ctx.dev(np.ascontiguousarray(c.transpose(2, 1, 0, 3))) for c in cts]
+    out = ctx.circuit_a(lm[0], lm[1], lm[2], ctx.dev(xb), ctx.dev(yb), ctx.dev(r), ctx.dev(s), layout=engine.LAYOUT_LIMB_MAJOR)
+    got = engine.to_np(out).transpose(2, 1, 0, 3)
+    if not (got == ref).all():
+        raise SystemExit("bench: parity gate failed — CUDA Circuit A differs from the oracle")
+    dec = engine.to_np(ctx.decrypt(ctx.dev(np.ascontiguousarray(got)), ctx.dev(osk), ncoeff=1))[:, 0]
+    for i in range(nq):
+        d2 = (int(xa[i]) - int(xb[i])) ** 2 + (int(ya[i]) - int(yb[i])) ** 2
+        if int(dec[i]) != (int(s[i]) * (d2 + int(r[i]))) % T:
+            raise SystemExit("bench: parity gate failed — decrypted blind distance is wrong")
+    return osk, opk
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from pplp_b200 import build, engine
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench: no CUDA device — pplp_b200 has no CPU fallback")
+    build.build()
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    dev = f"cuda:{local}"
+    ctx = engine.Context(N, t=T, device=local)
+    k = ctx.k
+    osk, opk = parity_gate(engine, ctx) if rank == 0 else (None, None)
+
+    # ---- resident run: limb-major [k][2][Q][N] slabs, uniform residues below each prime ----
+    Q = args.queries
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    cin = [ctx.empty(*ctx.ct_shape(Q, 2, None, engine.LAYOUT_LIMB_MAJOR)) for _ in range(3)]
+    for c in cin:
+        for j in range(k):
+            c[j].random_(0, ctx.q[j], generator=g)
+    out = ctx.empty(*ctx.ct_shape(Q, 2, None, engine.LAYOUT_LIMB_MAJOR))
+    xb = torch.randint(1, 1 << 27, (Q,), device=dev, generator=g)
+    yb = torch.randint(1, 1 << 27, (Q,), device=dev, generator=g)
+    rr = torch.randint(0, 1 << 32, (Q,), device=dev, generator=g)
+    ss = torch.randint(1, 1 << 32, (Q,), device=dev, generator=g)
+
+    def step():
+        ctx.circuit_a(cin[0], cin[1], cin[2], xb, yb, rr, ss, out=out, layout=engine.LAYOUT_LIMB_MAJOR)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    time.sleep(0.3)
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    t0 = time.time()
+    ev[0].record()
+    for i in range(args.steps):
+        step()
+        ev[i + 1].record()
+    barrier()
+    t1 = time.time()
+    total_ms = ev[0].elapsed_time(ev[-1])
+    kernel_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    clocks = sampler.stop(t0, t1)
+    tmax = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    total_ms_max = float(tmax.item())
+    value = world * Q * args.steps / (total_ms_max * 1e-3)
+
+    # ---- end to end: host ciphertexts (page-locked) through the C-ABI host entry ----
+    Qe = args.e2e_queries
+    per_ct = 2 * k * N
+    hc = [torch.empty((Qe, 2, k, N), dtype=torch.int64).pin_memory() for _ in range(3)]
+    hout = torch.empty((Qe, 2, k, N), dtype=torch.int64).pin_memory()
+    for t_, c in zip(hc, cin):   # fill from the device slabs (values < q_j per limb); layout SEAL on the host
+        t_.copy_(c[:, :, :Qe, :].permute(2, 1, 0, 3))
+    hpar = [x[:Qe].cpu().numpy().view(np.uint64).copy() for x in (xb, yb, rr, ss)]
+    e2e_steps = max(2, min(args.steps, 10))
+
+    def e2e_step():
+        ctx.circuit_a_host(hc[0], hc[1], hc[2], hout, hpar[0], hpar[1], hpar[2], hpar[3], chunk=128)
+
+    e2e_step()
+    barrier()
+    te0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - te0
+    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * Qe * e2e_steps / float(te.item())
+    # the host entry returned what the resident kernel computes
+    ref_slice = out[:, :, :Qe, :].permute(2, 1, 0, 3).cpu()
+    if not torch.equal(ref_slice, hout):
+        raise SystemExit("bench: host-buffer path and resident path disagree")
+
+    extras = {}
+    if not args.no_extras and rank == 0:
+        extras = run_extras(engine, ctx, torch, osk, opk)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = peaks()
+    bytes_per_query = 64 * k * N
+    avg_kernel_ms = float(np.mean(kernel_ms))
+    achieved = bytes_per_query * Q / (avg_kernel_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("circuit_a_kernel", {}).get("dram_bytes_per_query")
+            traffic = traffic * Q if traffic else None   # ncu capture at a smaller batch, scaled per query to this launch
+        except Exception:
+            traffic = None
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "queries_per_gpu_per_step": Q, "poly_modulus_degree": N, "limbs": k, "plain_modulus": "2^56",
+                   "layout": "limb-major [limb][poly][query][N]", "parallelism": f"query-sharded x{world}, no collective in the hot path",
+                   "cache": f"inputs {3 * Q * per_ct * 8 / 2**30:.1f} GiB per step >> 126 MB L2 (no flush needed)"},
+        "roofline": {"bound": "hbm", "kernel": "circuit_a_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_query * Q,
+                     "avg_launch_ms": avg_kernel_ms, "note": "event pairs bracket each pplp_circuit_a call (scalar-prepare kernel + main kernel)"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 3 * Qe * per_ct * 8 + 4 * Qe * 8, "d2h_bytes_per_step": Qe * per_ct * 8,
+                "queries_per_step": Qe, "steps": e2e_steps, "api": "pplp_circuit_a_host (pinned host ciphertexts, SEAL layout)"},
+        "gpu_launches": 2 * args.steps,
+        "clocks": clocks,
+    }
+    if world == 1:
+        threads = host_threads()
+        rate, per_step, sample = cpu_circuit_a_rate(3, 1, args.cpu_sample, threads)
+        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": f"{sample} queries/step x 3 steps, SEAL-4.1-equivalent CPU restatement (oracle/), {threads} host threads"}
+    if extras:
+        line["extras"] = extras
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_extras(engine, ctx, torch, osk, opk):
+    """Measured numbers for the other kernels of the path (not the headline): full protocol and NTT GB/s."""
+    ex = {}
+    try:
+        sk, pk = ctx.dev(osk), ctx.dev(opk)
+        nq, radius = 2048, 128
+        rng = np.random.default_rng(99)
+        r, s, w = 0x12345678, 0x9ABCDEF1, 0xBEEF
+        xb = np.full(nq, 123456888, dtype=np.uint64); yb = np.full(nq, 132465777, dtype=np.uint64)
+        xa = xb + rng.integers(0, 300, nq).astype(np.uint64); ya = yb + rng.integers(0, 300, nq).astype(np.uint64)
+        seeds = rng.integers(0, 1 << 63, size=(nq * 3, 8), dtype=np.uint64)
+        bf = engine.BloomBatch(ctx, radius, fpp=1e-4, rsw=[(r, s, w)]).build()
+        ctx.proximity_batch_host(pk, sk, xa, ya, xb, yb, seeds, bf, chunk=1024)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            blind, verdict, flags = ctx.proximity_batch_host(pk, sk, xa, ya, xb, yb, seeds, bf, chunk=1024)
+        dt = time.perf_counter() - t0
+        d2 = (xa.astype(np.int64) - xb.astype(np.int64)) ** 2 + (ya.astype(np.int64) - yb.astype(np.int64)) ** 2
+        expect = (np.uint64(s) * (d2.astype(np.uint64) + np.uint64(r))) & np.uint64(T - 1)
+        ex["protocol_e2e"] = {"value": nq * reps / dt, "unit": UNIT, "queries_per_step": nq,
+                              "what": "host coords -> 3 encrypts + Circuit A + decrypt + Bloom verdict -> host verdicts (pplp_proximity_batch_host)",
+                              "blind_distances_correct": bool((blind == expect).all()), "near_fraction": float(verdict.mean())}
+    except Exception as e:   # extras never invalidate the headline
+        ex["protocol_e2e"] = {"error": str(e)[:200]}
+    try:
+        rows_q, k = 4096, ctx.k
+        data = ctx.empty(k, 1, rows_q, N)
+        for j in range(k):
+            data[j].random_(0, ctx.q[j])
+        for inv in (False, True):
+            for _ in range(3):
+                ctx.ntt_(data, inverse=inv, layout=engine.LAYOUT_LIMB_MAJOR)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            reps = 10
+            for _ in range(reps):
+                ctx.ntt_(data, inverse=inv, layout=engine.LAYOUT_LIMB_MAJOR)
+            b.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b) / reps
+            ex["intt_gbs" if inv else "ntt_gbs"] = 16 * N * rows_q * k / (ms * 1e-3) / 1e9
+        ex["ntt_note"] = f"16*N bytes per limb transform, {rows_q * k} rows of N={N} per launch"
+    except Exception as e:
+        ex["ntt_gbs"] = {"error": str(e)[:200]}
+    return ex
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

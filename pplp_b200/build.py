@@ -4,6 +4,7 @@ nvcc cross-compiles without a GPU, so this runs on the CPU-only build container;
 box with the repository snapshot.  Usage: `python -m pplp_b200.build [--force]`.
 """
 import concurrent.futures
+import hashlib
 import os
 import shutil
 import subprocess
@@ -35,11 +36,29 @@ def _headers():
     return hs
 
 
+def _digest(paths):
+    h = hashlib.sha256()
+    for p in sorted(paths):
+        h.update(os.path.basename(p).encode())
+        h.update(open(p, "rb").read())
+    h.update(" ".join(NVCC_FLAGS[:-1]).encode())
+    return h.hexdigest()
+
+
+def _stamp_path(obj):
+    return obj + ".sha256"
+
+
 def _stale(target, deps):
-    if not os.path.exists(target):
+    """Content-hash staleness (mtimes do not survive the snapshot to the GPU box)."""
+    if not os.path.exists(target) or not os.path.exists(_stamp_path(target)):
         return True
-    t = os.path.getmtime(target)
-    return any(os.path.getmtime(d) > t for d in deps)
+    return open(_stamp_path(target)).read().strip() != _digest(deps)
+
+
+def _stamp(target, deps):
+    with open(_stamp_path(target), "w") as f:
+        f.write(_digest(deps))
 
 
 def sources():
@@ -59,11 +78,13 @@ def build(force=False, verbose=False):
         objs.append(obj)
         if force or _stale(obj, [src] + hdrs):
             cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
-            jobs.append((s, cmd))
+            jobs.append((s, cmd, obj, [src] + hdrs))
 
     def run(job):
-        name, cmd = job
+        name, cmd, obj, deps = job
         r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode == 0:
+            _stamp(obj, deps)
         return name, r
 
     if jobs:
@@ -73,7 +94,7 @@ def build(force=False, verbose=False):
                     sys.stderr.write(f"--- nvcc {name} ---\n{r.stdout}{r.stderr}\n")
                 if r.returncode != 0:
                     raise RuntimeError(f"pplp_b200: nvcc failed on {name}")
-    if force or jobs or _stale(LIB, objs):
+    if force or jobs or not os.path.exists(LIB):
         cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lz"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:

@@ -1,0 +1,352 @@
+// pplp_b200/csrc/behz.cu — ciphertext x ciphertext multiplication (BEHZ RNS variant of BFV) and relinearisation.
+//
+// These are the kernels BASELINE.json's north_star names beyond the reference's own circuit: "ciphertext dyadic multiply
+// and tensor product; relinearization key-switching with fused INTT->decompose->NTT->inner product; BFV scale-and-round
+// (Behz/HPS base conversion)".  The reference never calls them, so they follow SEAL 4.1's
+// routines step for step, with the same auxiliary primes, because BEHZ's fast base conversions are approximate but
+// deterministic: only the literal sequence reproduces SEAL's residues.
+//   [SEAL] evaluator.cpp bfv_multiply/bfv_square: fastbconv_m_tilde -> sm_mrq -> NTT -> tensor -> INTT -> *t ->
+//          fast_floor -> fastbconv_sk                        (util/rns.cpp RNSTool)
+//   [SEAL] evaluator.cpp switch_key_inplace (relinearize_internal) + KeyGenerator::create_relin_keys
+//
+// Kernels
+//   behz_extend_kernel     per coefficient, across limbs: q -> Bsk U {m_tilde} conversion and the Montgomery-style
+//                          reduction sm_mrq in one pass (the m_tilde residue never leaves registers)
+//   tensor_kernel          d0 = x0 y0, d1 = x0 y1 + x1 y0, d2 = x1 y1 in NTT form, any base
+//   behz_floor_sk_kernel   per coefficient: *t, fast_floor (divide by Q in base Bsk) and the Shenoy–Kumaresan
+//                          conversion back to q, fused
+//   relin_limb_kernel      one CTA per (ciphertext, key limb I): for every digit J the CTA reduces c2's limb J modulo
+//                          q_I, transforms it and multiply-accumulates it with both key components while the data is
+//                          still in registers (Shoup products with precomputed key quotients, lazily in [0,2q)), then
+//                          runs the two inverse transforms — the NTT-form digits never touch HBM
+//   relin_moddown_kernel   divide by the special prime with rounding and add into (c0, c1)
+#include "engine.hpp"
+#include "ntt.cuh"
+
+namespace pplp {
+
+// ---- BEHZ: base extension ------------------------------------------------------------------------------------------
+// in: [nq][2][k][n] (layout `lay`), out: [nq][2][nb][n] contiguous.  grid.y = query*2 + poly.
+__global__ void __launch_bounds__(256) behz_extend_kernel(const DevLevel *Lp, const u64 *__restrict__ in, Layout lay, u64 *__restrict__ out) {
+    const DevLevel &L = *Lp;
+    const int k = L.k, nb = L.nBsk, n = L.n;
+    const int qi = blockIdx.y >> 1, p = blockIdx.y & 1;
+    const u64 *src = in + qi * lay.sq + p * lay.sp;
+    u64 *dst = out + ((size_t)qi * 2 + p) * nb * n;
+    const u64 mt_mask = L.m_tilde - 1, mt_half = L.m_tilde >> 1;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        u64 z[kMaxLimbs];
+        u64 acc_mt = 0;
+#pragma unroll 4
+        for (int j = 0; j < k; ++j) {
+            const u64 q = L.q[j].q;
+            const u64 tmp = mul_shoup(src[j * lay.sl + i], L.mtilde_mod_q[j], q);   // x * m_tilde mod q_j
+            z[j] = mul_shoup(tmp, L.inv_punct[j], q);
+            acc_mt += z[j] * L.punct_mod_mtilde[j];                                  // mod 2^32 survives the wrap mod 2^64
+        }
+        const u64 r = ((acc_mt & mt_mask) * L.neg_inv_q_mod_mtilde) & mt_mask;       // sm_mrq: r = -x q^-1 mod m_tilde
+        for (int b = 0; b < nb; ++b) {
+            const Mod &mp = L.bsk[b];
+            U128 acc{0, 0};
+            for (int j = 0; j < k; ++j) mac128(acc, z[j], L.punct_mod_bsk[b][j]);
+            const u64 conv = barrett128(acc.lo, acc.hi, mp);
+            const u64 rc = r >= mt_half ? r + (mp.q - L.m_tilde) : r;                // centred representative of r
+            const u64 v = add_mod(mul_shoup(rc, L.q_mod_bsk[b], mp.q), conv, mp.q);
+            dst[(size_t)b * n + i] = mul_shoup(v, L.inv_mtilde_mod_bsk[b], mp.q);
+        }
+    }
+}
+
+// ---- tensor product (NTT form) ------------------------------------------------------------------------------------
+// x, y: [nq][2][nl][n]; d: [nq][3][nl][n].  grid.y = query*nl + limb.
+__global__ void __launch_bounds__(256) tensor_kernel(const DevMod *mods, RowMap map, const u64 *__restrict__ x, const u64 *__restrict__ y, u64 *__restrict__ d, int n) {
+    const int nl = map.nlimbs;
+    const int qi = blockIdx.y / nl, j = blockIdx.y % nl;
+    const Mod mq = mods[map.mod_id[j]].m;
+    const u64 *x0 = x + (((size_t)qi * 2 + 0) * nl + j) * n, *x1 = x + (((size_t)qi * 2 + 1) * nl + j) * n;
+    const u64 *y0 = y + (((size_t)qi * 2 + 0) * nl + j) * n, *y1 = y + (((size_t)qi * 2 + 1) * nl + j) * n;
+    u64 *d0 = d + (((size_t)qi * 3 + 0) * nl + j) * n, *d1 = d0 + (size_t)nl * n, *d2 = d1 + (size_t)nl * n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const u64 a0 = x0[i], a1 = x1[i], b0 = y0[i], b1 = y1[i];
+        d0[i] = mul_mod(a0, b0, mq);
+        d1[i] = add_mod(mul_mod(a0, b1, mq), mul_mod(a1, b0, mq), mq.q);
+        d2[i] = mul_mod(a1, b1, mq);
+    }
+}
+
+// ---- BEHZ: *t, floor, Shenoy–Kumaresan ------------------------------------------------------------------------------
+// dq: [nq][3][k][n], db: [nq][3][nb][n] (coefficient form, canonical) -> out (layout `lay`, 3 polys).  grid.y = query*3 + poly.
+__global__ void __launch_bounds__(256) behz_floor_sk_kernel(const DevLevel *Lp, const u64 *__restrict__ dq, const u64 *__restrict__ db, u64 *__restrict__ out, Layout lay) {
+    const DevLevel &L = *Lp;
+    const int k = L.k, nb = L.nBsk, nB = L.nB, n = L.n;
+    const int qi = blockIdx.y / 3, p = blockIdx.y % 3;
+    const u64 *sq = dq + ((size_t)qi * 3 + p) * k * n;
+    const u64 *sb = db + ((size_t)qi * 3 + p) * nb * n;
+    u64 *dst = out + qi * lay.sq + p * lay.sp;
+    const u64 msk = L.bsk[nB].q, msk_half = msk >> 1;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        u64 z[kMaxLimbs], fl[kMaxLimbs];
+        for (int j = 0; j < k; ++j) {
+            const u64 q = L.q[j].q;
+            const u64 xt = mul_shoup(sq[(size_t)j * n + i], L.t_mod_q[j], q);        // * t
+            z[j] = mul_shoup(xt, L.inv_punct[j], q);
+        }
+        for (int b = 0; b < nb; ++b) {                                                 // fast_floor
+            const Mod &mp = L.bsk[b];
+            U128 acc{0, 0};
+            for (int j = 0; j < k; ++j) mac128(acc, z[j], L.punct_mod_bsk[b][j]);
+            const u64 conv = barrett128(acc.lo, acc.hi, mp);
+            const u64 xb = mul_shoup(sb[(size_t)b * n + i], L.t_mod_bsk[b], mp.q);
+            fl[b] = mul_shoup(sub_mod(xb, conv, mp.q), L.inv_q_mod_bsk[b], mp.q);
+        }
+        // fastbconv_sk: B -> q and B -> m_sk, alpha = (conv_msk - x_msk) B^-1 mod m_sk, centred
+        for (int b = 0; b < nB; ++b) z[b] = mul_shoup(fl[b], L.inv_punctB[b], L.bsk[b].q);
+        U128 am{0, 0};
+        for (int b = 0; b < nB; ++b) mac128(am, z[b], L.punctB_mod_msk[b]);
+        const u64 conv_msk = barrett128(am.lo, am.hi, L.bsk[nB]);
+        const u64 alpha = mul_shoup(sub_mod(conv_msk, fl[nB], msk), L.inv_B_mod_msk, msk);
+        const bool neg = alpha > msk_half;
+        const u64 a_abs = neg ? msk - alpha : alpha;
+        for (int j = 0; j < k; ++j) {
+            const Mod &mq = L.q[j];
+            U128 acc{0, 0};
+            for (int b = 0; b < nB; ++b) mac128(acc, z[b], L.punctB_mod_q[j][b]);
+            const u64 conv = barrett128(acc.lo, acc.hi, mq);
+            const u64 corr = mul_shoup(a_abs, neg ? L.B_mod_q[j] : L.neg_B_mod_q[j], mq.q);
+            dst[j * lay.sl + i] = add_mod(corr, conv, mq.q);
+        }
+    }
+}
+
+__global__ void gather_ct_kernel(const u64 *__restrict__ src, Layout lay, u64 *__restrict__ dst, int npoly, int k, int n) {
+    int row = blockIdx.y;
+    const int j = row % k; row /= k;
+    const int p = row % npoly, qi = row / npoly;
+    const u64 *s = src + qi * lay.sq + p * lay.sp + j * lay.sl;
+    u64 *d = dst + (((size_t)qi * npoly + p) * k + j) * n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) d[i] = s[i];
+}
+
+size_t multiply_tmp_words(const Engine &E, size_t level, int nq, bool square) {
+    const size_t k = E.host.levels[level].q.size(), nb = (size_t)E.host.levels[level].dev.nBsk, n = E.host.n;
+    const size_t ext = (size_t)nq * 2 * (k + nb) * n;
+    return ext * (square ? 1 : 2) + (size_t)nq * 3 * (k + nb) * n;
+}
+
+// out (size 3) = a * b; a == b pointer-equal means square.  a, b, out share `lay` (npoly differs: strides given by caller).
+void launch_multiply(const Engine &E, size_t level, const u64 *a, const u64 *b, Layout in_lay, u64 *out, Layout out_lay, int nq, u64 *ws, cudaStream_t st) {
+    E.require_device();
+    if (nq == 0) return;
+    const HostLevel &HL = E.host.levels[level];
+    const int k = (int)HL.q.size(), nb = HL.dev.nBsk, n = (int)E.host.n;
+    const DevLevel *L = E.d_levels + level;
+    const bool square = (a == b);
+    const RowMap qm = E.qmap(level), bm = E.bskmap(level);
+    const size_t wq = (size_t)nq * 2 * k * n, wb = (size_t)nq * 2 * nb * n;
+    u64 *aq = ws, *ab = aq + wq;
+    u64 *bq = square ? aq : ab + wb, *bb = square ? ab : bq + wq;
+    u64 *dq = (square ? ab + wb : bb + wb), *db = dq + (size_t)nq * 3 * k * n;
+    const Layout ql{(size_t)2 * k * n, (size_t)k * n, (size_t)n}, bl{(size_t)2 * nb * n, (size_t)nb * n, (size_t)n};
+    dim3 ge((n + 255) / 256, nq * 2), gg((n + 1023) / 1024, nq * 2 * k);
+    auto extend = [&](const u64 *src, u64 *xq, u64 *xb) {
+        gather_ct_kernel<<<gg, 256, 0, st>>>(src, in_lay, xq, 2, k, n);
+        behz_extend_kernel<<<ge, 256, 0, st>>>(L, src, in_lay, xb);
+        launch_ntt(E, xq, ql, nq, 2, qm, false, st);
+        launch_ntt(E, xb, bl, nq, 2, bm, false, st);
+    };
+    extend(a, aq, ab);
+    if (!square) extend(b, bq, bb);
+    tensor_kernel<<<dim3((n + 1023) / 1024, nq * k), 256, 0, st>>>(E.d_mods, qm, aq, bq, dq, n);
+    tensor_kernel<<<dim3((n + 1023) / 1024, nq * nb), 256, 0, st>>>(E.d_mods, bm, ab, bb, db, n);
+    launch_ntt(E, dq, Layout{(size_t)3 * k * n, (size_t)k * n, (size_t)n}, nq, 3, qm, true, st);
+    launch_ntt(E, db, Layout{(size_t)3 * nb * n, (size_t)nb * n, (size_t)n}, nq, 3, bm, true, st);
+    behz_floor_sk_kernel<<<dim3((n + 255) / 256, nq * 3), 256, 0, st>>>(L, dq, db, out, out_lay);
+    PPLP_CUDA(cudaGetLastError());
+}
+
+// ---- relinearisation -------------------------------------------------------------------------------------------------
+// quot[i] = floor(w[i] * 2^64 / q_limb): Shoup quotients of key words, computed once per key.  rows of n words, limb = row % K.
+__global__ void shoup_quot_kernel(const DevMod *mods, const u64 *__restrict__ w, u64 *__restrict__ quot, int K, int n) {
+    const int row = blockIdx.y;
+    const u64 q = mods[row % K].m.q;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const size_t o = (size_t)row * n + i;
+        quot[o] = (u64)((((unsigned __int128)w[o]) << 64) / q);
+    }
+}
+void launch_shoup_quotients(const Engine &E, const u64 *w, u64 *quot, int nrows, cudaStream_t st) {
+    E.require_device();
+    const int n = (int)E.host.n, K = (int)E.host.K();
+    if (nrows == 0) return;
+    shoup_quot_kernel<<<dim3((n + 1023) / 1024, nrows), 256, 0, st>>>(E.d_mods, w, quot, K, n);
+    PPLP_CUDA(cudaGetLastError());
+}
+
+struct RelinArgs {
+    const u64 *c2; Layout lay;      // ciphertext batch; c2 = poly 2
+    const u64 *rk, *rkq;            // [digit][2][K][n] key words and their Shoup quotients
+    u64 *tmp;                       // [nq][2][k+1][n]: inverse-transformed accumulators, special limb last
+    int k, K, n;
+    const DevMod *mods;
+    u64 half;                       // P >> 1
+};
+
+template <int LOGM>
+__global__ void __launch_bounds__(NttShape<LOGM>::T) relin_limb_kernel(const RelinArgs a) {
+    using S = NttShape<LOGM>;
+    extern __shared__ __align__(16) u64 sm[];
+    const int tid = threadIdx.x;
+    const int I = blockIdx.x % (a.k + 1), qi = blockIdx.x / (a.k + 1);
+    const int key_index = (I == a.k) ? a.K - 1 : I;
+    const DevMod &md = a.mods[key_index];
+    const Mod mod = md.m;
+    const u64 q = mod.q, two_q = q << 1;
+    const u64 *c2 = a.c2 + qi * a.lay.sq + 2 * a.lay.sp;
+
+    u64 acc0[16], acc1[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) { acc0[r] = 0; acc1[r] = 0; }
+    for (int J = 0; J < a.k; ++J) {
+        u64 x[16];
+        const u64 *row = c2 + J * a.lay.sl;
+        if (J == key_index) CoarsePass<LOGM>::for_each(tid, [&](int r, int i) { x[r] = row[i]; });
+        else CoarsePass<LOGM>::for_each(tid, [&](int r, int i) { x[r] = barrett64(row[i], mod); });
+        block_ntt_forward<LOGM>(x, sm, tid, md.fwd, 0, 0, q);
+        const size_t koff = (((size_t)J * 2 + 0) * a.K + key_index) * a.n + 16 * tid;
+        const size_t koff1 = koff + (size_t)a.K * a.n;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const ulonglong2 w0 = __ldg(reinterpret_cast<const ulonglong2 *>(a.rk + koff + 2 * c));
+            const ulonglong2 g0 = __ldg(reinterpret_cast<const ulonglong2 *>(a.rkq + koff + 2 * c));
+            const ulonglong2 w1 = __ldg(reinterpret_cast<const ulonglong2 *>(a.rk + koff1 + 2 * c));
+            const ulonglong2 g1 = __ldg(reinterpret_cast<const ulonglong2 *>(a.rkq + koff1 + 2 * c));
+            u64 v;
+            v = acc0[2 * c] + mul_shoup_lazy(x[2 * c], w0.x, g0.x, q);         acc0[2 * c] = v >= two_q ? v - two_q : v;
+            v = acc0[2 * c + 1] + mul_shoup_lazy(x[2 * c + 1], w0.y, g0.y, q); acc0[2 * c + 1] = v >= two_q ? v - two_q : v;
+            v = acc1[2 * c] + mul_shoup_lazy(x[2 * c], w1.x, g1.x, q);         acc1[2 * c] = v >= two_q ? v - two_q : v;
+            v = acc1[2 * c + 1] + mul_shoup_lazy(x[2 * c + 1], w1.y, g1.y, q); acc1[2 * c + 1] = v >= two_q ? v - two_q : v;
+        }
+        __syncthreads();   // the next digit reuses the staging buffer
+    }
+    u64 *o0 = a.tmp + (((size_t)qi * 2 + 0) * (a.k + 1) + I) * a.n;
+    u64 *o1 = a.tmp + (((size_t)qi * 2 + 1) * (a.k + 1) + I) * a.n;
+    const bool special = (I == a.k);
+    block_ntt_inverse<LOGM, true>(acc0, sm, tid, md.inv, 0, 0, q, md.n_inv, md.inv1_n_inv);
+    CoarsePass<LOGM>::for_each(tid, [&](int r, int i) {
+        const u64 v = csub(acc0[r], q);
+        o0[i] = special ? add_mod(v, a.half, q) : v;
+    });
+    __syncthreads();
+    block_ntt_inverse<LOGM, true>(acc1, sm, tid, md.inv, 0, 0, q, md.n_inv, md.inv1_n_inv);
+    CoarsePass<LOGM>::for_each(tid, [&](int r, int i) {
+        const u64 v = csub(acc1[r], q);
+        o1[i] = special ? add_mod(v, a.half, q) : v;
+    });
+}
+
+// generic (N = 32768) pieces
+__global__ void relin_reduce_kernel(const DevMod *mods, const u64 *__restrict__ c2, Layout lay, u64 *__restrict__ dst, int k, int K, int n) {
+    // dst [nq][k+1][k][n]: digit J reduced modulo key limb I
+    int row = blockIdx.y;
+    const int J = row % k; row /= k;
+    const int I = row % (k + 1), qi = row / (k + 1);
+    const Mod mod = mods[I == k ? K - 1 : I].m;
+    const u64 *s = c2 + qi * lay.sq + 2 * lay.sp + J * lay.sl;
+    u64 *d = dst + (((size_t)qi * (k + 1) + I) * k + J) * n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) d[i] = barrett64(s[i], mod);
+}
+__global__ void relin_mac_kernel(const DevMod *mods, const u64 *__restrict__ digits, const u64 *__restrict__ rk, u64 *__restrict__ tmp, int k, int K, int n) {
+    int row = blockIdx.y;
+    const int I = row % (k + 1), qi = row / (k + 1);
+    const int key_index = I == k ? K - 1 : I;
+    const Mod mod = mods[key_index].m;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        u64 a0 = 0, a1 = 0;
+        for (int J = 0; J < k; ++J) {
+            const u64 x = digits[(((size_t)qi * (k + 1) + I) * k + J) * n + i];
+            a0 = add_mod(a0, mul_mod(x, rk[(((size_t)J * 2 + 0) * K + key_index) * n + i], mod), mod.q);
+            a1 = add_mod(a1, mul_mod(x, rk[(((size_t)J * 2 + 1) * K + key_index) * n + i], mod), mod.q);
+        }
+        tmp[(((size_t)qi * 2 + 0) * (k + 1) + I) * n + i] = a0;
+        tmp[(((size_t)qi * 2 + 1) * (k + 1) + I) * n + i] = a1;
+    }
+}
+__global__ void relin_add_half_kernel(u64 *tmp, int k, int n, u64 P, u64 half) {
+    const int qi = blockIdx.y >> 1, c = blockIdx.y & 1;
+    u64 *t = tmp + (((size_t)qi * 2 + c) * (k + 1) + k) * n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) t[i] = add_mod(t[i], half, P);
+}
+
+// out_c[j] = in_c[j] + P^-1 (acc_c[j] - ((t_last_c + half) mod P - half)) mod q_j.  KL = key-level constants.  grid.y = query*2 + comp.
+__global__ void __launch_bounds__(256) relin_moddown_kernel(const DevLevel *KLp, const u64 *__restrict__ tmp, const u64 *__restrict__ in, Layout in_lay, u64 *__restrict__ out,
+                                                            Layout out_lay, int k) {
+    const DevLevel &KL = *KLp;
+    const int n = KL.n;
+    const int qi = blockIdx.y >> 1, c = blockIdx.y & 1;
+    const u64 *acc = tmp + ((size_t)qi * 2 + c) * (k + 1) * n;
+    const u64 *src = in + qi * in_lay.sq + c * in_lay.sp;
+    u64 *dst = out + qi * out_lay.sq + c * out_lay.sp;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const u64 last = acc[(size_t)k * n + i];   // already (t_last + half) mod P
+        for (int j = 0; j < k; ++j) {
+            const Mod &mq = KL.q[j];
+            const u64 corr = sub_mod(barrett64(last, mq), KL.half_last_mod[j], mq.q);
+            const u64 v = mul_shoup(sub_mod(acc[(size_t)j * n + i], corr, mq.q), KL.inv_last[j], mq.q);
+            dst[j * out_lay.sl + i] = add_mod(src[j * in_lay.sl + i], v, mq.q);
+        }
+    }
+}
+
+size_t relin_tmp_words(const Engine &E, size_t level, int nq) {
+    const size_t k = E.host.levels[level].q.size(), n = E.host.n;
+    size_t w = (size_t)nq * 2 * (k + 1) * n;
+    if (E.host.logn == 15) w += (size_t)nq * (k + 1) * k * n;
+    return w;
+}
+
+template <int LOGM> static void run_relin_limb(const RelinArgs &a, int nq, cudaStream_t st) {
+    static bool done[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int bytes = NttShape<LOGM>::SMEM_WORDS * 8;
+    if (!done[dev]) { PPLP_CUDA(cudaFuncSetAttribute(relin_limb_kernel<LOGM>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)); done[dev] = true; }
+    relin_limb_kernel<LOGM><<<nq * (a.k + 1), NttShape<LOGM>::T, bytes, st>>>(a);
+}
+
+// in: size-3 ciphertexts (layout in_lay), out: size-2 (layout out_lay; may alias in when the strides agree)
+void launch_relinearize(const Engine &E, size_t level, const u64 *in, Layout in_lay, u64 *out, Layout out_lay, int nq, const u64 *rk, const u64 *rkq, u64 *ws,
+                        cudaStream_t st) {
+    E.require_device();
+    if (nq == 0) return;
+    const int k = (int)E.host.levels[level].q.size(), K = (int)E.host.K(), n = (int)E.host.n;
+    const u64 P = E.host.q[K - 1];
+    u64 *tmp = ws;
+    RelinArgs a{in, in_lay, rk, rkq, tmp, k, K, n, E.d_mods, P >> 1};
+    switch (E.host.logn) {
+    case 10: run_relin_limb<10>(a, nq, st); break;
+    case 11: run_relin_limb<11>(a, nq, st); break;
+    case 12: run_relin_limb<12>(a, nq, st); break;
+    case 13: run_relin_limb<13>(a, nq, st); break;
+    case 14: run_relin_limb<14>(a, nq, st); break;
+    case 15: {
+        u64 *digits = tmp + (size_t)nq * 2 * (k + 1) * n;
+        relin_reduce_kernel<<<dim3((n + 1023) / 1024, nq * (k + 1) * k), 256, 0, st>>>(E.d_mods, in, in_lay, digits, k, K, n);
+        for (int I = 0; I <= k; ++I) {   // rows of key limb I share a modulus
+            RowMap m; m.nlimbs = 1; m.mod_id[0] = I == k ? K - 1 : I;
+            launch_ntt(E, digits + (size_t)I * k * n, Layout{(size_t)(k + 1) * k * n, (size_t)n, 0}, nq, k, m, false, st);
+        }
+        relin_mac_kernel<<<dim3((n + 1023) / 1024, nq * (k + 1)), 256, 0, st>>>(E.d_mods, digits, rk, tmp, k, K, n);
+        for (int I = 0; I <= k; ++I) {
+            RowMap m; m.nlimbs = 1; m.mod_id[0] = I == k ? K - 1 : I;
+            launch_ntt(E, tmp + (size_t)I * n, Layout{(size_t)2 * (k + 1) * n, (size_t)(k + 1) * n, 0}, nq, 2, m, true, st);
+        }
+        relin_add_half_kernel<<<dim3((n + 1023) / 1024, nq * 2), 256, 0, st>>>(tmp, k, n, P, P >> 1);
+        break;
+    }
+    default: throw std::invalid_argument("pplp: relinearisation supports poly_modulus_degree 1024..32768");
+    }
+    relin_moddown_kernel<<<dim3((n + 255) / 256, nq * 2), 256, 0, st>>>(E.d_levels, tmp, in, in_lay, out, out_lay, k);
+    PPLP_CUDA(cudaGetLastError());
+}
+
+}  // namespace pplp

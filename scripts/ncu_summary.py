@@ -1,0 +1,47 @@
+#!/usr/bin/env python
+"""Summarise an .ncu-rep (raw page) into the handful of counters the roofline discussion needs.
+Usage: python scripts/ncu_summary.py gpurun_out/prof.ncu-rep [kernel-substring]"""
+import csv
+import subprocess
+import sys
+
+WANT = ['Kernel Name', 'Grid Size', 'Block Size', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
+        'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'dram__throughput.avg.pct_of_peak_sustained_elapsed',
+        'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'sm__warps_active.avg.pct_of_peak_sustained_active',
+        'launch__registers_per_thread', 'launch__waves_per_multiprocessor', 'launch__occupancy_limit_registers',
+        'launch__occupancy_limit_shared_mem', 'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active', 'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_fmaheavy.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
+        'lts__t_sector_hit_rate.pct', 'l1tex__t_sector_hit_rate.pct', 'sm__inst_executed.sum', 'smsp__inst_executed.sum',
+        'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct',
+        'smsp__warp_issue_stalled_barrier_per_warp_active.pct', 'smsp__warp_issue_stalled_math_pipe_throttle_per_warp_active.pct',
+        'smsp__warp_issue_stalled_short_scoreboard_per_warp_active.pct', 'smsp__warp_issue_stalled_mio_throttle_per_warp_active.pct',
+        'smsp__warp_issue_stalled_wait_per_warp_active.pct', 'smsp__warp_issue_stalled_not_selected_per_warp_active.pct',
+        'smsp__warp_issue_stalled_lg_throttle_per_warp_active.pct', 'smsp__warp_issue_stalled_dispatch_stall_per_warp_active.pct']
+
+
+def main():
+    rep = sys.argv[1]
+    filt = sys.argv[2] if len(sys.argv) > 2 else ''
+    out = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    for r in rows[2:]:
+        name = r[hdr.index('Kernel Name')]
+        if filt and filt not in name:
+            continue
+        print('---')
+        for w in WANT:
+            if w in hdr:
+                i = hdr.index(w)
+                print(f'{w} = {r[i]} {units[i]}')
+        if 'dram__bytes_read.sum' in hdr:
+            def val(m):
+                i = hdr.index(m); v = float(r[i].replace(',', '')); u = units[i]
+                return v * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}.get(u, 1)
+            print('dram_bytes_total =', val('dram__bytes_read.sum') + val('dram__bytes_write.sum'))
+
+
+if __name__ == '__main__':
+    main()

@@ -87,6 +87,8 @@ int pplp_host_free(void *ptr);
  * seed = the 64-byte seed of SEAL's Blake2xbPRNG (prng_seed_type).  d_sk: [K][N], d_pk: [2][K][N], both NTT form at
  * the key level, exactly the words SEAL serialises.  Synchronises. */
 int pplp_keygen(pplp_ctx *ctx, const uint64_t seed[8], uint64_t *d_sk, uint64_t *d_pk, void *stream);
+/* KeyGenerator::create_public_key for an existing secret key (its own PRNG seed).  Synchronises. */
+int pplp_public_keygen(pplp_ctx *ctx, const uint64_t seed[8], const uint64_t *d_sk, uint64_t *d_pk, void *stream);
 /* KeyGenerator::create_relin_keys  (north_star; no reference call site).  seeds: [k][8], one PRNG per decomposition
  * digit; d_rk: [k][2][K][N].  Synchronises. */
 int pplp_relin_keygen(pplp_ctx *ctx, const uint64_t *seeds, const uint64_t *d_sk, uint64_t *d_rk, void *stream);
@@ -131,9 +133,30 @@ int pplp_circuit_a(pplp_ctx *ctx, size_t level, const uint64_t *d_c0, const uint
  * double-buffered device slabs, overlapping the copies with the kernel.  Page-locked buffers recommended.  Synchronises. */
 int pplp_circuit_a_host(pplp_ctx *ctx, size_t level, const uint64_t *h_c0, const uint64_t *h_c1, const uint64_t *h_c2, uint64_t *h_out, size_t nq,
                         const uint64_t *h_xb, const uint64_t *h_yb, const uint64_t *h_r, const uint64_t *h_s, int *h_flags, size_t chunk);
+/* Evaluator::multiply / square (north_star; no reference call site): size-2 x size-2 -> size-3 with SEAL's BEHZ
+ * scale-and-round, step for step (fastbconv_m_tilde, sm_mrq, tensor, fast_floor, fastbconv_sk).  d_out: nq ciphertexts of
+ * 3 polynomials in `layout`.  pplp_square(a) == pplp_multiply(a, a). */
+int pplp_multiply(pplp_ctx *ctx, size_t level, const uint64_t *d_a, const uint64_t *d_b, uint64_t *d_out, int layout, size_t nq, void *stream);
+int pplp_square(pplp_ctx *ctx, size_t level, const uint64_t *d_a, uint64_t *d_out, int layout, size_t nq, void *stream);
+/* Evaluator::relinearize_inplace (north_star): size-3 -> size-2 with keys from pplp_relin_keygen.  d_rk_quot holds the
+ * keys' Shoup quotients floor(w * 2^64 / q) from pplp_relin_prepare (computed once per key set); NULL recomputes them
+ * into scratch on every call.  d_out: nq ciphertexts of 2 polynomials. */
+int pplp_relin_prepare(pplp_ctx *ctx, const uint64_t *d_rk, uint64_t *d_rk_quot, void *stream);
+int pplp_relinearize(pplp_ctx *ctx, size_t level, const uint64_t *d_in, uint64_t *d_out, int layout, size_t nq, const uint64_t *d_rk,
+                     const uint64_t *d_rk_quot, void *stream);
 /* Negacyclic NTT / inverse NTT of every row (Evaluator::transform_to_ntt_inplace semantics; the microbenchmark of
  * BASELINE.json config 4).  base 0 = the level's q primes, base 1 = the level's BEHZ base Bsk. */
 int pplp_ntt(pplp_ctx *ctx, size_t level, int base, uint64_t *d_data, int layout, size_t nq, size_t npoly, int inverse, void *stream);
+
+/* 1 in *h_out when every polynomial beyond c0 is zero — the state in which SEAL's evaluator throws
+ * std::logic_error("result ciphertext is transparent").  SEAL layout, one ciphertext.  Synchronises. */
+int pplp_is_transparent(pplp_ctx *ctx, size_t level, const uint64_t *d_ct, size_t size, int *h_out);
+
+/* ---- BatchEncoder (north_star; needs a prime t == 1 mod 2N, which the reference's t = 2^56 is not) ------------------
+ * encode: slot values [nq][count] (< t) -> plaintext coefficients [nq][N]; decode: the inverse, [nq][N] -> [nq][N].
+ * encode synchronises (range check of the inputs, as SEAL throws on values >= t). */
+int pplp_batch_encode(pplp_ctx *ctx, const uint64_t *d_values, size_t count, uint64_t *d_plain, size_t nq, void *stream);
+int pplp_batch_decode(pplp_ctx *ctx, const uint64_t *d_plain, uint64_t *d_values, size_t nq, void *stream);
 
 /* ---- Bloom filter  — include/bloomfilter.h of the reference ------------------------------------------------------
  * bloom_parameters::compute_optimal_parameters + bloom_filter ctor (:98-151, :167-179, :459-525).  Host only.

@@ -12,8 +12,45 @@
 
 using namespace pplp;
 
+// Staging slabs of the host-buffer entry points, kept across calls (cudaMalloc/cudaFree per call would cost more
+// than the copies they serve).
+struct HostPipe {
+    static constexpr int NB = 3;
+    struct Slab { cudaStream_t st = nullptr; u64 *c[3] = {nullptr, nullptr, nullptr}; u64 *sc = nullptr, *par = nullptr, *h_par = nullptr; int *flags = nullptr; };
+    Slab slab[NB];
+    size_t chunk = 0, ctw = 0, level = 0;
+    void release() {
+        for (auto &s : slab) {
+            if (s.st) { cudaStreamSynchronize(s.st); cudaStreamDestroy(s.st); }
+            for (auto &p : s.c) if (p) cudaFree(p);
+            if (s.sc) cudaFree(s.sc);
+            if (s.par) cudaFree(s.par);
+            if (s.flags) cudaFree(s.flags);
+            if (s.h_par) cudaFreeHost(s.h_par);
+            s = Slab();
+        }
+        chunk = 0;
+    }
+    void ensure(const Engine &E, size_t lvl, size_t ch, size_t words_per_ct) {
+        if (chunk == ch && ctw == words_per_ct && level == lvl) return;
+        release();
+        for (auto &s : slab) {
+            PPLP_CUDA(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+            for (auto &p : s.c) PPLP_CUDA(cudaMalloc(&p, ch * words_per_ct * 8));
+            PPLP_CUDA(cudaMalloc(&s.sc, circuit_a_scratch_words(E, lvl, (int)ch) * 8));
+            PPLP_CUDA(cudaMalloc(&s.par, ch * 4 * 8));
+            PPLP_CUDA(cudaMalloc(&s.flags, ch * sizeof(int)));
+            PPLP_CUDA(cudaMallocHost(&s.h_par, ch * 4 * 8));
+        }
+        chunk = ch; ctw = words_per_ct; level = lvl;
+    }
+};
+
 struct pplp_ctx {
     Engine eng;
+    HostPipe pipe;
+    std::mutex pipe_mutex;
+    ~pplp_ctx() { pipe.release(); }
 };
 
 namespace {
@@ -149,6 +186,20 @@ __global__ void proximity_plain_kernel(const u64 *__restrict__ xa, const u64 *__
     plain[3 * q] = u; plain[3 * q + 1] = x2; plain[3 * q + 2] = y2;
     if (flags && (u >= t || x2 >= t || y2 >= t)) atomicOr(&flags[q], 2);   // SEAL: "plain is not valid for encryption parameters"
 }
+// BatchEncoder: values[q][count] -> slots scattered into the NTT-domain vector (zero elsewhere); and the reverse gather
+__global__ void batch_scatter_kernel(const u64 *__restrict__ values, size_t count, const uint32_t *__restrict__ slot_index, u64 *__restrict__ out, int n) {
+    const int q = blockIdx.y;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        out[(size_t)q * n + slot_index[i]] = (size_t)i < count ? values[(size_t)q * count + i] : 0;
+}
+__global__ void batch_gather_kernel(const u64 *__restrict__ in, const uint32_t *__restrict__ slot_index, u64 *__restrict__ values, int n) {
+    const int q = blockIdx.y;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) values[(size_t)q * n + i] = in[(size_t)q * n + slot_index[i]];
+}
+__global__ void check_below_kernel(const u64 *__restrict__ v, size_t count, u64 bound, int *flag) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x)
+        if (v[i] >= bound) atomicOr(flag, 1);
+}
 __global__ void gather_u64_kernel(const u64 *__restrict__ src, const int *__restrict__ idx, int stride, int col, int n, u64 *__restrict__ dst) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = src[(idx ? idx[i] : 0) * stride + col];
@@ -176,6 +227,7 @@ void Engine::upload_tables(int dev) {
     std::vector<DevLevel> lv(host.levels.size());
     for (size_t i = 0; i < lv.size(); ++i) lv[i] = host.levels[i].dev;
     d_levels = upload(lv.data(), lv.size());
+    if (host.batching) d_slot_index = upload(host.slot_index.data(), host.slot_index.size());
     // keep scratch in the stream-ordered pool instead of returning it to the driver after every call
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
@@ -331,6 +383,13 @@ int pplp_keygen(pplp_ctx *ctx, const uint64_t seed[8], uint64_t *d_sk, uint64_t 
     return PPLP_OK;
     PPLP_CATCH
 }
+int pplp_public_keygen(pplp_ctx *ctx, const uint64_t seed[8], const uint64_t *d_sk, uint64_t *d_pk, void *stream) {
+    PPLP_TRY
+    Engine &E = dev_engine(ctx);
+    symmetric_zero_ntt(E, seed, d_sk, d_pk, -1, 0, S(stream));
+    return PPLP_OK;
+    PPLP_CATCH
+}
 int pplp_relin_keygen(pplp_ctx *ctx, const uint64_t *seeds, const uint64_t *d_sk, uint64_t *d_rk, void *stream) {
     PPLP_TRY
     Engine &E = dev_engine(ctx);
@@ -475,44 +534,75 @@ int pplp_circuit_a_host(pplp_ctx *ctx, size_t level, const uint64_t *h_c0, const
     Engine &E = dev_engine(ctx);
     const size_t k = check_level(E, level), n = E.host.n;
     if (nq == 0) return PPLP_OK;
-    if (chunk == 0) chunk = 256;
-    chunk = std::min(chunk, nq);
+    if (chunk == 0) chunk = 128;
     const size_t ctw = 2 * k * n;   // words per ciphertext
-    constexpr int NB = 3;           // slabs in flight: copy-in, compute, copy-out overlap
-    struct Slab { cudaStream_t st; u64 *c[3]; u64 *out; u64 *sc; u64 *par; int *flags; };
-    Slab sl[NB];
-    std::vector<void *> owned;
-    auto dalloc = [&](size_t bytes) { void *p; PPLP_CUDA(cudaMalloc(&p, bytes)); owned.push_back(p); return p; };
-    struct Cleanup {
-        std::vector<void *> &o; Slab *s; int nb;
-        ~Cleanup() { for (int i = 0; i < nb; ++i) if (s[i].st) cudaStreamDestroy(s[i].st); for (void *p : o) cudaFree(p); }
-    } cleanup{owned, sl, NB};
-    for (auto &s : sl) s.st = nullptr;
-    for (auto &s : sl) {
-        PPLP_CUDA(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
-        for (int i = 0; i < 3; ++i) s.c[i] = (u64 *)dalloc(chunk * ctw * 8);
-        s.out = s.c[0];   // in place on c0
-        s.sc = (u64 *)dalloc(circuit_a_scratch_words(E, level, (int)chunk) * 8);
-        s.par = (u64 *)dalloc(chunk * 4 * 8);
-        s.flags = (int *)dalloc(chunk * sizeof(int));
-    }
+    std::lock_guard<std::mutex> lock(ctx->pipe_mutex);
+    HostPipe &P = ctx->pipe;
+    P.ensure(E, level, chunk, ctw);
     const Layout lay = make_layout(PPLP_LAYOUT_SEAL, n, k, 2, chunk);
+    // Three slabs in flight, each on its own stream: copy-in of slab i+1 overlaps the kernel of slab i and the
+    // copy-out of slab i-1 (PCIe is full duplex; the kernel itself is ~100x faster than either copy).
     size_t done = 0;
     for (int it = 0; done < nq; ++it) {
-        Slab &s = sl[it % NB];
+        HostPipe::Slab &s = P.slab[it % HostPipe::NB];
         const size_t c = std::min(chunk, nq - done);
+        PPLP_CUDA(cudaStreamSynchronize(s.st));   // the pinned parameter staging of this slab is free again
+        const u64 *par[4] = {h_xb, h_yb, h_r, h_s};
+        for (int i = 0; i < 4; ++i) std::memcpy(s.h_par + i * chunk, par[i] + done, c * 8);
         const u64 *src[3] = {h_c0, h_c1, h_c2};
         for (int i = 0; i < 3; ++i) PPLP_CUDA(cudaMemcpyAsync(s.c[i], src[i] + done * ctw, c * ctw * 8, cudaMemcpyHostToDevice, s.st));
-        const u64 *par[4] = {h_xb, h_yb, h_r, h_s};
-        for (int i = 0; i < 4; ++i) PPLP_CUDA(cudaMemcpyAsync(s.par + i * chunk, par[i] + done, c * 8, cudaMemcpyHostToDevice, s.st));
+        PPLP_CUDA(cudaMemcpyAsync(s.par, s.h_par, chunk * 4 * 8, cudaMemcpyHostToDevice, s.st));
         if (h_flags) PPLP_CUDA(cudaMemsetAsync(s.flags, 0, c * sizeof(int), s.st));
-        launch_circuit_a(E, level, s.c[0], s.c[1], s.c[2], s.out, lay, (int)c, s.par, s.par + chunk, s.par + 2 * chunk, s.par + 3 * chunk, s.sc,
+        launch_circuit_a(E, level, s.c[0], s.c[1], s.c[2], s.c[0], lay, (int)c, s.par, s.par + chunk, s.par + 2 * chunk, s.par + 3 * chunk, s.sc,
                          h_flags ? s.flags : nullptr, s.st);
-        PPLP_CUDA(cudaMemcpyAsync(h_out + done * ctw, s.out, c * ctw * 8, cudaMemcpyDeviceToHost, s.st));
+        PPLP_CUDA(cudaMemcpyAsync(h_out + done * ctw, s.c[0], c * ctw * 8, cudaMemcpyDeviceToHost, s.st));
         if (h_flags) PPLP_CUDA(cudaMemcpyAsync(h_flags + done, s.flags, c * sizeof(int), cudaMemcpyDeviceToHost, s.st));
         done += c;
     }
-    for (auto &s : sl) PPLP_CUDA(cudaStreamSynchronize(s.st));
+    for (auto &s : P.slab) PPLP_CUDA(cudaStreamSynchronize(s.st));
+    return PPLP_OK;
+    PPLP_CATCH
+}
+
+int pplp_multiply(pplp_ctx *ctx, size_t level, const uint64_t *d_a, const uint64_t *d_b, uint64_t *d_out, int layout, size_t nq, void *stream) {
+    PPLP_TRY
+    Engine &E = dev_engine(ctx);
+    const size_t k = check_level(E, level), n = E.host.n;
+    if (nq == 0) return PPLP_OK;
+    const int nqi = to_int(nq, "query count");
+    cudaStream_t st = S(stream);
+    Scratch ws(multiply_tmp_words(E, level, nqi, d_a == d_b) * 8, st);
+    launch_multiply(E, level, d_a, d_b, make_layout(layout, n, k, 2, nq), d_out, make_layout(layout, n, k, 3, nq), nqi, ws.as<u64>(), st);
+    return PPLP_OK;
+    PPLP_CATCH
+}
+int pplp_square(pplp_ctx *ctx, size_t level, const uint64_t *d_a, uint64_t *d_out, int layout, size_t nq, void *stream) {
+    return pplp_multiply(ctx, level, d_a, d_a, d_out, layout, nq, stream);
+}
+int pplp_relin_prepare(pplp_ctx *ctx, const uint64_t *d_rk, uint64_t *d_rk_quot, void *stream) {
+    PPLP_TRY
+    Engine &E = dev_engine(ctx);
+    if (E.host.levels.size() < 2) throw std::logic_error("keyswitching is not supported by the context");
+    const size_t K = E.host.K(), nd = E.host.levels[1].q.size();
+    launch_shoup_quotients(E, d_rk, d_rk_quot, (int)(nd * 2 * K), S(stream));
+    return PPLP_OK;
+    PPLP_CATCH
+}
+int pplp_relinearize(pplp_ctx *ctx, size_t level, const uint64_t *d_in, uint64_t *d_out, int layout, size_t nq, const uint64_t *d_rk,
+                     const uint64_t *d_rk_quot, void *stream) {
+    PPLP_TRY
+    Engine &E = dev_engine(ctx);
+    const size_t k = check_level(E, level), n = E.host.n, K = E.host.K();
+    if (level == 0 && E.host.levels.size() > 1) throw std::invalid_argument("encrypted is not valid for encryption parameters");
+    if (E.host.levels.size() < 2) throw std::logic_error("keyswitching is not supported by the context");
+    if (nq == 0) return PPLP_OK;
+    const int nqi = to_int(nq, "query count");
+    cudaStream_t st = S(stream);
+    const size_t nd = E.host.levels[1].q.size();
+    Scratch ws(relin_tmp_words(E, level, nqi) * 8, st), quot(d_rk_quot ? 8 : nd * 2 * K * n * 8, st);
+    if (!d_rk_quot) launch_shoup_quotients(E, d_rk, quot.as<u64>(), (int)(nd * 2 * K), st);
+    launch_relinearize(E, level, d_in, make_layout(layout, n, k, 3, nq), d_out, make_layout(layout, n, k, 2, nq), nqi, d_rk,
+                       d_rk_quot ? d_rk_quot : quot.as<u64>(), ws.as<u64>(), st);
     return PPLP_OK;
     PPLP_CATCH
 }
@@ -524,6 +614,55 @@ int pplp_ntt(pplp_ctx *ctx, size_t level, int base, uint64_t *d_data, int layout
     if (base != 0 && base != 1) throw std::invalid_argument("pplp: base must be 0 (q) or 1 (Bsk)");
     const RowMap map = base == 0 ? E.qmap(level) : E.bskmap(level);
     launch_ntt(E, d_data, make_layout(layout, E.host.n, (size_t)map.nlimbs, npoly, nq), to_int(nq, "query count"), (int)npoly, map, inverse != 0, S(stream));
+    return PPLP_OK;
+    PPLP_CATCH
+}
+
+int pplp_is_transparent(pplp_ctx *ctx, size_t level, const uint64_t *d_ct, size_t size, int *h_out) {
+    PPLP_TRY
+    Engine &E = dev_engine(ctx);
+    const size_t k = check_level(E, level), n = E.host.n;
+    if (size < 2) { *h_out = 1; return PPLP_OK; }
+    Scratch flag(sizeof(int), nullptr);
+    *h_out = launch_is_zero(E, d_ct + k * n, (size - 1) * k * n, flag.as<int>(), nullptr);
+    return PPLP_OK;
+    PPLP_CATCH
+}
+
+// ---- BatchEncoder ----
+int pplp_batch_encode(pplp_ctx *ctx, const uint64_t *d_values, size_t count, uint64_t *d_plain, size_t nq, void *stream) {
+    PPLP_TRY
+    Engine &E = dev_engine(ctx);
+    if (!E.host.batching) throw std::invalid_argument("encryption parameters are not valid for batching");
+    const size_t n = E.host.n;
+    if (count > n) throw std::invalid_argument("values_matrix size is too large");
+    if (nq == 0) return PPLP_OK;
+    cudaStream_t st = S(stream);
+    Scratch flag(sizeof(int), st);
+    PPLP_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), st));
+    if (count) check_below_kernel<<<64, 256, 0, st>>>(d_values, nq * count, E.host.t, flag.as<int>());
+    int bad = 0;
+    PPLP_CUDA(cudaMemcpyAsync(&bad, flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PPLP_CUDA(cudaStreamSynchronize(st));
+    if (bad) throw std::invalid_argument("input value is larger than plain_modulus");
+    batch_scatter_kernel<<<dim3((unsigned)((n + 255) / 256), (unsigned)nq), 256, 0, st>>>(d_values, count, E.d_slot_index, d_plain, (int)n);
+    RowMap m; m.nlimbs = 1; m.mod_id[0] = E.host.plain_table_id;
+    launch_ntt(E, d_plain, Layout{n, 0, 0}, to_int(nq, "plaintext count"), 1, m, true, st);
+    return PPLP_OK;
+    PPLP_CATCH
+}
+int pplp_batch_decode(pplp_ctx *ctx, const uint64_t *d_plain, uint64_t *d_values, size_t nq, void *stream) {
+    PPLP_TRY
+    Engine &E = dev_engine(ctx);
+    if (!E.host.batching) throw std::invalid_argument("encryption parameters are not valid for batching");
+    const size_t n = E.host.n;
+    if (nq == 0) return PPLP_OK;
+    cudaStream_t st = S(stream);
+    Scratch tmp(nq * n * 8, st);
+    PPLP_CUDA(cudaMemcpyAsync(tmp.p, d_plain, nq * n * 8, cudaMemcpyDeviceToDevice, st));
+    RowMap m; m.nlimbs = 1; m.mod_id[0] = E.host.plain_table_id;
+    launch_ntt(E, tmp.as<u64>(), Layout{n, 0, 0}, to_int(nq, "plaintext count"), 1, m, false, st);
+    batch_gather_kernel<<<dim3((unsigned)((n + 255) / 256), (unsigned)nq), 256, 0, st>>>(tmp.as<u64>(), E.d_slot_index, d_values, (int)n);
     return PPLP_OK;
     PPLP_CATCH
 }

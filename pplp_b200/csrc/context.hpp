@@ -74,7 +74,8 @@ struct HostContext {
     std::vector<u64> aux;                    // BEHZ primes: m_sk, gamma, B...
     std::vector<HostTable> tables;           // ids 0..K-1 = q primes; K = m_sk; K+1+i = B_i
     bool batching = false;                   // t prime and == 1 mod 2N
-    HostTable plain_table;                   // NTT mod t (BatchEncoder), host only
+    int plain_table_id = -1;                 // id in `tables` of the NTT mod t (BatchEncoder), when batching
+    std::vector<uint32_t> slot_index;        // BatchEncoder: slot i lives at coefficient slot_index[i] of the NTT-domain vector
 
     size_t K() const { return q.size(); }
     size_t first_level() const { return levels.size() > 1 ? 1 : 0; }
@@ -142,7 +143,21 @@ struct HostContext {
         build_table(tables[Kk], logn, aux[0]);
         for (size_t i = 0; i <= Kk; ++i) build_table(tables[Kk + 1 + i], logn, aux[2 + i]);
         batching = hm::prime64(t) && (t - 1) % (2 * n) == 0;
-        if (batching) build_table(plain_table, logn, t);
+        if (batching) {
+            plain_table_id = (int)tables.size();
+            tables.emplace_back();
+            build_table(tables.back(), logn, t);
+            // [SEAL] batchencoder.cpp populate_matrix_reps_index_map: rows are the orbits of 3 and -3 modulo 2N
+            slot_index.resize(n);
+            const size_t row = n >> 1, m = n << 1;
+            u64 pos = 1;
+            auto rev = [&](u64 x) { u64 r = 0; for (int b = 0; b < logn; ++b) r |= ((x >> b) & 1) << (logn - 1 - b); return (uint32_t)r; };
+            for (size_t i = 0; i < row; ++i) {
+                slot_index[i] = rev((pos - 1) >> 1);
+                slot_index[row | i] = rev((m - pos - 1) >> 1);
+                pos = (pos * 3) & (m - 1);
+            }
+        }
 
         size_t chain = Kk > 1 ? Kk : 1;
         for (size_t li = 0; li < chain; ++li) {

@@ -24,6 +24,7 @@ struct Engine {
     DevLevel *d_levels = nullptr;    // [levels.size()]
     std::vector<void *> owned;       // device allocations freed with the engine
     std::vector<DevMod> h_mods;
+    uint32_t *d_slot_index = nullptr;   // BatchEncoder permutation (when batching)
 
     void require_device() const { if (device < 0) throw std::logic_error("pplp: context was created without a CUDA device"); }
     template <class T> T *upload(const T *src, size_t count) {
@@ -79,6 +80,16 @@ size_t decrypt_tmp_words(const Engine &E, size_t level, int nq, int size);
 void launch_expand_small(const Engine &E, const signed char *d_small /* [n] */, u64 *out /* [K][n] */, cudaStream_t st);
 void launch_pk_combine(const Engine &E, const u64 *a, const u64 *s, const u64 *e_ntt, u64 *c0, int digit /* -1: none */, u64 factor, cudaStream_t st);
 void launch_prng_stream(const Engine &E, const u64 *d_seed, int nstreams, int nrefill, u64 *out, cudaStream_t st);
+
+// ---- behz.cu ----
+// out (3 polynomials) = a * b with BEHZ scale-and-round; a == b (same pointer) squares.  ws: multiply_tmp_words().
+void launch_multiply(const Engine &E, size_t level, const u64 *a, const u64 *b, Layout in_lay, u64 *out, Layout out_lay, int nq, u64 *ws, cudaStream_t st);
+size_t multiply_tmp_words(const Engine &E, size_t level, int nq, bool square);
+// size-3 -> size-2 with relinearisation keys rk [digit][2][K][n] and their Shoup quotients rkq (same shape).
+void launch_relinearize(const Engine &E, size_t level, const u64 *in, Layout in_lay, u64 *out, Layout out_lay, int nq, const u64 *rk, const u64 *rkq, u64 *ws,
+                        cudaStream_t st);
+size_t relin_tmp_words(const Engine &E, size_t level, int nq);
+void launch_shoup_quotients(const Engine &E, const u64 *w, u64 *quot, int nrows /* rows of n words, limb = row % K */, cudaStream_t st);
 
 // ---- bloom.cu ----
 size_t bloom_table_stride(u64 m_bits);   // bytes between consecutive filters' tables (m/8 rounded up to 16)

@@ -219,6 +219,27 @@ class Context:
                                          _ptr(xb), _ptr(yb), _ptr(r), _ptr(s), _ptr(flags), chunk))
         return out
 
+    def multiply(self, a, b, level=None, layout=LAYOUT_SEAL):
+        nq, _ = self._dims(a, layout)
+        out = self.empty(*self.ct_shape(nq, 3, level, layout))
+        check(self.L.pplp_multiply(self.h, self.first_level if level is None else level, _ptr(a), _ptr(b), _ptr(out), layout, nq, self._st()))
+        return out
+
+    def square(self, a, level=None, layout=LAYOUT_SEAL):
+        return self.multiply(a, a, level, layout)
+
+    def relin_prepare(self, rk):
+        quot = _torch().empty_like(rk)
+        check(self.L.pplp_relin_prepare(self.h, _ptr(rk), _ptr(quot), self._st()))
+        return quot
+
+    def relinearize(self, ct3, rk, rk_quot=None, level=None, layout=LAYOUT_SEAL):
+        nq, _ = self._dims(ct3, layout)
+        out = self.empty(*self.ct_shape(nq, 2, level, layout))
+        check(self.L.pplp_relinearize(self.h, self.first_level if level is None else level, _ptr(ct3), _ptr(out), layout, nq, _ptr(rk), _ptr(rk_quot),
+                                      self._st()))
+        return out
+
     def ntt_(self, data, level=None, base=0, inverse=False, layout=LAYOUT_SEAL):
         nq, npoly = self._dims(data, layout)
         check(self.L.pplp_ntt(self.h, self.first_level if level is None else level, base, _ptr(data), layout, nq, npoly, 1 if inverse else 0, self._st()))

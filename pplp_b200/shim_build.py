@@ -1,0 +1,60 @@
+"""Builds the host-side drop-in artefacts with g++ (no CUDA toolchain needed — they only link libpplp_b200.so):
+
+  build/shim/shim_parity      tests/shim/shim_parity.cc: the reference's call sequence through include/seal/seal.h
+  build/dropin/{pplp,client,server,test_client,test_server}
+                              the REFERENCE's own drivers, compiled UNMODIFIED from /root/reference/src against
+                              include/seal/seal.h (only where /root/reference exists, i.e. the build container; the
+                              binaries travel to the GPU box, the sources never enter this repository)
+"""
+import os
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+REF = "/root/reference"
+COMMON = ["-std=c++17", "-O2", "-I", os.path.join(ROOT, "include"), "-L", PKG, "-lpplp_b200", "-lz", "-Wl,-rpath," + PKG, "-Wl,-rpath,$ORIGIN/../../pplp_b200"]
+# -include cstdint: src/demo.cc includes bloomfilter.h (which uses uint8_t) before any header that declares it; GCC >= 13
+# no longer leaks <cstdint> through <sstream>, so the reference needs this one flag on a current toolchain.
+DROPIN = {"pplp": "src/demo.cc", "client": "src/client.cc", "server": "src/server.cc", "test_client": "src/test/test_client.cc",
+          "test_server": "src/test/test_server.cc"}
+
+
+def _newer(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+
+
+def _run(cmd):
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+        raise RuntimeError("shim build failed: " + cmd[-1])
+
+
+def build(force=False):
+    hdrs = [os.path.join(ROOT, "include", "seal", "seal.h"), os.path.join(ROOT, "include", "pplp_b200.h")]
+    out = os.path.join(ROOT, "build", "shim")
+    os.makedirs(out, exist_ok=True)
+    src = os.path.join(ROOT, "tests", "shim", "shim_parity.cc")
+    exe = os.path.join(out, "shim_parity")
+    if force or _newer(exe, [src] + hdrs):
+        _run(["g++", "-Wall", src] + COMMON + ["-o", exe])
+    built = [exe]
+    if os.path.isdir(os.path.join(REF, "src")):
+        d = os.path.join(ROOT, "build", "dropin")
+        os.makedirs(d, exist_ok=True)
+        for name, rel in DROPIN.items():
+            exe = os.path.join(d, name)
+            s = os.path.join(REF, rel)
+            if force or _newer(exe, [s] + hdrs):
+                _run(["g++", "-w", "-include", "cstdint", "-I", os.path.join(REF, "include"), s] + COMMON + ["-o", exe])
+            built.append(exe)
+    return built
+
+
+if __name__ == "__main__":
+    for b in build(force="--force" in sys.argv):
+        print(b)

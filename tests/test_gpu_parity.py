@@ -414,3 +414,83 @@ def test_proximity_batch_matches_oracle(eng, oracle, n):
     # host-buffer entry
     b2, v2, f2 = ctx.proximity_batch_host(ctx.dev(opk), ctx.dev(osk), xa, ya, xb, yb, seeds, bf, chunk=7)
     assert (b2 == ref_blind).all() and (v2 == ref_verdict).all() and not f2.any()
+
+
+# ---- north_star kernels without a reference call site (SEAL semantics restated by the oracle; "parity unpinned") ----------
+@pytest.mark.parametrize("n,t", [(4096, T56), (8192, T56), (8192, 0xfffffffffb4001), (16384, T56), (32768, T56)])
+def test_multiply_and_square_match_oracle(eng, oracle, n, t):
+    ctx, octx = contexts(eng, oracle, n, t=t)
+    osk, opk = octx.keygen()
+    rng = np.random.default_rng(n)
+    nq = 3 if n <= 8192 else 1
+    a = np.stack([octx.encrypt(opk, rng.integers(0, min(t, 1 << 20), 3, dtype=np.uint64), seed=seed8(300 + i)) for i in range(nq)])
+    b = np.stack([octx.encrypt(opk, rng.integers(0, min(t, 1 << 20), 2, dtype=np.uint64), seed=seed8(400 + i)) for i in range(nq)])
+    got = eng.to_np(ctx.multiply(ctx.dev(a), ctx.dev(b)))
+    for i in range(nq):
+        assert (got[i] == octx.multiply(a[i], b[i])).all()
+    got = eng.to_np(ctx.square(ctx.dev(a)))
+    for i in range(nq):
+        assert (got[i] == octx.square(a[i])).all()
+    # limb-major batch layout
+    lm = ctx.dev(np.ascontiguousarray(a.transpose(2, 1, 0, 3)))
+    got_lm = eng.to_np(ctx.square(lm, layout=eng.LAYOUT_LIMB_MAJOR)).transpose(2, 1, 0, 3)
+    assert (got_lm == got).all()
+    # uniformly random residues drive every branch of the base conversions (centred r, alpha sign)
+    q = octx.q[: ctx.k]
+    junk = np.stack([np.stack([rand_residues(rng, q, n) for _ in range(2)]) for _ in range(2)])
+    got = eng.to_np(ctx.multiply(ctx.dev(junk[:1]), ctx.dev(junk[1:])))
+    assert (got[0] == octx.multiply(junk[0], junk[1])).all()
+
+
+@pytest.mark.parametrize("n", [4096, 8192, 16384, 32768])
+def test_relin_keygen_and_relinearize_match_oracle(eng, oracle, n):
+    ctx, octx = contexts(eng, oracle, n)
+    osk, opk = octx.keygen()
+    ork = octx.relin_keygen(osk)
+    rk = ctx.relin_keygen(np.stack([seed8(7)] * ctx.k), ctx.dev(osk))   # fixed-seed factory: every digit restarts the same stream
+    assert (eng.to_np(rk) == ork).all()
+    rng = np.random.default_rng(n + 3)
+    q = octx.q[: ctx.k]
+    nq = 3 if n <= 8192 else 1
+    ct3 = np.stack([np.stack([rand_residues(rng, q, n) for _ in range(3)]) for _ in range(nq)])
+    quot = ctx.relin_prepare(rk)
+    got = eng.to_np(ctx.relinearize(ctx.dev(ct3), rk, quot))
+    for i in range(nq):
+        assert (got[i] == octx.relinearize(ct3[i], ork)).all()
+    got2 = eng.to_np(ctx.relinearize(ctx.dev(ct3), rk, None))   # quotients recomputed on the fly
+    assert (got2 == got).all()
+    lm = ctx.dev(np.ascontiguousarray(ct3.transpose(2, 1, 0, 3)))
+    got_lm = eng.to_np(ctx.relinearize(lm, rk, quot, layout=eng.LAYOUT_LIMB_MAJOR)).transpose(2, 1, 0, 3)
+    assert (got_lm == got).all()
+
+
+def test_circuit_b_direct_form_decrypts_to_squared_distance(eng, oracle):
+    """north_star's direct form: Enc(xa)-xb, Enc(ya)-yb -> square -> relinearize -> add -> (+r) * s, against the oracle and the algebra."""
+    n = 8192
+    t = 0xfffffffffb4001   # PlainModulus::Batching(8192, 56): prime, so BatchEncoder-compatible
+    ctx, octx = contexts(eng, oracle, n, t=t)
+    osk, opk = octx.keygen()
+    ork = octx.relin_keygen(osk)
+    rk = ctx.dev(ork)
+    quot = ctx.relin_prepare(rk)
+    xa, ya, xb, yb, r, s = 123456789, 132456888, 123456888, 132465777, 0x1234, 3
+    ex = octx.encrypt(opk, [xa], seed=seed8(1))
+    ey = octx.encrypt(opk, [ya], seed=seed8(2))
+    # oracle
+    ox = octx.eval_plain("sub_plain", ex, [xb]); oy = octx.eval_plain("sub_plain", ey, [yb])
+    ox2 = octx.relinearize(octx.square(ox), ork); oy2 = octx.relinearize(octx.square(oy), ork)
+    od = octx.eval_ct("add", ox2, oy2)
+    od = octx.eval_plain("add_plain", od, [r])
+    od = octx.eval_plain("multiply_plain", od, [s])
+    # device
+    dx = ctx.dev(np.stack([ex, ey]))
+    ctx.add_plain_(dx, ctx.dev(np.array([[xb], [yb]], dtype=np.uint64)), subtract=True)
+    sq = ctx.relinearize(ctx.square(dx), rk, quot)
+    d = sq[:1].clone()
+    ctx.add_(d, sq[1:])
+    ctx.add_plain_(d, ctx.dev(np.array([[r]], dtype=np.uint64)))
+    ctx.multiply_plain_mono_(d, ctx.dev(np.array([s], dtype=np.uint64)))
+    assert (eng.to_np(d)[0] == od).all()
+    dec = eng.to_np(ctx.decrypt(d, ctx.dev(osk), ncoeff=1))[0, 0]
+    d2 = (xa - xb) ** 2 + (ya - yb) ** 2
+    assert int(dec) == (s * (d2 + r)) % t

@@ -1,0 +1,102 @@
+"""Drop-in boundary on the GPU: the SEAL-subset C++ header (include/seal/seal.h) driven like the reference drives SEAL.
+
+shim_parity replays src/demo.cc's call sequence with a fixed-seed Blake2xbPRNGFactory; every serialized artefact must
+equal, byte for byte, what the oracle's restatement of SEAL 4.1 produces for the same keys, seeds and inputs.  The
+reference's own drivers (compiled unmodified against the header in the build container) are run when present."""
+import os
+import re
+import socket
+import subprocess
+import tempfile
+import time
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+T56 = 1 << 56
+
+
+def seed8(x):
+    return np.array([(x * 0x9E3779B97F4A7C15 + i * 0xD1B54A32D192ED03) & 0xFFFFFFFFFFFFFFFF for i in range(8)], dtype=np.uint64)
+
+
+@pytest.fixture(scope="module")
+def shim():
+    from pplp_b200 import build, shim_build
+    build.build()
+    shim_build.build()
+    exe = os.path.join(ROOT, "build", "shim", "shim_parity")
+    assert os.path.exists(exe)
+    return exe
+
+
+@pytest.mark.parametrize("logn", [12, 13])
+def test_shim_artifacts_equal_oracle_bytes(shim, oracle, logn):
+    n = 1 << logn
+    xa, ya, xb, yb, r, s = 123456789, 132456888, 123456888, 132465777, 0x12345678, 0x9ABCDEF1
+    with tempfile.TemporaryDirectory() as d:
+        p = subprocess.run([shim, d, str(logn), str(xa), str(ya), str(xb), str(yb), str(r), str(s)], capture_output=True, text=True, timeout=300)
+        assert p.returncode == 0, p.stdout + p.stderr
+        assert "validation: valid" in p.stdout and "errors_caught: 3" in p.stdout
+        art = {f: open(os.path.join(d, f), "rb").read() for f in os.listdir(d)}
+    octx = oracle.context(n, oracle.bfv_default(n), T56, seed=seed8(7))
+    osk, opk = octx.keygen()
+    assert art["parms.bin"] == octx.save_parms()
+    assert art["sk.bin"] == octx.save_sk(osk)
+    assert art["pk.bin"] == octx.save_pk(opk)
+    vals = [(xa * xa + ya * ya) % (1 << 64), xa << 1, ya << 1]
+    cts = [octx.encrypt(opk, [v]) for v in vals]   # fixed-seed factory: every encrypt restarts the same stream
+    for name, ct in zip(["c1.bin", "c2.bin", "c3.bin"], cts):
+        assert art[name] == octx.save_ct(ct), name
+    assert len(art["c1.bin"]) == 113 + 16 * octx.k * n   # 524 401 bytes at N=8192
+    # the zlib framing is read back by the oracle's loader to the same ciphertext
+    back, level = octx.load_ct(art["c1_zlib.bin"])
+    assert level == octx.first and (back == cts[0]).all()
+    res = octx.circuit_a(cts[0], cts[1], cts[2], xb, yb, r, s)
+    assert art["result.bin"] == octx.save_ct(res)
+    dec = octx.decrypt(osk, res)
+    assert int(art["blind.txt"].decode(), 16) == int(dec[0])
+    if logn >= 13:
+        d2 = (xa - xb) ** 2 + (ya - yb) ** 2
+        assert int(dec[0]) == (s * (d2 + r)) % T56
+
+
+def _dropin(name):
+    p = os.path.join(ROOT, "build", "dropin", name)
+    if not os.path.exists(p):
+        pytest.skip("reference drivers are only built where /root/reference exists (build container)")
+    return p
+
+
+@pytest.mark.parametrize("args,expect", [(["-x", "123456789", "-y", "132456888", "-u", "123456888", "-v", "132465777", "-r", "128"], "far"),
+                                         (["-x", "123456891", "-y", "132465781", "-u", "123456888", "-v", "132465777", "-r", "128"], "near"),
+                                         ([], "far")])
+def test_reference_demo_runs_unmodified_on_the_gpu(shim, args, expect):
+    """BASELINE.json configs[0]: ./demo, default coords, radius 128 — the reference's src/demo.cc itself, linked to this library."""
+    exe = _dropin("pplp")
+    p = subprocess.run([exe] + args, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "Parameter validation (success): valid" in p.stdout
+    lines = p.stdout.strip().splitlines()
+    assert lines[-2] == expect, p.stdout[-600:]
+    assert re.match(r"Time measured: [0-9.]+ seconds\.", lines[-1])
+
+
+def test_reference_client_server_over_loopback(shim):
+    """src/server.cc + src/client.cc, unmodified, talking over 127.0.0.1:51022 with this library under both."""
+    server, client = _dropin("server"), _dropin("client")
+    with socket.socket() as s:
+        if s.connect_ex(("127.0.0.1", 51022)) == 0:
+            pytest.skip("port 51022 busy")
+    sp = subprocess.Popen([server, "-r", "256"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    try:
+        time.sleep(1.0)
+        cp = subprocess.run([client, "-x", "123456890", "-y", "132465780", "-r", "256"], capture_output=True, text=True, timeout=300)
+        so, _ = sp.communicate(timeout=300)
+    finally:
+        if sp.poll() is None:
+            sp.kill()
+    assert cp.returncode == 0, cp.stdout + cp.stderr + so
+    assert "near" in cp.stdout.splitlines()[-1] or "near" in cp.stdout, cp.stdout[-500:]

@@ -1,0 +1,44 @@
+"""Multi-GPU plumbing: queries are independent, so a batch is sharded by contiguous slices, one process per GPU, with no
+collective inside the hot path.  The only exchanges are the timing reduction and an optional final gather
+of results (blinded distances / verdicts, or result ciphertexts), both through torch.distributed (NCCL on GPUs, gloo in
+the CPU tests)."""
+import torch
+import torch.distributed as dist
+
+
+def shard_range(nq, rank, world):
+    """Contiguous slice [lo, hi) of nq queries owned by `rank`; sizes differ by at most one, earlier ranks get the extras."""
+    base, extra = divmod(nq, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_sizes(nq, world):
+    return [shard_range(nq, r, world)[1] - shard_range(nq, r, world)[0] for r in range(world)]
+
+
+def max_over_ranks(value, device="cpu"):
+    """Max of a scalar over all ranks (how every multi-GPU time is reported)."""
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def gather_rows(local, nq, dst=0):
+    """Gathers per-query rows (blinded distances, verdicts or whole result ciphertexts, first dimension = local queries)
+    from every rank to `dst` in query order.  Returns the [nq, ...] tensor on dst, None elsewhere."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return local
+    world, rank = dist.get_world_size(), dist.get_rank()
+    sizes = shard_sizes(nq, world)
+    assert local.shape[0] == sizes[rank]
+    pad = max(sizes)
+    buf = torch.zeros((pad,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    buf[: local.shape[0]] = local
+    if rank == dst:
+        parts = [torch.empty_like(buf) for _ in range(world)]
+        dist.gather(buf, parts, dst=dst)
+        return torch.cat([p[:s] for p, s in zip(parts, sizes)], dim=0)
+    dist.gather(buf, None, dst=dst)
+    return None

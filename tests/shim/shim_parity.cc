@@ -85,11 +85,11 @@ int main(int argc, char **argv) {
         dump(dir, "result.bin", saved(c1));
         Plaintext out;
         decryptor.decrypt(c1, out);
-        uint64_t blind = 0;
-        const std::string str = out.to_string();
-        util::hex_string_to_uint(str.c_str(), (int)str.size(), 1, &blind);
+        // constant coefficient (at N = 4096 the 72-bit q leaves no noise budget and the plaintext is a full polynomial)
+        const std::string str = hex(out[0]);
         std::printf("blind_distance: %s\n", str.c_str());
         dump(dir, "blind.txt", str);
+        if (n >= 8192 && out.to_string() != str) return 7;   // src/demo.cc:166-168 parses to_string() as one hex number
         // error behaviour on the path
         int errors = 0;
         try { evaluator.multiply_plain_inplace(c2, Plaintext("0")); } catch (const std::logic_error &) { ++errors; }

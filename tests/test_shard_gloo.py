@@ -1,0 +1,50 @@
+"""world_size-2 (and 3) CPU tests of the multi-GPU host logic over gloo: contiguous query sharding, max-over-ranks timing,
+and the final in-order gather of per-query results."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from pplp_b200.shard import gather_rows, max_over_ranks, shard_range, shard_sizes
+
+
+def test_shard_ranges_partition_exactly():
+    for nq in (0, 1, 7, 8, 1000, 1 << 20):
+        for world in (1, 2, 3, 4, 8):
+            spans = [shard_range(nq, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == nq
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = shard_sizes(nq, world)
+            assert sum(sizes) == nq and max(sizes) - min(sizes) <= 1
+
+
+def _worker(rank, world, port, nq):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lo, hi = shard_range(nq, rank, world)
+        # each rank "computes" its slice: blinded distance = f(query index), result rows = 4 words per query
+        idx = torch.arange(lo, hi, dtype=torch.int64)
+        blind = idx * 7919 + 13
+        rows = torch.stack([idx, idx + 1, idx * 2, idx * idx], dim=1)
+        g1 = gather_rows(blind, nq)
+        g2 = gather_rows(rows, nq)
+        t = max_over_ranks(1.0 + rank)
+        assert t == float(world)
+        if rank == 0:
+            full = torch.arange(nq, dtype=torch.int64)
+            assert torch.equal(g1, full * 7919 + 13)
+            assert torch.equal(g2, torch.stack([full, full + 1, full * 2, full * full], dim=1))
+        else:
+            assert g1 is None and g2 is None
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,nq", [(2, 11), (2, 4096), (3, 10)])
+def test_gather_in_query_order_over_gloo(world, nq):
+    port = 29500 + (os.getpid() % 2000) + world
+    mp.spawn(_worker, args=(world, port, nq), nprocs=world, join=True)

@@ -70,7 +70,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -256,10 +256,8 @@ def run_b200(args):
     total_ms = ev[0].elapsed_time(ev[-1])
     kernel_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
     clocks = sampler.stop(t0, t1)
-    tmax = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    total_ms_max = float(tmax.item())
+    from pplp_b200.shard import gather_rows, max_over_ranks
+    total_ms_max = max_over_ranks(total_ms, dev)   # device time, max over ranks
     value = world * Q * args.steps / (total_ms_max * 1e-3)
 
     # ---- end to end: host ciphertexts (page-locked) through the C-ABI host entry ----
@@ -282,18 +280,37 @@ def run_b200(args):
         e2e_step()
     barrier()
     e2e_s = time.perf_counter() - te0
-    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * Qe * e2e_steps / float(te.item())
+    e2e_value = world * Qe * e2e_steps / max_over_ranks(e2e_s, dev)
     # the host entry returned what the resident kernel computes
     ref_slice = out[:, :, :Qe, :].permute(2, 1, 0, 3).cpu()
     if not torch.equal(ref_slice, hout):
         raise SystemExit("bench: host-buffer path and resident path disagree")
 
+    # ---- the one exchange of the design: final gather of result ciphertexts to rank 0 (outside the hot-path figure) ----
+    gather = None
+    if world > 1:
+        gq = 128
+        local_rows = out[:, :, :gq, :].permute(2, 1, 0, 3).contiguous()   # [gq][2][k][N] per rank
+        gather_rows(local_rows, gq * world)
+        barrier()
+        ga, gb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ga.record()
+        gathered = gather_rows(local_rows, gq * world)
+        gb.record()
+        barrier()
+        gms = max_over_ranks(ga.elapsed_time(gb), dev)
+        if rank == 0:
+            ingest = (world - 1) * gq * per_ct * 8
+            gather = {"result_ciphertexts_per_s": gq * world / (gms * 1e-3), "rank0_ingest_GBps": ingest / (gms * 1e-3) / 1e9,
+                      "nvlink_peak_GBps": 770.0, "frac": ingest / (gms * 1e-3) / 1e9 / 770.0, "ciphertexts": gq * world,
+                      "ok": bool(torch.equal(gathered[:gq], local_rows)),
+                      "note": "NCCL gather to rank 0, timed separately; compute figures leave outputs on the producing GPU"}
+
     extras = {}
     if not args.no_extras and rank == 0:
         extras = run_extras(engine, ctx, torch, osk, opk)
+    if gather:
+        extras["gather"] = gather
 
     if rank != 0:
         if world > 1:

@@ -191,7 +191,7 @@ struct RelinArgs {
     u64 half;                       // P >> 1
 };
 
-template <int LOGM>
+template <int LOGM, int L>
 __global__ void __launch_bounds__(NttShape<LOGM>::T) relin_limb_kernel(const RelinArgs a) {
     using S = NttShape<LOGM>;
     extern __shared__ __align__(16) u64 sm[];
@@ -200,6 +200,7 @@ __global__ void __launch_bounds__(NttShape<LOGM>::T) relin_limb_kernel(const Rel
     const int key_index = (I == a.k) ? a.K - 1 : I;
     const DevMod &md = a.mods[key_index];
     const Mod mod = md.m;
+    const NttConsts nc = ntt_consts(md);
     const u64 q = mod.q, two_q = q << 1;
     const u64 *c2 = a.c2 + qi * a.lay.sq + 2 * a.lay.sp;
 
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(NttShape<LOGM>::T) relin_limb_kernel(const Rel
         const u64 *row = c2 + J * a.lay.sl;
         if (J == key_index) CoarsePass<LOGM>::for_each(tid, [&](int r, int i) { x[r] = row[i]; });
         else CoarsePass<LOGM>::for_each(tid, [&](int r, int i) { x[r] = barrett64(row[i], mod); });
-        block_ntt_forward<LOGM>(x, sm, tid, md.fwd, 0, 0, q);
+        block_ntt_forward<LOGM, Lazy<L>::F>(x, sm, tid, md.fwd, 0, 0, nc);
         const size_t koff = (((size_t)J * 2 + 0) * a.K + key_index) * a.n + 16 * tid;
         const size_t koff1 = koff + (size_t)a.K * a.n;
 #pragma unroll
@@ -231,13 +232,13 @@ __global__ void __launch_bounds__(NttShape<LOGM>::T) relin_limb_kernel(const Rel
     u64 *o0 = a.tmp + (((size_t)qi * 2 + 0) * (a.k + 1) + I) * a.n;
     u64 *o1 = a.tmp + (((size_t)qi * 2 + 1) * (a.k + 1) + I) * a.n;
     const bool special = (I == a.k);
-    block_ntt_inverse<LOGM, true>(acc0, sm, tid, md.inv, 0, 0, q, md.n_inv, md.inv1_n_inv);
+    block_ntt_inverse<LOGM, true, Lazy<L>::I>(acc0, sm, tid, md.inv, 0, 0, nc);
     CoarsePass<LOGM>::for_each(tid, [&](int r, int i) {
         const u64 v = csub(acc0[r], q);
         o0[i] = special ? add_mod(v, a.half, q) : v;
     });
     __syncthreads();
-    block_ntt_inverse<LOGM, true>(acc1, sm, tid, md.inv, 0, 0, q, md.n_inv, md.inv1_n_inv);
+    block_ntt_inverse<LOGM, true, Lazy<L>::I>(acc1, sm, tid, md.inv, 0, 0, nc);
     CoarsePass<LOGM>::for_each(tid, [&](int r, int i) {
         const u64 v = csub(acc1[r], q);
         o1[i] = special ? add_mod(v, a.half, q) : v;
@@ -304,13 +305,15 @@ size_t relin_tmp_words(const Engine &E, size_t level, int nq) {
     return w;
 }
 
-template <int LOGM> static void run_relin_limb(const RelinArgs &a, int nq, cudaStream_t st) {
-    static bool done[64] = {false};
-    int dev = 0;
-    cudaGetDevice(&dev);
+template <int LOGM, int L> static void run_relin_limb_l(const RelinArgs &a, int nq, cudaStream_t st) {
     const int bytes = NttShape<LOGM>::SMEM_WORDS * 8;
-    if (!done[dev]) { PPLP_CUDA(cudaFuncSetAttribute(relin_limb_kernel<LOGM>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)); done[dev] = true; }
-    relin_limb_kernel<LOGM><<<nq * (a.k + 1), NttShape<LOGM>::T, bytes, st>>>(a);
+    PPLP_CUDA(cudaFuncSetAttribute(relin_limb_kernel<LOGM, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    relin_limb_kernel<LOGM, L><<<nq * (a.k + 1), NttShape<LOGM>::T, bytes, st>>>(a);
+}
+template <int LOGM> static void run_relin_limb(int lazy, const RelinArgs &a, int nq, cudaStream_t st) {
+    if (lazy == 2) run_relin_limb_l<LOGM, 2>(a, nq, st);
+    else if (lazy == 1) run_relin_limb_l<LOGM, 1>(a, nq, st);
+    else run_relin_limb_l<LOGM, 0>(a, nq, st);
 }
 
 // in: size-3 ciphertexts (layout in_lay), out: size-2 (layout out_lay; may alias in when the strides agree)
@@ -322,12 +325,13 @@ void launch_relinearize(const Engine &E, size_t level, const u64 *in, Layout in_
     const u64 P = E.host.q[K - 1];
     u64 *tmp = ws;
     RelinArgs a{in, in_lay, rk, rkq, tmp, k, K, n, E.d_mods, P >> 1};
+    const int lazy = ntt_lazy_level(E.max_bits(E.qmap(0)), E.host.logn);
     switch (E.host.logn) {
-    case 10: run_relin_limb<10>(a, nq, st); break;
-    case 11: run_relin_limb<11>(a, nq, st); break;
-    case 12: run_relin_limb<12>(a, nq, st); break;
-    case 13: run_relin_limb<13>(a, nq, st); break;
-    case 14: run_relin_limb<14>(a, nq, st); break;
+    case 10: run_relin_limb<10>(lazy, a, nq, st); break;
+    case 11: run_relin_limb<11>(lazy, a, nq, st); break;
+    case 12: run_relin_limb<12>(lazy, a, nq, st); break;
+    case 13: run_relin_limb<13>(lazy, a, nq, st); break;
+    case 14: run_relin_limb<14>(lazy, a, nq, st); break;
     case 15: {
         u64 *digits = tmp + (size_t)nq * 2 * (k + 1) * n;
         relin_reduce_kernel<<<dim3((n + 1023) / 1024, nq * (k + 1) * k), 256, 0, st>>>(E.d_mods, in, in_lay, digits, k, K, n);

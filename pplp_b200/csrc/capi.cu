@@ -222,6 +222,8 @@ void Engine::upload_tables(int dev) {
         m.inv = upload(T.inv.data(), T.inv.size());
         m.n_inv = T.n_inv;
         m.inv1_n_inv = T.inv1_n_inv;
+        m.one_q = hm::shoup_quotient(1, T.q);
+        m.bits = hm::bitlen(T.q);
     }
     d_mods = upload(h_mods.data(), h_mods.size());
     std::vector<DevLevel> lv(host.levels.size());

@@ -114,7 +114,7 @@ struct EncLimbArgs {
     const DevMod *mods;
 };
 
-template <int LOGM>
+template <int LOGM, int L>
 __global__ void __launch_bounds__(NttShape<LOGM>::T) encrypt_limb_kernel(const EncLimbArgs a) {
     using S = NttShape<LOGM>;
     extern __shared__ __align__(16) u64 sm[];
@@ -122,6 +122,7 @@ __global__ void __launch_bounds__(NttShape<LOGM>::T) encrypt_limb_kernel(const E
     const int ct = blockIdx.x / a.K, j = blockIdx.x % a.K;   // limbs of one ciphertext adjacent: noise stays in L2/L1
     const DevMod &md = a.mods[j];
     const Mod mod = md.m;
+    const NttConsts nc = ntt_consts(md);
     const u64 q = mod.q;
     const signed char *nz = a.noise + (size_t)ct * 3 * a.n;
 
@@ -130,9 +131,9 @@ __global__ void __launch_bounds__(NttShape<LOGM>::T) encrypt_limb_kernel(const E
         const int v = nz[i];
         x[r] = v < 0 ? q - 1 : (u64)v;
     });
-    block_ntt_forward<LOGM>(x, sm, tid, md.fwd, 0, 0, q);
+    block_ntt_forward<LOGM, Lazy<L>::F>(x, sm, tid, md.fwd, 0, 0, nc);
 #pragma unroll
-    for (int r = 0; r < 16; ++r) uu[r] = canon4(x[r], q);
+    for (int r = 0; r < 16; ++r) uu[r] = forward_canon<Lazy<L>::F>(x[r], nc);
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
         const u64 *pk = a.pk + ((size_t)p * a.K + j) * a.n + 16 * tid;
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(NttShape<LOGM>::T) encrypt_limb_kernel(const E
             x[2 * c + 1] = mul_mod(uu[2 * c + 1], bv.y, mod);
         }
         __syncthreads();
-        block_ntt_inverse<LOGM, true>(x, sm, tid, md.inv, 0, 0, q, md.n_inv, md.inv1_n_inv);
+        block_ntt_inverse<LOGM, true, Lazy<L>::I>(x, sm, tid, md.inv, 0, 0, nc);
         u64 *out = a.tmp + (((size_t)ct * 2 + p) * a.K + j) * a.n;
         const signed char *e = nz + (size_t)(1 + p) * a.n;
         CoarsePass<LOGM>::for_each(tid, [&](int r, int i) {
@@ -247,13 +248,15 @@ size_t encrypt_tmp_words(const Engine &E, int nct) {
     return stream + noise + tmp + extra + 8;
 }
 
-template <int LOGM> static void run_encrypt_limb(const EncLimbArgs &a, int nct, cudaStream_t st) {
-    static bool done[64] = {false};
-    int dev = 0;
-    cudaGetDevice(&dev);
+template <int LOGM, int L> static void run_encrypt_limb_l(const EncLimbArgs &a, int nct, cudaStream_t st) {
     const int bytes = NttShape<LOGM>::SMEM_WORDS * 8;
-    if (!done[dev]) { PPLP_CUDA(cudaFuncSetAttribute(encrypt_limb_kernel<LOGM>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)); done[dev] = true; }
-    encrypt_limb_kernel<LOGM><<<nct * a.K, NttShape<LOGM>::T, bytes, st>>>(a);
+    PPLP_CUDA(cudaFuncSetAttribute(encrypt_limb_kernel<LOGM, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    encrypt_limb_kernel<LOGM, L><<<nct * a.K, NttShape<LOGM>::T, bytes, st>>>(a);
+}
+template <int LOGM> static void run_encrypt_limb(int lazy, const EncLimbArgs &a, int nct, cudaStream_t st) {
+    if (lazy == 2) run_encrypt_limb_l<LOGM, 2>(a, nct, st);
+    else if (lazy == 1) run_encrypt_limb_l<LOGM, 1>(a, nct, st);
+    else run_encrypt_limb_l<LOGM, 0>(a, nct, st);
 }
 
 void launch_encrypt(const Engine &E, const u64 *pk, const u64 *seeds, const u64 *plain, size_t plain_count, size_t plain_stride, u64 *ws, u64 *out,
@@ -270,12 +273,13 @@ void launch_encrypt(const Engine &E, const u64 *pk, const u64 *seeds, const u64 
     prng_stream_kernel<<<gs, 256, 0, st>>>(seeds, nrefill, stream);
     sample_encrypt_kernel<<<nct, 1024, 0, st>>>(stream, nrefill, n, noise, errflag);
     EncLimbArgs a{noise, pk, tmp, K, n, E.d_mods};
+    const int lazy = ntt_lazy_level(E.max_bits(E.qmap(0)), E.host.logn);
     switch (E.host.logn) {
-    case 10: run_encrypt_limb<10>(a, nct, st); break;
-    case 11: run_encrypt_limb<11>(a, nct, st); break;
-    case 12: run_encrypt_limb<12>(a, nct, st); break;
-    case 13: run_encrypt_limb<13>(a, nct, st); break;
-    case 14: run_encrypt_limb<14>(a, nct, st); break;
+    case 10: run_encrypt_limb<10>(lazy, a, nct, st); break;
+    case 11: run_encrypt_limb<11>(lazy, a, nct, st); break;
+    case 12: run_encrypt_limb<12>(lazy, a, nct, st); break;
+    case 13: run_encrypt_limb<13>(lazy, a, nct, st); break;
+    case 14: run_encrypt_limb<14>(lazy, a, nct, st); break;
     case 15: {
         RowMap map = E.qmap(0);
         dim3 g((n + 1023) / 1024, K, nct);

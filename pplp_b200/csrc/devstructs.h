@@ -15,6 +15,8 @@ struct DevMod {
     const ShoupW *inv;
     ShoupW n_inv;         // N^-1
     ShoupW inv1_n_inv;    // inv[1] * N^-1  (last Gentleman–Sande stage with the scaling folded in)
+    u64 one_q;            // floor(2^64 / q): Shoup quotient of the constant 1 (lazy reduction of any 64-bit value)
+    int bits;             // bit length of q
 };
 
 // How a batch of polynomials lies in HBM.  Element (query qi, poly p, limb j, coeff n) is at

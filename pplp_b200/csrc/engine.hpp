@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -39,6 +40,8 @@ struct Engine {
 
     RowMap qmap(size_t level) const { RowMap m; m.nlimbs = (int)host.levels[level].q.size(); for (int j = 0; j < m.nlimbs; ++j) m.mod_id[j] = j; return m; }
     RowMap bskmap(size_t level) const { RowMap m; const DevLevel &D = host.levels[level].dev; m.nlimbs = D.nBsk; for (int j = 0; j < m.nlimbs; ++j) m.mod_id[j] = D.bsk_mod_id[j]; return m; }
+    // widest modulus among the rows of a map -> which lazy-reduction variant of the NTT kernels is safe (ntt.cuh)
+    int max_bits(const RowMap &m) const { int b = 0; for (int j = 0; j < m.nlimbs; ++j) b = std::max(b, hm::bitlen(host.tables[m.mod_id[j]].q)); return b; }
     Layout seal_layout(size_t level, size_t npoly) const { size_t k = host.levels[level].q.size(); return Layout{npoly * k * host.n, k * host.n, host.n}; }
 };
 

@@ -2,15 +2,15 @@
 //
 // Kernels (one CTA = one RNS-limb polynomial of one query; grid = rows of the batch, limb-major so that CTAs that
 // share a twiddle table are co-resident and the table stays in L2):
-//   ntt_forward_kernel<LOGM>   global -> regs (coalesced) -> radix-16 passes -> smem -> coalesced stores
-//   ntt_inverse_kernel<LOGM>   the mirror image, N^-1 folded into the last stage
-//   polymul_kernel<LOGM>       out = INTT(NTT(a) (.) b) [+ c]: the dyadic product happens in registers between the
-//                              two transforms (fine layout of the forward == fine layout of the inverse), so the
-//                              NTT-form intermediate never touches HBM  (decrypt: c1*s + c0; multiply_plain generic)
-//   stage0 kernels             N = 32768 does not fit one CTA (256 KiB > 227 KiB smem): the first (last) butterfly stage
-//                              runs as a streaming pass over HBM and the two 16384-point halves go through the CTA kernel.
-// Algorithmic HBM bytes: 16*N per limb transform (read + write); polymul: 8*N*(2 + has_c) + b (L2-resident when
-// broadcast).  Roofline note in DESIGN.md: ~6.5*N Shoup butterflies per transform make these kernels integer-pipe bound.
+//   ntt_forward_kernel<LOGM,L>   global -> regs (coalesced) -> radix-16 passes -> smem -> coalesced stores
+//   ntt_inverse_kernel<LOGM,L>   the mirror image, N^-1 folded into the last stage
+//   polymul_kernel<LOGM,L>       out = INTT(NTT(a) (.) b) [+ c]: the dyadic product happens in registers between the
+//                                two transforms (fine layout of the forward == fine layout of the inverse), so the
+//                                NTT-form intermediate never touches HBM  (decrypt: c1*s + c0; multiply_plain generic)
+//   stage0 kernels               N = 32768 does not fit one CTA (256 KiB > 227 KiB smem): the first (last) butterfly stage
+//                                runs as a streaming pass over HBM and the two 16384-point halves go through the CTA kernel.
+// L is the lazy-reduction level (ntt.cuh): chosen on the host from the widest modulus among the rows of the launch.
+// Algorithmic HBM bytes: 16*N per limb transform (read + write); polymul: 8*N*(2 + has_c) + b (L2-resident when broadcast).
 #include "engine.hpp"
 #include "ntt.cuh"
 
@@ -31,7 +31,7 @@ __device__ __forceinline__ void decode_row(int row, int nq, int npoly, int &qi, 
     j = row / npoly;
 }
 
-template <int LOGM>
+template <int LOGM, int L>
 __global__ void __launch_bounds__(NttShape<LOGM>::T) ntt_forward_kernel(const NttArgs a) {
     using S = NttShape<LOGM>;
     extern __shared__ __align__(16) u64 sm[];
@@ -41,25 +41,25 @@ __global__ void __launch_bounds__(NttShape<LOGM>::T) ntt_forward_kernel(const Nt
     int qi, p, j;
     decode_row(blockIdx.x / nblk, a.nq, a.npoly, qi, p, j);
     const DevMod &md = a.mods[a.map.mod_id[j]];
-    const u64 q = md.m.q;
+    const NttConsts c = ntt_consts(md);
     u64 *ptr = a.data + qi * a.lay.sq + p * a.lay.sp + j * a.lay.sl + (size_t)blk * S::M;
 
     u64 x[16];
     CoarsePass<LOGM>::for_each(tid, [&](int r, int i) { x[r] = ptr[i]; });
-    block_ntt_forward<LOGM>(x, sm, tid, md.fwd, a.stage_base, blk, q);
+    block_ntt_forward<LOGM, Lazy<L>::F>(x, sm, tid, md.fwd, a.stage_base, blk, c);
 #pragma unroll
-    for (int r = 0; r < 16; ++r) x[r] = canon4(x[r], q);
+    for (int r = 0; r < 16; ++r) x[r] = forward_canon<Lazy<L>::F>(x[r], c);
     __syncthreads();
     FinePass<LOGM>::store_smem(x, sm, tid);
     __syncthreads();
 #pragma unroll
-    for (int c = 0; c < 16; ++c) {
-        const int i = tid + c * S::T;
+    for (int k = 0; k < 16; ++k) {
+        const int i = tid + k * S::T;
         ptr[i] = sm[smem_slot(i)];
     }
 }
 
-template <int LOGM>
+template <int LOGM, int L>
 __global__ void __launch_bounds__(NttShape<LOGM>::T) ntt_inverse_kernel(const NttArgs a) {
     using S = NttShape<LOGM>;
     extern __shared__ __align__(16) u64 sm[];
@@ -69,12 +69,12 @@ __global__ void __launch_bounds__(NttShape<LOGM>::T) ntt_inverse_kernel(const Nt
     int qi, p, j;
     decode_row(blockIdx.x / nblk, a.nq, a.npoly, qi, p, j);
     const DevMod &md = a.mods[a.map.mod_id[j]];
-    const u64 q = md.m.q;
+    const NttConsts c = ntt_consts(md);
     u64 *ptr = a.data + qi * a.lay.sq + p * a.lay.sp + j * a.lay.sl + (size_t)blk * S::M;
 
 #pragma unroll
-    for (int c = 0; c < 16; ++c) {
-        const int i = tid + c * S::T;
+    for (int k = 0; k < 16; ++k) {
+        const int i = tid + k * S::T;
         sm[smem_slot(i)] = ptr[i];
     }
     __syncthreads();
@@ -82,10 +82,12 @@ __global__ void __launch_bounds__(NttShape<LOGM>::T) ntt_inverse_kernel(const Nt
     FinePass<LOGM>::load_smem(x, sm, tid);
     __syncthreads();
     if (a.stage_base == 0) {
-        block_ntt_inverse<LOGM, true>(x, sm, tid, md.inv, 0, 0, q, md.n_inv, md.inv1_n_inv);
-        CoarsePass<LOGM>::for_each(tid, [&](int r, int i) { ptr[i] = csub(x[r], q); });
+        block_ntt_inverse<LOGM, true, Lazy<L>::I>(x, sm, tid, md.inv, 0, 0, c);
+        CoarsePass<LOGM>::for_each(tid, [&](int r, int i) { ptr[i] = csub(x[r], c.q); });
     } else {
-        block_ntt_inverse<LOGM, false>(x, sm, tid, md.inv, a.stage_base, blk, q, md.n_inv, md.inv1_n_inv);
+        // half of a 2M-point transform: never "free" (the bound analysis of ntt.cuh assumes the block is the whole transform)
+        constexpr int IM = Lazy<L>::I == NTT_FREE ? NTT_PASS : Lazy<L>::I;
+        block_ntt_inverse<LOGM, false, IM>(x, sm, tid, md.inv, a.stage_base, blk, c);
         CoarsePass<LOGM>::for_each(tid, [&](int r, int i) { ptr[i] = x[r]; });  // lazily in [0,2q); stage-0 pass canonicalises
     }
 }
@@ -100,7 +102,7 @@ __global__ void ntt_stage0_forward_kernel(const NttArgs a, int half_n) {
     const ShoupW w = ld_twiddle(md.fwd + 1);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < half_n; i += gridDim.x * blockDim.x) {
         u64 x = ptr[i], y = ptr[i + half_n];
-        ct_butterfly(x, y, w, q, two_q);
+        ct_butterfly<NTT_CLASSIC>(x, y, w, q, two_q);
         ptr[i] = x; ptr[i + half_n] = y;
     }
 }
@@ -129,15 +131,15 @@ struct PolymulArgs {
     const DevMod *mods;
 };
 
-template <int LOGM>
+template <int LOGM, int L>
 __global__ void __launch_bounds__(NttShape<LOGM>::T) polymul_kernel(const PolymulArgs a) {
-    using S = NttShape<LOGM>;
     extern __shared__ __align__(16) u64 sm[];
     const int tid = threadIdx.x;
     int qi, p, j;
     decode_row(blockIdx.x, a.nq, a.npoly, qi, p, j);
     const DevMod &md = a.mods[a.map.mod_id[j]];
     const Mod mod = md.m;
+    const NttConsts c = ntt_consts(md);
     const u64 q = mod.q;
     const u64 *pa = a.a + qi * a.a_lay.sq + p * a.a_lay.sp + j * a.a_lay.sl;
     const u64 *pb = a.b + qi * a.b_lay.sq + p * a.b_lay.sp + j * a.b_lay.sl;
@@ -145,16 +147,16 @@ __global__ void __launch_bounds__(NttShape<LOGM>::T) polymul_kernel(const Polymu
 
     u64 x[16];
     CoarsePass<LOGM>::for_each(tid, [&](int r, int i) { x[r] = pa[i]; });
-    block_ntt_forward<LOGM>(x, sm, tid, md.fwd, 0, 0, q);
+    block_ntt_forward<LOGM, Lazy<L>::F>(x, sm, tid, md.fwd, 0, 0, c);
     // dyadic product in the fine layout: thread owns coefficients 16*tid .. 16*tid+15 of the NTT-form operand
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        const ulonglong2 bv = __ldg(reinterpret_cast<const ulonglong2 *>(pb + 16 * tid + 2 * c));
-        x[2 * c] = mul_mod(canon4(x[2 * c], q), bv.x, mod);
-        x[2 * c + 1] = mul_mod(canon4(x[2 * c + 1], q), bv.y, mod);
+    for (int k = 0; k < 8; ++k) {
+        const ulonglong2 bv = __ldg(reinterpret_cast<const ulonglong2 *>(pb + 16 * tid + 2 * k));
+        x[2 * k] = mul_mod(forward_canon<Lazy<L>::F>(x[2 * k], c), bv.x, mod);
+        x[2 * k + 1] = mul_mod(forward_canon<Lazy<L>::F>(x[2 * k + 1], c), bv.y, mod);
     }
     __syncthreads();   // all threads are past their last smem read of the forward transform
-    block_ntt_inverse<LOGM, true>(x, sm, tid, md.inv, 0, 0, q, md.n_inv, md.inv1_n_inv);
+    block_ntt_inverse<LOGM, true, Lazy<L>::I>(x, sm, tid, md.inv, 0, 0, c);
     if (a.c) {
         const u64 *pc = a.c + qi * a.c_lay.sq + p * a.c_lay.sp + j * a.c_lay.sl;
         CoarsePass<LOGM>::for_each(tid, [&](int r, int i) { po[i] = add_mod(csub(x[r], q), pc[i], q); });
@@ -164,24 +166,33 @@ __global__ void __launch_bounds__(NttShape<LOGM>::T) polymul_kernel(const Polymu
 }
 
 // ---- launchers -----------------------------------------------------------------------------------------------------
-template <int LOGM> static void set_smem_attr_once() {
-    static bool done[64] = {false};
+template <class K> static void allow_smem(K kernel, int bytes) {
+    // set once per (kernel, device); the attribute is sticky
+    static thread_local const void *last = nullptr;
+    static thread_local int last_dev = -1;
     int dev = 0;
     cudaGetDevice(&dev);
-    if (done[dev]) return;
-    const int bytes = NttShape<LOGM>::SMEM_WORDS * 8;
-    PPLP_CUDA(cudaFuncSetAttribute(ntt_forward_kernel<LOGM>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    PPLP_CUDA(cudaFuncSetAttribute(ntt_inverse_kernel<LOGM>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    PPLP_CUDA(cudaFuncSetAttribute(polymul_kernel<LOGM>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    done[dev] = true;
+    if (last == (const void *)kernel && last_dev == dev) return;
+    PPLP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    last = (const void *)kernel;
+    last_dev = dev;
 }
 
-template <int LOGM> static void run_block_ntt(const NttArgs &a, int rows, bool inverse, cudaStream_t st) {
-    set_smem_attr_once<LOGM>();
+template <int LOGM, int L> static void run_block_ntt(const NttArgs &a, int rows, bool inverse, cudaStream_t st) {
     const int bytes = NttShape<LOGM>::SMEM_WORDS * 8;
     const int grid = rows << a.stage_base;
-    if (inverse) ntt_inverse_kernel<LOGM><<<grid, NttShape<LOGM>::T, bytes, st>>>(a);
-    else ntt_forward_kernel<LOGM><<<grid, NttShape<LOGM>::T, bytes, st>>>(a);
+    if (inverse) {
+        allow_smem(ntt_inverse_kernel<LOGM, L>, bytes);
+        ntt_inverse_kernel<LOGM, L><<<grid, NttShape<LOGM>::T, bytes, st>>>(a);
+    } else {
+        allow_smem(ntt_forward_kernel<LOGM, L>, bytes);
+        ntt_forward_kernel<LOGM, L><<<grid, NttShape<LOGM>::T, bytes, st>>>(a);
+    }
+}
+template <int LOGM> static void run_block_ntt_l(int level, const NttArgs &a, int rows, bool inverse, cudaStream_t st) {
+    if (level == 2) run_block_ntt<LOGM, 2>(a, rows, inverse, st);
+    else if (level == 1) run_block_ntt<LOGM, 1>(a, rows, inverse, st);
+    else run_block_ntt<LOGM, 0>(a, rows, inverse, st);
 }
 
 void launch_ntt(const Engine &E, u64 *data, Layout lay, int nq, int npoly, const RowMap &map, bool inverse, cudaStream_t st) {
@@ -190,21 +201,23 @@ void launch_ntt(const Engine &E, u64 *data, Layout lay, int nq, int npoly, const
     if (rows == 0) return;
     NttArgs a{data, lay, nq, npoly, 0, map, E.d_mods};
     const int logn = E.host.logn;
+    const int lazy = ntt_lazy_level(E.max_bits(map), logn);
     switch (logn) {
-    case 10: run_block_ntt<10>(a, rows, inverse, st); break;
-    case 11: run_block_ntt<11>(a, rows, inverse, st); break;
-    case 12: run_block_ntt<12>(a, rows, inverse, st); break;
-    case 13: run_block_ntt<13>(a, rows, inverse, st); break;
-    case 14: run_block_ntt<14>(a, rows, inverse, st); break;
+    case 10: run_block_ntt_l<10>(lazy, a, rows, inverse, st); break;
+    case 11: run_block_ntt_l<11>(lazy, a, rows, inverse, st); break;
+    case 12: run_block_ntt_l<12>(lazy, a, rows, inverse, st); break;
+    case 13: run_block_ntt_l<13>(lazy, a, rows, inverse, st); break;
+    case 14: run_block_ntt_l<14>(lazy, a, rows, inverse, st); break;
     case 15: {
+        // 15 stages: stage 0 streams (classic, values < 4q), then 14-stage blocks whose forward inputs are < 4q as required
         const int half_n = 1 << 14;
         dim3 g0(32, rows);
         a.stage_base = 1;
         if (!inverse) {
             ntt_stage0_forward_kernel<<<g0, 512, 0, st>>>(a, half_n);
-            run_block_ntt<14>(a, rows, false, st);
+            run_block_ntt_l<14>(lazy, a, rows, false, st);
         } else {
-            run_block_ntt<14>(a, rows, true, st);
+            run_block_ntt_l<14>(lazy, a, rows, true, st);
             ntt_stage0_inverse_kernel<<<g0, 512, 0, st>>>(a, half_n);
         }
         break;
@@ -214,9 +227,15 @@ void launch_ntt(const Engine &E, u64 *data, Layout lay, int nq, int npoly, const
     PPLP_CUDA(cudaGetLastError());
 }
 
-template <int LOGM> static void run_polymul(const PolymulArgs &a, int rows, cudaStream_t st) {
-    set_smem_attr_once<LOGM>();
-    polymul_kernel<LOGM><<<rows, NttShape<LOGM>::T, NttShape<LOGM>::SMEM_WORDS * 8, st>>>(a);
+template <int LOGM, int L> static void run_polymul(const PolymulArgs &a, int rows, cudaStream_t st) {
+    const int bytes = NttShape<LOGM>::SMEM_WORDS * 8;
+    allow_smem(polymul_kernel<LOGM, L>, bytes);
+    polymul_kernel<LOGM, L><<<rows, NttShape<LOGM>::T, bytes, st>>>(a);
+}
+template <int LOGM> static void run_polymul_l(int level, const PolymulArgs &a, int rows, cudaStream_t st) {
+    if (level == 2) run_polymul<LOGM, 2>(a, rows, st);
+    else if (level == 1) run_polymul<LOGM, 1>(a, rows, st);
+    else run_polymul<LOGM, 0>(a, rows, st);
 }
 
 void launch_polymul(const Engine &E, const u64 *a, Layout a_lay, const u64 *b_ntt, Layout b_lay, const u64 *c, Layout c_lay, u64 *out, Layout out_lay,
@@ -225,12 +244,13 @@ void launch_polymul(const Engine &E, const u64 *a, Layout a_lay, const u64 *b_nt
     const int rows = nq * npoly * map.nlimbs;
     if (rows == 0) return;
     PolymulArgs pa{a, a_lay, b_ntt, b_lay, c, c_lay, out, out_lay, nq, npoly, map, E.d_mods};
+    const int lazy = ntt_lazy_level(E.max_bits(map), E.host.logn);
     switch (E.host.logn) {
-    case 10: run_polymul<10>(pa, rows, st); break;
-    case 11: run_polymul<11>(pa, rows, st); break;
-    case 12: run_polymul<12>(pa, rows, st); break;
-    case 13: run_polymul<13>(pa, rows, st); break;
-    case 14: run_polymul<14>(pa, rows, st); break;
+    case 10: run_polymul_l<10>(lazy, pa, rows, st); break;
+    case 11: run_polymul_l<11>(lazy, pa, rows, st); break;
+    case 12: run_polymul_l<12>(lazy, pa, rows, st); break;
+    case 13: run_polymul_l<13>(lazy, pa, rows, st); break;
+    case 14: run_polymul_l<14>(lazy, pa, rows, st); break;
     default: throw std::invalid_argument("pplp: fused polymul supports poly_modulus_degree 1024..16384");
     }
     PPLP_CUDA(cudaGetLastError());

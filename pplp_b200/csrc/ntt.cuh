@@ -8,14 +8,36 @@
 //
 // How (B200).  One CTA owns one polynomial of M = 2^LOGM coefficients.  Each thread keeps 16 coefficients in
 // registers and runs radix-16 passes (4 butterfly stages each, 32 independent Shoup butterflies per thread per
-// pass) — the kernel is bound by the integer (IMAD) pipe, not HBM, so the design minimises instructions per
-// butterfly and keeps 16-way ILP per thread.  Between passes the CTA transposes through shared memory (padded by
-// one word per 16 so the stride-G accesses of every pass are bank-conflict-free).  A pass is in place: a thread writes the slots it read, so one __syncthreads per pass.
-// Twiddles (w, w' = floor(w 2^64/q)) are fetched as one 128-bit read-only load from the L2-resident table.
+// pass).  The kernels are bound by the integer pipes, not HBM (a 64-bit Shoup product is ten 32-bit multiplies), so
+// the design minimises instructions per butterfly:
+//   * twiddles are (w, w' = floor(w 2^64/q)) pairs fetched with one 128-bit read-only load from the L2-resident table;
+//   * Shoup's product accepts ANY 64-bit input and returns a value in [0,2q), so when the modulus leaves head-room in
+//     the 64-bit word the butterflies run WITHOUT per-stage conditional subtractions ("free" mode): forward values
+//     grow by at most 2q per stage, inverse sums at most double per stage, and a single multiply-by-one reduction
+//     canonicalises at the end.  Moduli too wide for that fall back to one reduction per radix-16 pass ("pass" mode,
+//     inverse only) or to Harvey's classic per-butterfly correction ("classic" mode: 60/61-bit primes).
+// Between passes the CTA transposes through shared memory (padded by one word per 16 so the stride-G accesses of every
+// pass are bank-conflict-free).  A pass is in place: a thread writes the slots it read, so one __syncthreads per pass.
 #pragma once
 #include "devstructs.h"
 
 namespace pplp {
+
+enum : int { NTT_CLASSIC = 0, NTT_PASS = 1, NTT_FREE = 2 };
+
+// Which lazy-reduction mode a transform of 2^logn points may use for a modulus of `bits` bits (host and device agree).
+// forward free:  inputs < 4q, growth 2q per stage: (4 + 2 logn) q < 2^64  <=  q < 2^58 for logn <= 15
+// inverse free:  inputs < 2q, doubling per stage:  2q 2^logn < 2^64
+// inverse pass:  one reduction per radix-16 pass:  2q 2^4 2 < 2^64      <=  q < 2^58
+// The kernels are instantiated for three combinations ("lazy level" L):
+//   L = 0: classic forward, classic inverse    (any modulus below 2^62)
+//   L = 1: free forward, per-pass inverse      (modulus of at most 58 bits)
+//   L = 2: free forward, free inverse          (bits + 1 + log2 N <= 63)
+inline int ntt_lazy_level(int bits, int logn) { return bits > 58 ? 0 : (bits + 1 + logn <= 63 ? 2 : 1); }
+template <int L> struct Lazy {
+    static constexpr int F = L == 0 ? NTT_CLASSIC : NTT_FREE;
+    static constexpr int I = L == 0 ? NTT_CLASSIC : (L == 1 ? NTT_PASS : NTT_FREE);
+};
 
 template <int LOGM> struct NttShape {
     static constexpr int M = 1 << LOGM;
@@ -30,17 +52,26 @@ template <int LOGM> struct NttShape {
 // lanes (LG = 4 passes) and 16-consecutive-per-thread (fine layout) — hits each bank at most twice per warp, the minimum.
 __device__ __forceinline__ int smem_slot(int i) { return i + (i >> 4); }
 
-// Harvey lazy butterflies.  Forward keeps values in [0,4q); inverse in [0,2q).
-__device__ __forceinline__ void ct_butterfly(u64 &x, u64 &y, const ShoupW w, const u64 q, const u64 two_q) {
-    u64 u = x >= two_q ? x - two_q : x;
-    u64 v = mul_shoup_lazy(y, w.w, w.wq, q);
-    x = u + v;
-    y = u - v + two_q;
+// a mod q into [0,2q) for any 64-bit a: Shoup's product with the constant 1 (quotient floor(2^64/q)).
+__device__ __forceinline__ u64 reduce_lazy(u64 a, u64 one_q, u64 q) { return a - __umul64hi(a, one_q) * q; }
+
+template <int MODE> __device__ __forceinline__ void ct_butterfly(u64 &x, u64 &y, const ShoupW w, const u64 q, const u64 two_q) {
+    const u64 v = mul_shoup_lazy(y, w.w, w.wq, q);
+    if constexpr (MODE == NTT_CLASSIC) {   // Harvey: values stay in [0,4q)
+        const u64 u = x >= two_q ? x - two_q : x;
+        x = u + v;
+        y = u - v + two_q;
+    } else {                               // free: bound grows by 2q per stage
+        y = x - v + two_q;
+        x = x + v;
+    }
 }
-__device__ __forceinline__ void gs_butterfly(u64 &x, u64 &y, const ShoupW w, const u64 q, const u64 two_q) {
-    u64 s = x + y;
-    u64 d = x - y + two_q;
-    x = s >= two_q ? s - two_q : s;
+// `big` is a multiple of q not smaller than any value y can hold at this stage (2q in classic mode).
+template <int MODE> __device__ __forceinline__ void gs_butterfly(u64 &x, u64 &y, const ShoupW w, const u64 q, const u64 two_q, const u64 big) {
+    const u64 s = x + y;
+    const u64 d = x - y + big;
+    if constexpr (MODE == NTT_CLASSIC) x = s >= two_q ? s - two_q : s;
+    else x = s;
     y = mul_shoup_lazy(d, w.w, w.wq, q);
 }
 
@@ -49,6 +80,16 @@ __device__ __forceinline__ ShoupW ld_twiddle(const ShoupW *p) {
     const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(p));
     r.w = v.x; r.wq = v.y;
     return r;
+}
+
+struct NttConsts {          // per-modulus scalars a transform needs besides the twiddle table
+    u64 q, two_q, one_q;    // one_q = floor(2^64 / q)
+    ShoupW n_inv, inv1_n_inv;
+};
+__device__ __forceinline__ NttConsts ntt_consts(const DevMod &md) {
+    NttConsts c;
+    c.q = md.m.q; c.two_q = md.m.q << 1; c.one_q = md.one_q; c.n_inv = md.n_inv; c.inv1_n_inv = md.inv1_n_inv;
+    return c;
 }
 
 // Geometry of pass (S0,R) of a 2^LOGM block: thread `tid` owns NU = 16>>R radix-2^R butterflies; butterfly u covers
@@ -80,18 +121,20 @@ template <int LOGM, int S0, int R> struct Pass {
     }
 
     // One butterfly stage V (local) of radix-2^R butterfly u.  Everything but tid-derived values is a compile-time constant.
-    template <int V, bool INVERSE, bool FOLD_SCALE>
-    __device__ static __forceinline__ void stage(u64 (&x)[16], int u, int h, const ShoupW *__restrict__ tw, int stage_base, int blk, u64 q, u64 two_q,
-                                                 ShoupW n_inv, ShoupW inv1_n_inv) {
+    template <int V, bool INVERSE, bool FOLD_SCALE, int MODE>
+    __device__ static __forceinline__ void stage(u64 (&x)[16], int u, int h, const ShoupW *__restrict__ tw, int stage_base, int blk, const NttConsts &c) {
         constexpr int HALF = 1 << (R - 1 - V);
         const int tbase = (1 << (stage_base + S0 + V)) + (blk << (S0 + V)) + (h << V);
+        // bound of the values entering this inverse stage, as a multiple of 2q (see gs_butterfly)
+        constexpr int GROW = MODE == NTT_FREE ? (LOGM - 1 - (S0 + V)) : (MODE == NTT_PASS ? (R - 1 - V) : 0);
+        const u64 big = c.two_q << GROW;
         if constexpr (INVERSE && FOLD_SCALE && V == 0) {
 #pragma unroll
             for (int i = 0; i < HALF; ++i) {
                 u64 &a = x[u * RR + i], &b = x[u * RR + i + HALF];
-                const u64 s = a + b, d = a - b + two_q;
-                a = mul_shoup_lazy(s, n_inv.w, n_inv.wq, q);          // Shoup accepts any 64-bit input
-                b = mul_shoup_lazy(d, inv1_n_inv.w, inv1_n_inv.wq, q);
+                const u64 s = a + b, d = a - b + big;
+                a = mul_shoup_lazy(s, c.n_inv.w, c.n_inv.wq, c.q);          // Shoup accepts any 64-bit input
+                b = mul_shoup_lazy(d, c.inv1_n_inv.w, c.inv1_n_inv.wq, c.q);
             }
         } else {
 #pragma unroll
@@ -99,8 +142,8 @@ template <int LOGM, int S0, int R> struct Pass {
                 const ShoupW w = ld_twiddle(tw + tbase + g);
 #pragma unroll
                 for (int i = 0; i < HALF; ++i) {
-                    if constexpr (INVERSE) gs_butterfly(x[u * RR + g * 2 * HALF + i], x[u * RR + g * 2 * HALF + i + HALF], w, q, two_q);
-                    else ct_butterfly(x[u * RR + g * 2 * HALF + i], x[u * RR + g * 2 * HALF + i + HALF], w, q, two_q);
+                    if constexpr (INVERSE) gs_butterfly<MODE>(x[u * RR + g * 2 * HALF + i], x[u * RR + g * 2 * HALF + i + HALF], w, c.q, c.two_q, big);
+                    else ct_butterfly<MODE>(x[u * RR + g * 2 * HALF + i], x[u * RR + g * 2 * HALF + i + HALF], w, c.q, c.two_q);
                 }
             }
         }
@@ -108,29 +151,32 @@ template <int LOGM, int S0, int R> struct Pass {
 
     // Forward stages S0 .. S0+R-1 (global stage = stage_base + local stage; blk = index of this block among the
     // 2^stage_base sub-transforms when M < N).
-    __device__ static __forceinline__ void forward(u64 (&x)[16], int tid, const ShoupW *__restrict__ tw, int stage_base, int blk, u64 q, u64 two_q) {
-        const ShoupW z{0, 0};
+    template <int MODE>
+    __device__ static __forceinline__ void forward(u64 (&x)[16], int tid, const ShoupW *__restrict__ tw, int stage_base, int blk, const NttConsts &c) {
 #pragma unroll
         for (int u = 0; u < NU; ++u) {
             const int h = hi(tid, u);
-            stage<0, false, false>(x, u, h, tw, stage_base, blk, q, two_q, z, z);
-            if constexpr (R >= 2) stage<(R >= 2 ? 1 : 0), false, false>(x, u, h, tw, stage_base, blk, q, two_q, z, z);
-            if constexpr (R >= 3) stage<(R >= 3 ? 2 : 0), false, false>(x, u, h, tw, stage_base, blk, q, two_q, z, z);
-            if constexpr (R >= 4) stage<(R >= 4 ? 3 : 0), false, false>(x, u, h, tw, stage_base, blk, q, two_q, z, z);
+            stage<0, false, false, MODE>(x, u, h, tw, stage_base, blk, c);
+            if constexpr (R >= 2) stage<(R >= 2 ? 1 : 0), false, false, MODE>(x, u, h, tw, stage_base, blk, c);
+            if constexpr (R >= 3) stage<(R >= 3 ? 2 : 0), false, false, MODE>(x, u, h, tw, stage_base, blk, c);
+            if constexpr (R >= 4) stage<(R >= 4 ? 3 : 0), false, false, MODE>(x, u, h, tw, stage_base, blk, c);
         }
     }
     // Inverse stages S0+R-1 .. S0.  When FOLD_SCALE (only legal for S0 == 0 and stage_base == 0) the last stage
     // multiplies by N^-1:  x = (u+v) N^-1,  y = (u-v) (inv[1] N^-1).
-    template <bool FOLD_SCALE>
-    __device__ static __forceinline__ void inverse(u64 (&x)[16], int tid, const ShoupW *__restrict__ tw, int stage_base, int blk, u64 q, u64 two_q,
-                                                   ShoupW n_inv, ShoupW inv1_n_inv) {
+    template <bool FOLD_SCALE, int MODE, bool REDUCE_FIRST = true>
+    __device__ static __forceinline__ void inverse(u64 (&x)[16], int tid, const ShoupW *__restrict__ tw, int stage_base, int blk, const NttConsts &c) {
+        if constexpr (MODE == NTT_PASS && REDUCE_FIRST) {   // back to [0,2q) before this pass doubles the bound R times
+#pragma unroll
+            for (int r = 0; r < 16; ++r) x[r] = reduce_lazy(x[r], c.one_q, c.q);
+        }
 #pragma unroll
         for (int u = 0; u < NU; ++u) {
             const int h = hi(tid, u);
-            if constexpr (R >= 4) stage<(R >= 4 ? 3 : 0), true, FOLD_SCALE>(x, u, h, tw, stage_base, blk, q, two_q, n_inv, inv1_n_inv);
-            if constexpr (R >= 3) stage<(R >= 3 ? 2 : 0), true, FOLD_SCALE>(x, u, h, tw, stage_base, blk, q, two_q, n_inv, inv1_n_inv);
-            if constexpr (R >= 2) stage<(R >= 2 ? 1 : 0), true, FOLD_SCALE>(x, u, h, tw, stage_base, blk, q, two_q, n_inv, inv1_n_inv);
-            stage<0, true, FOLD_SCALE>(x, u, h, tw, stage_base, blk, q, two_q, n_inv, inv1_n_inv);
+            if constexpr (R >= 4) stage<(R >= 4 ? 3 : 0), true, FOLD_SCALE, MODE>(x, u, h, tw, stage_base, blk, c);
+            if constexpr (R >= 3) stage<(R >= 3 ? 2 : 0), true, FOLD_SCALE, MODE>(x, u, h, tw, stage_base, blk, c);
+            if constexpr (R >= 2) stage<(R >= 2 ? 1 : 0), true, FOLD_SCALE, MODE>(x, u, h, tw, stage_base, blk, c);
+            stage<0, true, FOLD_SCALE, MODE>(x, u, h, tw, stage_base, blk, c);
         }
     }
 };
@@ -146,63 +192,73 @@ template <int LOGM, int P> struct FullPassAt {  // P-th radix-16 pass after the 
     using type = Pass<LOGM, NttShape<LOGM>::R0 + 4 * P, 4>;
 };
 
-// Forward: x holds the block in coarse layout, values < 4q (any value < 2^62 that is congruent is fine for x-side,
-// y-side inputs may be any 64-bit).  On return x holds the transform in fine layout, lazily in [0,4q).
-template <int LOGM>
-__device__ __forceinline__ void block_ntt_forward(u64 (&x)[16], u64 *sm, int tid, const ShoupW *__restrict__ tw, int stage_base, int blk, u64 q) {
+// Forward: x holds the block in coarse layout, values < 4q.  On return x holds the transform in fine layout, lazily
+// bounded by 4q (classic) or (4 + 2 log2 N) q (free); forward_canon() brings a value to [0,q).
+template <int LOGM, int MODE>
+__device__ __forceinline__ void block_ntt_forward(u64 (&x)[16], u64 *sm, int tid, const ShoupW *__restrict__ tw, int stage_base, int blk, const NttConsts &c) {
     using S = NttShape<LOGM>;
-    const u64 two_q = q << 1;
-    CoarsePass<LOGM>::forward(x, tid, tw, stage_base, blk, q, two_q);
+    CoarsePass<LOGM>::template forward<MODE>(x, tid, tw, stage_base, blk, c);
     CoarsePass<LOGM>::store_smem(x, sm, tid);
     __syncthreads();
     if constexpr (S::NFULL >= 1) {
         using P0 = typename FullPassAt<LOGM, 0>::type;
         P0::load_smem(x, sm, tid);
-        P0::forward(x, tid, tw, stage_base, blk, q, two_q);
+        P0::template forward<MODE>(x, tid, tw, stage_base, blk, c);
         if constexpr (S::NFULL > 1) { P0::store_smem(x, sm, tid); __syncthreads(); }
     }
     if constexpr (S::NFULL >= 2) {
         using P1 = typename FullPassAt<LOGM, 1>::type;
         P1::load_smem(x, sm, tid);
-        P1::forward(x, tid, tw, stage_base, blk, q, two_q);
+        P1::template forward<MODE>(x, tid, tw, stage_base, blk, c);
         if constexpr (S::NFULL > 2) { P1::store_smem(x, sm, tid); __syncthreads(); }
     }
     if constexpr (S::NFULL >= 3) {
         using P2 = typename FullPassAt<LOGM, 2>::type;
         P2::load_smem(x, sm, tid);
-        P2::forward(x, tid, tw, stage_base, blk, q, two_q);
+        P2::template forward<MODE>(x, tid, tw, stage_base, blk, c);
+    }
+}
+template <int MODE> __device__ __forceinline__ u64 forward_canon(u64 v, const NttConsts &c) {
+    if constexpr (MODE == NTT_CLASSIC) {   // [0,4q) -> [0,q)
+        v = v >= c.two_q ? v - c.two_q : v;
+        return v >= c.q ? v - c.q : v;
+    } else {
+        return csub(reduce_lazy(v, c.one_q, c.q), c.q);
     }
 }
 
 // Inverse: x holds the block in fine layout with values in [0,2q).  On return x holds the result in coarse layout,
-// lazily in [0,2q), scaled by N^-1 when FOLD_SCALE.
-template <int LOGM, bool FOLD_SCALE>
-__device__ __forceinline__ void block_ntt_inverse(u64 (&x)[16], u64 *sm, int tid, const ShoupW *__restrict__ tw, int stage_base, int blk, u64 q,
-                                                  ShoupW n_inv, ShoupW inv1_n_inv) {
+// in [0,2q) when FOLD_SCALE (scaled by N^-1); without FOLD_SCALE (half of a 2N-point transform) reduced to [0,2q) as well.
+template <int LOGM, bool FOLD_SCALE, int MODE>
+__device__ __forceinline__ void block_ntt_inverse(u64 (&x)[16], u64 *sm, int tid, const ShoupW *__restrict__ tw, int stage_base, int blk, const NttConsts &c) {
     using S = NttShape<LOGM>;
-    const u64 two_q = q << 1;
+    // The first executed pass starts from [0,2q): it needs no reduction even in pass mode.
     if constexpr (S::NFULL >= 3) {
         using P2 = typename FullPassAt<LOGM, 2>::type;
-        P2::template inverse<false>(x, tid, tw, stage_base, blk, q, two_q, n_inv, inv1_n_inv);
+        P2::template inverse<false, MODE, false>(x, tid, tw, stage_base, blk, c);
         P2::store_smem(x, sm, tid);
         __syncthreads();
     }
     if constexpr (S::NFULL >= 2) {
         using P1 = typename FullPassAt<LOGM, 1>::type;
         if constexpr (S::NFULL > 2) P1::load_smem(x, sm, tid);
-        P1::template inverse<false>(x, tid, tw, stage_base, blk, q, two_q, n_inv, inv1_n_inv);
+        P1::template inverse<false, MODE, (S::NFULL > 2)>(x, tid, tw, stage_base, blk, c);
         P1::store_smem(x, sm, tid);
         __syncthreads();
     }
     if constexpr (S::NFULL >= 1) {
         using P0 = typename FullPassAt<LOGM, 0>::type;
         if constexpr (S::NFULL > 1) P0::load_smem(x, sm, tid);
-        P0::template inverse<false>(x, tid, tw, stage_base, blk, q, two_q, n_inv, inv1_n_inv);
+        P0::template inverse<false, MODE, (S::NFULL > 1)>(x, tid, tw, stage_base, blk, c);
         P0::store_smem(x, sm, tid);
         __syncthreads();
     }
     CoarsePass<LOGM>::load_smem(x, sm, tid);
-    CoarsePass<LOGM>::template inverse<FOLD_SCALE>(x, tid, tw, stage_base, blk, q, two_q, n_inv, inv1_n_inv);
+    CoarsePass<LOGM>::template inverse<FOLD_SCALE, MODE, (S::NFULL > 0)>(x, tid, tw, stage_base, blk, c);
+    if constexpr (!FOLD_SCALE && MODE != NTT_CLASSIC) {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) x[r] = reduce_lazy(x[r], c.one_q, c.q);
+    }
 }
 
 // [0,4q) -> [0,q)

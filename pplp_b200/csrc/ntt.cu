@@ -32,7 +32,7 @@ __device__ __forceinline__ void decode_row(int row, int nq, int npoly, int &qi, 
 }
 
 template <int LOGM, int L>
-__global__ void __launch_bounds__(NttShape<LOGM>::T) ntt_forward_kernel(const NttArgs a) {
+__global__ void __launch_bounds__(NttShape<LOGM>::T, (LOGM <= 13 ? 2 : 1)) ntt_forward_kernel(const NttArgs a) {
     using S = NttShape<LOGM>;
     extern __shared__ __align__(16) u64 sm[];
     const int tid = threadIdx.x;
@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(NttShape<LOGM>::T) ntt_forward_kernel(const Nt
 }
 
 template <int LOGM, int L>
-__global__ void __launch_bounds__(NttShape<LOGM>::T) ntt_inverse_kernel(const NttArgs a) {
+__global__ void __launch_bounds__(NttShape<LOGM>::T, (LOGM <= 13 ? 2 : 1)) ntt_inverse_kernel(const NttArgs a) {
     using S = NttShape<LOGM>;
     extern __shared__ __align__(16) u64 sm[];
     const int tid = threadIdx.x;

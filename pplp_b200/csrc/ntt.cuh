@@ -53,10 +53,10 @@ template <int LOGM> struct NttShape {
 __device__ __forceinline__ int smem_slot(int i) { return i + (i >> 4); }
 
 // a mod q into [0,2q) for any 64-bit a: Shoup's product with the constant 1 (quotient floor(2^64/q)).
-__device__ __forceinline__ u64 reduce_lazy(u64 a, u64 one_q, u64 q) { return a - __umul64hi(a, one_q) * q; }
+__device__ __forceinline__ u64 reduce_lazy(u64 a, u64 one_q, u64 q) { return a - umulhi_cc(a, one_q) * q; }
 
 template <int MODE> __device__ __forceinline__ void ct_butterfly(u64 &x, u64 &y, const ShoupW w, const u64 q, const u64 two_q) {
-    const u64 v = mul_shoup_lazy(y, w.w, w.wq, q);
+    const u64 v = mul_shoup_lazy_nq(y, w.w, w.wq, 0 - q);
     if constexpr (MODE == NTT_CLASSIC) {   // Harvey: values stay in [0,4q)
         const u64 u = x >= two_q ? x - two_q : x;
         x = u + v;
@@ -72,7 +72,7 @@ template <int MODE> __device__ __forceinline__ void gs_butterfly(u64 &x, u64 &y,
     const u64 d = x - y + big;
     if constexpr (MODE == NTT_CLASSIC) x = s >= two_q ? s - two_q : s;
     else x = s;
-    y = mul_shoup_lazy(d, w.w, w.wq, q);
+    y = mul_shoup_lazy_nq(d, w.w, w.wq, 0 - q);
 }
 
 __device__ __forceinline__ ShoupW ld_twiddle(const ShoupW *p) {
@@ -133,8 +133,8 @@ template <int LOGM, int S0, int R> struct Pass {
             for (int i = 0; i < HALF; ++i) {
                 u64 &a = x[u * RR + i], &b = x[u * RR + i + HALF];
                 const u64 s = a + b, d = a - b + big;
-                a = mul_shoup_lazy(s, c.n_inv.w, c.n_inv.wq, c.q);          // Shoup accepts any 64-bit input
-                b = mul_shoup_lazy(d, c.inv1_n_inv.w, c.inv1_n_inv.wq, c.q);
+                a = mul_shoup_lazy_nq(s, c.n_inv.w, c.n_inv.wq, 0 - c.q);          // Shoup accepts any 64-bit input
+                b = mul_shoup_lazy_nq(d, c.inv1_n_inv.w, c.inv1_n_inv.wq, 0 - c.q);
             }
         } else {
 #pragma unroll

@@ -171,6 +171,16 @@ int pplp_bloom_build(pplp_ctx *ctx, uint8_t *d_tables, uint64_t m_bits, const ui
 /* src/client.cc:158: verdict[q] = contains((bd[q*bd_stride] << bitlen(w_f)) | w_f), f = d_fidx ? d_fidx[q] : 0 */
 int pplp_bloom_query(pplp_ctx *ctx, const uint8_t *d_tables, uint64_t m_bits, const uint32_t *d_salts, uint32_t k, const uint64_t *d_bd, size_t bd_stride,
                      const uint64_t *d_rsw, const int *d_fidx, size_t nq, uint8_t *d_verdict, void *stream);
+/* bloom_filter::serialize / compute_serialization_size / ctor-from-buffer (include/bloomfilter.h:228-278), the bytes the
+ * server sends after w (src/server.cc:135-142) and the client parses (src/client.cc:135-136): packed 44-byte header
+ * {u32 k; u64 m; u64 projected; u64 inserted; u64 seed'; f64 fpp}, k salts, m/8 table bytes.  Synchronises.
+ * serialize returns the byte count written to h_out (0 on failure); deserialize uploads the table to d_table (capacity
+ * cap_bytes, at least pplp_bloom_table_stride(m)) and fills the geometry. */
+size_t pplp_bloom_serialized_size(uint32_t k, uint64_t m_bits);
+size_t pplp_bloom_serialize(pplp_ctx *ctx, const uint8_t *d_table, uint32_t k, uint64_t m_bits, uint64_t projected, uint64_t inserted, uint64_t seed,
+                            double fpp, const uint32_t *h_salts, uint8_t *h_out, size_t cap);
+int pplp_bloom_deserialize(pplp_ctx *ctx, const uint8_t *h_buf, size_t len, uint8_t *d_table, size_t cap_bytes, uint32_t *k_out, uint64_t *m_bits_out,
+                           uint64_t *projected_out, uint64_t *inserted_out, uint64_t *seed_out, double *fpp_out, uint32_t *h_salts);
 /* bloom_filter::insert / contains on explicit 8-byte keys (filter 0) */
 int pplp_bloom_insert_keys(pplp_ctx *ctx, uint8_t *d_table, uint64_t m_bits, const uint32_t *d_salts, uint32_t k, const uint64_t *d_keys, size_t nkeys,
                            void *stream);

@@ -699,6 +699,36 @@ int pplp_bloom_query(pplp_ctx *ctx, const uint8_t *d_tables, uint64_t m_bits, co
     return PPLP_OK;
     PPLP_CATCH
 }
+size_t pplp_bloom_serialized_size(uint32_t k, uint64_t m_bits) { return bloomh::serialized_size(k, m_bits); }
+size_t pplp_bloom_serialize(pplp_ctx *ctx, const uint8_t *d_table, uint32_t k, uint64_t m_bits, uint64_t projected, uint64_t inserted, uint64_t seed,
+                            double fpp, const uint32_t *h_salts, uint8_t *h_out, size_t cap) {
+    try {
+        dev_engine(ctx);
+        const size_t need = bloomh::serialized_size(k, m_bits);
+        if (k == 0 || k > 128 || m_bits == 0 || m_bits % 8 || cap < need) { fail(PPLP_EINVAL, "pplp: Bloom serialisation buffer too small or bad geometry"); return 0; }
+        bloomh::Params P;
+        P.k = k; P.m_bits = m_bits; P.projected = projected; P.seed = seed; P.fpp = fpp;
+        P.salts.assign(h_salts, h_salts + k);
+        bloomh::write_header(h_out, P, inserted);
+        PPLP_CUDA(cudaMemcpy(h_out + bloomh::kHeaderBytes + 4 * (size_t)k, d_table, m_bits / 8, cudaMemcpyDeviceToHost));
+        return need;
+    } catch (const std::exception &e) { fail(PPLP_ERUNTIME, e.what()); return 0; }
+}
+int pplp_bloom_deserialize(pplp_ctx *ctx, const uint8_t *h_buf, size_t len, uint8_t *d_table, size_t cap_bytes, uint32_t *k_out, uint64_t *m_bits_out,
+                           uint64_t *projected_out, uint64_t *inserted_out, uint64_t *seed_out, double *fpp_out, uint32_t *h_salts) {
+    PPLP_TRY
+    dev_engine(ctx);
+    bloomh::Params P;
+    uint64_t inserted = 0;
+    if (!bloomh::read_header(h_buf, len, P, inserted)) throw std::invalid_argument("pplp: malformed Bloom filter buffer");
+    if (P.m_bits % 8 || cap_bytes < bloom_table_stride(P.m_bits)) throw std::invalid_argument("pplp: Bloom table buffer too small");
+    PPLP_CUDA(cudaMemset(d_table, 0, bloom_table_stride(P.m_bits)));
+    PPLP_CUDA(cudaMemcpy(d_table, h_buf + bloomh::kHeaderBytes + 4 * (size_t)P.k, P.m_bits / 8, cudaMemcpyHostToDevice));
+    *k_out = P.k; *m_bits_out = P.m_bits; *projected_out = P.projected; *inserted_out = inserted; *seed_out = P.seed; *fpp_out = P.fpp;
+    std::copy(P.salts.begin(), P.salts.end(), h_salts);
+    return PPLP_OK;
+    PPLP_CATCH
+}
 int pplp_bloom_insert_keys(pplp_ctx *ctx, uint8_t *d_table, uint64_t m_bits, const uint32_t *d_salts, uint32_t k, const uint64_t *d_keys, size_t nkeys,
                            void *stream) {
     PPLP_TRY

@@ -245,6 +245,19 @@ class Context:
         check(self.L.pplp_ntt(self.h, self.first_level if level is None else level, base, _ptr(data), layout, nq, npoly, 1 if inverse else 0, self._st()))
         return data
 
+    def batch_encode(self, values):
+        """BatchEncoder::encode for a batch: values [nq, count] (< t) -> plaintext coefficients [nq, N]."""
+        nq, count = values.shape
+        out = self.empty(nq, self.n)
+        check(self.L.pplp_batch_encode(self.h, _ptr(values), count, _ptr(out), nq, self._st()))
+        return out
+
+    def batch_decode(self, plain):
+        nq = plain.shape[0]
+        out = self.empty(nq, self.n)
+        check(self.L.pplp_batch_decode(self.h, _ptr(plain), _ptr(out), nq, self._st()))
+        return out
+
     def prng_stream(self, seeds, nrefill):
         ns = seeds.shape[0]
         out = self.empty(ns, nrefill * 512)
@@ -320,3 +333,39 @@ class BloomBatch:
 
     def table_bytes(self, f=0):
         return to_np(self.tables[f, : self.m_bits // 8], np.uint8)
+
+    def serialize(self, f=0, inserted=None):
+        """The reference's wire image of filter f (bloom_filter::serialize, include/bloomfilter.h:247-278)."""
+        L = self.ctx.L
+        size = L.pplp_bloom_serialized_size(self.k, self.m_bits)
+        out = np.zeros(size, dtype=np.uint8)
+        n = L.pplp_bloom_serialize(self.ctx.h, _ptr(self.tables[f]), self.k, self.m_bits, self.count, self.count if inserted is None else inserted,
+                                   self.seed, self.fpp, self.salts_host.ctypes.data, out.ctypes.data, size)
+        if n != size:
+            raise capi.PplpError(-1, L.pplp_last_error().decode())
+        return out.tobytes()
+
+    @classmethod
+    def from_buffer(cls, ctx, buf, w=0):
+        """bloom_filter(buffer) as the client does (src/client.cc:135-136); w is the word sent in front of it."""
+        torch = _torch()
+        b = np.frombuffer(buf, dtype=np.uint8)
+        k, m = int(np.frombuffer(buf[:4], dtype=np.uint32)[0]), int(np.frombuffer(buf[4:12], dtype=np.uint64)[0])
+        self = cls.__new__(cls)
+        self.ctx = ctx
+        self.stride = int(ctx.L.pplp_bloom_table_stride(m))
+        self.tables = torch.zeros((1, self.stride), dtype=torch.uint8, device=ctx.device)
+        ko, mo, po, io, so = C.c_uint32(), C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+        fo = C.c_double()
+        salts = np.zeros(128, dtype=np.uint32)
+        check(ctx.L.pplp_bloom_deserialize(ctx.h, b.ctypes.data, b.size, _ptr(self.tables), self.stride, C.addressof(ko), C.addressof(mo), C.addressof(po),
+                                           C.addressof(io), C.addressof(so), C.addressof(fo), salts.ctypes.data))
+        self.k, self.m_bits, self.count, self.inserted, self.seed, self.fpp = ko.value, mo.value, po.value, io.value, so.value, fo.value
+        assert (self.k, self.m_bits) == (k, m)
+        self.salts_host = salts[: self.k].copy()
+        self.salts = from_np(self.salts_host, ctx.device)
+        self.rsw_host = np.array([[0, 0, w]], dtype=np.uint64)
+        self.rsw = from_np(self.rsw_host, ctx.device)
+        self.nf = 1
+        self.radius = None
+        return self

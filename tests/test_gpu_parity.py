@@ -494,3 +494,27 @@ def test_circuit_b_direct_form_decrypts_to_squared_distance(eng, oracle):
     dec = eng.to_np(ctx.decrypt(d, ctx.dev(osk), ncoeff=1))[0, 0]
     d2 = (xa - xb) ** 2 + (ya - yb) ** 2
     assert int(dec) == (s * (d2 + r)) % t
+
+
+def test_bloom_wire_format_matches_reference_golden(eng, oracle):
+    """serialize() bytes equal the reference header's (FNV of the golden fixture), and the client-side constructor from a
+    buffer (src/client.cc:135-136) answers the same queries."""
+    ctx, _ = contexts(eng, oracle, 4096)
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "bloom_golden.json")))
+
+    def fnv1a64(b):
+        h = 0xCBF29CE484222325
+        for x in b:
+            h = ((h ^ int(x)) * 0x100000001B3) & 0xFFFFFFFFFFFFFFFF
+        return h
+
+    for case in gold["cases"][:4]:
+        bf = eng.BloomBatch(ctx, case["radius"], fpp=case["fpp"], rsw=[(case["r"], case["s"], case["w"])]).build()
+        wire = bf.serialize()
+        assert "%016x" % fnv1a64(wire) == case["serialized_fnv1a64"]
+        back = eng.BloomBatch.from_buffer(ctx, wire, w=case["w"])
+        assert (back.k, back.m_bits) == (bf.k, bf.m_bits) and (back.table_bytes(0) == bf.table_bytes(0)).all()
+        assert back.serialize(inserted=back.inserted) == wire
+        d2 = np.array([0, 1, case["n"] - 1, case["n"], 3 * case["n"]], dtype=np.uint64)
+        bd = (np.uint64(case["s"]) * (d2 + np.uint64(case["r"]))) & np.uint64(T56 - 1)
+        assert (eng.to_np(back.query(ctx.dev(bd)), np.uint8) == eng.to_np(bf.query(ctx.dev(bd)), np.uint8)).all()

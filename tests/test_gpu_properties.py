@@ -1,0 +1,161 @@
+"""Full-size GPU tests through size-independent properties (BASELINE.json configs at sizes the oracle cannot replay in
+seconds): encrypt -> evaluate -> decrypt round trips against the protocol algebra, NTT linearity / invertibility over the
+config-4 sweep, Bloom filters at the reference's largest radius, the many-server-points batch of config 5, and the
+slot-wise meaning of BatchEncoder + square + relinearize.  Everything goes through the C ABI."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+T56 = 1 << 56
+
+
+def seed8(x):
+    return np.array([(x * 0x9E3779B97F4A7C15 + i * 0xD1B54A32D192ED03) & 0xFFFFFFFFFFFFFFFF for i in range(8)], dtype=np.uint64)
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("gpu-marked test run without a CUDA device")
+    from pplp_b200 import build, engine
+    build.build()
+    return engine
+
+
+@pytest.mark.parametrize("n,nq", [(8192, 1536), (16384, 256)])   # BASELINE.json configs[1] / configs[2]
+def test_encrypt_circuit_a_decrypt_round_trip_at_batch_size(eng, n, nq):
+    ctx = eng.Context(n, t=T56, device=0)
+    sk, pk = ctx.keygen(seed8(11))
+    rng = np.random.default_rng(n)
+    xa = rng.integers(0, 1 << 27, nq, dtype=np.uint64); ya = rng.integers(0, 1 << 27, nq, dtype=np.uint64)
+    xb = rng.integers(1, 1 << 27, nq, dtype=np.uint64); yb = rng.integers(1, 1 << 27, nq, dtype=np.uint64)
+    r = rng.integers(0, 1 << 32, nq, dtype=np.uint64); s = rng.integers(1, 1 << 32, nq, dtype=np.uint64)
+    cts = []
+    for i, vals in enumerate([xa * xa + ya * ya, xa << np.uint64(1), ya << np.uint64(1)]):
+        seeds = rng.integers(0, 1 << 63, size=(nq, 8), dtype=np.uint64)
+        cts.append(ctx.encrypt(pk, ctx.dev(seeds), ctx.dev(vals[:, None]), layout=eng.LAYOUT_LIMB_MAJOR))
+    out = ctx.circuit_a(cts[0], cts[1], cts[2], ctx.dev(xb), ctx.dev(yb), ctx.dev(r), ctx.dev(s), layout=eng.LAYOUT_LIMB_MAJOR)
+    dec = eng.to_np(ctx.decrypt(out, sk, ncoeff=2, layout=eng.LAYOUT_LIMB_MAJOR))
+    d2 = (xa.astype(object) - xb.astype(object)) ** 2 + (ya.astype(object) - yb.astype(object)) ** 2
+    expect = np.array([(int(s[i]) * (int(d2[i]) + int(r[i]))) % T56 for i in range(nq)], dtype=np.uint64)
+    assert (dec[:, 0] == expect).all()
+    assert not dec[:, 1].any()   # constant plaintexts stay constant
+
+
+def _sweep_primes(oracle, n, limbs):
+    q = oracle.bfv_default(n)[:limbs]
+    if len(q) < limbs:   # top up as SURVEY.md §8d config 4 says: get_primes(2N, 50, ...)
+        extra = [p for p in oracle.get_primes(2 * n, 50, limbs) if p not in q]
+        q = q + extra[: limbs - len(q)]
+    return q
+
+
+@pytest.mark.parametrize("n", [4096, 8192, 16384, 32768])
+@pytest.mark.parametrize("limbs", [3, 8])
+def test_ntt_sweep_linearity_and_inverse(eng, oracle, n, limbs):
+    """BASELINE.json config 4: N = 4096..32768, 3..8 RNS limbs.  NTT(a+b) = NTT(a)+NTT(b), INTT(NTT(a)) = a, on a
+    batch large enough to cover several waves; one row per modulus is also checked against the oracle."""
+    q = _sweep_primes(oracle, n, limbs)
+    ctx = eng.Context(n, q=q, t=1 << 20, device=0, enforce_security=False)
+    assert ctx.ok, ctx.error_message
+    import torch
+    rows = max(8, (1 << 21) // n)
+    a = ctx.empty(limbs, 1, rows, n); b = ctx.empty(limbs, 1, rows, n)
+    for j in range(limbs):
+        a[j].random_(0, q[j]); b[j].random_(0, q[j])
+    qt = torch.tensor(q, dtype=torch.int64, device=ctx.device).view(limbs, 1, 1, 1)
+    s = a + b
+    s = torch.where(s >= qt, s - qt, s)
+    fa = ctx.ntt_(a.clone(), level=0, layout=eng.LAYOUT_LIMB_MAJOR)
+    fb = ctx.ntt_(b.clone(), level=0, layout=eng.LAYOUT_LIMB_MAJOR)
+    fs = ctx.ntt_(s.clone(), level=0, layout=eng.LAYOUT_LIMB_MAJOR)
+    lin = fa + fb
+    lin = torch.where(lin >= qt, lin - qt, lin)
+    assert torch.equal(fs, lin)
+    back = ctx.ntt_(fa.clone(), level=0, inverse=True, layout=eng.LAYOUT_LIMB_MAJOR)
+    assert torch.equal(back, a)
+    octx = oracle.context(n, q, 1 << 20)
+    for j in (0, limbs - 1):
+        row = eng.to_np(a[j, 0, rows - 1])
+        assert (eng.to_np(fa[j, 0, rows - 1]) == octx.ntt(0, j, row)).all()
+
+
+def test_bloom_radius_4096_matches_oracle_and_has_no_false_negatives(eng, oracle):
+    """The reference's largest sweep point (src/test/test_server.cc:45-59): 16.7 M inserts x 13 hashes into a 40 MB table."""
+    from tests.oracle_lib import OracleBloom
+    ctx = eng.Context(4096, device=0)
+    radius, (r, s, w) = 4096, (0x89ABCDEF, 0x7654321F, 0x9A5B)
+    bf = eng.BloomBatch(ctx, radius, fpp=1e-4, rsw=[(r, s, w)]).build()
+    assert (bf.k, bf.m_bits) == (13, 321668808)
+    ob = OracleBloom(oracle.lib, "orc", radius * radius, 1e-4)
+    ob.insert_blinded_range(r, s, w, radius * radius)
+    assert (bf.table_bytes(0) == ob.table()).all()
+    import torch
+    di = torch.arange(0, radius * radius, 997, dtype=torch.int64, device=ctx.device)
+    bd = (di + r) * s   # int64 wrap == uint64 wrap; the client sees it mod 2^56, which agrees after << 16
+    bd56 = bd & ((1 << 56) - 1)
+    assert bool(bf.query(bd56).all())
+    far = torch.arange(radius * radius, radius * radius + 4096, dtype=torch.int64, device=ctx.device)
+    fp = bf.query(((far + r) * s) & ((1 << 56) - 1)).float().mean().item()
+    assert fp < 0.01
+
+
+def test_many_server_points_batch(eng):
+    """BASELINE.json config 5, scaled to a test: every client against every server point, each point with its own blinds
+    (r, s, w) and Bloom filter; verdict == (d^2 < radius^2) and blinded distance == s*(d^2+r) mod 2^56."""
+    n, radius, npts, ncl = 8192, 64, 24, 16
+    ctx = eng.Context(n, t=T56, device=0)
+    sk, pk = ctx.keygen(seed8(21))
+    rng = np.random.default_rng(5)
+    rsw = np.stack([rng.integers(0, 1 << 32, npts, dtype=np.uint64), rng.integers(1, 1 << 32, npts, dtype=np.uint64),
+                    rng.integers(1, 1 << 16, npts, dtype=np.uint64)], axis=1)
+    px = rng.integers(1000, 1 << 27, npts, dtype=np.uint64); py = rng.integers(1000, 1 << 27, npts, dtype=np.uint64)
+    bf = eng.BloomBatch(ctx, radius, fpp=1e-4, rsw=rsw).build()
+    # clients scattered around the server points so that both verdicts occur
+    home = rng.integers(0, npts, ncl)
+    cx = px[home] + rng.integers(0, 60, ncl).astype(np.uint64)
+    cy = py[home] + rng.integers(0, 60, ncl).astype(np.uint64)
+    fidx = np.repeat(np.arange(npts, dtype=np.int32), ncl)
+    xa = np.tile(cx, npts); ya = np.tile(cy, npts)
+    xb = px[fidx]; yb = py[fidx]
+    nq = npts * ncl
+    seeds = rng.integers(0, 1 << 63, size=(nq * 3, 8), dtype=np.uint64)
+    blind, verdict, flags = ctx.proximity_batch(pk, sk, ctx.dev(xa), ctx.dev(ya), ctx.dev(xb), ctx.dev(yb), ctx.dev(seeds), bf, fidx=ctx.dev(fidx), chunk=100)
+    d2 = (xa.astype(np.int64) - xb.astype(np.int64)) ** 2 + (ya.astype(np.int64) - yb.astype(np.int64)) ** 2
+    expect = np.array([(int(rsw[f, 1]) * (int(d) + int(rsw[f, 0]))) % T56 for f, d in zip(fidx, d2)], dtype=np.uint64)
+    assert (eng.to_np(blind) == expect).all()
+    near = d2 < radius * radius
+    got = verdict.cpu().numpy().astype(bool)
+    assert got[near].all()                                    # a Bloom filter has no false negatives
+    assert (got[~near]).mean() < 0.01 and near.any() and (~near).any()
+    assert not flags.any().item()
+
+
+@pytest.mark.parametrize("n", [8192, 16384])
+def test_batch_encoder_square_relinearize_is_slotwise(eng, oracle, n):
+    """north_star's slot-batched direct form: BatchEncoder -> encrypt -> (x - xb)^2 via sub_plain, square, relinearize ->
+    decrypt -> decode gives the slot-wise squares; encode/decode also match the oracle's BatchEncoder bit for bit."""
+    t = eng.plain_batching(n, 40)
+    ctx = eng.Context(n, t=t, device=0)
+    assert ctx.batching
+    octx = oracle.context(n, oracle.bfv_default(n), t, seed=seed8(7))
+    rng = np.random.default_rng(n)
+    vals = rng.integers(0, 1 << 19, size=(2, n), dtype=np.uint64)
+    plain = ctx.batch_encode(ctx.dev(vals))
+    for i in range(2):
+        assert (eng.to_np(plain[i]) == octx.batch_encode(vals[i])).all()
+    assert (eng.to_np(ctx.batch_decode(plain)) == vals).all()
+    short = ctx.batch_encode(ctx.dev(vals[:, :5]))   # fewer values than slots: the rest are zero
+    assert (eng.to_np(short[0]) == octx.batch_encode(vals[0, :5])).all()
+    sk, pk = ctx.keygen(seed8(31))
+    rk = ctx.relin_keygen(np.stack([seed8(40 + i) for i in range(ctx.k)]), sk)
+    quot = ctx.relin_prepare(rk)
+    ct = ctx.encrypt(pk, ctx.dev(np.stack([seed8(50), seed8(51)])), plain)
+    xb = rng.integers(0, 1 << 19, size=(2, n), dtype=np.uint64)
+    ctx.add_plain_(ct, ctx.batch_encode(ctx.dev(xb)), subtract=True)
+    sq = ctx.relinearize(ctx.square(ct), rk, quot)
+    dec = ctx.batch_decode(ctx.decrypt(sq, sk))
+    diff = vals.astype(object) - xb.astype(object)
+    expect = np.array([[int(v) * int(v) % t for v in row] for row in diff], dtype=np.uint64)
+    assert (eng.to_np(dec) == expect).all()

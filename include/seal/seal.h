@@ -13,6 +13,7 @@
 //   * There is no CPU fallback: constructing a SEALContext needs a CUDA device (PPLP_DEVICE selects it, default 0).
 // Wire formats: SEAL 4.1 streams, compr_mode zlib (default here) and none; see DESIGN.md "wire formats".
 #pragma once
+#include <dlfcn.h>
 #include <zlib.h>
 
 #include <array>
@@ -65,6 +66,61 @@ inline void os_random(void *dst, std::size_t n) {   // [SEAL] random_bytes: OS e
     }
 }
 inline int bits_of(std::uint64_t v) { int b = 0; while (v) { ++b; v >>= 1; } return b; }
+
+// zstd is SEAL's default stream compression.  Only the runtime library (libzstd.so.1) is needed: the handful of entry
+// points used here have had a stable ABI since zstd 1.0 and are resolved with dlopen, so the shim builds without zstd's
+// headers and still reads what a stock SEAL peer sends (and writes what it accepts).
+struct Zstd {
+    struct InBuf { const void *src; std::size_t size, pos; };
+    struct OutBuf { void *dst; std::size_t size, pos; };
+    void *lib = nullptr;
+    std::size_t (*compress)(void *, std::size_t, const void *, std::size_t, int) = nullptr;
+    std::size_t (*compress_bound)(std::size_t) = nullptr;
+    unsigned (*is_error)(std::size_t) = nullptr;
+    void *(*create_dstream)() = nullptr;
+    std::size_t (*free_dstream)(void *) = nullptr;
+    std::size_t (*decompress_stream)(void *, OutBuf *, InBuf *) = nullptr;
+    Zstd() {
+        for (const char *name : {"libzstd.so.1", "libzstd.so"}) {
+            lib = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+            if (lib) break;
+        }
+        if (!lib) return;
+        compress = reinterpret_cast<decltype(compress)>(dlsym(lib, "ZSTD_compress"));
+        compress_bound = reinterpret_cast<decltype(compress_bound)>(dlsym(lib, "ZSTD_compressBound"));
+        is_error = reinterpret_cast<decltype(is_error)>(dlsym(lib, "ZSTD_isError"));
+        create_dstream = reinterpret_cast<decltype(create_dstream)>(dlsym(lib, "ZSTD_createDStream"));
+        free_dstream = reinterpret_cast<decltype(free_dstream)>(dlsym(lib, "ZSTD_freeDStream"));
+        decompress_stream = reinterpret_cast<decltype(decompress_stream)>(dlsym(lib, "ZSTD_decompressStream"));
+        if (!compress || !compress_bound || !is_error || !create_dstream || !free_dstream || !decompress_stream) lib = nullptr;
+    }
+    static const Zstd &get() { static const Zstd z; return z; }
+    bool ok() const { return lib != nullptr; }
+    std::string deflate(const void *src, std::size_t len) const {
+        std::string out(compress_bound(len), '\0');
+        const std::size_t n = compress(&out[0], out.size(), src, len, 3);   // ZSTD_CLEVEL_DEFAULT, as SEAL
+        if (is_error(n)) throw std::logic_error("stream compression failed");
+        out.resize(n);
+        return out;
+    }
+    std::string inflate(const void *src, std::size_t len) const {
+        void *ds = create_dstream();
+        if (!ds) throw std::logic_error("stream decompression failed");
+        std::string out(len * 4 + (1 << 16), '\0');
+        InBuf in{src, len, 0};
+        OutBuf ob{&out[0], out.size(), 0};
+        for (;;) {
+            const std::size_t rc = decompress_stream(ds, &ob, &in);
+            if (is_error(rc)) { free_dstream(ds); throw std::logic_error("stream decompression failed"); }
+            if (rc == 0 && in.pos == in.size) break;                       // frame complete, input consumed
+            if (ob.pos == ob.size) { out.resize(out.size() * 2); ob.dst = &out[0]; ob.size = out.size(); }
+            else if (in.pos == in.size && rc != 0) { free_dstream(ds); throw std::logic_error("stream decompression failed"); }
+        }
+        free_dstream(ds);
+        out.resize(ob.pos);
+        return out;
+    }
+};
 }  // namespace detail
 
 inline void random_bytes(seal_byte *buf, std::size_t count) { detail::os_random(buf, count); }   // src/demo.cc:116-118
@@ -105,8 +161,9 @@ inline void hex_string_to_uint(const char *hex_string, int char_count, std::size
 struct Serialization {
     // SEAL's default is zstd (else zlib).  A compressed default is REQUIRED for the reference's transport: src/server.cc:69
     // receives the parameters with one 128-byte recv, and an uncompressed parameter object is 177 bytes at N = 8192
-    // (70 bytes deflated).  zlib is the compressed mode this build can write; SEAL's load() accepts it.
-    static constexpr compr_mode_type compr_mode_default = compr_mode_type::zlib;
+    // (70 bytes deflated).  zstd when libzstd.so.1 can be loaded (what a stock SEAL build uses), zlib otherwise; SEAL's
+    // load() auto-detects either from the header.
+    static inline const compr_mode_type compr_mode_default = detail::Zstd::get().ok() ? compr_mode_type::zstd : compr_mode_type::zlib;
     static constexpr std::uint16_t seal_magic = 0xA15E;
     static constexpr std::uint8_t seal_header_size = 0x10;
 };
@@ -176,9 +233,20 @@ template <class Body> void read_object(Source &src, Body body) {
         Source inner(plain.data(), plain.size());
         body(inner);
     } else {
-        throw std::logic_error("unsupported compression mode: this build reads compr_mode none and zlib");
+        if (!Zstd::get().ok()) throw std::logic_error("unsupported compression mode: zstd stream but libzstd.so.1 is not loadable");
+        const std::string plain = Zstd::get().inflate(src.p + src.pos, (std::size_t)total - 16);
+        Source inner(plain.data(), plain.size());
+        body(inner);
     }
     src.pos = start + (std::size_t)total;
+}
+inline std::string zstd_object(const std::string &plain_obj) {
+    if (!Zstd::get().ok()) throw std::invalid_argument("unsupported compression mode: libzstd.so.1 is not loadable");
+    std::string out = plain_obj.substr(0, 16) + Zstd::get().deflate(plain_obj.data() + 16, plain_obj.size() - 16);
+    out[5] = 2;
+    const std::uint64_t total = out.size();
+    std::memcpy(&out[8], &total, 8);
+    return out;
 }
 // Re-wraps a mode-none object (header + members) as a zlib object.
 inline std::string deflate_object(const std::string &plain_obj) {
@@ -195,8 +263,13 @@ inline std::string deflate_object(const std::string &plain_obj) {
     return out;
 }
 inline std::streamoff emit(std::ostream &stream, const std::string &obj, compr_mode_type mode) {
-    if (mode == compr_mode_type::zstd) throw std::invalid_argument("unsupported compression mode");
     const std::string &o = obj;
+    if (mode == compr_mode_type::zstd) {
+        const std::string z = zstd_object(o);
+        stream.write(z.data(), (std::streamsize)z.size());
+        if (!stream) throw std::runtime_error("I/O error");
+        return (std::streamoff)z.size();
+    }
     if (mode == compr_mode_type::zlib) {
         const std::string z = deflate_object(o);
         stream.write(z.data(), (std::streamsize)z.size());

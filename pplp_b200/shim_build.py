@@ -13,7 +13,7 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 REF = "/root/reference"
-COMMON = ["-std=c++17", "-O2", "-I", os.path.join(ROOT, "include"), "-L", PKG, "-lpplp_b200", "-lz", "-Wl,-rpath," + PKG, "-Wl,-rpath,$ORIGIN/../../pplp_b200"]
+COMMON = ["-std=c++17", "-O2", "-I", os.path.join(ROOT, "include"), "-L", PKG, "-lpplp_b200", "-lz", "-ldl", "-Wl,-rpath," + PKG, "-Wl,-rpath,$ORIGIN/../../pplp_b200"]
 # -include cstdint: src/demo.cc includes bloomfilter.h (which uses uint8_t) before any header that declares it; GCC >= 13
 # no longer leaks <cstdint> through <sstream>, so the reference needs this one flag on a current toolchain.
 DROPIN = {"pplp": "src/demo.cc", "client": "src/client.cc", "server": "src/server.cc", "test_client": "src/test/test_client.cc",
@@ -38,11 +38,13 @@ def build(force=False):
     hdrs = [os.path.join(ROOT, "include", "seal", "seal.h"), os.path.join(ROOT, "include", "pplp_b200.h")]
     out = os.path.join(ROOT, "build", "shim")
     os.makedirs(out, exist_ok=True)
-    src = os.path.join(ROOT, "tests", "shim", "shim_parity.cc")
-    exe = os.path.join(out, "shim_parity")
-    if force or _newer(exe, [src] + hdrs):
-        _run(["g++", "-Wall", src] + COMMON + ["-o", exe])
-    built = [exe]
+    built = []
+    for name in ("shim_parity", "host_logic"):
+        src = os.path.join(ROOT, "tests", "shim", name + ".cc")
+        exe = os.path.join(out, name)
+        if force or _newer(exe, [src] + hdrs):
+            _run(["g++", "-Wall", src] + COMMON + ["-o", exe])
+        built.append(exe)
     if os.path.isdir(os.path.join(REF, "src")):
         d = os.path.join(ROOT, "build", "dropin")
         os.makedirs(d, exist_ok=True)

@@ -23,7 +23,27 @@ template <class T> static std::string saved(const T &obj, compr_mode_type mode =
     return ss.str();
 }
 
+// shim_parity --reload <in> <out> <log2 N>: load a ciphertext stream written by ANOTHER producer (any compr_mode) and
+// write it back uncompressed — the interoperability direction "foreign SEAL peer -> this library".
+static int reload(const char *in, const char *out, int logn) {
+    EncryptionParameters parms(scheme_type::bfv);
+    const size_t n = size_t(1) << logn;
+    parms.set_poly_modulus_degree(n);
+    parms.set_coeff_modulus(CoeffModulus::BFVDefault(n));
+    parms.set_plain_modulus(uint64_t(1) << 56);
+    SEALContext context(parms);
+    std::ifstream f(in, std::ios::binary);
+    Ciphertext c;
+    c.load(context, f);
+    std::ofstream o(out, std::ios::binary);
+    c.save(o, compr_mode_type::none);
+    return 0;
+}
+
 int main(int argc, char **argv) {
+    if (argc == 5 && std::string(argv[1]) == "--reload") {
+        try { return reload(argv[2], argv[3], std::atoi(argv[4])); } catch (const std::exception &e) { std::fprintf(stderr, "exception: %s\n", e.what()); return 1; }
+    }
     if (argc < 9) { std::fprintf(stderr, "usage\n"); return 2; }
     const std::string dir = argv[1];
     const size_t n = size_t(1) << std::atoi(argv[2]);
@@ -66,6 +86,18 @@ int main(int argc, char **argv) {
         dump(dir, "c2.bin", saved(c2));
         dump(dir, "c3.bin", saved(c3));
         dump(dir, "c1_zlib.bin", saved(c1, compr_mode_type::zlib));
+        std::printf("default_compr_mode: %d\n", (int)Serialization::compr_mode_default);
+        if (Serialization::compr_mode_default == compr_mode_type::zstd) {
+            dump(dir, "c1_zstd.bin", saved(c1, compr_mode_type::zstd));
+            std::stringstream z(saved(c1, compr_mode_type::zstd));
+            Ciphertext v;
+            v.load(context, z);
+            if (v.to_host() != c1.to_host()) return 8;
+            std::stringstream dflt;
+            parms.save(dflt);                       // what src/client.cc:93 sends; must fit the server's 128-byte recv
+            if (dflt.str().size() > 128) return 9;
+            dump(dir, "parms_default.bin", dflt.str());
+        }
         {   // save -> load round trips (src/demo.cc:143-145), both framings
             std::stringstream a(saved(c1)), b(saved(c1, compr_mode_type::zlib));
             Ciphertext x, y;

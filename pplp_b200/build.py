@@ -20,7 +20,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr",
     "-I", os.path.join(ROOT, "include"),
-]
+] + os.environ.get("PPLP_NVCC_EXTRA", "").split()   # experiments only (e.g. -DPPLP_NTT_MIN_CTAS=1); part of the staleness digest
 
 
 def _nvcc():
@@ -41,7 +41,7 @@ def _digest(paths):
     for p in sorted(paths):
         h.update(os.path.basename(p).encode())
         h.update(open(p, "rb").read())
-    h.update(" ".join(NVCC_FLAGS[:-1]).encode())
+    h.update(" ".join(f for f in NVCC_FLAGS if not f.startswith("/")).encode())
     return h.hexdigest()
 
 

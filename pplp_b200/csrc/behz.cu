@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(NttShape<LOGM>::T) relin_limb_kernel(const Rel
     const int key_index = (I == a.k) ? a.K - 1 : I;
     const DevMod &md = a.mods[key_index];
     const Mod mod = md.m;
-    const NttConsts nc = ntt_consts(md);
+    const NttConsts nc = ntt_consts<L>(md);
     const u64 q = mod.q, two_q = q << 1;
     const u64 *c2 = a.c2 + qi * a.lay.sq + 2 * a.lay.sp;
 
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(NttShape<LOGM>::T) relin_limb_kernel(const Rel
         const u64 *row = c2 + J * a.lay.sl;
         if (J == key_index) CoarsePass<LOGM>::for_each(tid, [&](int r, int i) { x[r] = row[i]; });
         else CoarsePass<LOGM>::for_each(tid, [&](int r, int i) { x[r] = barrett64(row[i], mod); });
-        block_ntt_forward<LOGM, Lazy<L>::F>(x, sm, tid, md.fwd, 0, 0, nc);
+        block_ntt_forward<LOGM, Lazy<L>::F>(x, sm, tid, fwd_table<L>(md), 0, 0, nc);
         const size_t koff = (((size_t)J * 2 + 0) * a.K + key_index) * a.n + 16 * tid;
         const size_t koff1 = koff + (size_t)a.K * a.n;
 #pragma unroll
@@ -232,13 +232,13 @@ __global__ void __launch_bounds__(NttShape<LOGM>::T) relin_limb_kernel(const Rel
     u64 *o0 = a.tmp + (((size_t)qi * 2 + 0) * (a.k + 1) + I) * a.n;
     u64 *o1 = a.tmp + (((size_t)qi * 2 + 1) * (a.k + 1) + I) * a.n;
     const bool special = (I == a.k);
-    block_ntt_inverse<LOGM, true, Lazy<L>::I>(acc0, sm, tid, md.inv, 0, 0, nc);
+    block_ntt_inverse<LOGM, true, Lazy<L>::I>(acc0, sm, tid, inv_table<L>(md), 0, 0, nc);
     CoarsePass<LOGM>::for_each(tid, [&](int r, int i) {
         const u64 v = csub(acc0[r], q);
         o0[i] = special ? add_mod(v, a.half, q) : v;
     });
     __syncthreads();
-    block_ntt_inverse<LOGM, true, Lazy<L>::I>(acc1, sm, tid, md.inv, 0, 0, nc);
+    block_ntt_inverse<LOGM, true, Lazy<L>::I>(acc1, sm, tid, inv_table<L>(md), 0, 0, nc);
     CoarsePass<LOGM>::for_each(tid, [&](int r, int i) {
         const u64 v = csub(acc1[r], q);
         o1[i] = special ? add_mod(v, a.half, q) : v;
@@ -311,7 +311,8 @@ template <int LOGM, int L> static void run_relin_limb_l(const RelinArgs &a, int 
     relin_limb_kernel<LOGM, L><<<nq * (a.k + 1), NttShape<LOGM>::T, bytes, st>>>(a);
 }
 template <int LOGM> static void run_relin_limb(int lazy, const RelinArgs &a, int nq, cudaStream_t st) {
-    if (lazy == 2) run_relin_limb_l<LOGM, 2>(a, nq, st);
+    if (lazy == 3) run_relin_limb_l<LOGM, 3>(a, nq, st);
+    else if (lazy == 2) run_relin_limb_l<LOGM, 2>(a, nq, st);
     else if (lazy == 1) run_relin_limb_l<LOGM, 1>(a, nq, st);
     else run_relin_limb_l<LOGM, 0>(a, nq, st);
 }

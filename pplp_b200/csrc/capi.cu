@@ -224,6 +224,19 @@ void Engine::upload_tables(int dev) {
         m.inv1_n_inv = T.inv1_n_inv;
         m.one_q = hm::shoup_quotient(1, T.q);
         m.bits = hm::bitlen(T.q);
+        m.fwd_d = m.inv_d = nullptr;
+        m.n_inv_d = m.inv1_n_inv_d = ShoupW{0, 0};
+        m.one_d = 0;
+        if (m.bits <= 45) {   // FP64-assisted tables: second word = bits of the correctly rounded double w/q (w, q < 2^53 are exact)
+            auto ratio = [&](u64 w) { const double c = (double)w / (double)T.q; u64 b; std::memcpy(&b, &c, 8); return b; };
+            std::vector<ShoupW> fd(T.fwd.size()), id(T.inv.size());
+            for (size_t t = 0; t < T.fwd.size(); ++t) { fd[t].w = T.fwd[t].w; fd[t].wq = ratio(T.fwd[t].w); id[t].w = T.inv[t].w; id[t].wq = ratio(T.inv[t].w); }
+            m.fwd_d = upload(fd.data(), fd.size());
+            m.inv_d = upload(id.data(), id.size());
+            m.n_inv_d = ShoupW{T.n_inv.w, ratio(T.n_inv.w)};
+            m.inv1_n_inv_d = ShoupW{T.inv1_n_inv.w, ratio(T.inv1_n_inv.w)};
+            m.one_d = ratio(1);
+        }
     }
     d_mods = upload(h_mods.data(), h_mods.size());
     std::vector<DevLevel> lv(host.levels.size());

@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(NttShape<LOGM>::T) encrypt_limb_kernel(const E
     const int ct = blockIdx.x / a.K, j = blockIdx.x % a.K;   // limbs of one ciphertext adjacent: noise stays in L2/L1
     const DevMod &md = a.mods[j];
     const Mod mod = md.m;
-    const NttConsts nc = ntt_consts(md);
+    const NttConsts nc = ntt_consts<L>(md);
     const u64 q = mod.q;
     const signed char *nz = a.noise + (size_t)ct * 3 * a.n;
 
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(NttShape<LOGM>::T) encrypt_limb_kernel(const E
         const int v = nz[i];
         x[r] = v < 0 ? q - 1 : (u64)v;
     });
-    block_ntt_forward<LOGM, Lazy<L>::F>(x, sm, tid, md.fwd, 0, 0, nc);
+    block_ntt_forward<LOGM, Lazy<L>::F>(x, sm, tid, fwd_table<L>(md), 0, 0, nc);
 #pragma unroll
     for (int r = 0; r < 16; ++r) uu[r] = forward_canon<Lazy<L>::F>(x[r], nc);
 #pragma unroll
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(NttShape<LOGM>::T) encrypt_limb_kernel(const E
             x[2 * c + 1] = mul_mod(uu[2 * c + 1], bv.y, mod);
         }
         __syncthreads();
-        block_ntt_inverse<LOGM, true, Lazy<L>::I>(x, sm, tid, md.inv, 0, 0, nc);
+        block_ntt_inverse<LOGM, true, Lazy<L>::I>(x, sm, tid, inv_table<L>(md), 0, 0, nc);
         u64 *out = a.tmp + (((size_t)ct * 2 + p) * a.K + j) * a.n;
         const signed char *e = nz + (size_t)(1 + p) * a.n;
         CoarsePass<LOGM>::for_each(tid, [&](int r, int i) {
@@ -254,7 +254,8 @@ template <int LOGM, int L> static void run_encrypt_limb_l(const EncLimbArgs &a, 
     encrypt_limb_kernel<LOGM, L><<<nct * a.K, NttShape<LOGM>::T, bytes, st>>>(a);
 }
 template <int LOGM> static void run_encrypt_limb(int lazy, const EncLimbArgs &a, int nct, cudaStream_t st) {
-    if (lazy == 2) run_encrypt_limb_l<LOGM, 2>(a, nct, st);
+    if (lazy == 3) run_encrypt_limb_l<LOGM, 3>(a, nct, st);
+    else if (lazy == 2) run_encrypt_limb_l<LOGM, 2>(a, nct, st);
     else if (lazy == 1) run_encrypt_limb_l<LOGM, 1>(a, nct, st);
     else run_encrypt_limb_l<LOGM, 0>(a, nct, st);
 }

@@ -73,6 +73,38 @@ __device__ __forceinline__ u64 shoup_tail(u64 a, u64 w, u64 h, u64 nq) {   // a*
 }
 __device__ __forceinline__ u64 mul_shoup_lazy_nq(u64 a, u64 w, u64 wq, u64 nq) { return shoup_tail(a, w, umulhi_cc(a, wq), nq); }
 
+// FP64-assisted product for moduli below 2^46 (BFVDefault at N <= 8192): the quotient estimate comes from ONE double
+// multiply-add on the FP64 pipe instead of a 64x64 high product (four wide multiplies on the integer-multiply pipe,
+// the pipe that bounds every transform).  Requires a < 2^51 and c = fl(w/q):
+//   a_d = a exactly (mantissa trick), p = RN(a_d*c + 2^52) so its mantissa holds h = RN(a*w/q + err), |h - a*w/q| < 1,
+//   result = a*w - (h-1)*q  in (0, 2q)  — the same lazy range as Shoup's product, so the bound analysis is unchanged.
+constexpr double kTwo52 = 4503599627370496.0;
+__device__ __forceinline__ u64 shoup_tail_add(u64 a, u64 w, u64 h, u64 nq, u64 addend) {   // a*w + h*nq + addend mod 2^64
+    const u32 a0 = (u32)a, a1 = (u32)(a >> 32), w0 = (u32)w, w1 = (u32)(w >> 32);
+    const u32 h0 = (u32)h, h1 = (u32)(h >> 32), n0 = (u32)nq, n1 = (u32)(nq >> 32);
+    u64 r;
+    asm("{\n\t.reg .u64 acc;\n\t.reg .u32 lo, hi;\n\t"
+        "mad.wide.u32 acc, %1, %3, %9;\n\t"
+        "mad.wide.u32 acc, %5, %7, acc;\n\t"
+        "mov.b64 {lo, hi}, acc;\n\t"
+        "mad.lo.u32 hi, %1, %4, hi;\n\t"
+        "mad.lo.u32 hi, %2, %3, hi;\n\t"
+        "mad.lo.u32 hi, %5, %8, hi;\n\t"
+        "mad.lo.u32 hi, %6, %7, hi;\n\t"
+        "mov.b64 %0, {lo, hi};\n\t}"
+        : "=l"(r)
+        : "r"(a0), "r"(a1), "r"(w0), "r"(w1), "r"(h0), "r"(h1), "r"(n0), "r"(n1), "l"(addend));
+    return r;
+}
+__device__ __forceinline__ u64 quotient_f64(u64 a, u64 c_bits) {   // RN(a * c), a < 2^51, as an integer
+    const double ad = __longlong_as_double((long long)(a | 0x4330000000000000ULL)) - kTwo52;
+    const double p = __fma_rn(ad, __longlong_as_double((long long)c_bits), kTwo52);
+    return (u64)__double_as_longlong(p) & 0x000FFFFFFFFFFFFFULL;
+}
+__device__ __forceinline__ u64 mul_f64_lazy(u64 a, u64 w, u64 c_bits, u64 q) { return shoup_tail_add(a, w, quotient_f64(a, c_bits), 0 - q, q); }
+// a mod q into (0,2q) for a < 2^51, with c_bits = fl(1/q)
+__device__ __forceinline__ u64 reduce_f64(u64 a, u64 one_d, u64 q) { return a + q - quotient_f64(a, one_d) * q; }
+
 // Barrett constants of a modulus: ratio = floor(2^128 / q) as (hi, lo).
 struct Mod { u64 q, r_hi, r_lo; };
 

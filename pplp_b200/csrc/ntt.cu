@@ -14,6 +14,11 @@
 #include "engine.hpp"
 #include "ntt.cuh"
 
+// CTAs per SM the stand-alone transforms are compiled for when N <= 8192 (2 => 64 registers per thread, 32 warps per SM)
+#ifndef PPLP_NTT_MIN_CTAS
+#define PPLP_NTT_MIN_CTAS 2
+#endif
+
 namespace pplp {
 
 struct NttArgs {
@@ -32,7 +37,7 @@ __device__ __forceinline__ void decode_row(int row, int nq, int npoly, int &qi, 
 }
 
 template <int LOGM, int L>
-__global__ void __launch_bounds__(NttShape<LOGM>::T, (LOGM <= 13 ? 2 : 1)) ntt_forward_kernel(const NttArgs a) {
+__global__ void __launch_bounds__(NttShape<LOGM>::T, (LOGM <= 13 ? PPLP_NTT_MIN_CTAS : 1)) ntt_forward_kernel(const NttArgs a) {
     using S = NttShape<LOGM>;
     extern __shared__ __align__(16) u64 sm[];
     const int tid = threadIdx.x;
@@ -41,12 +46,12 @@ __global__ void __launch_bounds__(NttShape<LOGM>::T, (LOGM <= 13 ? 2 : 1)) ntt_f
     int qi, p, j;
     decode_row(blockIdx.x / nblk, a.nq, a.npoly, qi, p, j);
     const DevMod &md = a.mods[a.map.mod_id[j]];
-    const NttConsts c = ntt_consts(md);
+    const NttConsts c = ntt_consts<L>(md);
     u64 *ptr = a.data + qi * a.lay.sq + p * a.lay.sp + j * a.lay.sl + (size_t)blk * S::M;
 
     u64 x[16];
     CoarsePass<LOGM>::for_each(tid, [&](int r, int i) { x[r] = ptr[i]; });
-    block_ntt_forward<LOGM, Lazy<L>::F>(x, sm, tid, md.fwd, a.stage_base, blk, c);
+    block_ntt_forward<LOGM, Lazy<L>::F>(x, sm, tid, fwd_table<L>(md), a.stage_base, blk, c);
 #pragma unroll
     for (int r = 0; r < 16; ++r) x[r] = forward_canon<Lazy<L>::F>(x[r], c);
     __syncthreads();
@@ -60,7 +65,7 @@ __global__ void __launch_bounds__(NttShape<LOGM>::T, (LOGM <= 13 ? 2 : 1)) ntt_f
 }
 
 template <int LOGM, int L>
-__global__ void __launch_bounds__(NttShape<LOGM>::T, (LOGM <= 13 ? 2 : 1)) ntt_inverse_kernel(const NttArgs a) {
+__global__ void __launch_bounds__(NttShape<LOGM>::T, (LOGM <= 13 ? PPLP_NTT_MIN_CTAS : 1)) ntt_inverse_kernel(const NttArgs a) {
     using S = NttShape<LOGM>;
     extern __shared__ __align__(16) u64 sm[];
     const int tid = threadIdx.x;
@@ -69,7 +74,7 @@ __global__ void __launch_bounds__(NttShape<LOGM>::T, (LOGM <= 13 ? 2 : 1)) ntt_i
     int qi, p, j;
     decode_row(blockIdx.x / nblk, a.nq, a.npoly, qi, p, j);
     const DevMod &md = a.mods[a.map.mod_id[j]];
-    const NttConsts c = ntt_consts(md);
+    const NttConsts c = ntt_consts<L>(md);
     u64 *ptr = a.data + qi * a.lay.sq + p * a.lay.sp + j * a.lay.sl + (size_t)blk * S::M;
 
 #pragma unroll
@@ -82,12 +87,12 @@ __global__ void __launch_bounds__(NttShape<LOGM>::T, (LOGM <= 13 ? 2 : 1)) ntt_i
     FinePass<LOGM>::load_smem(x, sm, tid);
     __syncthreads();
     if (a.stage_base == 0) {
-        block_ntt_inverse<LOGM, true, Lazy<L>::I>(x, sm, tid, md.inv, 0, 0, c);
+        block_ntt_inverse<LOGM, true, Lazy<L>::I>(x, sm, tid, inv_table<L>(md), 0, 0, c);
         CoarsePass<LOGM>::for_each(tid, [&](int r, int i) { ptr[i] = csub(x[r], c.q); });
     } else {
         // half of a 2M-point transform: never "free" (the bound analysis of ntt.cuh assumes the block is the whole transform)
         constexpr int IM = Lazy<L>::I == NTT_FREE ? NTT_PASS : Lazy<L>::I;
-        block_ntt_inverse<LOGM, false, IM>(x, sm, tid, md.inv, a.stage_base, blk, c);
+        block_ntt_inverse<LOGM, false, IM>(x, sm, tid, inv_table<L>(md), a.stage_base, blk, c);
         CoarsePass<LOGM>::for_each(tid, [&](int r, int i) { ptr[i] = x[r]; });  // lazily in [0,2q); stage-0 pass canonicalises
     }
 }
@@ -139,7 +144,7 @@ __global__ void __launch_bounds__(NttShape<LOGM>::T) polymul_kernel(const Polymu
     decode_row(blockIdx.x, a.nq, a.npoly, qi, p, j);
     const DevMod &md = a.mods[a.map.mod_id[j]];
     const Mod mod = md.m;
-    const NttConsts c = ntt_consts(md);
+    const NttConsts c = ntt_consts<L>(md);
     const u64 q = mod.q;
     const u64 *pa = a.a + qi * a.a_lay.sq + p * a.a_lay.sp + j * a.a_lay.sl;
     const u64 *pb = a.b + qi * a.b_lay.sq + p * a.b_lay.sp + j * a.b_lay.sl;
@@ -147,7 +152,7 @@ __global__ void __launch_bounds__(NttShape<LOGM>::T) polymul_kernel(const Polymu
 
     u64 x[16];
     CoarsePass<LOGM>::for_each(tid, [&](int r, int i) { x[r] = pa[i]; });
-    block_ntt_forward<LOGM, Lazy<L>::F>(x, sm, tid, md.fwd, 0, 0, c);
+    block_ntt_forward<LOGM, Lazy<L>::F>(x, sm, tid, fwd_table<L>(md), 0, 0, c);
     // dyadic product in the fine layout: thread owns coefficients 16*tid .. 16*tid+15 of the NTT-form operand
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -156,7 +161,7 @@ __global__ void __launch_bounds__(NttShape<LOGM>::T) polymul_kernel(const Polymu
         x[2 * k + 1] = mul_mod(forward_canon<Lazy<L>::F>(x[2 * k + 1], c), bv.y, mod);
     }
     __syncthreads();   // all threads are past their last smem read of the forward transform
-    block_ntt_inverse<LOGM, true, Lazy<L>::I>(x, sm, tid, md.inv, 0, 0, c);
+    block_ntt_inverse<LOGM, true, Lazy<L>::I>(x, sm, tid, inv_table<L>(md), 0, 0, c);
     if (a.c) {
         const u64 *pc = a.c + qi * a.c_lay.sq + p * a.c_lay.sp + j * a.c_lay.sl;
         CoarsePass<LOGM>::for_each(tid, [&](int r, int i) { po[i] = add_mod(csub(x[r], q), pc[i], q); });
@@ -190,7 +195,8 @@ template <int LOGM, int L> static void run_block_ntt(const NttArgs &a, int rows,
     }
 }
 template <int LOGM> static void run_block_ntt_l(int level, const NttArgs &a, int rows, bool inverse, cudaStream_t st) {
-    if (level == 2) run_block_ntt<LOGM, 2>(a, rows, inverse, st);
+    if (level == 3) run_block_ntt<LOGM, 3>(a, rows, inverse, st);
+    else if (level == 2) run_block_ntt<LOGM, 2>(a, rows, inverse, st);
     else if (level == 1) run_block_ntt<LOGM, 1>(a, rows, inverse, st);
     else run_block_ntt<LOGM, 0>(a, rows, inverse, st);
 }
@@ -233,7 +239,8 @@ template <int LOGM, int L> static void run_polymul(const PolymulArgs &a, int row
     polymul_kernel<LOGM, L><<<rows, NttShape<LOGM>::T, bytes, st>>>(a);
 }
 template <int LOGM> static void run_polymul_l(int level, const PolymulArgs &a, int rows, cudaStream_t st) {
-    if (level == 2) run_polymul<LOGM, 2>(a, rows, st);
+    if (level == 3) run_polymul<LOGM, 3>(a, rows, st);
+    else if (level == 2) run_polymul<LOGM, 2>(a, rows, st);
     else if (level == 1) run_polymul<LOGM, 1>(a, rows, st);
     else run_polymul<LOGM, 0>(a, rows, st);
 }

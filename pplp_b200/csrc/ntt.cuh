@@ -23,7 +23,7 @@
 
 namespace pplp {
 
-enum : int { NTT_CLASSIC = 0, NTT_PASS = 1, NTT_FREE = 2 };
+enum : int { NTT_CLASSIC = 0, NTT_PASS = 1, NTT_FREE = 2, NTT_F64 = 3 };
 
 // Which lazy-reduction mode a transform of 2^logn points may use for a modulus of `bits` bits (host and device agree).
 // forward free:  inputs < 4q, growth 2q per stage: (4 + 2 logn) q < 2^64  <=  q < 2^58 for logn <= 15
@@ -33,10 +33,13 @@ enum : int { NTT_CLASSIC = 0, NTT_PASS = 1, NTT_FREE = 2 };
 //   L = 0: classic forward, classic inverse    (any modulus below 2^62)
 //   L = 1: free forward, per-pass inverse      (modulus of at most 58 bits)
 //   L = 2: free forward, free inverse          (bits + 1 + log2 N <= 63)
-inline int ntt_lazy_level(int bits, int logn) { return bits > 58 ? 0 : (bits + 1 + logn <= 63 ? 2 : 1); }
+//   L = 3: FP64-assisted products (modarith.cuh mul_f64_lazy): free forward, per-pass inverse, every multiplicand
+//          below 2^51: forward (4 + 2 log2 N) q <= 34 q, inverse 2 (2q 2^3) = 32 q  =>  modulus of at most 45 bits
+//          (BFVDefault up to N = 8192).  Twiddle tables then carry (w, fl(w/q)) instead of (w, floor(w 2^64/q)).
+inline int ntt_lazy_level(int bits, int logn) { return bits <= 45 ? 3 : (bits > 58 ? 0 : (bits + 1 + logn <= 63 ? 2 : 1)); }
 template <int L> struct Lazy {
-    static constexpr int F = L == 0 ? NTT_CLASSIC : NTT_FREE;
-    static constexpr int I = L == 0 ? NTT_CLASSIC : (L == 1 ? NTT_PASS : NTT_FREE);
+    static constexpr int F = L == 0 ? NTT_CLASSIC : (L == 3 ? NTT_F64 : NTT_FREE);
+    static constexpr int I = L == 0 ? NTT_CLASSIC : (L == 1 ? NTT_PASS : (L == 3 ? NTT_F64 : NTT_FREE));
 };
 
 template <int LOGM> struct NttShape {
@@ -54,9 +57,19 @@ __device__ __forceinline__ int smem_slot(int i) { return i + (i >> 4); }
 
 // a mod q into [0,2q) for any 64-bit a: Shoup's product with the constant 1 (quotient floor(2^64/q)).
 __device__ __forceinline__ u64 reduce_lazy(u64 a, u64 one_q, u64 q) { return a - umulhi_cc(a, one_q) * q; }
+// mode-dispatched product by a table constant and lazy reduction (in NTT_F64 mode the second word of a twiddle and
+// `one_q` hold the bits of the doubles fl(w/q) and fl(1/q))
+template <int MODE> __device__ __forceinline__ u64 twiddle_mul(u64 a, const ShoupW w, const u64 q) {
+    if constexpr (MODE == NTT_F64) return mul_f64_lazy(a, w.w, w.wq, q);
+    else return mul_shoup_lazy_nq(a, w.w, w.wq, 0 - q);
+}
+template <int MODE> __device__ __forceinline__ u64 reduce_mode(u64 a, u64 one_q, u64 q) {
+    if constexpr (MODE == NTT_F64) return reduce_f64(a, one_q, q);
+    else return reduce_lazy(a, one_q, q);
+}
 
 template <int MODE> __device__ __forceinline__ void ct_butterfly(u64 &x, u64 &y, const ShoupW w, const u64 q, const u64 two_q) {
-    const u64 v = mul_shoup_lazy_nq(y, w.w, w.wq, 0 - q);
+    const u64 v = twiddle_mul<MODE>(y, w, q);
     if constexpr (MODE == NTT_CLASSIC) {   // Harvey: values stay in [0,4q)
         const u64 u = x >= two_q ? x - two_q : x;
         x = u + v;
@@ -72,7 +85,7 @@ template <int MODE> __device__ __forceinline__ void gs_butterfly(u64 &x, u64 &y,
     const u64 d = x - y + big;
     if constexpr (MODE == NTT_CLASSIC) x = s >= two_q ? s - two_q : s;
     else x = s;
-    y = mul_shoup_lazy_nq(d, w.w, w.wq, 0 - q);
+    y = twiddle_mul<MODE>(d, w, q);
 }
 
 __device__ __forceinline__ ShoupW ld_twiddle(const ShoupW *p) {
@@ -86,11 +99,15 @@ struct NttConsts {          // per-modulus scalars a transform needs besides the
     u64 q, two_q, one_q;    // one_q = floor(2^64 / q)
     ShoupW n_inv, inv1_n_inv;
 };
-__device__ __forceinline__ NttConsts ntt_consts(const DevMod &md) {
+template <int L> __device__ __forceinline__ NttConsts ntt_consts(const DevMod &md) {
     NttConsts c;
-    c.q = md.m.q; c.two_q = md.m.q << 1; c.one_q = md.one_q; c.n_inv = md.n_inv; c.inv1_n_inv = md.inv1_n_inv;
+    c.q = md.m.q; c.two_q = md.m.q << 1;
+    if constexpr (L == 3) { c.one_q = md.one_d; c.n_inv = md.n_inv_d; c.inv1_n_inv = md.inv1_n_inv_d; }
+    else { c.one_q = md.one_q; c.n_inv = md.n_inv; c.inv1_n_inv = md.inv1_n_inv; }
     return c;
 }
+template <int L> __device__ __forceinline__ const ShoupW *fwd_table(const DevMod &md) { return L == 3 ? md.fwd_d : md.fwd; }
+template <int L> __device__ __forceinline__ const ShoupW *inv_table(const DevMod &md) { return L == 3 ? md.inv_d : md.inv; }
 
 // Geometry of pass (S0,R) of a 2^LOGM block: thread `tid` owns NU = 16>>R radix-2^R butterflies; butterfly u covers
 // indices  (hi << (LG+R)) + (e << LG) + lo,  e = 0..2^R-1,  where c = tid + u*T, lo = c & (G-1), hi = c >> LG,
@@ -126,20 +143,24 @@ template <int LOGM, int S0, int R> struct Pass {
         constexpr int HALF = 1 << (R - 1 - V);
         const int tbase = (1 << (stage_base + S0 + V)) + (blk << (S0 + V)) + (h << V);
         // bound of the values entering this inverse stage, as a multiple of 2q (see gs_butterfly)
-        constexpr int GROW = MODE == NTT_FREE ? (LOGM - 1 - (S0 + V)) : (MODE == NTT_PASS ? (R - 1 - V) : 0);
+        constexpr int GROW = MODE == NTT_FREE ? (LOGM - 1 - (S0 + V)) : ((MODE == NTT_PASS || MODE == NTT_F64) ? (R - 1 - V) : 0);
         const u64 big = c.two_q << GROW;
         if constexpr (INVERSE && FOLD_SCALE && V == 0) {
 #pragma unroll
             for (int i = 0; i < HALF; ++i) {
                 u64 &a = x[u * RR + i], &b = x[u * RR + i + HALF];
                 const u64 s = a + b, d = a - b + big;
-                a = mul_shoup_lazy_nq(s, c.n_inv.w, c.n_inv.wq, 0 - c.q);          // Shoup accepts any 64-bit input
-                b = mul_shoup_lazy_nq(d, c.inv1_n_inv.w, c.inv1_n_inv.wq, 0 - c.q);
+                a = twiddle_mul<MODE>(s, c.n_inv, c.q);
+                b = twiddle_mul<MODE>(d, c.inv1_n_inv, c.q);
             }
         } else {
 #pragma unroll
             for (int g = 0; g < (1 << V); ++g) {
+#ifdef PPLP_NTT_FAKE_TWIDDLE   // timing experiment only (wrong results): every twiddle load hits one cached line
+                const ShoupW w = ld_twiddle(tw + ((tbase + g) & 7));
+#else
                 const ShoupW w = ld_twiddle(tw + tbase + g);
+#endif
 #pragma unroll
                 for (int i = 0; i < HALF; ++i) {
                     if constexpr (INVERSE) gs_butterfly<MODE>(x[u * RR + g * 2 * HALF + i], x[u * RR + g * 2 * HALF + i + HALF], w, c.q, c.two_q, big);
@@ -166,9 +187,9 @@ template <int LOGM, int S0, int R> struct Pass {
     // multiplies by N^-1:  x = (u+v) N^-1,  y = (u-v) (inv[1] N^-1).
     template <bool FOLD_SCALE, int MODE, bool REDUCE_FIRST = true>
     __device__ static __forceinline__ void inverse(u64 (&x)[16], int tid, const ShoupW *__restrict__ tw, int stage_base, int blk, const NttConsts &c) {
-        if constexpr (MODE == NTT_PASS && REDUCE_FIRST) {   // back to [0,2q) before this pass doubles the bound R times
+        if constexpr ((MODE == NTT_PASS || MODE == NTT_F64) && REDUCE_FIRST) {   // back to [0,2q) before this pass doubles the bound R times
 #pragma unroll
-            for (int r = 0; r < 16; ++r) x[r] = reduce_lazy(x[r], c.one_q, c.q);
+            for (int r = 0; r < 16; ++r) x[r] = reduce_mode<MODE>(x[r], c.one_q, c.q);
         }
 #pragma unroll
         for (int u = 0; u < NU; ++u) {
@@ -223,7 +244,7 @@ template <int MODE> __device__ __forceinline__ u64 forward_canon(u64 v, const Nt
         v = v >= c.two_q ? v - c.two_q : v;
         return v >= c.q ? v - c.q : v;
     } else {
-        return csub(reduce_lazy(v, c.one_q, c.q), c.q);
+        return csub(reduce_mode<MODE>(v, c.one_q, c.q), c.q);
     }
 }
 
@@ -257,7 +278,7 @@ __device__ __forceinline__ void block_ntt_inverse(u64 (&x)[16], u64 *sm, int tid
     CoarsePass<LOGM>::template inverse<FOLD_SCALE, MODE, (S::NFULL > 0)>(x, tid, tw, stage_base, blk, c);
     if constexpr (!FOLD_SCALE && MODE != NTT_CLASSIC) {
 #pragma unroll
-        for (int r = 0; r < 16; ++r) x[r] = reduce_lazy(x[r], c.one_q, c.q);
+        for (int r = 0; r < 16; ++r) x[r] = reduce_mode<MODE>(x[r], c.one_q, c.q);
     }
 }
 

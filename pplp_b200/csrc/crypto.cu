@@ -188,6 +188,96 @@ __global__ void __launch_bounds__(256) modswitch_kernel(const DevLevel *KLp, con
     }
 }
 
+// ---- split encryption pipeline (K > 1, N <= 16384) -------------------------------------------------------------------
+// The fused kernel above keeps NTT(u) and the running transform in registers (128 per thread, one CTA per SM).  Splitting
+// it lets every kernel run at two CTAs per SM and moves the modulus switch into the epilogue of the inverse transforms:
+//   enc_forward_kernel          U_j = NTT(u mod q_j), stored in NTT order                              (nct*K CTAs)
+//   enc_inverse_kernel<SPECIAL> T = INTT(U_P (.) pk_p,P) + e_p for the special prime P; stores (T + P/2) mod P   (nct*2 CTAs)
+//   enc_inverse_kernel<DATA>    per data limb: T = INTT(U_j (.) pk_p,j) + e_p, then divide-and-round by P using the stored
+//                               special-limb row, then c0 += round(Q m/t); writes the ciphertext directly (nct*2*k CTAs)
+struct EncSplitArgs {
+    const signed char *noise;   // [nct][3][n]
+    const u64 *pk;              // [2][K][n] NTT form
+    u64 *U;                     // [nct][K][n]
+    u64 *last;                  // [nct][2][n]
+    u64 *out;
+    Layout lay;
+    const u64 *plain;
+    int plain_count;
+    size_t plain_stride;
+    int K, n;
+    const DevMod *mods;
+    const DevLevel *KL, *DL;
+};
+
+template <int LOGM, int L>
+__global__ void __launch_bounds__(NttShape<LOGM>::T, (LOGM <= 13 ? 2 : 1)) enc_forward_kernel(const EncSplitArgs a) {
+    extern __shared__ __align__(16) u64 sm[];
+    const int tid = threadIdx.x;
+    const int ct = blockIdx.x / a.K, j = blockIdx.x % a.K;
+    const DevMod &md = a.mods[j];
+    const NttConsts nc = ntt_consts<L>(md);
+    const u64 q = nc.q;
+    const signed char *nz = a.noise + (size_t)ct * 3 * a.n;
+    u64 x[16];
+    CoarsePass<LOGM>::for_each(tid, [&](int r, int i) {
+        const int v = nz[i];
+        x[r] = v < 0 ? q - 1 : (u64)v;
+    });
+    block_ntt_forward<LOGM, Lazy<L>::F>(x, sm, tid, fwd_table<L>(md), 0, 0, nc);
+    ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(a.U + ((size_t)ct * a.K + j) * a.n + 16 * tid);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) dst[c] = make_ulonglong2(forward_canon<Lazy<L>::F>(x[2 * c], nc), forward_canon<Lazy<L>::F>(x[2 * c + 1], nc));
+}
+
+template <int LOGM, int L, bool SPECIAL>
+__global__ void __launch_bounds__(NttShape<LOGM>::T, (LOGM <= 13 ? 2 : 1)) enc_inverse_kernel(const EncSplitArgs a) {
+    extern __shared__ __align__(16) u64 sm[];
+    const int tid = threadIdx.x;
+    const int k = a.K - 1;
+    int ct, p, j;
+    if (SPECIAL) { ct = blockIdx.x >> 1; p = blockIdx.x & 1; j = a.K - 1; }
+    else { j = blockIdx.x % k; p = (blockIdx.x / k) & 1; ct = blockIdx.x / (2 * k); }
+    const DevMod &md = a.mods[j];
+    const Mod mod = md.m;
+    const NttConsts nc = ntt_consts<L>(md);
+    const u64 q = mod.q;
+    const ulonglong2 *up = reinterpret_cast<const ulonglong2 *>(a.U + ((size_t)ct * a.K + j) * a.n + 16 * tid);
+    const ulonglong2 *pkp = reinterpret_cast<const ulonglong2 *>(a.pk + ((size_t)p * a.K + j) * a.n + 16 * tid);
+    u64 x[16];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const ulonglong2 uv = up[c];
+        const ulonglong2 bv = __ldg(pkp + c);
+        x[2 * c] = mul_mod(uv.x, bv.x, mod);
+        x[2 * c + 1] = mul_mod(uv.y, bv.y, mod);
+    }
+    block_ntt_inverse<LOGM, true, Lazy<L>::I>(x, sm, tid, inv_table<L>(md), 0, 0, nc);
+    const signed char *e = a.noise + ((size_t)ct * 3 + 1 + p) * a.n;
+    u64 *lastp = a.last + ((size_t)ct * 2 + p) * a.n;
+    if (SPECIAL) {
+        const u64 half = a.KL->half_last;
+        CoarsePass<LOGM>::for_each(tid, [&](int r, int i) {
+            const int ev = e[i];
+            const u64 v = add_mod(csub(x[r], q), ev < 0 ? q - (u64)(-ev) : (u64)ev, q);
+            lastp[i] = add_mod(v, half, q);
+        });
+    } else {
+        const DevLevel &KL = *a.KL;
+        const u64 half_mod = KL.half_last_mod[j];
+        const ShoupW inv_last = KL.inv_last[j];
+        u64 *dst = a.out + ct * a.lay.sq + p * a.lay.sp + j * a.lay.sl;
+        CoarsePass<LOGM>::for_each(tid, [&](int r, int i) {
+            const int ev = e[i];
+            u64 v = add_mod(csub(x[r], q), ev < 0 ? q - (u64)(-ev) : (u64)ev, q);
+            const u64 corr = sub_mod(barrett64(lastp[i], mod), half_mod, q);
+            v = mul_shoup(sub_mod(v, corr, q), inv_last, q);
+            if (p == 0 && i < a.plain_count) v = add_mod(v, dev_scaled_plain(*a.DL, a.plain[ct * a.plain_stride + i], j), q);
+            dst[i] = v;
+        });
+    }
+}
+
 // single-prime chain (K == 1): no modulus switching, tmp is already the ciphertext
 __global__ void __launch_bounds__(256) copy_addplain_kernel(const DevLevel *DLp, const u64 *__restrict__ tmp, u64 *__restrict__ out, Layout lay,
                                                             const u64 *__restrict__ plain, int plain_count, size_t plain_stride) {
@@ -260,6 +350,22 @@ template <int LOGM> static void run_encrypt_limb(int lazy, const EncLimbArgs &a,
     else run_encrypt_limb_l<LOGM, 0>(a, nct, st);
 }
 
+template <int LOGM, int L> static void run_encrypt_split_l(const EncSplitArgs &a, int nct, cudaStream_t st) {
+    const int bytes = NttShape<LOGM>::SMEM_WORDS * 8, T = NttShape<LOGM>::T;
+    PPLP_CUDA(cudaFuncSetAttribute(enc_forward_kernel<LOGM, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    PPLP_CUDA(cudaFuncSetAttribute(enc_inverse_kernel<LOGM, L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    PPLP_CUDA(cudaFuncSetAttribute(enc_inverse_kernel<LOGM, L, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    enc_forward_kernel<LOGM, L><<<nct * a.K, T, bytes, st>>>(a);
+    enc_inverse_kernel<LOGM, L, true><<<nct * 2, T, bytes, st>>>(a);
+    enc_inverse_kernel<LOGM, L, false><<<nct * 2 * (a.K - 1), T, bytes, st>>>(a);
+}
+template <int LOGM> static void run_encrypt_split(int lazy, const EncSplitArgs &a, int nct, cudaStream_t st) {
+    if (lazy == 3) run_encrypt_split_l<LOGM, 3>(a, nct, st);
+    else if (lazy == 2) run_encrypt_split_l<LOGM, 2>(a, nct, st);
+    else if (lazy == 1) run_encrypt_split_l<LOGM, 1>(a, nct, st);
+    else run_encrypt_split_l<LOGM, 0>(a, nct, st);
+}
+
 void launch_encrypt(const Engine &E, const u64 *pk, const u64 *seeds, const u64 *plain, size_t plain_count, size_t plain_stride, u64 *ws, u64 *out,
                     Layout out_lay, int nct, int *errflag, cudaStream_t st) {
     E.require_device();
@@ -273,8 +379,21 @@ void launch_encrypt(const Engine &E, const u64 *pk, const u64 *seeds, const u64 
     dim3 gs((nrefill + kRefillsPerCta - 1) / kRefillsPerCta, nct);
     prng_stream_kernel<<<gs, 256, 0, st>>>(seeds, nrefill, stream);
     sample_encrypt_kernel<<<nct, 1024, 0, st>>>(stream, nrefill, n, noise, errflag);
-    EncLimbArgs a{noise, pk, tmp, K, n, E.d_mods};
     const int lazy = ntt_lazy_level(E.max_bits(E.qmap(0)), E.host.logn);
+    const size_t first = E.host.first_level();
+    if (K > 1 && E.host.logn <= 14) {   // split pipeline: forward, special-limb inverse, data-limb inverse + modulus switch + plaintext
+        EncSplitArgs sa{noise, pk, tmp, tmp + (size_t)nct * K * n, out, out_lay, plain, (int)plain_count, plain_stride, K, n, E.d_mods, E.d_levels, E.d_levels + first};
+        switch (E.host.logn) {
+        case 10: run_encrypt_split<10>(lazy, sa, nct, st); break;
+        case 11: run_encrypt_split<11>(lazy, sa, nct, st); break;
+        case 12: run_encrypt_split<12>(lazy, sa, nct, st); break;
+        case 13: run_encrypt_split<13>(lazy, sa, nct, st); break;
+        default: run_encrypt_split<14>(lazy, sa, nct, st); break;
+        }
+        PPLP_CUDA(cudaGetLastError());
+        return;
+    }
+    EncLimbArgs a{noise, pk, tmp, K, n, E.d_mods};
     switch (E.host.logn) {
     case 10: run_encrypt_limb<10>(lazy, a, nct, st); break;
     case 11: run_encrypt_limb<11>(lazy, a, nct, st); break;
@@ -295,7 +414,6 @@ void launch_encrypt(const Engine &E, const u64 *pk, const u64 *seeds, const u64 
     default: throw std::invalid_argument("pplp: encryption kernels support poly_modulus_degree 1024..32768");
     }
     dim3 gm((n + 255) / 256, nct * 2);
-    const size_t first = E.host.first_level();
     if (K > 1) modswitch_kernel<<<gm, 256, 0, st>>>(E.d_levels, E.d_levels + first, tmp, out, out_lay, plain, (int)plain_count, plain_stride);
     else copy_addplain_kernel<<<gm, 256, 0, st>>>(E.d_levels, tmp, out, out_lay, plain, (int)plain_count, plain_stride);
     PPLP_CUDA(cudaGetLastError());
@@ -303,12 +421,15 @@ void launch_encrypt(const Engine &E, const u64 *pk, const u64 *seeds, const u64 
 
 // ---- decryption ----------------------------------------------------------------------------------------------------
 // x [nq][k][n] (= c0 + c1 s (+ c2 s^2), canonical) -> m [nq][ncoeff]   ([SEAL] RNSTool::decrypt_scale_and_round)
-__global__ void __launch_bounds__(256) scale_round_kernel(const DevLevel *Lp, const u64 *__restrict__ x, u64 *__restrict__ plain, size_t plain_stride, int ncoeff) {
+// x is addressed as x[qi*xq + j*xl + i].
+__global__ void __launch_bounds__(256) scale_round_kernel(const DevLevel *Lp, const u64 *__restrict__ x, size_t xq, size_t xl, u64 *__restrict__ plain,
+                                                          size_t plain_stride, int ncoeff) {
     const DevLevel &L = *Lp;
-    const int k = L.k, n = L.n;
+    const int k = L.k;
+    const size_t n = xl;
     const int qi = blockIdx.y;
     const u64 t = L.t, gamma = L.gamma.q, gamma_half = gamma >> 1;
-    const u64 *src = x + (size_t)qi * k * n;
+    const u64 *src = x + (size_t)qi * xq;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ncoeff; i += gridDim.x * blockDim.x) {
         U128 at{0, 0}, ag{0, 0};
         for (int j = 0; j < k; ++j) {
@@ -353,10 +474,54 @@ __global__ void add_rows_kernel(const DevMod *mods, u64 *__restrict__ acc, const
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) d[i] = add_mod(d[i], s[i], q);
 }
 
+// ---- constant-coefficient decryption ---------------------------------------------------------------------------------
+// The protocol only ever reads coefficient 0 of the plaintext (src/client.cc:153-154 parses it as one hex number).  In
+// R_q = Z_q[x]/(x^N + 1):  (c1 s)[0] = c1[0] s[0] - sum_{i>=1} c1[i] s[N-i], a dot product in the coefficient domain,
+// so x_j[0] = c0_j[0] + <c1_j, sneg_j> needs no transform at all: one streaming read of c1.  Exact modular arithmetic,
+// hence the same canonical residues as the NTT route.
+__global__ void negacyclic_flip_kernel(const DevMod *mods, const u64 *__restrict__ s_coef, u64 *__restrict__ sneg, int n) {
+    const int j = blockIdx.y;
+    const u64 q = mods[j].m.q;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        sneg[(size_t)j * n + i] = i == 0 ? s_coef[(size_t)j * n] : neg_mod(s_coef[(size_t)j * n + (n - i)], q);
+}
+// grid.x = query * k + limb; xout [nq][k]
+__global__ void __launch_bounds__(256) coeff0_dot_kernel(const DevMod *mods, const u64 *__restrict__ ct, Layout lay, const u64 *__restrict__ sneg, u64 *__restrict__ xout, int k,
+                                                         int n) {
+    __shared__ u64 part[8];
+    const int qi = blockIdx.x / k, j = blockIdx.x % k;
+    const Mod mq = mods[j].m;
+    const u64 *c1 = ct + qi * lay.sq + lay.sp + j * lay.sl;
+    const u64 *sn = sneg + (size_t)j * n;
+    u64 sum = 0;
+    U128 acc{0, 0};
+    int pending = 0;
+    for (int i = 2 * threadIdx.x; i < n; i += 512) {
+        const ulonglong2 a = ldg_stream(c1 + i);
+        const ulonglong2 b = __ldg(reinterpret_cast<const ulonglong2 *>(sn + i));
+        mac128(acc, a.x, b.x);
+        mac128(acc, a.y, b.y);
+        if (++pending == 16) {   // 32 products below 2^122 each: fold before the 128-bit accumulator can wrap
+            sum = add_mod(sum, barrett128(acc.lo, acc.hi, mq), mq.q);
+            acc = U128{0, 0};
+            pending = 0;
+        }
+    }
+    sum = add_mod(sum, barrett128(acc.lo, acc.hi, mq), mq.q);
+    for (int o = 16; o > 0; o >>= 1) sum = add_mod(sum, __shfl_xor_sync(0xffffffffu, sum, o), mq.q);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u64 total = ct[qi * lay.sq + j * lay.sl];   // c0_j[0]
+        for (int w = 0; w < 8; ++w) total = add_mod(total, part[w], mq.q);
+        xout[(size_t)qi * k + j] = total;
+    }
+}
+
 size_t decrypt_tmp_words(const Engine &E, size_t level, int nq, int size) {
     const size_t k = E.host.levels[level].q.size(), n = E.host.n;
     const bool generic = size > 2 || E.host.logn == 15;
-    return (size_t)nq * k * n * (generic ? 3 : 1);
+    return (size_t)nq * k * n * (generic ? 3 : 1) + 2 * k * n + 16;   // + room for the constant-coefficient path's key images
 }
 
 void launch_decrypt(const Engine &E, size_t level, const u64 *ct, Layout lay, int nq, int size, const u64 *sk, u64 *tmp, u64 *plain_out, size_t plain_stride,
@@ -366,6 +531,16 @@ void launch_decrypt(const Engine &E, size_t level, const u64 *ct, Layout lay, in
     const int k = (int)E.host.levels[level].q.size(), n = (int)E.host.n;
     RowMap map = E.qmap(level);
     const Layout tl{(size_t)k * n, 0, (size_t)n};
+    if (size == 2 && ncoeff == 1) {
+        u64 *s_coef = tmp, *sneg = tmp + (size_t)k * n, *xout = sneg + (size_t)k * n;
+        PPLP_CUDA(cudaMemcpyAsync(s_coef, sk, (size_t)k * n * 8, cudaMemcpyDeviceToDevice, st));   // data limb j == key limb j
+        launch_ntt(E, s_coef, tl, 1, 1, map, true, st);
+        negacyclic_flip_kernel<<<dim3((n + 255) / 256, k), 256, 0, st>>>(E.d_mods, s_coef, sneg, n);
+        coeff0_dot_kernel<<<nq * k, 256, 0, st>>>(E.d_mods, ct, lay, sneg, xout, k, n);
+        scale_round_kernel<<<dim3(1, nq), 32, 0, st>>>(E.d_levels + level, xout, (size_t)k, 1, plain_out, plain_stride, 1);
+        PPLP_CUDA(cudaGetLastError());
+        return;
+    }
     if (size == 2 && E.host.logn <= 14) {
         // x = INTT(NTT(c1) (.) s) + c0 in one kernel
         Layout a_lay = lay, c_lay = lay;
@@ -389,7 +564,7 @@ void launch_decrypt(const Engine &E, size_t level, const u64 *ct, Layout lay, in
         add_rows_kernel<<<g, 256, 0, st>>>(E.d_mods, tmp, ct, lay, 0, k, n);
     }
     dim3 gs((ncoeff + 255) / 256, nq);
-    scale_round_kernel<<<gs, 256, 0, st>>>(E.d_levels + level, tmp, plain_out, plain_stride, ncoeff);
+    scale_round_kernel<<<gs, 256, 0, st>>>(E.d_levels + level, tmp, (size_t)k * n, (size_t)n, plain_out, plain_stride, ncoeff);
     PPLP_CUDA(cudaGetLastError());
 }
 

@@ -518,3 +518,24 @@ def test_bloom_wire_format_matches_reference_golden(eng, oracle):
         d2 = np.array([0, 1, case["n"] - 1, case["n"], 3 * case["n"]], dtype=np.uint64)
         bd = (np.uint64(case["s"]) * (d2 + np.uint64(case["r"]))) & np.uint64(T56 - 1)
         assert (eng.to_np(back.query(ctx.dev(bd)), np.uint8) == eng.to_np(bf.query(ctx.dev(bd)), np.uint8)).all()
+
+
+@pytest.mark.parametrize("n", [4096, 8192, 16384, 32768])
+def test_constant_coefficient_decrypt_equals_full_decrypt(eng, oracle, n):
+    """ncoeff = 1 takes the transform-free dot-product route ((c1 s)[0] = c1[0]s[0] - sum c1[i] s[N-i]); it must return
+    exactly coefficient 0 of the full decryption, also for ciphertexts that are pure noise, in both layouts."""
+    ctx, octx = contexts(eng, oracle, n)
+    osk, _ = octx.keygen()
+    sk = ctx.dev(osk)
+    rng = np.random.default_rng(n + 77)
+    q = octx.q[: ctx.k]
+    nq = 5
+    junk = np.stack([np.stack([rand_residues(rng, q, n) for _ in range(2)]) for _ in range(nq)])
+    full = eng.to_np(ctx.decrypt(ctx.dev(junk), sk))
+    one = eng.to_np(ctx.decrypt(ctx.dev(junk), sk, ncoeff=1))
+    assert (one[:, 0] == full[:, 0]).all()
+    ref = octx.decrypt(osk, junk[0])
+    assert int(one[0, 0]) == int(ref[0])
+    lm = ctx.dev(np.ascontiguousarray(junk.transpose(2, 1, 0, 3)))
+    one_lm = eng.to_np(ctx.decrypt(lm, sk, ncoeff=1, layout=eng.LAYOUT_LIMB_MAJOR))
+    assert (one_lm[:, 0] == full[:, 0]).all()

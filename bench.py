@@ -379,6 +379,21 @@ def run_extras(engine, ctx, torch, osk, opk):
         ex["protocol_e2e"] = {"value": nq * reps / dt, "unit": UNIT, "queries_per_step": nq,
                               "what": "host coords -> 3 encrypts + Circuit A + decrypt + Bloom verdict -> host verdicts (pplp_proximity_batch_host)",
                               "blind_distances_correct": bool((blind == expect).all()), "near_fraction": float(verdict.mean())}
+        # the same protocol on the host cores (CPU restatement), a small sample: context for the number above
+        from tests import oracle_lib
+        from tests.oracle_lib import OracleBloom
+        orc = oracle_lib.load()
+        octx = orc.context(N, ctx.q, T, seed=seed8(7))
+        ob = OracleBloom(orc.lib, "orc", radius * radius, 1e-4)
+        ob.insert_blinded_range(r, s, w, radius * radius)
+        threads = host_threads()
+        ns = max(threads, 2 * threads)
+        t0 = time.perf_counter()
+        cb, cv, stage_ns = octx.protocol_batch(opk, osk, xa[:ns], ya[:ns], xb[:ns], yb[:ns], r, s, w, seeds[: ns * 3], bloom=ob, nthreads=threads)
+        cdt = time.perf_counter() - t0
+        ex["protocol_cpu"] = {"value": ns / cdt, "unit": UNIT, "cores": threads, "sample": f"{ns} queries", "kind": "port",
+                              "agrees_with_gpu": bool((cb == blind[:ns]).all() and (cv == verdict[:ns]).all()),
+                              "stage_ms_per_query": {k: float(v) / ns / 1e6 for k, v in zip(["d_enc", "d_homoCalc", "d_dec", "d_bfQuery"], stage_ns)}}
     except Exception as e:   # extras never invalidate the headline
         ex["protocol_e2e"] = {"error": str(e)[:200]}
     try:

@@ -227,12 +227,27 @@ void Engine::upload_tables(int dev) {
         m.fwd_d = m.inv_d = nullptr;
         m.n_inv_d = m.inv1_n_inv_d = ShoupW{0, 0};
         m.one_d = 0;
+        m.fine_fwd = m.fine_inv = m.fine_fwd_d = m.fine_inv_d = nullptr;
+        const int logn = host.logn;
+        auto fine = [&](const std::vector<ShoupW> &tab) -> const ShoupW * {   // thread-interleaved last four stages
+            if (logn < 4) return nullptr;
+            const size_t nt = host.n / 16;
+            std::vector<ShoupW> f(15 * nt);
+            for (int V = 0; V < 4; ++V)
+                for (size_t g = 0; g < (size_t(1) << V); ++g)
+                    for (size_t t = 0; t < nt; ++t) f[((size_t(1) << V) - 1 + g) * nt + t] = tab[(size_t(1) << (logn - 4 + V)) + (t << V) + g];
+            return upload(f.data(), f.size());
+        };
+        m.fine_fwd = fine(T.fwd);
+        m.fine_inv = fine(T.inv);
         if (m.bits <= 45) {   // FP64-assisted tables: second word = bits of the correctly rounded double w/q (w, q < 2^53 are exact)
             auto ratio = [&](u64 w) { const double c = (double)w / (double)T.q; u64 b; std::memcpy(&b, &c, 8); return b; };
             std::vector<ShoupW> fd(T.fwd.size()), id(T.inv.size());
             for (size_t t = 0; t < T.fwd.size(); ++t) { fd[t].w = T.fwd[t].w; fd[t].wq = ratio(T.fwd[t].w); id[t].w = T.inv[t].w; id[t].wq = ratio(T.inv[t].w); }
             m.fwd_d = upload(fd.data(), fd.size());
             m.inv_d = upload(id.data(), id.size());
+            m.fine_fwd_d = fine(fd);
+            m.fine_inv_d = fine(id);
             m.n_inv_d = ShoupW{T.n_inv.w, ratio(T.n_inv.w)};
             m.inv1_n_inv_d = ShoupW{T.inv1_n_inv.w, ratio(T.inv1_n_inv.w)};
             m.one_d = ratio(1);

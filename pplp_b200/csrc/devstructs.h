@@ -22,6 +22,9 @@ struct DevMod {
     const ShoupW *inv_d;
     ShoupW n_inv_d, inv1_n_inv_d;
     u64 one_d;            // bits of fl(1/q)
+    // thread-interleaved copies of the twiddles of the last four stages: entry ((2^V - 1 + g) * N/16 + t) is the twiddle of
+    // stage logN-4+V, group (t << V) + g  — what thread t of the fine pass needs, laid out so a warp's load coalesces
+    const ShoupW *fine_fwd, *fine_inv, *fine_fwd_d, *fine_inv_d;
 };
 
 // How a batch of polynomials lies in HBM.  Element (query qi, poly p, limb j, coeff n) is at

@@ -98,12 +98,13 @@ __device__ __forceinline__ ShoupW ld_twiddle(const ShoupW *p) {
 struct NttConsts {          // per-modulus scalars a transform needs besides the twiddle table
     u64 q, two_q, one_q;    // one_q = floor(2^64 / q)
     ShoupW n_inv, inv1_n_inv;
+    const ShoupW *fine_fwd, *fine_inv;   // thread-interleaved twiddles of the last four stages (see Pass::stage)
 };
 template <int L> __device__ __forceinline__ NttConsts ntt_consts(const DevMod &md) {
     NttConsts c;
     c.q = md.m.q; c.two_q = md.m.q << 1;
-    if constexpr (L == 3) { c.one_q = md.one_d; c.n_inv = md.n_inv_d; c.inv1_n_inv = md.inv1_n_inv_d; }
-    else { c.one_q = md.one_q; c.n_inv = md.n_inv; c.inv1_n_inv = md.inv1_n_inv; }
+    if constexpr (L == 3) { c.one_q = md.one_d; c.n_inv = md.n_inv_d; c.inv1_n_inv = md.inv1_n_inv_d; c.fine_fwd = md.fine_fwd_d; c.fine_inv = md.fine_inv_d; }
+    else { c.one_q = md.one_q; c.n_inv = md.n_inv; c.inv1_n_inv = md.inv1_n_inv; c.fine_fwd = md.fine_fwd; c.fine_inv = md.fine_inv; }
     return c;
 }
 template <int L> __device__ __forceinline__ const ShoupW *fwd_table(const DevMod &md) { return L == 3 ? md.fwd_d : md.fwd; }
@@ -159,7 +160,12 @@ template <int LOGM, int S0, int R> struct Pass {
 #ifdef PPLP_NTT_FAKE_TWIDDLE   // timing experiment only (wrong results): every twiddle load hits one cached line
                 const ShoupW w = ld_twiddle(tw + ((tbase + g) & 7));
 #else
-                const ShoupW w = ld_twiddle(tw + tbase + g);
+                // The last four stages give every thread its own 15 twiddles.  In the natural table a warp's load
+                // touches 32 separate 128-byte lines; the "fine" copy stores them thread-interleaved
+                // ([stage-local twiddle][thread]) so the same load is one coalesced 512-byte access.
+                ShoupW w;
+                if constexpr (LG == 0) w = ld_twiddle((INVERSE ? c.fine_inv : c.fine_fwd) + (size_t)((1 << V) - 1 + g) * (T << stage_base) + (blk * T + h));
+                else w = ld_twiddle(tw + tbase + g);
 #endif
 #pragma unroll
                 for (int i = 0; i < HALF; ++i) {

@@ -138,9 +138,10 @@ int pplp_circuit_a_host(pplp_ctx *ctx, size_t level, const uint64_t *h_c0, const
  * 3 polynomials in `layout`.  pplp_square(a) == pplp_multiply(a, a). */
 int pplp_multiply(pplp_ctx *ctx, size_t level, const uint64_t *d_a, const uint64_t *d_b, uint64_t *d_out, int layout, size_t nq, void *stream);
 int pplp_square(pplp_ctx *ctx, size_t level, const uint64_t *d_a, uint64_t *d_out, int layout, size_t nq, void *stream);
-/* Evaluator::relinearize_inplace (north_star): size-3 -> size-2 with keys from pplp_relin_keygen.  d_rk_quot holds the
- * keys' Shoup quotients floor(w * 2^64 / q) from pplp_relin_prepare (computed once per key set); NULL recomputes them
- * into scratch on every call.  d_out: nq ciphertexts of 2 polynomials. */
+/* Evaluator::relinearize_inplace (north_star): size-3 -> size-2 with keys from pplp_relin_keygen.  d_rk_quot is the
+ * prepared key image from pplp_relin_prepare (computed once per key set): TWICE the size of d_rk, {key word, Shoup
+ * quotient floor(w * 2^64 / q)} pairs in the kernels' coalesced register order; NULL rebuilds it into scratch on every
+ * call.  d_out: nq ciphertexts of 2 polynomials. */
 int pplp_relin_prepare(pplp_ctx *ctx, const uint64_t *d_rk, uint64_t *d_rk_quot, void *stream);
 int pplp_relinearize(pplp_ctx *ctx, size_t level, const uint64_t *d_in, uint64_t *d_out, int layout, size_t nq, const uint64_t *d_rk,
                      const uint64_t *d_rk_quot, void *stream);

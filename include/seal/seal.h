@@ -11,7 +11,8 @@
 //   * Errors: std::invalid_argument / std::logic_error / std::runtime_error exactly where SEAL throws them on the
 //     reference's path (invalid parameters are recorded in the context, not thrown).
 //   * There is no CPU fallback: constructing a SEALContext needs a CUDA device (PPLP_DEVICE selects it, default 0).
-// Wire formats: SEAL 4.1 streams, compr_mode zlib (default here) and none; see DESIGN.md "wire formats".
+// Wire formats: SEAL 4.1 streams in compr_mode none, zlib and zstd (default: zstd when libzstd.so.1 loads, else zlib);
+// see DESIGN.md "wire formats".
 #pragma once
 #include <dlfcn.h>
 #include <zlib.h>
@@ -855,7 +856,7 @@ public:
         if (pplp_ctx_num_levels(core_->h) < 2) throw std::logic_error("keyswitching is not supported by the context");
         const std::size_t nd = core_->limbs(1), per = 2 * core_->K * core_->n;
         destination.words_.resize(core_, nd * per);
-        destination.quotients_.resize(core_, nd * per);
+        destination.quotients_.resize(core_, 2 * nd * per);   // {word, Shoup quotient} pairs
         destination.digits_ = nd;
         destination.id_ = core_->id(0);
         std::vector<std::uint64_t> seeds(nd * 8);

@@ -166,12 +166,17 @@ void launch_multiply(const Engine &E, size_t level, const u64 *a, const u64 *b, 
 
 // ---- relinearisation -------------------------------------------------------------------------------------------------
 // quot[i] = floor(w[i] * 2^64 / q_limb): Shoup quotients of key words, computed once per key.  rows of n words, limb = row % K.
-__global__ void shoup_quot_kernel(const DevMod *mods, const u64 *__restrict__ w, u64 *__restrict__ quot, int K, int n) {
+// The prepared image holds {w, quotient} pairs (one 128-bit load per key coefficient) in the thread-interleaved order of
+// the kernels' fine register layout: coefficient 16 t + r of a row sits at pair index r * (n/16) + t, so a warp's load
+// of "its r-th coefficient" is one coalesced 512-byte access.
+__global__ void shoup_quot_kernel(const DevMod *mods, const u64 *__restrict__ w, u64 *__restrict__ prepared, int K, int n) {
     const int row = blockIdx.y;
     const u64 q = mods[row % K].m.q;
+    const int T = n / 16;
+    ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(prepared) + (size_t)row * n;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const size_t o = (size_t)row * n + i;
-        quot[o] = (u64)((((unsigned __int128)w[o]) << 64) / q);
+        const u64 v = w[(size_t)row * n + i];
+        dst[(size_t)(i & 15) * T + (i >> 4)] = make_ulonglong2(v, (u64)((((unsigned __int128)v) << 64) / q));
     }
 }
 void launch_shoup_quotients(const Engine &E, const u64 *w, u64 *quot, int nrows, cudaStream_t st) {
@@ -213,19 +218,15 @@ __global__ void __launch_bounds__(NttShape<LOGM>::T) relin_limb_kernel(const Rel
         if (J == key_index) CoarsePass<LOGM>::for_each(tid, [&](int r, int i) { x[r] = row[i]; });
         else CoarsePass<LOGM>::for_each(tid, [&](int r, int i) { x[r] = barrett64(row[i], mod); });
         block_ntt_forward<LOGM, Lazy<L>::F>(x, sm, tid, fwd_table<L>(md), 0, 0, nc);
-        const size_t koff = (((size_t)J * 2 + 0) * a.K + key_index) * a.n + 16 * tid;
-        const size_t koff1 = koff + (size_t)a.K * a.n;
+        const ulonglong2 *k0 = reinterpret_cast<const ulonglong2 *>(a.rkq) + (((size_t)J * 2 + 0) * a.K + key_index) * a.n + tid;
+        const ulonglong2 *k1 = k0 + (size_t)a.K * a.n;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const ulonglong2 w0 = __ldg(reinterpret_cast<const ulonglong2 *>(a.rk + koff + 2 * c));
-            const ulonglong2 g0 = __ldg(reinterpret_cast<const ulonglong2 *>(a.rkq + koff + 2 * c));
-            const ulonglong2 w1 = __ldg(reinterpret_cast<const ulonglong2 *>(a.rk + koff1 + 2 * c));
-            const ulonglong2 g1 = __ldg(reinterpret_cast<const ulonglong2 *>(a.rkq + koff1 + 2 * c));
+        for (int r = 0; r < 16; ++r) {
+            const ulonglong2 w0 = __ldg(k0 + (size_t)r * S::T);   // {key word, Shoup quotient} of coefficient 16 tid + r
+            const ulonglong2 w1 = __ldg(k1 + (size_t)r * S::T);
             u64 v;
-            v = acc0[2 * c] + mul_shoup_lazy(x[2 * c], w0.x, g0.x, q);         acc0[2 * c] = v >= two_q ? v - two_q : v;
-            v = acc0[2 * c + 1] + mul_shoup_lazy(x[2 * c + 1], w0.y, g0.y, q); acc0[2 * c + 1] = v >= two_q ? v - two_q : v;
-            v = acc1[2 * c] + mul_shoup_lazy(x[2 * c], w1.x, g1.x, q);         acc1[2 * c] = v >= two_q ? v - two_q : v;
-            v = acc1[2 * c + 1] + mul_shoup_lazy(x[2 * c + 1], w1.y, g1.y, q); acc1[2 * c + 1] = v >= two_q ? v - two_q : v;
+            v = acc0[r] + mul_shoup_lazy_nq(x[r], w0.x, w0.y, 0 - q); acc0[r] = v >= two_q ? v - two_q : v;
+            v = acc1[r] + mul_shoup_lazy_nq(x[r], w1.x, w1.y, 0 - q); acc1[r] = v >= two_q ? v - two_q : v;
         }
         __syncthreads();   // the next digit reuses the staging buffer
     }

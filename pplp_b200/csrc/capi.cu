@@ -629,7 +629,7 @@ int pplp_relinearize(pplp_ctx *ctx, size_t level, const uint64_t *d_in, uint64_t
     const int nqi = to_int(nq, "query count");
     cudaStream_t st = S(stream);
     const size_t nd = E.host.levels[1].q.size();
-    Scratch ws(relin_tmp_words(E, level, nqi) * 8, st), quot(d_rk_quot ? 8 : nd * 2 * K * n * 8, st);
+    Scratch ws(relin_tmp_words(E, level, nqi) * 8, st), quot(d_rk_quot ? 8 : nd * 2 * K * n * 16, st);
     if (!d_rk_quot) launch_shoup_quotients(E, d_rk, quot.as<u64>(), (int)(nd * 2 * K), st);
     launch_relinearize(E, level, d_in, make_layout(layout, n, k, 3, nq), d_out, make_layout(layout, n, k, 2, nq), nqi, d_rk,
                        d_rk_quot ? d_rk_quot : quot.as<u64>(), ws.as<u64>(), st);

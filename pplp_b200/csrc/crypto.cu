@@ -195,6 +195,15 @@ __global__ void __launch_bounds__(256) modswitch_kernel(const DevLevel *KLp, con
 //   enc_inverse_kernel<SPECIAL> T = INTT(U_P (.) pk_p,P) + e_p for the special prime P; stores (T + P/2) mod P   (nct*2 CTAs)
 //   enc_inverse_kernel<DATA>    per data limb: T = INTT(U_j (.) pk_p,j) + e_p, then divide-and-round by P using the stored
 //                               special-limb row, then c0 += round(Q m/t); writes the ciphertext directly (nct*2*k CTAs)
+// rows of n words -> thread-interleaved order of the fine register layout: pair c of thread t (words 16t+2c, 16t+2c+1)
+// moves to pair index c*(n/16) + t
+__global__ void interleave_fine_kernel(const u64 *__restrict__ src, u64 *__restrict__ dst, int n) {
+    const ulonglong2 *s = reinterpret_cast<const ulonglong2 *>(src + (size_t)blockIdx.y * n);
+    ulonglong2 *d = reinterpret_cast<ulonglong2 *>(dst + (size_t)blockIdx.y * n);
+    const int T = n / 16;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n / 2; i += gridDim.x * blockDim.x) d[(i & 7) * T + (i >> 3)] = s[i];
+}
+
 struct EncSplitArgs {
     const signed char *noise;   // [nct][3][n]
     const u64 *pk;              // [2][K][n] NTT form
@@ -225,9 +234,10 @@ __global__ void __launch_bounds__(NttShape<LOGM>::T, (LOGM <= 13 ? 2 : 1)) enc_f
         x[r] = v < 0 ? q - 1 : (u64)v;
     });
     block_ntt_forward<LOGM, Lazy<L>::F>(x, sm, tid, fwd_table<L>(md), 0, 0, nc);
-    ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(a.U + ((size_t)ct * a.K + j) * a.n + 16 * tid);
+    // thread-interleaved order (pair c of thread t at [c*T + t]): the store and the later loads coalesce
+    ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(a.U + ((size_t)ct * a.K + j) * a.n);
 #pragma unroll
-    for (int c = 0; c < 8; ++c) dst[c] = make_ulonglong2(forward_canon<Lazy<L>::F>(x[2 * c], nc), forward_canon<Lazy<L>::F>(x[2 * c + 1], nc));
+    for (int c = 0; c < 8; ++c) dst[c * NttShape<LOGM>::T + tid] = make_ulonglong2(forward_canon<Lazy<L>::F>(x[2 * c], nc), forward_canon<Lazy<L>::F>(x[2 * c + 1], nc));
 }
 
 template <int LOGM, int L, bool SPECIAL>
@@ -242,13 +252,13 @@ __global__ void __launch_bounds__(NttShape<LOGM>::T, (LOGM <= 13 ? 2 : 1)) enc_i
     const Mod mod = md.m;
     const NttConsts nc = ntt_consts<L>(md);
     const u64 q = mod.q;
-    const ulonglong2 *up = reinterpret_cast<const ulonglong2 *>(a.U + ((size_t)ct * a.K + j) * a.n + 16 * tid);
-    const ulonglong2 *pkp = reinterpret_cast<const ulonglong2 *>(a.pk + ((size_t)p * a.K + j) * a.n + 16 * tid);
+    const ulonglong2 *up = reinterpret_cast<const ulonglong2 *>(a.U + ((size_t)ct * a.K + j) * a.n);
+    const ulonglong2 *pkp = reinterpret_cast<const ulonglong2 *>(a.pk + ((size_t)p * a.K + j) * a.n);   // interleaved copy of the key
     u64 x[16];
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-        const ulonglong2 uv = up[c];
-        const ulonglong2 bv = __ldg(pkp + c);
+        const ulonglong2 uv = up[c * NttShape<LOGM>::T + tid];
+        const ulonglong2 bv = __ldg(pkp + c * NttShape<LOGM>::T + tid);
         x[2 * c] = mul_mod(uv.x, bv.x, mod);
         x[2 * c + 1] = mul_mod(uv.y, bv.y, mod);
     }
@@ -334,7 +344,7 @@ size_t encrypt_tmp_words(const Engine &E, int nct) {
     const size_t stream = (size_t)nct * encrypt_stream_refills((int)n) * (kRefillBytes / 8);
     const size_t noise = ((size_t)nct * 3 * n + 7) / 8 + 2;
     const size_t tmp = (size_t)nct * 2 * K * n;
-    const size_t extra = E.host.logn == 15 ? (size_t)nct * K * n : 0;
+    const size_t extra = E.host.logn == 15 ? (size_t)nct * K * n : 2 * K * n;   // N = 32768: NTT(u) rows; else the interleaved key
     return stream + noise + tmp + extra + 8;
 }
 
@@ -382,7 +392,8 @@ void launch_encrypt(const Engine &E, const u64 *pk, const u64 *seeds, const u64 
     const int lazy = ntt_lazy_level(E.max_bits(E.qmap(0)), E.host.logn);
     const size_t first = E.host.first_level();
     if (K > 1 && E.host.logn <= 14) {   // split pipeline: forward, special-limb inverse, data-limb inverse + modulus switch + plaintext
-        EncSplitArgs sa{noise, pk, tmp, tmp + (size_t)nct * K * n, out, out_lay, plain, (int)plain_count, plain_stride, K, n, E.d_mods, E.d_levels, E.d_levels + first};
+        interleave_fine_kernel<<<dim3((n / 2 + 255) / 256, 2 * K), 256, 0, st>>>(pk, extra, n);
+        EncSplitArgs sa{noise, extra, tmp, tmp + (size_t)nct * K * n, out, out_lay, plain, (int)plain_count, plain_stride, K, n, E.d_mods, E.d_levels, E.d_levels + first};
         switch (E.host.logn) {
         case 10: run_encrypt_split<10>(lazy, sa, nct, st); break;
         case 11: run_encrypt_split<11>(lazy, sa, nct, st); break;

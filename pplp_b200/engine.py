@@ -229,7 +229,7 @@ class Context:
         return self.multiply(a, a, level, layout)
 
     def relin_prepare(self, rk):
-        quot = _torch().empty_like(rk)
+        quot = self.empty(2, *rk.shape)   # {word, Shoup quotient} pairs, twice the key's size
         check(self.L.pplp_relin_prepare(self.h, _ptr(rk), _ptr(quot), self._st()))
         return quot
 

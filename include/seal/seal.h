@@ -674,6 +674,7 @@ private:
     friend class PublicKey;
     friend class KeyGenerator;
     friend class RelinKeys;
+    friend struct BatchBridge;
     void write_members(detail::Sink &s) const {
         const std::vector<std::uint64_t> host = words_.download();
         s.raw(id_.data(), 32);
@@ -1073,6 +1074,26 @@ public:
 
 private:
     detail::CorePtr core_;
+};
+
+// ---- not part of SEAL: bridge between per-object API and the batched C ABI -------------------------------------------
+// A server that coalesces many clients loads their ciphertexts with Ciphertext::load (validation included), packs the
+// residues into one contiguous device slab, runs ONE batched call (e.g. pplp_circuit_a) and wraps slices of the result
+// back into Ciphertext objects to save() them per client.  tools/batch_server.cc is the worked example.
+struct BatchBridge {
+    static pplp_ctx *handle(const SEALContext &context) { return context.core()->h; }
+    static std::size_t words(const Ciphertext &c) { return c.size_ * c.k_ * c.n_; }
+    static std::size_t level(const Ciphertext &c) { return c.level_; }
+    // copies c's residues ([poly][limb][N]) to d_dst (device), asynchronously on the default stream
+    static void export_words(const Ciphertext &c, std::uint64_t *d_dst) {
+        detail::check(pplp_d2d(c.words_.core()->h, d_dst, c.words_.data(), words(c) * 8, nullptr));
+    }
+    // makes c a coefficient-form ciphertext of `size` polynomials at `level` holding the residues at d_src (device)
+    static void import_words(Ciphertext &c, const SEALContext &context, std::size_t level, std::size_t size, const std::uint64_t *d_src) {
+        c.shape(context.core(), level, size);
+        c.ntt_ = false; c.scale_ = 1.0; c.correction_ = 1;
+        detail::check(pplp_d2d(context.core()->h, c.words_.data(), d_src, words(c) * 8, nullptr));
+    }
 };
 
 }  // namespace seal

@@ -45,6 +45,13 @@ def build(force=False):
         if force or _newer(exe, [src] + hdrs):
             _run(["g++", "-Wall", src] + COMMON + ["-o", exe])
         built.append(exe)
+    tools = os.path.join(ROOT, "build", "tools")
+    os.makedirs(tools, exist_ok=True)
+    src = os.path.join(ROOT, "tools", "batch_server.cc")
+    exe = os.path.join(tools, "batch_server")
+    if force or _newer(exe, [src] + hdrs):
+        _run(["g++", "-Wall", src] + COMMON + ["-o", exe])
+    built.append(exe)
     if os.path.isdir(os.path.join(REF, "src")):
         d = os.path.join(ROOT, "build", "dropin")
         os.makedirs(d, exist_ok=True)

@@ -124,3 +124,28 @@ def test_reference_client_server_over_loopback(shim):
             sp.kill()
     assert cp.returncode == 0, cp.stdout + cp.stderr + so
     assert "near" in cp.stdout.splitlines()[-1] or "near" in cp.stdout, cp.stdout[-500:]
+
+
+def test_batch_server_serves_unmodified_reference_clients(shim):
+    """tools/batch_server.cc: three of the reference's own `client` binaries, one batched GPU evaluation, each client gets
+    its own Bloom filter and encrypted result in the reference's framing and reaches the right verdict."""
+    client = _dropin("client")
+    server = os.path.join(ROOT, "build", "tools", "batch_server")
+    assert os.path.exists(server)
+    port = 51122
+    sp = subprocess.Popen([server, "-p", str(port), "-n", "3", "-r", "256"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                          env=dict(os.environ, PPLP_BATCH_SERVER_DEBUG="1"))
+    try:
+        time.sleep(1.5)
+        # server point defaults to (123456888, 132465777): d^2 = 13 (near), 25 (near), 79 024 122 (far; radius^2 = 65 536)
+        coords = [("123456890", "132465780"), ("123456891", "132465781"), ("123456789", "132456888")]
+        procs = [subprocess.Popen([client, "-p", str(port), "-x", x, "-y", y, "-r", "256"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+                 for x, y in coords]
+        outs = [p.communicate(timeout=300)[0] for p in procs]
+        so, _ = sp.communicate(timeout=300)
+    finally:
+        if sp.poll() is None:
+            sp.kill()
+    assert "served 3 clients in one batch" in so, so
+    verdicts = [[ln for ln in o.splitlines() if ln.startswith("Result of proximity test")][-1] for o in outs]
+    assert verdicts == ["Result of proximity test: near", "Result of proximity test: near", "Result of proximity test: far"], (outs, so)

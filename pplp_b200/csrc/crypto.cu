@@ -195,13 +195,20 @@ __global__ void __launch_bounds__(256) modswitch_kernel(const DevLevel *KLp, con
 //   enc_inverse_kernel<SPECIAL> T = INTT(U_P (.) pk_p,P) + e_p for the special prime P; stores (T + P/2) mod P   (nct*2 CTAs)
 //   enc_inverse_kernel<DATA>    per data limb: T = INTT(U_j (.) pk_p,j) + e_p, then divide-and-round by P using the stored
 //                               special-limb row, then c0 += round(Q m/t); writes the ciphertext directly (nct*2*k CTAs)
-// rows of n words -> thread-interleaved order of the fine register layout: pair c of thread t (words 16t+2c, 16t+2c+1)
-// moves to pair index c*(n/16) + t
-__global__ void interleave_fine_kernel(const u64 *__restrict__ src, u64 *__restrict__ dst, int n) {
-    const ulonglong2 *s = reinterpret_cast<const ulonglong2 *>(src + (size_t)blockIdx.y * n);
-    ulonglong2 *d = reinterpret_cast<ulonglong2 *>(dst + (size_t)blockIdx.y * n);
+// The public key is a constant of the whole call: prepare it once as {word, second} pairs, second = Shoup quotient
+// floor(w 2^64 / q) or, for the FP64-assisted kernels, the bits of fl(w/q), in the thread-interleaved order of the fine
+// register layout (coefficient 16 t + r at pair index r*(n/16) + t).  The dyadic product U (.) pk then costs one
+// constant-operand product per coefficient instead of a 128-bit Barrett reduction, and its loads coalesce.
+__global__ void prepare_key_kernel(const DevMod *mods, const u64 *__restrict__ src, u64 *__restrict__ dst, int K, int n, int f64) {
+    const int row = blockIdx.y;
+    const u64 q = mods[row % K].m.q;
     const int T = n / 16;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n / 2; i += gridDim.x * blockDim.x) d[(i & 7) * T + (i >> 3)] = s[i];
+    ulonglong2 *d = reinterpret_cast<ulonglong2 *>(dst) + (size_t)row * n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const u64 w = src[(size_t)row * n + i];
+        const u64 second = f64 ? (u64)__double_as_longlong(__ddiv_rn((double)w, (double)q)) : (u64)((((u128)w) << 64) / q);
+        d[(size_t)(i & 15) * T + (i >> 4)] = make_ulonglong2(w, second);
+    }
 }
 
 struct EncSplitArgs {
@@ -241,7 +248,10 @@ __global__ void __launch_bounds__(NttShape<LOGM>::T, (LOGM <= 13 ? 2 : 1)) enc_f
 }
 
 template <int LOGM, int L, bool SPECIAL>
-__global__ void __launch_bounds__(NttShape<LOGM>::T, (LOGM <= 13 ? 2 : 1)) enc_inverse_kernel(const EncSplitArgs a) {
+#ifndef PPLP_ENC_INV_MIN_CTAS
+#define PPLP_ENC_INV_MIN_CTAS 2
+#endif
+__global__ void __launch_bounds__(NttShape<LOGM>::T, (LOGM <= 13 ? PPLP_ENC_INV_MIN_CTAS : 1)) enc_inverse_kernel(const EncSplitArgs a) {
     extern __shared__ __align__(16) u64 sm[];
     const int tid = threadIdx.x;
     const int k = a.K - 1;
@@ -253,14 +263,14 @@ __global__ void __launch_bounds__(NttShape<LOGM>::T, (LOGM <= 13 ? 2 : 1)) enc_i
     const NttConsts nc = ntt_consts<L>(md);
     const u64 q = mod.q;
     const ulonglong2 *up = reinterpret_cast<const ulonglong2 *>(a.U + ((size_t)ct * a.K + j) * a.n);
-    const ulonglong2 *pkp = reinterpret_cast<const ulonglong2 *>(a.pk + ((size_t)p * a.K + j) * a.n);   // interleaved copy of the key
+    const ulonglong2 *pkp = reinterpret_cast<const ulonglong2 *>(a.pk) + ((size_t)p * a.K + j) * a.n;   // prepared {word, second} pairs
     u64 x[16];
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
         const ulonglong2 uv = up[c * NttShape<LOGM>::T + tid];
-        const ulonglong2 bv = __ldg(pkp + c * NttShape<LOGM>::T + tid);
-        x[2 * c] = mul_mod(uv.x, bv.x, mod);
-        x[2 * c + 1] = mul_mod(uv.y, bv.y, mod);
+        const ulonglong2 k0 = __ldg(pkp + (2 * c) * NttShape<LOGM>::T + tid), k1 = __ldg(pkp + (2 * c + 1) * NttShape<LOGM>::T + tid);
+        x[2 * c] = twiddle_mul<Lazy<L>::I>(uv.x, ShoupW{k0.x, k0.y}, q);       // lazily below 2q: what the inverse transform accepts
+        x[2 * c + 1] = twiddle_mul<Lazy<L>::I>(uv.y, ShoupW{k1.x, k1.y}, q);
     }
     block_ntt_inverse<LOGM, true, Lazy<L>::I>(x, sm, tid, inv_table<L>(md), 0, 0, nc);
     const signed char *e = a.noise + ((size_t)ct * 3 + 1 + p) * a.n;
@@ -281,7 +291,7 @@ __global__ void __launch_bounds__(NttShape<LOGM>::T, (LOGM <= 13 ? 2 : 1)) enc_i
             const int ev = e[i];
             u64 v = add_mod(csub(x[r], q), ev < 0 ? q - (u64)(-ev) : (u64)ev, q);
             const u64 corr = sub_mod(barrett64(lastp[i], mod), half_mod, q);
-            v = mul_shoup(sub_mod(v, corr, q), inv_last, q);
+            v = csub(mul_shoup_lazy_nq(sub_mod(v, corr, q), inv_last.w, inv_last.wq, 0 - q), q);
             if (p == 0 && i < a.plain_count) v = add_mod(v, dev_scaled_plain(*a.DL, a.plain[ct * a.plain_stride + i], j), q);
             dst[i] = v;
         });
@@ -344,7 +354,7 @@ size_t encrypt_tmp_words(const Engine &E, int nct) {
     const size_t stream = (size_t)nct * encrypt_stream_refills((int)n) * (kRefillBytes / 8);
     const size_t noise = ((size_t)nct * 3 * n + 7) / 8 + 2;
     const size_t tmp = (size_t)nct * 2 * K * n;
-    const size_t extra = E.host.logn == 15 ? (size_t)nct * K * n : 2 * K * n;   // N = 32768: NTT(u) rows; else the interleaved key
+    const size_t extra = E.host.logn == 15 ? (size_t)nct * K * n : 4 * K * n;   // N = 32768: NTT(u) rows; else the prepared key pairs
     return stream + noise + tmp + extra + 8;
 }
 
@@ -392,7 +402,7 @@ void launch_encrypt(const Engine &E, const u64 *pk, const u64 *seeds, const u64 
     const int lazy = ntt_lazy_level(E.max_bits(E.qmap(0)), E.host.logn);
     const size_t first = E.host.first_level();
     if (K > 1 && E.host.logn <= 14) {   // split pipeline: forward, special-limb inverse, data-limb inverse + modulus switch + plaintext
-        interleave_fine_kernel<<<dim3((n / 2 + 255) / 256, 2 * K), 256, 0, st>>>(pk, extra, n);
+        prepare_key_kernel<<<dim3((n + 255) / 256, 2 * K), 256, 0, st>>>(E.d_mods, pk, extra, K, n, lazy == 3 ? 1 : 0);
         EncSplitArgs sa{noise, extra, tmp, tmp + (size_t)nct * K * n, out, out_lay, plain, (int)plain_count, plain_stride, K, n, E.d_mods, E.d_levels, E.d_levels + first};
         switch (E.host.logn) {
         case 10: run_encrypt_split<10>(lazy, sa, nct, st); break;

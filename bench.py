@@ -33,6 +33,7 @@ T = 1 << 56
 METRIC = "proximity_queries_per_sec"
 UNIT = "queries/s"
 WORKLOAD = "circuitA_bfv_n8192_k4_t2^56_batched"
+LIMBS = 4
 
 
 def parse_args():
@@ -41,7 +42,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--queries", type=int, default=8192, help="queries per GPU per step (resident run)")
+    ap.add_argument("--degree", type=int, default=8192, help="poly_modulus_degree (8192 = BASELINE configs[1]; 16384 = configs[2])")
+    ap.add_argument("--queries", type=int, default=0, help="queries per GPU per step (resident run); 0 = 8192 at N=8192, scaled by 8192/N")
     ap.add_argument("--e2e-queries", type=int, default=1024, help="queries per GPU per step (host-buffer run)")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the CPU baseline sample (0 = calibrate to ~10 s)")
@@ -160,7 +162,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "queries_per_step": sample, "poly_modulus_degree": N, "limbs": 4, "plain_modulus": "2^56"},
+        "config": {"workload": WORKLOAD, "queries_per_step": sample, "poly_modulus_degree": N, "limbs": LIMBS, "plain_modulus": "2^56"},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{sample} queries/step x {args.steps} steps, SEAL-4.1-equivalent CPU restatement (oracle/), {threads} host threads"},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -325,7 +327,8 @@ def run_b200(args):
     if os.path.exists(tp):
         try:
             traffic = json.load(open(tp)).get("circuit_a_kernel", {}).get("dram_bytes_per_query")
-            traffic = traffic * Q if traffic else None   # ncu capture at a smaller batch, scaled per query to this launch
+            # ncu capture at a smaller batch (N=8192, k=4): scaled per query, and per ciphertext size, to this launch
+            traffic = traffic * Q * (N * k) / (8192 * 4) if traffic else None
         except Exception:
             traffic = None
     line = {
@@ -421,6 +424,15 @@ def run_extras(engine, ctx, torch, osk, opk):
 
 if __name__ == "__main__":
     a = parse_args()
+    N = a.degree
+    _k = {4096: 2, 8192: 4, 16384: 8, 32768: 15}.get(N)
+    if _k is None:
+        raise SystemExit("bench: --degree must be 4096, 8192, 16384 or 32768")
+    LIMBS = _k
+    WORKLOAD = f"circuitA_bfv_n{N}_k{_k}_t2^56_batched"
+    if a.queries <= 0:
+        a.queries = max(256, 8192 * 8192 * 4 // (N * _k))       # same bytes per step as 8192 queries at N=8192
+    a.e2e_queries = max(64, a.e2e_queries * 8192 * 4 // (N * _k))
     if a.impl == "reference":
         run_reference(a)
     else:

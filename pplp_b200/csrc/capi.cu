@@ -102,80 +102,25 @@ struct Scratch {
     Scratch &operator=(const Scratch &) = delete;
 };
 
-// SEAL's Blake2xbPRNG on the host (key generation only): 4096-byte refills blake2xb(counter; key = seed).
-struct HostPrng {
-    u64 seed[8];
-    u64 counter = 0;
-    unsigned char buf[4096];
-    size_t head = 4096;
-    explicit HostPrng(const u64 *s) { std::memcpy(seed, s, 64); }
-    void refill() {
-        u64 root[8];
-        b2::xof_root(seed, counter++, root);
-        for (unsigned b = 0; b < 64; ++b) b2::xof_block(root, b, reinterpret_cast<u64 *>(buf + 64 * b));
-        head = 0;
+// Key generation: the samplers run on the device (crypto.cu); the host only ships the 64-byte seed and checks the
+// "stream exhausted" flag.  [SEAL] KeyGenerator::generate_sk / create_public_key / create_relin_keys.
+struct KeygenScratch {
+    Scratch ws, seed, flag;
+    KeygenScratch(const Engine &E, const u64 *h_seed, cudaStream_t st) : ws(keygen_tmp_words(E) * 8, st), seed(64, st), flag(sizeof(int), st) {
+        PPLP_CUDA(cudaMemcpyAsync(seed.p, h_seed, 64, cudaMemcpyHostToDevice, st));
+        PPLP_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), st));
     }
-    void bytes(void *dst, size_t n) {
-        unsigned char *d = static_cast<unsigned char *>(dst);
-        while (n) {
-            if (head == 4096) refill();
-            size_t take = std::min(n, (size_t)4096 - head);
-            std::memcpy(d, buf + head, take);
-            head += take; d += take; n -= take;
-        }
+    void finish(cudaStream_t st) {
+        int bad = 0;
+        PPLP_CUDA(cudaMemcpyAsync(&bad, flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        PPLP_CUDA(cudaStreamSynchronize(st));
+        if (bad) throw std::logic_error("pplp: PRNG stream reserve exhausted during key generation");
     }
-    u32 word() { u32 w; bytes(&w, 4); return w; }
 };
-// [SEAL] sample_poly_ternary draws std::uniform_int_distribution<uint64_t>(0,2) from a 32-bit generator.  With
-// libstdc++ (GCC >= 11) that is Lemire's multiply-shift: product = draw * 3, reject when the low half is below
-// 2^32 mod 3 = 1 (i.e. only draw == 0), result = high half.  Spelled out so it does not depend on the host library.
-void host_ternary(HostPrng &g, size_t n, signed char *out) {
-    for (size_t i = 0; i < n; ++i) {
-        u32 w;
-        do { w = g.word(); } while (w == 0);
-        out[i] = (signed char)((int)(((u64)w * 3) >> 32) - 1);
-    }
-}
-void host_cbd(HostPrng &g, size_t n, signed char *out) {
-    for (size_t i = 0; i < n; ++i) {
-        unsigned char x[6];
-        g.bytes(x, 6);
-        x[2] &= 0x1F; x[5] &= 0x1F;
-        out[i] = (signed char)(__builtin_popcount(x[0]) + __builtin_popcount(x[1]) + __builtin_popcount(x[2]) - __builtin_popcount(x[3]) -
-                               __builtin_popcount(x[4]) - __builtin_popcount(x[5]));
-    }
-}
-void host_uniform(HostPrng &g, const std::vector<u64> &q, size_t n, u64 *out) {
-    g.bytes(out, q.size() * n * 8);
-    for (size_t j = 0; j < q.size(); ++j) {
-        const u64 max_multiple = ~u64(0) - (~u64(0) % q[j]) - 1;
-        for (size_t i = 0; i < n; ++i) {
-            u64 r = out[j * n + i];
-            while (r >= max_multiple) g.bytes(&r, 8);
-            out[j * n + i] = r % q[j];
-        }
-    }
-}
-
-// Symmetric encryption of zero at the key level in NTT form ([SEAL] encrypt_zero_symmetric, is_ntt_form = true,
-// save_seed = false): c1 = a uniform (taken as NTT form), c0 = -(a s + e).  Optionally adds factor*s^2 on limb `digit`.
 void symmetric_zero_ntt(Engine &E, const u64 *seed, const u64 *d_sk, u64 *d_out /* [2][K][n] */, int digit, u64 factor, cudaStream_t st) {
-    const size_t n = E.host.n, K = E.host.K();
-    HostPrng bootstrap(seed);
-    u64 public_seed[8];
-    bootstrap.bytes(public_seed, 64);
-    HostPrng ct_prng(public_seed);
-    std::vector<u64> a(K * n);
-    host_uniform(ct_prng, E.host.q, n, a.data());
-    std::vector<signed char> e(n);
-    host_cbd(bootstrap, n, e.data());
-    Scratch d_e(n, st), d_en(K * n * 8, st);
-    PPLP_CUDA(cudaMemcpyAsync(d_out + K * n, a.data(), K * n * 8, cudaMemcpyHostToDevice, st));
-    PPLP_CUDA(cudaMemcpyAsync(d_e.p, e.data(), n, cudaMemcpyHostToDevice, st));
-    launch_expand_small(E, d_e.as<signed char>(), d_en.as<u64>(), st);
-    launch_ntt(E, d_en.as<u64>(), E.seal_layout(0, 1), 1, 1, E.qmap(0), false, st);
-    launch_pk_combine(E, d_out + K * n, d_sk, d_en.as<u64>(), d_out, digit, factor, st);
-    PPLP_CUDA(cudaStreamSynchronize(st));   // host staging vectors die here
+    KeygenScratch k(E, seed, st);
+    launch_symmetric_zero(E, k.seed.as<u64>(), d_sk, d_out, digit, factor, k.ws.as<u64>(), k.flag.as<int>(), st);
+    k.finish(st);
 }
 
 __global__ void proximity_plain_kernel(const u64 *__restrict__ xa, const u64 *__restrict__ ya, int nq, u64 t, u64 *__restrict__ plain, int *flags) {
@@ -398,16 +343,10 @@ int pplp_keygen(pplp_ctx *ctx, const uint64_t seed[8], uint64_t *d_sk, uint64_t 
     PPLP_TRY
     Engine &E = dev_engine(ctx);
     cudaStream_t st = S(stream);
-    const size_t n = E.host.n;
     {   // secret key: ternary, then NTT at the key level ([SEAL] KeyGenerator::generate_sk)
-        HostPrng g(seed);
-        std::vector<signed char> s(n);
-        host_ternary(g, n, s.data());
-        Scratch d_s(n, st);
-        PPLP_CUDA(cudaMemcpyAsync(d_s.p, s.data(), n, cudaMemcpyHostToDevice, st));
-        launch_expand_small(E, d_s.as<signed char>(), d_sk, st);
-        launch_ntt(E, d_sk, E.seal_layout(0, 1), 1, 1, E.qmap(0), false, st);
-        PPLP_CUDA(cudaStreamSynchronize(st));
+        KeygenScratch k(E, seed, st);
+        launch_keygen_secret(E, k.seed.as<u64>(), d_sk, k.ws.as<u64>(), k.flag.as<int>(), st);
+        k.finish(st);
     }
     if (d_pk) symmetric_zero_ntt(E, seed, d_sk, d_pk, -1, 0, st);
     return PPLP_OK;

@@ -628,6 +628,111 @@ void launch_pk_combine(const Engine &E, const u64 *a, const u64 *s, const u64 *e
     PPLP_CUDA(cudaGetLastError());
 }
 
+// ---- key generation samplers on the device -------------------------------------------------------------------------------
+// [SEAL] sample_poly_uniform: K*n 64-bit words of the stream, word (j,i) reduced modulo q_j unless it is >= the largest
+// multiple of q_j below 2^64 - 1, in which case it is REPLACED by the next unused word of the stream (repeatedly), in
+// (j,i) order.  Rejections are rare (q/2^64 per word), so the bulk runs in parallel and one thread replays the few
+// rejected positions in order afterwards.
+// spare stream words / reject-list capacity: a 60-bit prime rejects one word in 16
+inline int uniform_reject_cap(int K, int n) { return K * n / 8 + 1024; }
+__global__ void uniform_bulk_kernel(const DevMod *mods, const u64 *__restrict__ stream, u64 *__restrict__ out, int K, int n, int cap, int *reject_count, int *reject_list) {
+    const int j = blockIdx.y;
+    const Mod mq = mods[j].m;
+    const u64 max_multiple = ~u64(0) - (~u64(0) % mq.q) - 1;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const size_t idx = (size_t)j * n + i;
+        const u64 r = stream[idx];
+        if (r >= max_multiple) {
+            const int slot = atomicAdd(reject_count, 1);
+            if (slot < cap) reject_list[slot] = (int)idx;
+        } else {
+            out[idx] = barrett64(r, mq);
+        }
+    }
+}
+__global__ void uniform_fixup_kernel(const DevMod *mods, const u64 *__restrict__ stream, size_t stream_words, u64 *__restrict__ out, int K, int n, int cap,
+                                     const int *reject_count, int *reject_list, int *errflag) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int count = *reject_count;
+    if (count > cap) { atomicExch(errflag, 1); return; }
+    for (int a = 1; a < count; ++a) {   // order of consumption is the order of positions
+        const int v = reject_list[a];
+        int b = a - 1;
+        while (b >= 0 && reject_list[b] > v) { reject_list[b + 1] = reject_list[b]; --b; }
+        reject_list[b + 1] = v;
+    }
+    size_t tail = (size_t)K * n;
+    for (int a = 0; a < count; ++a) {
+        const int idx = reject_list[a];
+        const Mod mq = mods[idx / n].m;
+        const u64 max_multiple = ~u64(0) - (~u64(0) % mq.q) - 1;
+        u64 r;
+        do {
+            if (tail >= stream_words) { atomicExch(errflag, 1); return; }
+            r = stream[tail++];
+        } while (r >= max_multiple);
+        out[idx] = barrett64(r, mq);
+    }
+}
+// centred binomial samples from a stream at a byte offset (multiple of 2): e [n] as int8
+__global__ void cbd_at_kernel(const u64 *__restrict__ stream, size_t byte_offset, int n, signed char *__restrict__ e) {
+    const unsigned short *h = reinterpret_cast<const unsigned short *>(reinterpret_cast<const unsigned char *>(stream) + byte_offset);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned w0 = h[3 * i], w1 = h[3 * i + 1], w2 = h[3 * i + 2];
+        e[i] = (signed char)(__popc(w0) + __popc(w1 & 0x1Fu) - __popc(w1 >> 8) - __popc(w2 & 0xFFu) - __popc((w2 >> 8) & 0x1Fu));
+    }
+}
+
+size_t keygen_tmp_words(const Engine &E) {
+    const size_t n = E.host.n, K = E.host.K();
+    const size_t enc = (size_t)encrypt_stream_refills((int)n) * (kRefillBytes / 8) + (3 * n + 7) / 8 + 2;   // secret key: reuse the encryption sampler
+    const size_t boot = ((64 + 6 * n + kRefillBytes - 1) / kRefillBytes) * (kRefillBytes / 8);
+    const size_t cap = (size_t)uniform_reject_cap((int)K, (int)n);
+    const size_t ct = ((K * n + cap) * 8 / kRefillBytes + 2) * (kRefillBytes / 8);
+    return 8 + std::max(enc, boot + ct + (n + 7) / 8 + K * n + cap + 16);
+}
+
+// secret key: ternary from the PRNG of `d_seed`, NTT form at the key level ([SEAL] KeyGenerator::generate_sk)
+void launch_keygen_secret(const Engine &E, const u64 *d_seed, u64 *d_sk, u64 *ws, int *errflag, cudaStream_t st) {
+    E.require_device();
+    const int n = (int)E.host.n;
+    const int nrefill = encrypt_stream_refills(n);
+    u64 *stream = ws;
+    signed char *noise = reinterpret_cast<signed char *>(stream + (size_t)nrefill * (kRefillBytes / 8));
+    prng_stream_kernel<<<dim3((nrefill + kRefillsPerCta - 1) / kRefillsPerCta, 1), 256, 0, st>>>(d_seed, nrefill, stream);
+    sample_encrypt_kernel<<<1, 1024, 0, st>>>(stream, nrefill, n, noise, errflag);   // its first n samples are the ternary draws
+    launch_expand_small(E, noise, d_sk, st);
+    launch_ntt(E, d_sk, E.seal_layout(0, 1), 1, 1, E.qmap(0), false, st);
+    PPLP_CUDA(cudaGetLastError());
+}
+
+// symmetric encryption of zero, NTT form, key level ([SEAL] encrypt_zero_symmetric with is_ntt_form = true, save_seed = false):
+// bootstrap PRNG(seed) -> 64-byte public seed, then the noise e; PRNG(public seed) -> uniform a (taken as NTT form);
+// out = (-(a s + e) [+ factor s^2 on limb `digit`], a)
+void launch_symmetric_zero(const Engine &E, const u64 *d_seed, const u64 *d_sk, u64 *d_out, int digit, u64 factor, u64 *ws, int *errflag, cudaStream_t st) {
+    E.require_device();
+    const int n = (int)E.host.n, K = (int)E.host.K();
+    const int nboot = (64 + 6 * n + kRefillBytes - 1) / kRefillBytes;
+    const int cap = uniform_reject_cap(K, n);
+    const int nct = (int)(((size_t)K * n + cap) * 8 / kRefillBytes + 2);
+    u64 *boot = ws;
+    u64 *cts = boot + (size_t)nboot * (kRefillBytes / 8);
+    signed char *e = reinterpret_cast<signed char *>(cts + (size_t)nct * (kRefillBytes / 8));
+    u64 *e_rows = reinterpret_cast<u64 *>(e) + (n + 7) / 8;
+    int *rej = reinterpret_cast<int *>(e_rows + (size_t)K * n);
+    prng_stream_kernel<<<dim3((nboot + kRefillsPerCta - 1) / kRefillsPerCta, 1), 256, 0, st>>>(d_seed, nboot, boot);
+    prng_stream_kernel<<<dim3((nct + kRefillsPerCta - 1) / kRefillsPerCta, 1), 256, 0, st>>>(boot, nct, cts);   // seed = first 64 bytes of the bootstrap stream
+    PPLP_CUDA(cudaMemsetAsync(rej, 0, sizeof(int), st));
+    u64 *a = d_out + (size_t)K * n;
+    uniform_bulk_kernel<<<dim3((n + 255) / 256, K), 256, 0, st>>>(E.d_mods, cts, a, K, n, cap, rej, rej + 1);
+    uniform_fixup_kernel<<<1, 32, 0, st>>>(E.d_mods, cts, (size_t)nct * (kRefillBytes / 8), a, K, n, cap, rej, rej + 1, errflag);
+    cbd_at_kernel<<<(n + 255) / 256, 256, 0, st>>>(boot, 64, n, e);
+    launch_expand_small(E, e, e_rows, st);
+    launch_ntt(E, e_rows, E.seal_layout(0, 1), 1, 1, E.qmap(0), false, st);
+    launch_pk_combine(E, a, d_sk, e_rows, d_out, digit, factor, st);
+    PPLP_CUDA(cudaGetLastError());
+}
+
 // raw PRNG stream for tests and for host-driven samplers: out [nrefill*4096 bytes]
 void launch_prng_stream(const Engine &E, const u64 *d_seed, int nstreams, int nrefill, u64 *out, cudaStream_t st) {
     E.require_device();

@@ -539,3 +539,55 @@ def test_constant_coefficient_decrypt_equals_full_decrypt(eng, oracle, n):
     lm = ctx.dev(np.ascontiguousarray(junk.transpose(2, 1, 0, 3)))
     one_lm = eng.to_np(ctx.decrypt(lm, sk, ncoeff=1, layout=eng.LAYOUT_LIMB_MAJOR))
     assert (one_lm[:, 0] == full[:, 0]).all()
+
+
+def _is_prime_u64(m):
+    if m < 2:
+        return False
+    for p in (2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37):
+        if m % p == 0:
+            return m == p
+    d, r = m - 1, 0
+    while d % 2 == 0:
+        d //= 2
+        r += 1
+    for a in (2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37):   # deterministic below 3.3e24
+        x = pow(a, d, m)
+        if x in (1, m - 1):
+            continue
+        for _ in range(r - 1):
+            x = x * x % m
+            if x == m - 1:
+                break
+        else:
+            return False
+    return True
+
+
+def test_keygen_uniform_rejections_match_oracle(eng, oracle):
+    """sample_poly_uniform rejects a word when it is >= the largest multiple of q below 2^64 - 1, i.e. with probability
+    (2^64 mod q) / 2^64.  SEAL's own primes sit just under a power of two, so 2^64 mod q is tiny and the branch is never
+    taken; primes near 2^64 / (m + 1/2) make 2^64 mod q ~ q/2 (about 3 % of the words).  The device sampler must then
+    replay the rejections in stream order exactly like the sequential reference loop."""
+    n = 4096
+    q = []
+    for m in (16, 17, 18):
+        c = (int(2**64 / (m + 0.5)) // (2 * n)) * (2 * n) + 1
+        while not _is_prime_u64(c):
+            c -= 2 * n
+        q.append(c)
+    assert all(x.bit_length() == 60 for x in q)
+    ctx, octx = contexts(eng, oracle, n, t=1 << 20, q=q, enforce_security=False)
+    sk, pk = ctx.keygen(seed8(7))   # the oracle context's factory seed
+    osk, opk = octx.keygen()
+    assert (eng.to_np(sk) == osk).all()
+    assert (eng.to_np(pk) == opk).all()
+    # how many words were actually rejected for this key (so the test cannot pass vacuously)
+    import ctypes as C
+    raw = np.zeros(3 * n * 8, dtype=np.uint8)
+    boot = np.zeros(64, dtype=np.uint8)
+    oracle.lib.orc_prng_bytes(seed8(7).ctypes.data_as(C.POINTER(C.c_uint64)), 64, boot.ctypes.data_as(C.POINTER(C.c_uint8)))
+    oracle.lib.orc_prng_bytes(boot.view(np.uint64).ctypes.data_as(C.POINTER(C.c_uint64)), raw.size, raw.ctypes.data_as(C.POINTER(C.c_uint8)))
+    words = raw.view(np.uint64).reshape(3, n)
+    rejected = sum(int((words[j] >= np.uint64((2**64 - 1) - ((2**64 - 1) % q[j]) - 1)).sum()) for j in range(3))
+    assert rejected >= 100

@@ -224,9 +224,10 @@ __global__ void __launch_bounds__(NttShape<LOGM>::T) relin_limb_kernel(const Rel
         for (int r = 0; r < 16; ++r) {
             const ulonglong2 w0 = __ldg(k0 + (size_t)r * S::T);   // {key word, Shoup quotient} of coefficient 16 tid + r
             const ulonglong2 w1 = __ldg(k1 + (size_t)r * S::T);
+            const u64 xr = forward_lazy<Lazy<L>::F>(x[r], nc);
             u64 v;
-            v = acc0[r] + mul_shoup_lazy_nq(x[r], w0.x, w0.y, 0 - q); acc0[r] = v >= two_q ? v - two_q : v;
-            v = acc1[r] + mul_shoup_lazy_nq(x[r], w1.x, w1.y, 0 - q); acc1[r] = v >= two_q ? v - two_q : v;
+            v = acc0[r] + mul_shoup_lazy_nq(xr, w0.x, w0.y, 0 - q); acc0[r] = v >= two_q ? v - two_q : v;
+            v = acc1[r] + mul_shoup_lazy_nq(xr, w1.x, w1.y, 0 - q); acc1[r] = v >= two_q ? v - two_q : v;
         }
         __syncthreads();   // the next digit reuses the staging buffer
     }

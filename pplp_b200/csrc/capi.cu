@@ -185,17 +185,18 @@ void Engine::upload_tables(int dev) {
         };
         m.fine_fwd = fine(T.fwd);
         m.fine_inv = fine(T.inv);
-        if (m.bits <= 45) {   // FP64-assisted tables: second word = bits of the correctly rounded double w/q (w, q < 2^53 are exact)
-            auto ratio = [&](u64 w) { const double c = (double)w / (double)T.q; u64 b; std::memcpy(&b, &c, 8); return b; };
+        if (m.bits <= 44) {   // FP64-pipe tables (ntt.cuh L = 3): {bits of double(w), bits of the correctly rounded double w/q}; w, q < 2^53 are exact
+            auto dbits = [](double c) { u64 b; std::memcpy(&b, &c, 8); return b; };
+            auto pair = [&](u64 w) { return ShoupW{dbits((double)w), dbits((double)w / (double)T.q)}; };
             std::vector<ShoupW> fd(T.fwd.size()), id(T.inv.size());
-            for (size_t t = 0; t < T.fwd.size(); ++t) { fd[t].w = T.fwd[t].w; fd[t].wq = ratio(T.fwd[t].w); id[t].w = T.inv[t].w; id[t].wq = ratio(T.inv[t].w); }
+            for (size_t t = 0; t < T.fwd.size(); ++t) { fd[t] = pair(T.fwd[t].w); id[t] = pair(T.inv[t].w); }
             m.fwd_d = upload(fd.data(), fd.size());
             m.inv_d = upload(id.data(), id.size());
             m.fine_fwd_d = fine(fd);
             m.fine_inv_d = fine(id);
-            m.n_inv_d = ShoupW{T.n_inv.w, ratio(T.n_inv.w)};
-            m.inv1_n_inv_d = ShoupW{T.inv1_n_inv.w, ratio(T.inv1_n_inv.w)};
-            m.one_d = ratio(1);
+            m.n_inv_d = pair(T.n_inv.w);
+            m.inv1_n_inv_d = pair(T.inv1_n_inv.w);
+            m.one_d = dbits(1.0 / (double)T.q);
         }
     }
     d_mods = upload(h_mods.data(), h_mods.size());

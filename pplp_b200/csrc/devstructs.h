@@ -17,7 +17,7 @@ struct DevMod {
     ShoupW inv1_n_inv;    // inv[1] * N^-1  (last Gentleman–Sande stage with the scaling folded in)
     u64 one_q;            // floor(2^64 / q): Shoup quotient of the constant 1 (lazy reduction of any 64-bit value)
     int bits;             // bit length of q
-    // FP64-assisted variant (moduli of at most 45 bits, else null): twiddles as (w, bits of the double fl(w/q))
+    // FP64-pipe variant (ntt.cuh L = 3; moduli of at most 44 bits, else null): twiddles as bits of (double(w), fl(w/q))
     const ShoupW *fwd_d;
     const ShoupW *inv_d;
     ShoupW n_inv_d, inv1_n_inv_d;

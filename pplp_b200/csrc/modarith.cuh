@@ -105,6 +105,33 @@ __device__ __forceinline__ u64 mul_f64_lazy(u64 a, u64 w, u64 c_bits, u64 q) { r
 // a mod q into (0,2q) for a < 2^51, with c_bits = fl(1/q)
 __device__ __forceinline__ u64 reduce_f64(u64 a, u64 one_d, u64 q) { return a + q - quotient_f64(a, one_d) * q; }
 
+// ---- butterflies entirely on the FP64 pipe (moduli below 2^44.4) -----------------------------------------------------
+// B200 issues 64 double-precision FMAs per clock per SM, against ten 32-bit multiplies (four of them half rate) for one
+// integer Shoup product, and the two pipes are separate.  With residues held as exact integers in doubles:
+//   t = a*w mod q:  h = RN(a*w), l = a*w - h (exact, one FMA), c = RN(a * fl(w/q)) (the 1.5*2^52 trick),
+//                   r = fma(-c, q, h) (exact: h - c q is an integer below 2^53), t = r + l = a*w - c*q  EXACTLY,
+//   |t| <= q (1/2 + |a| 2^-53)  for |a| <= 2^51 (so that a*fl(w/q) + 1.5*2^52 stays in [2^52, 2^53] and rounds to an integer).
+// Six FP64 instructions per product, eight per butterfly (microbenchmark: 8.0 butterflies/clk/SM vs 4.4 / 3.3 for the
+// FP64-assisted / integer forms).  Values are signed, so no 2q offsets; they are exact, so canonical results are
+// bit-identical to any other evaluation order.
+constexpr double kRound52 = 6755399441055744.0;   // 1.5 * 2^52
+__device__ __forceinline__ double as_d(u64 bits) { return __longlong_as_double((long long)bits); }
+__device__ __forceinline__ u64 as_u(double d) { return (u64)__double_as_longlong(d); }
+__device__ __forceinline__ double u64_to_f64(u64 a) { return __dsub_rn(as_d(a | 0x4330000000000000ULL), kTwo52); }   // a < 2^52
+// integer-valued double v with 0 <= v + offset < 2^52  ->  u64 (v + offset); bias = offset + 2^52 precomputed
+__device__ __forceinline__ u64 f64_to_u64_biased(double v, double bias) { return as_u(__dadd_rn(v, bias)) & 0x000FFFFFFFFFFFFFULL; }
+__device__ __forceinline__ double mulmod_f64(double a, double w, double wi, double q) {
+    const double h = __dmul_rn(a, w);
+    const double l = __fma_rn(a, w, -h);
+    const double c = __dsub_rn(__fma_rn(a, wi, kRound52), kRound52);
+    return __dadd_rn(__fma_rn(-c, q, h), l);
+}
+// a mod q into [-q/2 - eps, q/2 + eps] for |a| <= 2^51, qi = fl(1/q)
+__device__ __forceinline__ double reduce_sym_f64(double a, double qi, double q) {
+    const double c = __dsub_rn(__fma_rn(a, qi, kRound52), kRound52);
+    return __fma_rn(-c, q, a);
+}
+
 // Barrett constants of a modulus: ratio = floor(2^128 / q) as (hi, lo).
 struct Mod { u64 q, r_hi, r_lo; };
 

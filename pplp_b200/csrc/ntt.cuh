@@ -33,10 +33,15 @@ enum : int { NTT_CLASSIC = 0, NTT_PASS = 1, NTT_FREE = 2, NTT_F64 = 3 };
 //   L = 0: classic forward, classic inverse    (any modulus below 2^62)
 //   L = 1: free forward, per-pass inverse      (modulus of at most 58 bits)
 //   L = 2: free forward, free inverse          (bits + 1 + log2 N <= 63)
-//   L = 3: FP64-assisted products (modarith.cuh mul_f64_lazy): free forward, per-pass inverse, every multiplicand
-//          below 2^51: forward (4 + 2 log2 N) q <= 34 q, inverse 2 (2q 2^3) = 32 q  =>  modulus of at most 45 bits
-//          (BFVDefault up to N = 8192).  Twiddle tables then carry (w, fl(w/q)) instead of (w, floor(w 2^64/q)).
-inline int ntt_lazy_level(int bits, int logn) { return bits <= 45 ? 3 : (bits > 58 ? 0 : (bits + 1 + logn <= 63 ? 2 : 1)); }
+//   L = 3: the whole transform on the FP64 pipe (modarith.cuh mulmod_f64; 8 double-precision instructions per butterfly,
+//          2.4x the butterfly rate of the integer pipe).  Inside a transform the registers hold the BIT PATTERNS of
+//          doubles (exact signed integers); block_ntt_forward/inverse convert at entry, forward_canon / forward_lazy /
+//          the inverse's exit convert back.  Every multiplicand must stay within 2^51:
+//            forward: |x| <= (4 + 0.75 log2 N) q <= 15.25 q   (inputs below 4q, a product is at most 0.75 q)
+//            inverse: a radix-16 pass fed with |x| <= 6q leaves 96 q in register 0 of each butterfly (the all-sums
+//                     path) and at most 6 q elsewhere; register 0 is reduced at the end of the pass  =>  96 q <= 2^51,
+//          i.e. modulus of at most 44 bits (BFVDefault up to N = 8192).  Twiddle tables carry (double w, fl(w/q)).
+inline int ntt_lazy_level(int bits, int logn) { return bits <= 44 ? 3 : (bits > 58 ? 0 : (bits + 1 + logn <= 63 ? 2 : 1)); }
 template <int L> struct Lazy {
     static constexpr int F = L == 0 ? NTT_CLASSIC : (L == 3 ? NTT_F64 : NTT_FREE);
     static constexpr int I = L == 0 ? NTT_CLASSIC : (L == 1 ? NTT_PASS : (L == 3 ? NTT_F64 : NTT_FREE));
@@ -69,6 +74,12 @@ template <int MODE> __device__ __forceinline__ u64 reduce_mode(u64 a, u64 one_q,
 }
 
 template <int MODE> __device__ __forceinline__ void ct_butterfly(u64 &x, u64 &y, const ShoupW w, const u64 q, const u64 two_q) {
+    if constexpr (MODE == NTT_F64) {       // q carries the bits of double(q); signed values, no offsets
+        const double xd = as_d(x), t = mulmod_f64(as_d(y), as_d(w.w), as_d(w.wq), as_d(q));
+        y = as_u(__dsub_rn(xd, t));
+        x = as_u(__dadd_rn(xd, t));
+        return;
+    }
     const u64 v = twiddle_mul<MODE>(y, w, q);
     if constexpr (MODE == NTT_CLASSIC) {   // Harvey: values stay in [0,4q)
         const u64 u = x >= two_q ? x - two_q : x;
@@ -81,6 +92,12 @@ template <int MODE> __device__ __forceinline__ void ct_butterfly(u64 &x, u64 &y,
 }
 // `big` is a multiple of q not smaller than any value y can hold at this stage (2q in classic mode).
 template <int MODE> __device__ __forceinline__ void gs_butterfly(u64 &x, u64 &y, const ShoupW w, const u64 q, const u64 two_q, const u64 big) {
+    if constexpr (MODE == NTT_F64) {
+        const double xd = as_d(x), yd = as_d(y);
+        x = as_u(__dadd_rn(xd, yd));
+        y = as_u(mulmod_f64(__dsub_rn(xd, yd), as_d(w.w), as_d(w.wq), as_d(q)));
+        return;
+    }
     const u64 s = x + y;
     const u64 d = x - y + big;
     if constexpr (MODE == NTT_CLASSIC) x = s >= two_q ? s - two_q : s;
@@ -96,13 +113,15 @@ __device__ __forceinline__ ShoupW ld_twiddle(const ShoupW *p) {
 }
 
 struct NttConsts {          // per-modulus scalars a transform needs besides the twiddle table
-    u64 q, two_q, one_q;    // one_q = floor(2^64 / q)
+    u64 q, two_q, one_q;    // one_q = floor(2^64 / q)   (L = 3: bits of fl(1/q))
+    u64 qd;                 // L = 3: bits of double(q)
     ShoupW n_inv, inv1_n_inv;
     const ShoupW *fine_fwd, *fine_inv;   // thread-interleaved twiddles of the last four stages (see Pass::stage)
 };
 template <int L> __device__ __forceinline__ NttConsts ntt_consts(const DevMod &md) {
     NttConsts c;
     c.q = md.m.q; c.two_q = md.m.q << 1;
+    c.qd = as_u((double)md.m.q);
     if constexpr (L == 3) { c.one_q = md.one_d; c.n_inv = md.n_inv_d; c.inv1_n_inv = md.inv1_n_inv_d; c.fine_fwd = md.fine_fwd_d; c.fine_inv = md.fine_inv_d; }
     else { c.one_q = md.one_q; c.n_inv = md.n_inv; c.inv1_n_inv = md.inv1_n_inv; c.fine_fwd = md.fine_fwd; c.fine_inv = md.fine_inv; }
     return c;
@@ -144,15 +163,22 @@ template <int LOGM, int S0, int R> struct Pass {
         constexpr int HALF = 1 << (R - 1 - V);
         const int tbase = (1 << (stage_base + S0 + V)) + (blk << (S0 + V)) + (h << V);
         // bound of the values entering this inverse stage, as a multiple of 2q (see gs_butterfly)
-        constexpr int GROW = MODE == NTT_FREE ? (LOGM - 1 - (S0 + V)) : ((MODE == NTT_PASS || MODE == NTT_F64) ? (R - 1 - V) : 0);
+        constexpr int GROW = MODE == NTT_FREE ? (LOGM - 1 - (S0 + V)) : (MODE == NTT_PASS ? (R - 1 - V) : 0);
         const u64 big = c.two_q << GROW;
+        const u64 qm = MODE == NTT_F64 ? c.qd : c.q;   // what the butterflies take as "q"
         if constexpr (INVERSE && FOLD_SCALE && V == 0) {
 #pragma unroll
             for (int i = 0; i < HALF; ++i) {
                 u64 &a = x[u * RR + i], &b = x[u * RR + i + HALF];
-                const u64 s = a + b, d = a - b + big;
-                a = twiddle_mul<MODE>(s, c.n_inv, c.q);
-                b = twiddle_mul<MODE>(d, c.inv1_n_inv, c.q);
+                if constexpr (MODE == NTT_F64) {
+                    const double ad = as_d(a), bd = as_d(b);
+                    a = as_u(mulmod_f64(__dadd_rn(ad, bd), as_d(c.n_inv.w), as_d(c.n_inv.wq), as_d(qm)));
+                    b = as_u(mulmod_f64(__dsub_rn(ad, bd), as_d(c.inv1_n_inv.w), as_d(c.inv1_n_inv.wq), as_d(qm)));
+                } else {
+                    const u64 s = a + b, d = a - b + big;
+                    a = twiddle_mul<MODE>(s, c.n_inv, c.q);
+                    b = twiddle_mul<MODE>(d, c.inv1_n_inv, c.q);
+                }
             }
         } else {
 #pragma unroll
@@ -169,8 +195,8 @@ template <int LOGM, int S0, int R> struct Pass {
 #endif
 #pragma unroll
                 for (int i = 0; i < HALF; ++i) {
-                    if constexpr (INVERSE) gs_butterfly<MODE>(x[u * RR + g * 2 * HALF + i], x[u * RR + g * 2 * HALF + i + HALF], w, c.q, c.two_q, big);
-                    else ct_butterfly<MODE>(x[u * RR + g * 2 * HALF + i], x[u * RR + g * 2 * HALF + i + HALF], w, c.q, c.two_q);
+                    if constexpr (INVERSE) gs_butterfly<MODE>(x[u * RR + g * 2 * HALF + i], x[u * RR + g * 2 * HALF + i + HALF], w, qm, c.two_q, big);
+                    else ct_butterfly<MODE>(x[u * RR + g * 2 * HALF + i], x[u * RR + g * 2 * HALF + i + HALF], w, qm, c.two_q);
                 }
             }
         }
@@ -193,7 +219,7 @@ template <int LOGM, int S0, int R> struct Pass {
     // multiplies by N^-1:  x = (u+v) N^-1,  y = (u-v) (inv[1] N^-1).
     template <bool FOLD_SCALE, int MODE, bool REDUCE_FIRST = true>
     __device__ static __forceinline__ void inverse(u64 (&x)[16], int tid, const ShoupW *__restrict__ tw, int stage_base, int blk, const NttConsts &c) {
-        if constexpr ((MODE == NTT_PASS || MODE == NTT_F64) && REDUCE_FIRST) {   // back to [0,2q) before this pass doubles the bound R times
+        if constexpr (MODE == NTT_PASS && REDUCE_FIRST) {   // back to [0,2q) before this pass doubles the bound R times
 #pragma unroll
             for (int r = 0; r < 16; ++r) x[r] = reduce_mode<MODE>(x[r], c.one_q, c.q);
         }
@@ -204,6 +230,9 @@ template <int LOGM, int S0, int R> struct Pass {
             if constexpr (R >= 3) stage<(R >= 3 ? 2 : 0), true, FOLD_SCALE, MODE>(x, u, h, tw, stage_base, blk, c);
             if constexpr (R >= 2) stage<(R >= 2 ? 1 : 0), true, FOLD_SCALE, MODE>(x, u, h, tw, stage_base, blk, c);
             stage<0, true, FOLD_SCALE, MODE>(x, u, h, tw, stage_base, blk, c);
+            // FP64 mode: register 0 of the butterfly took the sum branch in every stage (up to 2^R times the input bound);
+            // every other register is a sum of at most 2^(R-1) products (<= 6q).  Reduce that one register.
+            if constexpr (MODE == NTT_F64 && !FOLD_SCALE) x[u * RR] = as_u(reduce_sym_f64(as_d(x[u * RR]), as_d(c.one_q), as_d(c.qd)));
         }
     }
 };
@@ -224,6 +253,10 @@ template <int LOGM, int P> struct FullPassAt {  // P-th radix-16 pass after the 
 template <int LOGM, int MODE>
 __device__ __forceinline__ void block_ntt_forward(u64 (&x)[16], u64 *sm, int tid, const ShoupW *__restrict__ tw, int stage_base, int blk, const NttConsts &c) {
     using S = NttShape<LOGM>;
+    if constexpr (MODE == NTT_F64) {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) x[r] = as_u(u64_to_f64(x[r]));
+    }
     CoarsePass<LOGM>::template forward<MODE>(x, tid, tw, stage_base, blk, c);
     CoarsePass<LOGM>::store_smem(x, sm, tid);
     __syncthreads();
@@ -249,9 +282,18 @@ template <int MODE> __device__ __forceinline__ u64 forward_canon(u64 v, const Nt
     if constexpr (MODE == NTT_CLASSIC) {   // [0,4q) -> [0,q)
         v = v >= c.two_q ? v - c.two_q : v;
         return v >= c.q ? v - c.q : v;
+    } else if constexpr (MODE == NTT_F64) {   // signed double -> [-q/2, q/2] -> (+q, as an integer) -> [0,q)
+        const double qd = as_d(c.qd);
+        return csub(f64_to_u64_biased(reduce_sym_f64(as_d(v), as_d(c.one_q), qd), __dadd_rn(qd, kTwo52)), c.q);
     } else {
         return csub(reduce_mode<MODE>(v, c.one_q, c.q), c.q);
     }
+}
+// The forward transform's output as SOME non-negative 64-bit representative (for consumers that accept any 64-bit
+// input, e.g. a Shoup product): identity except in FP64 mode, where |v| <= 15.25 q is shifted by 16 q.
+template <int MODE> __device__ __forceinline__ u64 forward_lazy(u64 v, const NttConsts &c) {
+    if constexpr (MODE == NTT_F64) return f64_to_u64_biased(as_d(v), __fma_rn(16.0, as_d(c.qd), kTwo52));
+    else return v;
 }
 
 // Inverse: x holds the block in fine layout with values in [0,2q).  On return x holds the result in coarse layout,
@@ -259,6 +301,10 @@ template <int MODE> __device__ __forceinline__ u64 forward_canon(u64 v, const Nt
 template <int LOGM, bool FOLD_SCALE, int MODE>
 __device__ __forceinline__ void block_ntt_inverse(u64 (&x)[16], u64 *sm, int tid, const ShoupW *__restrict__ tw, int stage_base, int blk, const NttConsts &c) {
     using S = NttShape<LOGM>;
+    if constexpr (MODE == NTT_F64) {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) x[r] = as_u(u64_to_f64(x[r]));
+    }
     // The first executed pass starts from [0,2q): it needs no reduction even in pass mode.
     if constexpr (S::NFULL >= 3) {
         using P2 = typename FullPassAt<LOGM, 2>::type;
@@ -282,7 +328,11 @@ __device__ __forceinline__ void block_ntt_inverse(u64 (&x)[16], u64 *sm, int tid
     }
     CoarsePass<LOGM>::load_smem(x, sm, tid);
     CoarsePass<LOGM>::template inverse<FOLD_SCALE, MODE, (S::NFULL > 0)>(x, tid, tw, stage_base, blk, c);
-    if constexpr (!FOLD_SCALE && MODE != NTT_CLASSIC) {
+    if constexpr (MODE == NTT_F64) {   // products (FOLD_SCALE: |x| <= 0.75 q) or reduced values, shifted by q: (0, 2q) as integers
+        const double qd = as_d(c.qd), bias = __dadd_rn(qd, kTwo52);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) x[r] = f64_to_u64_biased(FOLD_SCALE ? as_d(x[r]) : reduce_sym_f64(as_d(x[r]), as_d(c.one_q), qd), bias);
+    } else if constexpr (!FOLD_SCALE && MODE != NTT_CLASSIC) {
 #pragma unroll
         for (int r = 0; r < 16; ++r) x[r] = reduce_mode<MODE>(x[r], c.one_q, c.q);
     }

@@ -1,0 +1,219 @@
+// pplp_b200/csrc/ntt32.cuh — the FP64-pipe negacyclic NTT with 32 coefficients per thread (moduli of at most 44 bits).
+//
+// Same function as ntt.cuh (SEAL's ntt_negacyclic_harvey / inverse_ntt_negacyclic_harvey, [SEAL] util/ntt.cpp), same
+// exact-integers-in-doubles arithmetic as its L = 3 mode (modarith.cuh mulmod_f64), different schedule.  With the
+// butterflies on the FP64 pipe (8 instructions each, 64 lanes per clock per SM) the 16-per-thread kernels are no longer
+// bound by arithmetic but by everything around it: four CTA-wide barriers, eight shared-memory transposes' worth of
+// traffic and their address arithmetic.  This schedule has ONE CTA barrier:
+//
+//   M = 2^LOGM points, T = M/32 threads (8 warps at M = 8192), 32 doubles per thread, two CTAs per SM.
+//   pass A  stages 0..4            thread t holds  e*T + t           (what a coalesced global load gives)
+//   -- transpose through shared memory, __syncthreads --
+//   pass B  stages 5..LOGM-6       warp w, lane l hold  1024 w + 32 e + l   (a warp owns 1024 contiguous points from here on)
+//   -- transpose inside the warp's own 1024 words, __syncwarp --
+//   pass C  stages LOGM-5..LOGM-1  thread t holds  32 t + e          (32 consecutive points: 256 contiguous bytes)
+//
+// The inverse runs the mirror image (C', B', A' with N^-1 folded into the last stage).  Pass-A twiddles are the same 31
+// values for the whole CTA (staged in shared memory), pass-B twiddles are warp-uniform, pass-C twiddles are per-thread
+// and come from a thread-interleaved copy of the table so that a warp's load is one contiguous 512 bytes.
+//
+// Ranges (q < 2^44, every multiplicand must stay within 2^51 = 128 q; a product is at most 0.75 q in magnitude):
+//   forward: |x| <= (4 + 0.75 * 13) q.
+//   inverse: sums double per stage.  After a pass of R stages fed with |x| <= X, register j of a radix-2^R group holds at
+//   most X 2^R (j = 0, the all-sums path) or 0.75 q 2^(R-1-msb(j)).  After each pass the registers whose bound would
+//   exceed 96 q inside the next pass are reduced to [-q/2, q/2] (three instructions each; one to four registers of 32).
+#pragma once
+#include "devstructs.h"
+
+namespace pplp {
+
+template <int LOGM> struct Ntt32Shape {
+    static_assert(LOGM >= 11 && LOGM <= 13, "32-per-thread FP64 transforms cover 2048..8192 points");
+    static constexpr int M = 1 << LOGM;
+    static constexpr int T = M / 32;            // threads per CTA
+    static constexpr int SB = LOGM - 10;        // stages of pass B
+    static constexpr int SMEM_WORDS = M + (M >> 5) + 64;   // one pad word per 32 + 31 pass-A twiddles (two words each)
+    static constexpr int TW_OFF = M + (M >> 5);
+};
+__device__ __forceinline__ int slot32(int i) { return i + (i >> 5); }
+
+struct Ntt32Consts {
+    double q, qinv;                 // double(q), fl(1/q)
+    ShoupW n_inv, inv1_n_inv;       // bits of (double w, fl(w/q))
+    const ShoupW *tw;               // natural table (bits of doubles): fwd_d or inv_d
+    const ShoupW *fine;             // thread-interleaved last five stages: entry ((2^v - 1 + j) * T + t) = tw[2^(LOGM-5+v) + (t << v) + j]
+};
+
+__device__ __forceinline__ void bf_ct(u64 &x, u64 &y, const ShoupW w, const double q) {
+    const double xd = as_d(x), t = mulmod_f64(as_d(y), as_d(w.w), as_d(w.wq), q);
+    y = as_u(__dsub_rn(xd, t));
+    x = as_u(__dadd_rn(xd, t));
+}
+__device__ __forceinline__ void bf_gs(u64 &x, u64 &y, const ShoupW w, const double q) {
+    const double xd = as_d(x), yd = as_d(y);
+    x = as_u(__dadd_rn(xd, yd));
+    y = as_u(mulmod_f64(__dsub_rn(xd, yd), as_d(w.w), as_d(w.wq), q));
+}
+__device__ __forceinline__ ShoupW ld_tw(const ShoupW *p) {
+    const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(p));
+    return ShoupW{v.x, v.y};
+}
+__device__ __forceinline__ ShoupW lds_tw(const u64 *sm, int i) {
+    const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(sm + 2 * i);
+    return ShoupW{v.x, v.y};
+}
+
+// bound (in units of q) of register j after an inverse pass of R stages whose inputs were bounded by X
+__host__ __device__ constexpr double gs_bound(int j, int R, double X) {
+    if (j == 0) return X * (1 << R);
+    int msb = 0;
+    for (int b = 0; b < R; ++b) if (j >> b & 1) msb = b;
+    return 0.75 * (1 << (R - 1 - msb));
+}
+constexpr double kGsLimit = 96.0;
+
+// Shared memory: a CTA that runs several transforms must __syncthreads() between them (the next transform's first writes
+// may land in words another warp is still reading).
+// ---- forward ----------------------------------------------------------------------------------------------------------
+// x: the block as u64 values below 4q, x[e] = coefficient e*T + tid.  On return x[e] = bits of the double holding output
+// 32*tid + e, |x| <= 14 q; ntt32_canon() brings it to [0,q).  sm: Ntt32Shape::SMEM_WORDS words.
+template <int LOGM>
+__device__ __forceinline__ void ntt32_forward(u64 (&x)[32], u64 *sm, int tid, const Ntt32Consts &c) {
+    using S = Ntt32Shape<LOGM>;
+    const int lane = tid & 31, warp = tid >> 5;
+    u64 *twA = sm + S::TW_OFF;
+    if (tid < 31) *reinterpret_cast<ulonglong2 *>(twA + 2 * tid) = __ldg(reinterpret_cast<const ulonglong2 *>(c.tw + 1 + tid));
+#pragma unroll
+    for (int e = 0; e < 32; ++e) x[e] = as_u(u64_to_f64(x[e]));
+    __syncthreads();
+    // pass A: stage s pairs e bit (4 - s); group = e >> (5 - s); twiddle tw[2^s + group]
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+#pragma unroll
+        for (int g = 0; g < (1 << s); ++g) {
+            const ShoupW w = lds_tw(twA, (1 << s) - 1 + g);
+            const int half = 16 >> s;
+#pragma unroll
+            for (int i = 0; i < half; ++i) bf_ct(x[g * 2 * half + i], x[g * 2 * half + i + half], w, c.q);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 32; ++e) sm[slot32(e * S::T + tid)] = x[e];
+    __syncthreads();
+    u64 *wsm = sm;   // the warp's 1024 points live at indices [1024 warp, 1024 warp + 1024)
+    const int wbase = warp << 10;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) x[e] = wsm[slot32(wbase + e * 32 + lane)];
+    // pass B: stage 5 + v pairs e bit (SB - 1 - v); group = (32 warp + e) >> (SB - v)
+    if constexpr (S::SB > 0) {
+#pragma unroll
+        for (int v = 0; v < S::SB; ++v) {
+            const int half = 1 << (S::SB - 1 - v);
+#pragma unroll
+            for (int g = 0; g < (32 >> (S::SB - v)); ++g) {
+                const ShoupW w = ld_tw(c.tw + (32 << v) + (((warp << 5) >> (S::SB - v)) + g));
+#pragma unroll
+                for (int i = 0; i < half; ++i) bf_ct(x[g * 2 * half + i], x[g * 2 * half + i + half], w, c.q);
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) wsm[slot32(wbase + e * 32 + lane)] = x[e];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < 32; ++e) x[e] = wsm[slot32(wbase + lane * 32 + e)];
+    // pass C: stage LOGM - 5 + v pairs e bit (4 - v); group = (tid << v) + (e >> (5 - v))
+#pragma unroll
+    for (int v = 0; v < 5; ++v) {
+        const int half = 16 >> v;
+#pragma unroll
+        for (int g = 0; g < (1 << v); ++g) {
+            const ShoupW w = ld_tw(c.fine + (size_t)((1 << v) - 1 + g) * S::T + tid);
+#pragma unroll
+            for (int i = 0; i < half; ++i) bf_ct(x[g * 2 * half + i], x[g * 2 * half + i + half], w, c.q);
+        }
+    }
+}
+// signed double (|v| <= 2^51) -> canonical residue
+__device__ __forceinline__ u64 ntt32_canon(u64 v, const Ntt32Consts &c, u64 q) {
+    return csub(f64_to_u64_biased(reduce_sym_f64(as_d(v), c.qinv, c.q), __dadd_rn(c.q, kTwo52)), q);
+}
+
+// ---- inverse ----------------------------------------------------------------------------------------------------------
+// x[e] = coefficient 32*tid + e as u64 below 2q.  On return x[e] = output e*T + tid as u64 in (0, 2q), scaled by N^-1.
+template <int LOGM>
+__device__ __forceinline__ void ntt32_inverse(u64 (&x)[32], u64 *sm, int tid, const Ntt32Consts &c) {
+    using S = Ntt32Shape<LOGM>;
+    const int lane = tid & 31, warp = tid >> 5;
+    u64 *twA = sm + S::TW_OFF;
+    if (tid < 31) *reinterpret_cast<ulonglong2 *>(twA + 2 * tid) = __ldg(reinterpret_cast<const ulonglong2 *>(c.tw + 1 + tid));
+#pragma unroll
+    for (int e = 0; e < 32; ++e) x[e] = as_u(u64_to_f64(x[e]));
+    // pass C': stages LOGM-1 .. LOGM-5
+#pragma unroll
+    for (int v = 4; v >= 0; --v) {
+        const int half = 16 >> v;
+#pragma unroll
+        for (int g = 0; g < (1 << v); ++g) {
+            const ShoupW w = ld_tw(c.fine + (size_t)((1 << v) - 1 + g) * S::T + tid);
+#pragma unroll
+            for (int i = 0; i < half; ++i) bf_gs(x[g * 2 * half + i], x[g * 2 * half + i + half], w, c.q);
+        }
+    }
+    constexpr int RNEXT = S::SB > 0 ? S::SB : 5;   // stages of the pass that follows C'
+#pragma unroll
+    for (int e = 0; e < 32; ++e)
+        if (gs_bound(e, 5, 2.0) * (1 << RNEXT) > kGsLimit) x[e] = as_u(reduce_sym_f64(as_d(x[e]), c.qinv, c.q));
+    u64 *wsm = sm;
+    const int wbase = warp << 10;
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < 32; ++e) wsm[slot32(wbase + lane * 32 + e)] = x[e];
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < 32; ++e) x[e] = wsm[slot32(wbase + e * 32 + lane)];
+    if constexpr (S::SB > 0) {
+        // pass B': stages LOGM-6 .. 5
+#pragma unroll
+        for (int v = S::SB - 1; v >= 0; --v) {
+            const int half = 1 << (S::SB - 1 - v);
+#pragma unroll
+            for (int g = 0; g < (32 >> (S::SB - v)); ++g) {
+                const ShoupW w = ld_tw(c.tw + (32 << v) + (((warp << 5) >> (S::SB - v)) + g));
+#pragma unroll
+                for (int i = 0; i < half; ++i) bf_gs(x[g * 2 * half + i], x[g * 2 * half + i + half], w, c.q);
+            }
+        }
+        // inputs of B' were bounded by 12 q (or 0.5 q where reduced); the next pass has five stages
+#pragma unroll
+        for (int e = 0; e < 32; ++e)
+            if (gs_bound(e & ((1 << S::SB) - 1), S::SB, 12.0) * 32 > kGsLimit) x[e] = as_u(reduce_sym_f64(as_d(x[e]), c.qinv, c.q));
+        __syncwarp();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) wsm[slot32(wbase + e * 32 + lane)] = x[e];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 32; ++e) x[e] = sm[slot32(e * S::T + tid)];
+    // pass A': stages 4 .. 1, then stage 0 with N^-1 folded in
+#pragma unroll
+    for (int s = 4; s >= 1; --s) {
+        const int half = 16 >> s;
+#pragma unroll
+        for (int g = 0; g < (1 << s); ++g) {
+            const ShoupW w = lds_tw(twA, (1 << s) - 1 + g);
+#pragma unroll
+            for (int i = 0; i < half; ++i) bf_gs(x[g * 2 * half + i], x[g * 2 * half + i + half], w, c.q);
+        }
+    }
+    const double bias = __dadd_rn(c.q, kTwo52);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const double ad = as_d(x[i]), bd = as_d(x[i + 16]);
+        x[i] = f64_to_u64_biased(mulmod_f64(__dadd_rn(ad, bd), as_d(c.n_inv.w), as_d(c.n_inv.wq), c.q), bias);
+        x[i + 16] = f64_to_u64_biased(mulmod_f64(__dsub_rn(ad, bd), as_d(c.inv1_n_inv.w), as_d(c.inv1_n_inv.wq), c.q), bias);
+    }
+}
+
+}  // namespace pplp

@@ -173,6 +173,7 @@ void Engine::upload_tables(int dev) {
         m.n_inv_d = m.inv1_n_inv_d = ShoupW{0, 0};
         m.one_d = 0;
         m.fine_fwd = m.fine_inv = m.fine_fwd_d = m.fine_inv_d = nullptr;
+        m.fine32_fwd_d = m.fine32_inv_d = nullptr;
         const int logn = host.logn;
         auto fine = [&](const std::vector<ShoupW> &tab) -> const ShoupW * {   // thread-interleaved last four stages
             if (logn < 4) return nullptr;
@@ -197,6 +198,18 @@ void Engine::upload_tables(int dev) {
             m.n_inv_d = pair(T.n_inv.w);
             m.inv1_n_inv_d = pair(T.inv1_n_inv.w);
             m.one_d = dbits(1.0 / (double)T.q);
+            if (logn >= 11 && logn <= 13) {
+                auto fine32 = [&](const std::vector<ShoupW> &tab) -> const ShoupW * {
+                    const size_t nt = host.n / 32;
+                    std::vector<ShoupW> f(31 * nt);
+                    for (int V = 0; V < 5; ++V)
+                        for (size_t g = 0; g < (size_t(1) << V); ++g)
+                            for (size_t t = 0; t < nt; ++t) f[((size_t(1) << V) - 1 + g) * nt + t] = tab[(size_t(1) << (logn - 5 + V)) + (t << V) + g];
+                    return upload(f.data(), f.size());
+                };
+                m.fine32_fwd_d = fine32(fd);
+                m.fine32_inv_d = fine32(id);
+            }
         }
     }
     d_mods = upload(h_mods.data(), h_mods.size());

@@ -25,6 +25,9 @@ struct DevMod {
     // thread-interleaved copies of the twiddles of the last four stages: entry ((2^V - 1 + g) * N/16 + t) is the twiddle of
     // stage logN-4+V, group (t << V) + g  — what thread t of the fine pass needs, laid out so a warp's load coalesces
     const ShoupW *fine_fwd, *fine_inv, *fine_fwd_d, *fine_inv_d;
+    // ntt32.cuh (32 coefficients per thread, N = 2048..8192): the last FIVE stages thread-interleaved,
+    // entry ((2^v - 1 + j) * N/32 + t) = twiddle of stage logN-5+v, group (t << v) + j; bits of (double(w), fl(w/q)); else null
+    const ShoupW *fine32_fwd_d, *fine32_inv_d;
 };
 
 // How a batch of polynomials lies in HBM.  Element (query qi, poly p, limb j, coeff n) is at

@@ -13,6 +13,7 @@
 // Algorithmic HBM bytes: 16*N per limb transform (read + write); polymul: 8*N*(2 + has_c) + b (L2-resident when broadcast).
 #include "engine.hpp"
 #include "ntt.cuh"
+#include "ntt32.cuh"
 
 // CTAs per SM the stand-alone transforms are compiled for when N <= 8192 (2 => 64 registers per thread, 32 warps per SM)
 #ifndef PPLP_NTT_MIN_CTAS
@@ -95,6 +96,46 @@ __global__ void __launch_bounds__(NttShape<LOGM>::T, (LOGM <= 13 ? PPLP_NTT_MIN_
         block_ntt_inverse<LOGM, false, IM>(x, sm, tid, inv_table<L>(md), a.stage_base, blk, c);
         CoarsePass<LOGM>::for_each(tid, [&](int r, int i) { ptr[i] = x[r]; });  // lazily in [0,2q); stage-0 pass canonicalises
     }
+}
+
+// ---- 32 coefficients per thread, FP64 pipe (ntt32.cuh): the stand-alone transforms for moduli <= 44 bits, N = 2048..8192 ----
+template <int LOGM>
+__global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T) ntt32_forward_kernel(const NttArgs a) {
+    using S = Ntt32Shape<LOGM>;
+    extern __shared__ __align__(16) u64 sm[];
+    const int tid = threadIdx.x;
+    int qi, p, j;
+    decode_row(blockIdx.x, a.nq, a.npoly, qi, p, j);
+    const DevMod &md = a.mods[a.map.mod_id[j]];
+    const Ntt32Consts c = ntt32_consts(md, false);
+    u64 *ptr = a.data + qi * a.lay.sq + p * a.lay.sp + j * a.lay.sl;
+    // Opaque to the optimiser: otherwise the row address is re-derived from its components at every use, the components
+    // stay live through the transform, and the register scheduler sinks the twiddle loads next to their uses.
+    asm volatile("" : "+l"(ptr));
+    u64 x[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) x[e] = ptr[e * S::T + tid];
+    ntt32_forward<LOGM>(x, sm, tid, c);
+#pragma unroll
+    for (int e = 0; e < 32; ++e) x[e] = ntt32_canon(x[e], c, md.m.q);
+    ntt32_store_row(x, sm, tid, ptr);
+}
+template <int LOGM>
+__global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T) ntt32_inverse_kernel(const NttArgs a) {
+    using S = Ntt32Shape<LOGM>;
+    extern __shared__ __align__(16) u64 sm[];
+    const int tid = threadIdx.x;
+    int qi, p, j;
+    decode_row(blockIdx.x, a.nq, a.npoly, qi, p, j);
+    const DevMod &md = a.mods[a.map.mod_id[j]];
+    const Ntt32Consts c = ntt32_consts(md, true);
+    u64 *ptr = a.data + qi * a.lay.sq + p * a.lay.sp + j * a.lay.sl;
+    u64 x[32];
+    ntt32_load_row(x, sm, tid, ptr);
+    ntt32_inverse<LOGM>(x, sm, tid, c);
+    const u64 q = md.m.q;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) ptr[e * S::T + tid] = csub(x[e], q);
 }
 
 // Streaming butterfly stage 0 for N = 2*M (gap N/2, single twiddle fwd[1]).  Output lazily < 4q (forward) / canonical (inverse).
@@ -194,7 +235,20 @@ template <int LOGM, int L> static void run_block_ntt(const NttArgs &a, int rows,
         ntt_forward_kernel<LOGM, L><<<grid, NttShape<LOGM>::T, bytes, st>>>(a);
     }
 }
+template <int LOGM> static void run_ntt32(const NttArgs &a, int rows, bool inverse, cudaStream_t st) {
+    const int bytes = Ntt32Shape<LOGM>::SMEM_WORDS * 8;
+    if (inverse) {
+        allow_smem(ntt32_inverse_kernel<LOGM>, bytes);
+        ntt32_inverse_kernel<LOGM><<<rows, Ntt32Shape<LOGM>::T, bytes, st>>>(a);
+    } else {
+        allow_smem(ntt32_forward_kernel<LOGM>, bytes);
+        ntt32_forward_kernel<LOGM><<<rows, Ntt32Shape<LOGM>::T, bytes, st>>>(a);
+    }
+}
 template <int LOGM> static void run_block_ntt_l(int level, const NttArgs &a, int rows, bool inverse, cudaStream_t st) {
+    if constexpr (LOGM >= 11 && LOGM <= 13) {
+        if (level == 3 && a.stage_base == 0) { run_ntt32<LOGM>(a, rows, inverse, st); return; }
+    }
     if (level == 3) run_block_ntt<LOGM, 3>(a, rows, inverse, st);
     else if (level == 2) run_block_ntt<LOGM, 2>(a, rows, inverse, st);
     else if (level == 1) run_block_ntt<LOGM, 1>(a, rows, inverse, st);

@@ -23,6 +23,7 @@
 //   most X 2^R (j = 0, the all-sums path) or 0.75 q 2^(R-1-msb(j)).  After each pass the registers whose bound would
 //   exceed 96 q inside the next pass are reduced to [-q/2, q/2] (three instructions each; one to four registers of 32).
 #pragma once
+#include <type_traits>
 #include "devstructs.h"
 
 namespace pplp {
@@ -44,6 +45,35 @@ struct Ntt32Consts {
     const ShoupW *fine;             // thread-interleaved last five stages: entry ((2^v - 1 + j) * T + t) = tw[2^(LOGM-5+v) + (t << v) + j]
 };
 
+__device__ __forceinline__ Ntt32Consts ntt32_consts(const DevMod &md, bool inverse) {
+    Ntt32Consts c;
+    c.q = (double)md.m.q; c.qinv = as_d(md.one_d);
+    c.n_inv = md.n_inv_d; c.inv1_n_inv = md.inv1_n_inv_d;
+    c.tw = inverse ? md.inv_d : md.fwd_d;
+    c.fine = inverse ? md.fine32_inv_d : md.fine32_fwd_d;
+    return c;
+}
+// Global <-> register staging through the warp's own 1024 words (coalesced 256-byte accesses on the global side):
+// registers in the "contiguous" layout x[e] = row[32 tid + e].
+__device__ __forceinline__ void ntt32_store_row(const u64 (&x)[32], u64 *sm, int tid, u64 *row) {
+    const int lane = tid & 31, wbase = (tid >> 5) << 10;
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < 32; ++e) sm[slot32(wbase + lane * 32 + e)] = x[e];
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < 32; ++e) row[wbase + e * 32 + lane] = sm[slot32(wbase + e * 32 + lane)];
+}
+__device__ __forceinline__ void ntt32_load_row(u64 (&x)[32], u64 *sm, int tid, const u64 *row) {
+    const int lane = tid & 31, wbase = (tid >> 5) << 10;
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < 32; ++e) sm[slot32(wbase + e * 32 + lane)] = row[wbase + e * 32 + lane];
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < 32; ++e) x[e] = sm[slot32(wbase + lane * 32 + e)];
+}
+
 __device__ __forceinline__ void bf_ct(u64 &x, u64 &y, const ShoupW w, const double q) {
     const double xd = as_d(x), t = mulmod_f64(as_d(y), as_d(w.w), as_d(w.wq), q);
     y = as_u(__dsub_rn(xd, t));
@@ -62,6 +92,45 @@ __device__ __forceinline__ ShoupW lds_tw(const u64 *sm, int i) {
     const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(sm + 2 * i);
     return ShoupW{v.x, v.y};
 }
+
+// Twiddle loads run LOOK entries ahead of their use (a rolling register queue): the L2 round trip of a per-thread
+// twiddle is several hundred cycles, far more than the compiler's own scheduling hides once registers are tight.
+#ifndef PPLP_NTT32_LOOK
+#define PPLP_NTT32_LOOK 4
+#endif
+// (indices are passed as integral constants so that every register-array subscript is a compile-time constant)
+template <int K> using IntC = std::integral_constant<int, K>;
+template <int I, int N, class F> __device__ __forceinline__ void static_for(F f) {
+    if constexpr (I < N) { f(IntC<I>{}); static_for<I + 1, N>(f); }
+}
+template <int NTW, int LOOK, class AddrF, class BodyF>
+__device__ __forceinline__ void tw_pipeline(AddrF addr, BodyF body) {
+    ShoupW queue[LOOK];
+    static_for<0, (LOOK < NTW ? LOOK : NTW)>([&](auto i) { queue[decltype(i)::value] = ld_tw(addr(i)); });
+    static_for<0, NTW>([&](auto k) {
+        constexpr int K = decltype(k)::value;
+        const ShoupW w = queue[K % LOOK];
+        if constexpr (K + LOOK < NTW) queue[K % LOOK] = ld_tw(addr(IntC<K + LOOK>{}));
+        body(k, w);
+    });
+}
+// row r of a five-stage thread-local pass: stage v = floor(log2(r + 1)), group g = r + 1 - 2^v
+__host__ __device__ constexpr int row_stage(int r) { int v = 0; while ((2 << v) <= r + 1) ++v; return v; }
+// the order in which the inverse consumes those rows: stages 4, 3, 2, 1, 0
+__host__ __device__ constexpr int inv_row(int k) { return k < 16 ? 15 + k : (k < 24 ? 7 + (k - 16) : (k < 28 ? 3 + (k - 24) : (k < 30 ? 1 + (k - 28) : 0))); }
+// pass B (SB stages over 32 registers): twiddle k in forward order -> (stage v, group g)
+template <int SB> struct PassB {
+    static constexpr int NTW = 32 - (32 >> SB);   // sum over v of 32 >> (SB - v)
+    __host__ __device__ static constexpr int stage(int k) { int v = 0, base = 0; while (k >= base + (32 >> (SB - v))) { base += 32 >> (SB - v); ++v; } return v; }
+    __host__ __device__ static constexpr int group(int k) { int v = 0, base = 0; while (k >= base + (32 >> (SB - v))) { base += 32 >> (SB - v); ++v; } return k - base; }
+    __host__ __device__ static constexpr int inv_k(int k) {   // k-th twiddle the inverse consumes (stages SB-1 .. 0)
+        int v = SB - 1, base = 0;
+        while (k >= base + (32 >> (SB - v))) { base += 32 >> (SB - v); --v; }
+        int first = 0;
+        for (int u = 0; u < v; ++u) first += 32 >> (SB - u);
+        return first + (k - base);
+    }
+};
 
 // bound (in units of q) of register j after an inverse pass of R stages whose inputs were bounded by X
 __host__ __device__ constexpr double gs_bound(int j, int R, double X) {
@@ -106,16 +175,14 @@ __device__ __forceinline__ void ntt32_forward(u64 (&x)[32], u64 *sm, int tid, co
     for (int e = 0; e < 32; ++e) x[e] = wsm[slot32(wbase + e * 32 + lane)];
     // pass B: stage 5 + v pairs e bit (SB - 1 - v); group = (32 warp + e) >> (SB - v)
     if constexpr (S::SB > 0) {
-#pragma unroll
-        for (int v = 0; v < S::SB; ++v) {
-            const int half = 1 << (S::SB - 1 - v);
-#pragma unroll
-            for (int g = 0; g < (32 >> (S::SB - v)); ++g) {
-                const ShoupW w = ld_tw(c.tw + (32 << v) + (((warp << 5) >> (S::SB - v)) + g));
+        using PB = PassB<S::SB>;
+        tw_pipeline<PB::NTW, PPLP_NTT32_LOOK>(
+            [&](auto k) { constexpr int K = decltype(k)::value, v = PB::stage(K); return c.tw + (32 << v) + (((warp << 5) >> (S::SB - v)) + PB::group(K)); },
+            [&](auto k, const ShoupW w) {
+                constexpr int K = decltype(k)::value, v = PB::stage(K), g = PB::group(K), half = 1 << (S::SB - 1 - v);
 #pragma unroll
                 for (int i = 0; i < half; ++i) bf_ct(x[g * 2 * half + i], x[g * 2 * half + i + half], w, c.q);
-            }
-        }
+            });
         __syncwarp();
 #pragma unroll
         for (int e = 0; e < 32; ++e) wsm[slot32(wbase + e * 32 + lane)] = x[e];
@@ -124,16 +191,13 @@ __device__ __forceinline__ void ntt32_forward(u64 (&x)[32], u64 *sm, int tid, co
 #pragma unroll
     for (int e = 0; e < 32; ++e) x[e] = wsm[slot32(wbase + lane * 32 + e)];
     // pass C: stage LOGM - 5 + v pairs e bit (4 - v); group = (tid << v) + (e >> (5 - v))
-#pragma unroll
-    for (int v = 0; v < 5; ++v) {
-        const int half = 16 >> v;
-#pragma unroll
-        for (int g = 0; g < (1 << v); ++g) {
-            const ShoupW w = ld_tw(c.fine + (size_t)((1 << v) - 1 + g) * S::T + tid);
+    tw_pipeline<31, PPLP_NTT32_LOOK>(
+        [&](auto k) { return c.fine + (size_t)decltype(k)::value * S::T + tid; },
+        [&](auto k, const ShoupW w) {
+            constexpr int r = decltype(k)::value, v = row_stage(r), g = r + 1 - (1 << v), half = 16 >> v;
 #pragma unroll
             for (int i = 0; i < half; ++i) bf_ct(x[g * 2 * half + i], x[g * 2 * half + i + half], w, c.q);
-        }
-    }
+        });
 }
 // signed double (|v| <= 2^51) -> canonical residue
 __device__ __forceinline__ u64 ntt32_canon(u64 v, const Ntt32Consts &c, u64 q) {
@@ -151,16 +215,13 @@ __device__ __forceinline__ void ntt32_inverse(u64 (&x)[32], u64 *sm, int tid, co
 #pragma unroll
     for (int e = 0; e < 32; ++e) x[e] = as_u(u64_to_f64(x[e]));
     // pass C': stages LOGM-1 .. LOGM-5
-#pragma unroll
-    for (int v = 4; v >= 0; --v) {
-        const int half = 16 >> v;
-#pragma unroll
-        for (int g = 0; g < (1 << v); ++g) {
-            const ShoupW w = ld_tw(c.fine + (size_t)((1 << v) - 1 + g) * S::T + tid);
+    tw_pipeline<31, PPLP_NTT32_LOOK>(
+        [&](auto k) { return c.fine + (size_t)inv_row(decltype(k)::value) * S::T + tid; },
+        [&](auto k, const ShoupW w) {
+            constexpr int r = inv_row(decltype(k)::value), v = row_stage(r), g = r + 1 - (1 << v), half = 16 >> v;
 #pragma unroll
             for (int i = 0; i < half; ++i) bf_gs(x[g * 2 * half + i], x[g * 2 * half + i + half], w, c.q);
-        }
-    }
+        });
     constexpr int RNEXT = S::SB > 0 ? S::SB : 5;   // stages of the pass that follows C'
 #pragma unroll
     for (int e = 0; e < 32; ++e)
@@ -175,16 +236,14 @@ __device__ __forceinline__ void ntt32_inverse(u64 (&x)[32], u64 *sm, int tid, co
     for (int e = 0; e < 32; ++e) x[e] = wsm[slot32(wbase + e * 32 + lane)];
     if constexpr (S::SB > 0) {
         // pass B': stages LOGM-6 .. 5
-#pragma unroll
-        for (int v = S::SB - 1; v >= 0; --v) {
-            const int half = 1 << (S::SB - 1 - v);
-#pragma unroll
-            for (int g = 0; g < (32 >> (S::SB - v)); ++g) {
-                const ShoupW w = ld_tw(c.tw + (32 << v) + (((warp << 5) >> (S::SB - v)) + g));
+        using PB = PassB<S::SB>;
+        tw_pipeline<PB::NTW, PPLP_NTT32_LOOK>(
+            [&](auto k) { constexpr int f = PB::inv_k(decltype(k)::value), v = PB::stage(f); return c.tw + (32 << v) + (((warp << 5) >> (S::SB - v)) + PB::group(f)); },
+            [&](auto k, const ShoupW w) {
+                constexpr int f = PB::inv_k(decltype(k)::value), v = PB::stage(f), g = PB::group(f), half = 1 << (S::SB - 1 - v);
 #pragma unroll
                 for (int i = 0; i < half; ++i) bf_gs(x[g * 2 * half + i], x[g * 2 * half + i + half], w, c.q);
-            }
-        }
+            });
         // inputs of B' were bounded by 12 q (or 0.5 q where reduced); the next pass has five stages
 #pragma unroll
         for (int e = 0; e < 32; ++e)

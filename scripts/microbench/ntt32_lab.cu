@@ -13,7 +13,7 @@ using namespace pplp;
 struct LabMod { u64 q; Ntt32Consts f, i; };
 
 template <int LOGM, int STORE>
-__global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T) fwd_kernel(u64 *data, const LabMod *mods, int rows_per_mod) {
+__global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T) fwd_kernel(u64 *data, const LabMod *mods, int rows_per_mod, int pf) {
     using S = Ntt32Shape<LOGM>;
     extern __shared__ __align__(16) u64 sm[];
     const int tid = threadIdx.x;
@@ -23,6 +23,10 @@ __global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T
     u64 x[32];
 #pragma unroll
     for (int e = 0; e < 32; ++e) x[e] = ptr[e * S::T + tid];
+    if (pf && blockIdx.x + pf < gridDim.x) {   // pull the row a later CTA of this SM slot will read into L2
+        const char *nx = reinterpret_cast<const char *>(ptr + (size_t)pf * S::M);
+        for (int o = tid * 128; o < S::M * 8; o += S::T * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + o));
+    }
     ntt32_forward<LOGM>(x, sm, tid, c);
 #pragma unroll
     for (int e = 0; e < 32; ++e) x[e] = ntt32_canon(x[e], c, md.q);
@@ -40,7 +44,7 @@ __global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T
     }
 }
 template <int LOGM, int LOAD>
-__global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T) inv_kernel(u64 *data, const LabMod *mods, int rows_per_mod) {
+__global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T) inv_kernel(u64 *data, const LabMod *mods, int rows_per_mod, int pf) {
     using S = Ntt32Shape<LOGM>;
     extern __shared__ __align__(16) u64 sm[];
     const int tid = threadIdx.x;
@@ -48,6 +52,10 @@ __global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T
     const Ntt32Consts c = md.i;
     u64 *ptr = data + (size_t)blockIdx.x * S::M;
     u64 x[32];
+    if (pf && blockIdx.x + pf < gridDim.x) {
+        const char *nx = reinterpret_cast<const char *>(ptr + (size_t)pf * S::M);
+        for (int o = tid * 128; o < S::M * 8; o += S::T * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + o));
+    }
     if (LOAD == 0) {
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
@@ -131,9 +139,10 @@ template <int LOGM> void run(int rows) {
     CK(cudaFuncSetAttribute(inv_kernel<LOGM, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     // correctness: rows 0, rpm, 2rpm+1, last
     const int check[4] = {0, rpm, 2 * rpm + 1, rows - 1};
+    int pf = 296;
     for (int variant = 0; variant < 2; ++variant) {
         CK(cudaMemcpy(d, h.data(), h.size() * 8, cudaMemcpyHostToDevice));
-        if (variant == 0) fwd_kernel<LOGM, 0><<<rows, S::T, bytes>>>(d, d_mods, rpm); else fwd_kernel<LOGM, 1><<<rows, S::T, bytes>>>(d, d_mods, rpm);
+        if (variant == 0) fwd_kernel<LOGM, 0><<<rows, S::T, bytes>>>(d, d_mods, rpm, pf); else fwd_kernel<LOGM, 1><<<rows, S::T, bytes>>>(d, d_mods, rpm, pf);
         CK(cudaDeviceSynchronize());
         std::vector<u64> got(n), ref(n);
         bool ok = true;
@@ -144,7 +153,7 @@ template <int LOGM> void run(int rows) {
             if (got != ref) { ok = false; int bad = 0; for (int i = 0; i < n; ++i) if (got[i] != ref[i]) { if (bad++ < 4) printf("  fwd row %d idx %d got %llu ref %llu\n", r, i, (unsigned long long)got[i], (unsigned long long)ref[i]); } printf("  %d mismatches\n", bad); }
         }
         printf("N=%d forward variant %d: %s\n", n, variant, ok ? "OK" : "MISMATCH");
-        if (variant == 0) inv_kernel<LOGM, 0><<<rows, S::T, bytes>>>(d, d_mods, rpm); else inv_kernel<LOGM, 1><<<rows, S::T, bytes>>>(d, d_mods, rpm);
+        if (variant == 0) inv_kernel<LOGM, 0><<<rows, S::T, bytes>>>(d, d_mods, rpm, pf); else inv_kernel<LOGM, 1><<<rows, S::T, bytes>>>(d, d_mods, rpm, pf);
         CK(cudaDeviceSynchronize());
         ok = true;
         for (int r : check) {
@@ -154,7 +163,7 @@ template <int LOGM> void run(int rows) {
         printf("N=%d inverse(forward) variant %d: %s\n", n, variant, ok ? "round trip OK" : "MISMATCH");
         // inverse against the host on raw data
         CK(cudaMemcpy(d, h.data(), h.size() * 8, cudaMemcpyHostToDevice));
-        if (variant == 0) inv_kernel<LOGM, 0><<<rows, S::T, bytes>>>(d, d_mods, rpm); else inv_kernel<LOGM, 1><<<rows, S::T, bytes>>>(d, d_mods, rpm);
+        if (variant == 0) inv_kernel<LOGM, 0><<<rows, S::T, bytes>>>(d, d_mods, rpm, pf); else inv_kernel<LOGM, 1><<<rows, S::T, bytes>>>(d, d_mods, rpm, pf);
         CK(cudaDeviceSynchronize());
         ok = true;
         for (int r : {0, rows - 1}) {
@@ -166,19 +175,20 @@ template <int LOGM> void run(int rows) {
         printf("N=%d inverse vs host variant %d: %s\n", n, variant, ok ? "OK" : "MISMATCH");
     }
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    for (int pf : {0})
     for (int k = 0; k < 4; ++k) {
         float best = 1e9;
         for (int rep = 0; rep < 6; ++rep) {
             cudaEventRecord(a);
-            if (k == 0) fwd_kernel<LOGM, 0><<<rows, S::T, bytes>>>(d, d_mods, rpm);
-            else if (k == 1) fwd_kernel<LOGM, 1><<<rows, S::T, bytes>>>(d, d_mods, rpm);
-            else if (k == 2) inv_kernel<LOGM, 0><<<rows, S::T, bytes>>>(d, d_mods, rpm);
-            else inv_kernel<LOGM, 1><<<rows, S::T, bytes>>>(d, d_mods, rpm);
+            if (k == 0) fwd_kernel<LOGM, 0><<<rows, S::T, bytes>>>(d, d_mods, rpm, pf);
+            else if (k == 1) fwd_kernel<LOGM, 1><<<rows, S::T, bytes>>>(d, d_mods, rpm, pf);
+            else if (k == 2) inv_kernel<LOGM, 0><<<rows, S::T, bytes>>>(d, d_mods, rpm, pf);
+            else inv_kernel<LOGM, 1><<<rows, S::T, bytes>>>(d, d_mods, rpm, pf);
             cudaEventRecord(b); cudaEventSynchronize(b);
             float ms; cudaEventElapsedTime(&ms, a, b);
             if (rep >= 2 && ms < best) best = ms;
         }
-        printf("N=%d %s io-variant %d: %.4f ms  %.1f GB/s\n", n, k < 2 ? "forward" : "inverse", k & 1, best, 16.0 * n * rows / (best * 1e-3) / 1e9);
+        printf("N=%d pf=%d %s io-variant %d: %.4f ms  %.1f GB/s\n", n, pf, k < 2 ? "forward" : "inverse", k & 1, best, 16.0 * n * rows / (best * 1e-3) / 1e9);
     }
     CK(cudaGetLastError());
     cudaFree(d);

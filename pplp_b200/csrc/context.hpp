@@ -198,6 +198,7 @@ struct HostContext {
             for (size_t j = 0; j + 1 < k; ++j) {
                 D.inv_last[j] = make_shoup(hm::inverse_or_throw(last % ql[j], ql[j]), ql[j]);
                 D.half_last_mod[j] = D.half_last % ql[j];
+                D.last_cover[j] = ((last + ql[j] - 1) / ql[j]) * ql[j];
             }
         }
         // --- RNSTool: auxiliary bases ---

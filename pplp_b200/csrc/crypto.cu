@@ -15,9 +15,11 @@
 //                          One forward transform feeds both inverse transforms; nothing NTT-form touches HBM.
 //   modswitch_kernel       divide_and_round_q_last (drop the special prime) fused with the scaling-variant plaintext
 //                          addition c0 += round(Q m / t): the only cross-limb step.
+#include <cstdlib>
 #include "blake2.cuh"
 #include "engine.hpp"
 #include "ntt.cuh"
+#include "ntt32.cuh"
 
 namespace pplp {
 
@@ -283,18 +285,51 @@ __global__ void __launch_bounds__(NttShape<LOGM>::T, (LOGM <= 13 ? PPLP_ENC_INV_
             lastp[i] = add_mod(v, half, q);
         });
     } else {
+        // divide-and-round by P: (T + e - ((last - P/2) mod q)) P^-1.  Shoup's product takes any 64-bit input, so the
+        // bracket is formed without a single reduction: x in (0,2q), e small and signed, last < P <= cover (a multiple of q).
         const DevLevel &KL = *a.KL;
-        const u64 half_mod = KL.half_last_mod[j];
+        const u64 offset = KL.half_last_mod[j] + KL.last_cover[j];
         const ShoupW inv_last = KL.inv_last[j];
         u64 *dst = a.out + ct * a.lay.sq + p * a.lay.sp + j * a.lay.sl;
         CoarsePass<LOGM>::for_each(tid, [&](int r, int i) {
-            const int ev = e[i];
-            u64 v = add_mod(csub(x[r], q), ev < 0 ? q - (u64)(-ev) : (u64)ev, q);
-            const u64 corr = sub_mod(barrett64(lastp[i], mod), half_mod, q);
-            v = csub(mul_shoup_lazy_nq(sub_mod(v, corr, q), inv_last.w, inv_last.wq, 0 - q), q);
-            if (p == 0 && i < a.plain_count) v = add_mod(v, dev_scaled_plain(*a.DL, a.plain[ct * a.plain_stride + i], j), q);
-            dst[i] = v;
+            const u64 t = x[r] + (u64)(long long)e[i] + offset - lastp[i];
+            dst[i] = csub(mul_shoup_lazy_nq(t, inv_last.w, inv_last.wq, 0 - q), q);
         });
+        // c0 += round(Q m / t) on the (few) plaintext coefficients: kept out of the unrolled loop (it carries a 128-bit
+        // division).  Every thread owns its coefficients in both loops (index = tid mod T), so this reads its own store.
+        if (p == 0)
+            for (int i = tid; i < a.plain_count; i += NttShape<LOGM>::T) dst[i] = add_mod(dst[i], dev_scaled_plain(*a.DL, a.plain[ct * a.plain_stride + i], j), q);
+    }
+}
+
+// ---- the forward transform of the split pipeline on the 32-per-thread FP64 schedule (ntt32.cuh): N = 2048..8192, moduli
+// of at most 44 bits.  (The inverse kernels stay on the 16-per-thread schedule: with their load-heavy prologue and
+// epilogue, 32 warps per SM hide more latency than the leaner transform saves — measured 213 k vs 194 k queries/s.)
+template <int LOGM>
+__global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T) enc32_forward_kernel(const EncSplitArgs a) {
+    using S = Ntt32Shape<LOGM>;
+    extern __shared__ __align__(16) u64 sm[];
+    const int tid = threadIdx.x;
+    const int ct = blockIdx.x / a.K, j = blockIdx.x % a.K;
+    const DevMod &md = a.mods[j];
+    const Ntt32Consts c = ntt32_consts(md, false);
+    const u64 q = md.m.q;
+    const signed char *nz = a.noise + (size_t)ct * 3 * a.n;
+    asm volatile("" : "+l"(nz));
+    u64 x[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+        const int v = nz[e * S::T + tid];
+        x[e] = v < 0 ? q - 1 : (u64)v;
+    }
+    ntt32_forward<LOGM>(x, sm, tid, c);
+    // U in the interleaving the 16-per-thread inverse kernels read (pair h of their thread t' at [h * n/16 + t']): this
+    // thread's 32 coefficients are those of t' = 2 tid and 2 tid + 1, so each store covers two adjacent pairs (32 bytes).
+    ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(a.U + ((size_t)ct * a.K + j) * a.n) + 2 * tid;
+#pragma unroll
+    for (int h = 0; h < 8; ++h) {
+        dst[h * 2 * S::T] = make_ulonglong2(ntt32_canon(x[2 * h], c, q), ntt32_canon(x[2 * h + 1], c, q));
+        dst[h * 2 * S::T + 1] = make_ulonglong2(ntt32_canon(x[16 + 2 * h], c, q), ntt32_canon(x[16 + 2 * h + 1], c, q));
     }
 }
 
@@ -379,6 +414,17 @@ template <int LOGM, int L> static void run_encrypt_split_l(const EncSplitArgs &a
     enc_inverse_kernel<LOGM, L, true><<<nct * 2, T, bytes, st>>>(a);
     enc_inverse_kernel<LOGM, L, false><<<nct * 2 * (a.K - 1), T, bytes, st>>>(a);
 }
+template <int LOGM> static void run_encrypt_split32(const EncSplitArgs &a, int nct, cudaStream_t st) {
+    if constexpr (LOGM >= 11 && LOGM <= 13) {
+        const int bytes32 = Ntt32Shape<LOGM>::SMEM_WORDS * 8, bytes = NttShape<LOGM>::SMEM_WORDS * 8, T = NttShape<LOGM>::T;
+        PPLP_CUDA(cudaFuncSetAttribute(enc32_forward_kernel<LOGM>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes32));
+        PPLP_CUDA(cudaFuncSetAttribute(enc_inverse_kernel<LOGM, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        PPLP_CUDA(cudaFuncSetAttribute(enc_inverse_kernel<LOGM, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        enc32_forward_kernel<LOGM><<<nct * a.K, Ntt32Shape<LOGM>::T, bytes32, st>>>(a);
+        enc_inverse_kernel<LOGM, 3, true><<<nct * 2, T, bytes, st>>>(a);
+        enc_inverse_kernel<LOGM, 3, false><<<nct * 2 * (a.K - 1), T, bytes, st>>>(a);
+    }
+}
 template <int LOGM> static void run_encrypt_split(int lazy, const EncSplitArgs &a, int nct, cudaStream_t st) {
     if (lazy == 3) run_encrypt_split_l<LOGM, 3>(a, nct, st);
     else if (lazy == 2) run_encrypt_split_l<LOGM, 2>(a, nct, st);
@@ -402,13 +448,15 @@ void launch_encrypt(const Engine &E, const u64 *pk, const u64 *seeds, const u64 
     const int lazy = ntt_lazy_level(E.max_bits(E.qmap(0)), E.host.logn);
     const size_t first = E.host.first_level();
     if (K > 1 && E.host.logn <= 14) {   // split pipeline: forward, special-limb inverse, data-limb inverse + modulus switch + plaintext
+        static const bool wide_ok = !(std::getenv("PPLP_ENC_WIDE") && std::getenv("PPLP_ENC_WIDE")[0] == '0');   // experiment hook
+        const bool wide = wide_ok && lazy == 3 && E.host.logn >= 11 && E.host.logn <= 13;   // forward transform on the 32-per-thread FP64 schedule (ntt32.cuh)
         prepare_key_kernel<<<dim3((n + 255) / 256, 2 * K), 256, 0, st>>>(E.d_mods, pk, extra, K, n, lazy == 3 ? 1 : 0);
         EncSplitArgs sa{noise, extra, tmp, tmp + (size_t)nct * K * n, out, out_lay, plain, (int)plain_count, plain_stride, K, n, E.d_mods, E.d_levels, E.d_levels + first};
         switch (E.host.logn) {
         case 10: run_encrypt_split<10>(lazy, sa, nct, st); break;
-        case 11: run_encrypt_split<11>(lazy, sa, nct, st); break;
-        case 12: run_encrypt_split<12>(lazy, sa, nct, st); break;
-        case 13: run_encrypt_split<13>(lazy, sa, nct, st); break;
+        case 11: if (wide) run_encrypt_split32<11>(sa, nct, st); else run_encrypt_split<11>(lazy, sa, nct, st); break;
+        case 12: if (wide) run_encrypt_split32<12>(sa, nct, st); else run_encrypt_split<12>(lazy, sa, nct, st); break;
+        case 13: if (wide) run_encrypt_split32<13>(sa, nct, st); else run_encrypt_split<13>(lazy, sa, nct, st); break;
         default: run_encrypt_split<14>(lazy, sa, nct, st); break;
         }
         PPLP_CUDA(cudaGetLastError());

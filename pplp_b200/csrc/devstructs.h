@@ -51,6 +51,7 @@ struct DevLevel {
     ShoupW inv_last[kMaxLimbs];  // q_{k-1}^-1 mod q_j
     u64 half_last;               // q_{k-1} >> 1
     u64 half_last_mod[kMaxLimbs];
+    u64 last_cover[kMaxLimbs];   // the smallest multiple of q_j that is >= q_{k-1}: lets (x - last) be formed without reducing last
     // decrypt_scale_and_round: base {t, gamma}
     Mod gamma;
     ShoupW t_gamma[kMaxLimbs];     // t*gamma mod q_j

@@ -6,7 +6,7 @@
 // [SEAL] encryptor.cpp, decryptor.cpp, keygenerator.cpp, util/rlwe.cpp, util/rns.cpp, randomgen.cpp, util/blake2xb.c.
 //
 // Encryption of one ciphertext (K key-level limbs, k = K-1 data limbs):
-//   prng_stream_kernel     BLAKE2Xb stream of the ciphertext's own PRNG: every 64-byte block is one independent
+//   prng_root/block_kernel BLAKE2Xb stream of the ciphertext's own PRNG: every 64-byte block is one independent
 //                          compression of the refill's root hash, so the stream is generated 64 B per thread
 //   sample_encrypt_kernel  u <- ternary (libstdc++ uniform_int_distribution<u64>(0,2) over 32-bit draws, i.e.
 //                          Lemire's method: only a zero draw is rejected), e0, e1 <- centred binomial (6 bytes each);
@@ -27,34 +27,47 @@ typedef unsigned __int128 u128;
 
 // ---- PRNG stream ---------------------------------------------------------------------------------------------------
 constexpr int kRefillBytes = 4096;       // [SEAL] UniformRandomGenerator buffer size
-constexpr int kRefillsPerCta = 32;
 
-__global__ void __launch_bounds__(256) prng_stream_kernel(const u64 *__restrict__ seeds, int nrefill, u64 *__restrict__ stream) {
-    __shared__ u64 roots[kRefillsPerCta][8];
-    const int ct = blockIdx.y;
-    const int refill0 = blockIdx.x * kRefillsPerCta;
-    const u64 *seed = seeds + (size_t)ct * 8;
-    if (threadIdx.x < kRefillsPerCta && refill0 + threadIdx.x < nrefill) {
-        u64 s[8], root[8];
+// Two kernels so that no warp ever waits for another one's serial work: the root hashes (two chained compressions per
+// 4096-byte refill) are a small launch of their own and are parked in the first 64 bytes of the refill they belong to;
+// the block kernel then runs ONE compression per thread with nothing but a load-side barrier (the thread producing
+// block 0 overwrites the parked root).  The kernel is bound by the integer ALU pipe: a BLAKE2b compression is 96 G
+// functions of 22 ALU-pipe instructions each (64-bit adds, xors and rotates as 32-bit pairs).
+__global__ void __launch_bounds__(128) prng_root_kernel(const u64 *__restrict__ seeds, int nstreams, int nrefill, u64 *__restrict__ stream) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= nstreams * nrefill) return;
+    const int ct = g / nrefill, r = g % nrefill;
+    u64 s[8], root[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s[i] = seed[i];
-        b2::xof_root(s, (u64)(refill0 + threadIdx.x), root);
+    for (int i = 0; i < 8; ++i) s[i] = seeds[(size_t)ct * 8 + i];
+    b2::xof_root(s, (u64)r, root);
+    ulonglong2 *o = reinterpret_cast<ulonglong2 *>(stream + (size_t)g * (kRefillBytes / 8));
 #pragma unroll
-        for (int i = 0; i < 8; ++i) roots[threadIdx.x][i] = root[i];
+    for (int i = 0; i < 4; ++i) o[i] = make_ulonglong2(root[2 * i], root[2 * i + 1]);
+}
+__global__ void __launch_bounds__(256) prng_block_kernel(size_t nblocks, u64 *__restrict__ stream) {
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // block g = (refill g / 64, block g % 64); 256 % 64 == 0
+    const bool live = g < nblocks;
+    u64 root[8], out[8];
+    if (live) {
+        const ulonglong2 *rp = reinterpret_cast<const ulonglong2 *>(stream + (g >> 6) * (kRefillBytes / 8));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const ulonglong2 v = rp[i]; root[2 * i] = v.x; root[2 * i + 1] = v.y; }
     }
-    __syncthreads();
-    u64 *dst = stream + (size_t)ct * nrefill * (kRefillBytes / 8);
-    for (int idx = threadIdx.x; idx < kRefillsPerCta * 64; idx += 256) {
-        const int r = idx >> 6, b = idx & 63;
-        if (refill0 + r >= nrefill) break;
-        u64 root[8], out[8];
+    __syncthreads();   // every reader of a parked root is in this CTA
+    if (!live) return;
+    b2::xof_block(root, (unsigned)(g & 63), out);
+    ulonglong2 *o = reinterpret_cast<ulonglong2 *>(stream + g * 8);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) root[i] = roots[r][i];
-        b2::xof_block(root, (unsigned)b, out);
-        ulonglong2 *o = reinterpret_cast<ulonglong2 *>(dst + ((size_t)(refill0 + r) * 64 + b) * 8);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) o[i] = make_ulonglong2(out[2 * i], out[2 * i + 1]);
-    }
+    for (int i = 0; i < 4; ++i) o[i] = make_ulonglong2(out[2 * i], out[2 * i + 1]);
+}
+// stream [nstreams][nrefill * 4096 bytes] = the first nrefill buffers of Blake2xbPRNG(seed_s); seeds must not alias stream
+static void run_prng_stream(const u64 *seeds, int nstreams, int nrefill, u64 *stream, cudaStream_t st) {
+    const int roots = nstreams * nrefill;
+    if (roots == 0) return;
+    prng_root_kernel<<<(roots + 127) / 128, 128, 0, st>>>(seeds, nstreams, nrefill, stream);
+    const size_t nblocks = (size_t)roots * 64;
+    prng_block_kernel<<<(unsigned)((nblocks + 255) / 256), 256, 0, st>>>(nblocks, stream);
 }
 
 int encrypt_stream_refills(int n) { return (16 * n + kRefillBytes - 1) / kRefillBytes + 1; }  // + 1024 spare draws for rejections
@@ -442,8 +455,7 @@ void launch_encrypt(const Engine &E, const u64 *pk, const u64 *seeds, const u64 
     signed char *noise = reinterpret_cast<signed char *>(stream + (size_t)nct * nrefill * (kRefillBytes / 8));
     u64 *tmp = reinterpret_cast<u64 *>(noise) + ((size_t)nct * 3 * n + 7) / 8 + 2;
     u64 *extra = tmp + (size_t)nct * 2 * K * n;
-    dim3 gs((nrefill + kRefillsPerCta - 1) / kRefillsPerCta, nct);
-    prng_stream_kernel<<<gs, 256, 0, st>>>(seeds, nrefill, stream);
+    run_prng_stream(seeds, nct, nrefill, stream, st);
     sample_encrypt_kernel<<<nct, 1024, 0, st>>>(stream, nrefill, n, noise, errflag);
     const int lazy = ntt_lazy_level(E.max_bits(E.qmap(0)), E.host.logn);
     const size_t first = E.host.first_level();
@@ -747,7 +759,7 @@ void launch_keygen_secret(const Engine &E, const u64 *d_seed, u64 *d_sk, u64 *ws
     const int nrefill = encrypt_stream_refills(n);
     u64 *stream = ws;
     signed char *noise = reinterpret_cast<signed char *>(stream + (size_t)nrefill * (kRefillBytes / 8));
-    prng_stream_kernel<<<dim3((nrefill + kRefillsPerCta - 1) / kRefillsPerCta, 1), 256, 0, st>>>(d_seed, nrefill, stream);
+    run_prng_stream(d_seed, 1, nrefill, stream, st);
     sample_encrypt_kernel<<<1, 1024, 0, st>>>(stream, nrefill, n, noise, errflag);   // its first n samples are the ternary draws
     launch_expand_small(E, noise, d_sk, st);
     launch_ntt(E, d_sk, E.seal_layout(0, 1), 1, 1, E.qmap(0), false, st);
@@ -768,8 +780,8 @@ void launch_symmetric_zero(const Engine &E, const u64 *d_seed, const u64 *d_sk, 
     signed char *e = reinterpret_cast<signed char *>(cts + (size_t)nct * (kRefillBytes / 8));
     u64 *e_rows = reinterpret_cast<u64 *>(e) + (n + 7) / 8;
     int *rej = reinterpret_cast<int *>(e_rows + (size_t)K * n);
-    prng_stream_kernel<<<dim3((nboot + kRefillsPerCta - 1) / kRefillsPerCta, 1), 256, 0, st>>>(d_seed, nboot, boot);
-    prng_stream_kernel<<<dim3((nct + kRefillsPerCta - 1) / kRefillsPerCta, 1), 256, 0, st>>>(boot, nct, cts);   // seed = first 64 bytes of the bootstrap stream
+    run_prng_stream(d_seed, 1, nboot, boot, st);
+    run_prng_stream(boot, 1, nct, cts, st);   // seed = first 64 bytes of the bootstrap stream
     PPLP_CUDA(cudaMemsetAsync(rej, 0, sizeof(int), st));
     u64 *a = d_out + (size_t)K * n;
     uniform_bulk_kernel<<<dim3((n + 255) / 256, K), 256, 0, st>>>(E.d_mods, cts, a, K, n, cap, rej, rej + 1);
@@ -784,8 +796,7 @@ void launch_symmetric_zero(const Engine &E, const u64 *d_seed, const u64 *d_sk, 
 // raw PRNG stream for tests and for host-driven samplers: out [nrefill*4096 bytes]
 void launch_prng_stream(const Engine &E, const u64 *d_seed, int nstreams, int nrefill, u64 *out, cudaStream_t st) {
     E.require_device();
-    dim3 gs((nrefill + kRefillsPerCta - 1) / kRefillsPerCta, nstreams);
-    prng_stream_kernel<<<gs, 256, 0, st>>>(d_seed, nrefill, out);
+    run_prng_stream(d_seed, nstreams, nrefill, out, st);
     PPLP_CUDA(cudaGetLastError());
 }
 

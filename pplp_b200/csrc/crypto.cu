@@ -210,10 +210,10 @@ __global__ void __launch_bounds__(256) modswitch_kernel(const DevLevel *KLp, con
 //   enc_inverse_kernel<SPECIAL> T = INTT(U_P (.) pk_p,P) + e_p for the special prime P; stores (T + P/2) mod P   (nct*2 CTAs)
 //   enc_inverse_kernel<DATA>    per data limb: T = INTT(U_j (.) pk_p,j) + e_p, then divide-and-round by P using the stored
 //                               special-limb row, then c0 += round(Q m/t); writes the ciphertext directly (nct*2*k CTAs)
-// The public key is a constant of the whole call: prepare it once as {word, second} pairs, second = Shoup quotient
-// floor(w 2^64 / q) or, for the FP64-assisted kernels, the bits of fl(w/q), in the thread-interleaved order of the fine
-// register layout (coefficient 16 t + r at pair index r*(n/16) + t).  The dyadic product U (.) pk then costs one
-// constant-operand product per coefficient instead of a 128-bit Barrett reduction, and its loads coalesce.
+// The public key is a constant of the whole call: prepare it once in the thread-interleaved order of the fine register
+// layout so its loads coalesce — as {word, Shoup quotient floor(w 2^64 / q)} pairs for the integer kernels (coefficient
+// 16 t + r at pair index r*(n/16) + t: one constant-operand product per coefficient instead of a 128-bit Barrett), as
+// bare words for the FP64 kernels (whose quotient estimate needs no precomputation: modarith.cuh mul_f64_var).
 __global__ void prepare_key_kernel(const DevMod *mods, const u64 *__restrict__ src, u64 *__restrict__ dst, int K, int n, int f64) {
     const int row = blockIdx.y;
     const u64 q = mods[row % K].m.q;
@@ -221,7 +221,11 @@ __global__ void prepare_key_kernel(const DevMod *mods, const u64 *__restrict__ s
     ulonglong2 *d = reinterpret_cast<ulonglong2 *>(dst) + (size_t)row * n;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const u64 w = src[(size_t)row * n + i];
-        const u64 second = f64 ? (u64)__double_as_longlong(__ddiv_rn((double)w, (double)q)) : (u64)((((u128)w) << 64) / q);
+        if (f64) {   // FP64 kernels take the bare word (mul_f64_var): pair h of thread t at [h*T + t], like U
+            dst[(size_t)row * n + (((size_t)((i & 15) >> 1) * T + (i >> 4)) << 1) + (i & 1)] = w;
+            continue;
+        }
+        const u64 second = (u64)((((u128)w) << 64) / q);
         d[(size_t)(i & 15) * T + (i >> 4)] = make_ulonglong2(w, second);
     }
 }
@@ -278,14 +282,25 @@ __global__ void __launch_bounds__(NttShape<LOGM>::T, (LOGM <= 13 ? PPLP_ENC_INV_
     const NttConsts nc = ntt_consts<L>(md);
     const u64 q = mod.q;
     const ulonglong2 *up = reinterpret_cast<const ulonglong2 *>(a.U + ((size_t)ct * a.K + j) * a.n);
-    const ulonglong2 *pkp = reinterpret_cast<const ulonglong2 *>(a.pk) + ((size_t)p * a.K + j) * a.n;   // prepared {word, second} pairs
     u64 x[16];
+    if constexpr (L == 3) {   // prepared key = bare words in U's interleaving
+        const ulonglong2 *pkp = reinterpret_cast<const ulonglong2 *>(a.pk + ((size_t)p * a.K + j) * a.n);
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        const ulonglong2 uv = up[c * NttShape<LOGM>::T + tid];
-        const ulonglong2 k0 = __ldg(pkp + (2 * c) * NttShape<LOGM>::T + tid), k1 = __ldg(pkp + (2 * c + 1) * NttShape<LOGM>::T + tid);
-        x[2 * c] = twiddle_mul<Lazy<L>::I>(uv.x, ShoupW{k0.x, k0.y}, q);       // lazily below 2q: what the inverse transform accepts
-        x[2 * c + 1] = twiddle_mul<Lazy<L>::I>(uv.y, ShoupW{k1.x, k1.y}, q);
+        for (int c = 0; c < 8; ++c) {
+            const ulonglong2 uv = up[c * NttShape<LOGM>::T + tid];
+            const ulonglong2 kw = __ldg(pkp + c * NttShape<LOGM>::T + tid);
+            x[2 * c] = mul_f64_var(uv.x, kw.x, nc.one_q, q);       // lazily below 2q: what the inverse transform accepts
+            x[2 * c + 1] = mul_f64_var(uv.y, kw.y, nc.one_q, q);
+        }
+    } else {
+        const ulonglong2 *pkp = reinterpret_cast<const ulonglong2 *>(a.pk) + ((size_t)p * a.K + j) * a.n;   // prepared {word, Shoup quotient} pairs
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const ulonglong2 uv = up[c * NttShape<LOGM>::T + tid];
+            const ulonglong2 k0 = __ldg(pkp + (2 * c) * NttShape<LOGM>::T + tid), k1 = __ldg(pkp + (2 * c + 1) * NttShape<LOGM>::T + tid);
+            x[2 * c] = twiddle_mul<Lazy<L>::I>(uv.x, ShoupW{k0.x, k0.y}, q);
+            x[2 * c + 1] = twiddle_mul<Lazy<L>::I>(uv.y, ShoupW{k1.x, k1.y}, q);
+        }
     }
     block_ntt_inverse<LOGM, true, Lazy<L>::I>(x, sm, tid, inv_table<L>(md), 0, 0, nc);
     const signed char *e = a.noise + ((size_t)ct * 3 + 1 + p) * a.n;

@@ -313,6 +313,9 @@ template <int LOGM, int L> static void run_relin_limb_l(const RelinArgs &a, int 
     relin_limb_kernel<LOGM, L><<<nq * (a.k + 1), NttShape<LOGM>::T, bytes, st>>>(a);
 }
 template <int LOGM> static void run_relin_limb(int lazy, const RelinArgs &a, int nq, cudaStream_t st) {
+    if constexpr (LOGM >= 12) {
+        if (lazy == 4) { run_relin_limb_l<LOGM, 4>(a, nq, st); return; }
+    }
     if (lazy == 3) run_relin_limb_l<LOGM, 3>(a, nq, st);
     else if (lazy == 2) run_relin_limb_l<LOGM, 2>(a, nq, st);
     else if (lazy == 1) run_relin_limb_l<LOGM, 1>(a, nq, st);

@@ -186,7 +186,7 @@ void Engine::upload_tables(int dev) {
         };
         m.fine_fwd = fine(T.fwd);
         m.fine_inv = fine(T.inv);
-        if (m.bits <= 44) {   // FP64-pipe tables (ntt.cuh L = 3): {bits of double(w), bits of the correctly rounded double w/q}; w, q < 2^53 are exact
+        if (m.bits <= 49) {   // FP64-pipe tables (ntt.cuh L = 3, 4): {bits of double(w), bits of the correctly rounded double w/q}; w, q < 2^53 are exact
             auto dbits = [](double c) { u64 b; std::memcpy(&b, &c, 8); return b; };
             auto pair = [&](u64 w) { return ShoupW{dbits((double)w), dbits((double)w / (double)T.q)}; };
             std::vector<ShoupW> fd(T.fwd.size()), id(T.inv.size());
@@ -198,7 +198,7 @@ void Engine::upload_tables(int dev) {
             m.n_inv_d = pair(T.n_inv.w);
             m.inv1_n_inv_d = pair(T.inv1_n_inv.w);
             m.one_d = dbits(1.0 / (double)T.q);
-            if (logn >= 11 && logn <= 13) {
+            if (m.bits <= 44 && logn >= 11 && logn <= 13) {
                 auto fine32 = [&](const std::vector<ShoupW> &tab) -> const ShoupW * {
                     const size_t nt = host.n / 32;
                     std::vector<ShoupW> f(31 * nt);

@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(NttShape<LOGM>::T, (LOGM <= 13 ? PPLP_ENC_INV_
     const u64 q = mod.q;
     const ulonglong2 *up = reinterpret_cast<const ulonglong2 *>(a.U + ((size_t)ct * a.K + j) * a.n);
     u64 x[16];
-    if constexpr (L == 3) {   // prepared key = bare words in U's interleaving
+    if constexpr (L >= 3) {   // prepared key = bare words in U's interleaving
         const ulonglong2 *pkp = reinterpret_cast<const ulonglong2 *>(a.pk + ((size_t)p * a.K + j) * a.n);
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
@@ -427,6 +427,9 @@ template <int LOGM, int L> static void run_encrypt_limb_l(const EncLimbArgs &a, 
     encrypt_limb_kernel<LOGM, L><<<nct * a.K, NttShape<LOGM>::T, bytes, st>>>(a);
 }
 template <int LOGM> static void run_encrypt_limb(int lazy, const EncLimbArgs &a, int nct, cudaStream_t st) {
+    if constexpr (LOGM >= 12) {
+        if (lazy == 4) { run_encrypt_limb_l<LOGM, 4>(a, nct, st); return; }
+    }
     if (lazy == 3) run_encrypt_limb_l<LOGM, 3>(a, nct, st);
     else if (lazy == 2) run_encrypt_limb_l<LOGM, 2>(a, nct, st);
     else if (lazy == 1) run_encrypt_limb_l<LOGM, 1>(a, nct, st);
@@ -454,6 +457,9 @@ template <int LOGM> static void run_encrypt_split32(const EncSplitArgs &a, int n
     }
 }
 template <int LOGM> static void run_encrypt_split(int lazy, const EncSplitArgs &a, int nct, cudaStream_t st) {
+    if constexpr (LOGM >= 12) {
+        if (lazy == 4) { run_encrypt_split_l<LOGM, 4>(a, nct, st); return; }
+    }
     if (lazy == 3) run_encrypt_split_l<LOGM, 3>(a, nct, st);
     else if (lazy == 2) run_encrypt_split_l<LOGM, 2>(a, nct, st);
     else if (lazy == 1) run_encrypt_split_l<LOGM, 1>(a, nct, st);
@@ -477,7 +483,7 @@ void launch_encrypt(const Engine &E, const u64 *pk, const u64 *seeds, const u64 
     if (K > 1 && E.host.logn <= 14) {   // split pipeline: forward, special-limb inverse, data-limb inverse + modulus switch + plaintext
         static const bool wide_ok = !(std::getenv("PPLP_ENC_WIDE") && std::getenv("PPLP_ENC_WIDE")[0] == '0');   // experiment hook
         const bool wide = wide_ok && lazy == 3 && E.host.logn >= 11 && E.host.logn <= 13;   // forward transform on the 32-per-thread FP64 schedule (ntt32.cuh)
-        prepare_key_kernel<<<dim3((n + 255) / 256, 2 * K), 256, 0, st>>>(E.d_mods, pk, extra, K, n, lazy == 3 ? 1 : 0);
+        prepare_key_kernel<<<dim3((n + 255) / 256, 2 * K), 256, 0, st>>>(E.d_mods, pk, extra, K, n, lazy >= 3 ? 1 : 0);
         EncSplitArgs sa{noise, extra, tmp, tmp + (size_t)nct * K * n, out, out_lay, plain, (int)plain_count, plain_stride, K, n, E.d_mods, E.d_levels, E.d_levels + first};
         switch (E.host.logn) {
         case 10: run_encrypt_split<10>(lazy, sa, nct, st); break;

@@ -249,6 +249,9 @@ template <int LOGM> static void run_block_ntt_l(int level, const NttArgs &a, int
     if constexpr (LOGM >= 11 && LOGM <= 13) {
         if (level == 3 && a.stage_base == 0) { run_ntt32<LOGM>(a, rows, inverse, st); return; }
     }
+    if constexpr (LOGM >= 12) {
+        if (level == 4) { run_block_ntt<LOGM, 4>(a, rows, inverse, st); return; }
+    }
     if (level == 3) run_block_ntt<LOGM, 3>(a, rows, inverse, st);
     else if (level == 2) run_block_ntt<LOGM, 2>(a, rows, inverse, st);
     else if (level == 1) run_block_ntt<LOGM, 1>(a, rows, inverse, st);
@@ -293,6 +296,9 @@ template <int LOGM, int L> static void run_polymul(const PolymulArgs &a, int row
     polymul_kernel<LOGM, L><<<rows, NttShape<LOGM>::T, bytes, st>>>(a);
 }
 template <int LOGM> static void run_polymul_l(int level, const PolymulArgs &a, int rows, cudaStream_t st) {
+    if constexpr (LOGM >= 12) {
+        if (level == 4) { run_polymul<LOGM, 4>(a, rows, st); return; }
+    }
     if (level == 3) run_polymul<LOGM, 3>(a, rows, st);
     else if (level == 2) run_polymul<LOGM, 2>(a, rows, st);
     else if (level == 1) run_polymul<LOGM, 1>(a, rows, st);

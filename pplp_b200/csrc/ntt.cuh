@@ -23,7 +23,8 @@
 
 namespace pplp {
 
-enum : int { NTT_CLASSIC = 0, NTT_PASS = 1, NTT_FREE = 2, NTT_F64 = 3 };
+enum : int { NTT_CLASSIC = 0, NTT_PASS = 1, NTT_FREE = 2, NTT_F64 = 3, NTT_F64W = 4 };
+__host__ __device__ constexpr bool is_f64(int mode) { return mode == NTT_F64 || mode == NTT_F64W; }
 
 // Which lazy-reduction mode a transform of 2^logn points may use for a modulus of `bits` bits (host and device agree).
 // forward free:  inputs < 4q, growth 2q per stage: (4 + 2 logn) q < 2^64  <=  q < 2^58 for logn <= 15
@@ -41,10 +42,19 @@ enum : int { NTT_CLASSIC = 0, NTT_PASS = 1, NTT_FREE = 2, NTT_F64 = 3 };
 //            inverse: a radix-16 pass fed with |x| <= 6q leaves 96 q in register 0 of each butterfly (the all-sums
 //                     path) and at most 6 q elsewhere; register 0 is reduced at the end of the pass  =>  96 q <= 2^51,
 //          i.e. modulus of at most 44 bits (BFVDefault up to N = 8192).  Twiddle tables carry (double w, fl(w/q)).
-inline int ntt_lazy_level(int bits, int logn) { return bits <= 44 ? 3 : (bits > 58 ? 0 : (bits + 1 + logn <= 63 ? 2 : 1)); }
+//   L = 4: the same arithmetic for moduli of 45..49 bits (N <= 16384: BFVDefault's 48/49-bit primes), where the budget
+//          is only 2^51 = 4 q.  Forward: inputs must be canonical; every pass but the first starts by reducing its 16
+//          registers to [-q/2, q/2] (a pass adds at most 4 * 0.75 q).  Inverse: inputs below 2q are centred to (-q, q)
+//          while being converted; after every second stage of a pass that stage's sum outputs (at most 4 q) are
+//          reduced, so a multiplicand never exceeds 2 * 2 q.  About 9.3 FP64 instructions per butterfly instead of 8.
+inline int ntt_lazy_level(int bits, int logn) {
+    if (bits <= 44) return 3;
+    if (bits <= 49 && logn >= 12 && logn <= 14) return 4;   // instantiated for N = 4096..16384 only
+    return bits > 58 ? 0 : (bits + 1 + logn <= 63 ? 2 : 1);
+}
 template <int L> struct Lazy {
-    static constexpr int F = L == 0 ? NTT_CLASSIC : (L == 3 ? NTT_F64 : NTT_FREE);
-    static constexpr int I = L == 0 ? NTT_CLASSIC : (L == 1 ? NTT_PASS : (L == 3 ? NTT_F64 : NTT_FREE));
+    static constexpr int F = L == 0 ? NTT_CLASSIC : (L == 3 ? NTT_F64 : (L == 4 ? NTT_F64W : NTT_FREE));
+    static constexpr int I = L == 0 ? NTT_CLASSIC : (L == 1 ? NTT_PASS : (L == 3 ? NTT_F64 : (L == 4 ? NTT_F64W : NTT_FREE)));
 };
 
 template <int LOGM> struct NttShape {
@@ -65,16 +75,16 @@ __device__ __forceinline__ u64 reduce_lazy(u64 a, u64 one_q, u64 q) { return a -
 // mode-dispatched product by a table constant and lazy reduction (in NTT_F64 mode the second word of a twiddle and
 // `one_q` hold the bits of the doubles fl(w/q) and fl(1/q))
 template <int MODE> __device__ __forceinline__ u64 twiddle_mul(u64 a, const ShoupW w, const u64 q) {
-    if constexpr (MODE == NTT_F64) return mul_f64_lazy(a, w.w, w.wq, q);
+    if constexpr (is_f64(MODE)) return mul_f64_lazy(a, w.w, w.wq, q);
     else return mul_shoup_lazy_nq(a, w.w, w.wq, 0 - q);
 }
 template <int MODE> __device__ __forceinline__ u64 reduce_mode(u64 a, u64 one_q, u64 q) {
-    if constexpr (MODE == NTT_F64) return reduce_f64(a, one_q, q);
+    if constexpr (is_f64(MODE)) return reduce_f64(a, one_q, q);
     else return reduce_lazy(a, one_q, q);
 }
 
 template <int MODE> __device__ __forceinline__ void ct_butterfly(u64 &x, u64 &y, const ShoupW w, const u64 q, const u64 two_q) {
-    if constexpr (MODE == NTT_F64) {       // q carries the bits of double(q); signed values, no offsets
+    if constexpr (is_f64(MODE)) {       // q carries the bits of double(q); signed values, no offsets
         const double xd = as_d(x), t = mulmod_f64(as_d(y), as_d(w.w), as_d(w.wq), as_d(q));
         y = as_u(__dsub_rn(xd, t));
         x = as_u(__dadd_rn(xd, t));
@@ -92,7 +102,7 @@ template <int MODE> __device__ __forceinline__ void ct_butterfly(u64 &x, u64 &y,
 }
 // `big` is a multiple of q not smaller than any value y can hold at this stage (2q in classic mode).
 template <int MODE> __device__ __forceinline__ void gs_butterfly(u64 &x, u64 &y, const ShoupW w, const u64 q, const u64 two_q, const u64 big) {
-    if constexpr (MODE == NTT_F64) {
+    if constexpr (is_f64(MODE)) {
         const double xd = as_d(x), yd = as_d(y);
         x = as_u(__dadd_rn(xd, yd));
         y = as_u(mulmod_f64(__dsub_rn(xd, yd), as_d(w.w), as_d(w.wq), as_d(q)));
@@ -122,12 +132,12 @@ template <int L> __device__ __forceinline__ NttConsts ntt_consts(const DevMod &m
     NttConsts c;
     c.q = md.m.q; c.two_q = md.m.q << 1;
     c.qd = as_u((double)md.m.q);
-    if constexpr (L == 3) { c.one_q = md.one_d; c.n_inv = md.n_inv_d; c.inv1_n_inv = md.inv1_n_inv_d; c.fine_fwd = md.fine_fwd_d; c.fine_inv = md.fine_inv_d; }
+    if constexpr (L >= 3) { c.one_q = md.one_d; c.n_inv = md.n_inv_d; c.inv1_n_inv = md.inv1_n_inv_d; c.fine_fwd = md.fine_fwd_d; c.fine_inv = md.fine_inv_d; }
     else { c.one_q = md.one_q; c.n_inv = md.n_inv; c.inv1_n_inv = md.inv1_n_inv; c.fine_fwd = md.fine_fwd; c.fine_inv = md.fine_inv; }
     return c;
 }
-template <int L> __device__ __forceinline__ const ShoupW *fwd_table(const DevMod &md) { return L == 3 ? md.fwd_d : md.fwd; }
-template <int L> __device__ __forceinline__ const ShoupW *inv_table(const DevMod &md) { return L == 3 ? md.inv_d : md.inv; }
+template <int L> __device__ __forceinline__ const ShoupW *fwd_table(const DevMod &md) { return L >= 3 ? md.fwd_d : md.fwd; }
+template <int L> __device__ __forceinline__ const ShoupW *inv_table(const DevMod &md) { return L >= 3 ? md.inv_d : md.inv; }
 
 // Geometry of pass (S0,R) of a 2^LOGM block: thread `tid` owns NU = 16>>R radix-2^R butterflies; butterfly u covers
 // indices  (hi << (LG+R)) + (e << LG) + lo,  e = 0..2^R-1,  where c = tid + u*T, lo = c & (G-1), hi = c >> LG,
@@ -165,12 +175,12 @@ template <int LOGM, int S0, int R> struct Pass {
         // bound of the values entering this inverse stage, as a multiple of 2q (see gs_butterfly)
         constexpr int GROW = MODE == NTT_FREE ? (LOGM - 1 - (S0 + V)) : (MODE == NTT_PASS ? (R - 1 - V) : 0);
         const u64 big = c.two_q << GROW;
-        const u64 qm = MODE == NTT_F64 ? c.qd : c.q;   // what the butterflies take as "q"
+        const u64 qm = is_f64(MODE) ? c.qd : c.q;   // what the butterflies take as "q"
         if constexpr (INVERSE && FOLD_SCALE && V == 0) {
 #pragma unroll
             for (int i = 0; i < HALF; ++i) {
                 u64 &a = x[u * RR + i], &b = x[u * RR + i + HALF];
-                if constexpr (MODE == NTT_F64) {
+                if constexpr (is_f64(MODE)) {
                     const double ad = as_d(a), bd = as_d(b);
                     a = as_u(mulmod_f64(__dadd_rn(ad, bd), as_d(c.n_inv.w), as_d(c.n_inv.wq), as_d(qm)));
                     b = as_u(mulmod_f64(__dsub_rn(ad, bd), as_d(c.inv1_n_inv.w), as_d(c.inv1_n_inv.wq), as_d(qm)));
@@ -204,8 +214,12 @@ template <int LOGM, int S0, int R> struct Pass {
 
     // Forward stages S0 .. S0+R-1 (global stage = stage_base + local stage; blk = index of this block among the
     // 2^stage_base sub-transforms when M < N).
-    template <int MODE>
+    template <int MODE, bool REDUCE_FIRST = false>
     __device__ static __forceinline__ void forward(u64 (&x)[16], int tid, const ShoupW *__restrict__ tw, int stage_base, int blk, const NttConsts &c) {
+        if constexpr (MODE == NTT_F64W && REDUCE_FIRST) {   // back to [-q/2, q/2]: the pass adds at most R * 0.75 q, the budget is 4 q
+#pragma unroll
+            for (int r = 0; r < 16; ++r) x[r] = as_u(reduce_sym_f64(as_d(x[r]), as_d(c.one_q), as_d(c.qd)));
+        }
 #pragma unroll
         for (int u = 0; u < NU; ++u) {
             const int h = hi(tid, u);
@@ -214,6 +228,18 @@ template <int LOGM, int S0, int R> struct Pass {
             if constexpr (R >= 3) stage<(R >= 3 ? 2 : 0), false, false, MODE>(x, u, h, tw, stage_base, blk, c);
             if constexpr (R >= 4) stage<(R >= 4 ? 3 : 0), false, false, MODE>(x, u, h, tw, stage_base, blk, c);
         }
+    }
+    // wide FP64 mode: bring the sum outputs of inverse stage V of butterfly u back to [-q/2, q/2]
+    template <int V>
+    __device__ static __forceinline__ void reduce_sums(u64 (&x)[16], int u, const NttConsts &c) {
+        constexpr int HALF = 1 << (R - 1 - V);
+#pragma unroll
+        for (int g = 0; g < (1 << V); ++g)
+#pragma unroll
+            for (int i = 0; i < HALF; ++i) {
+                u64 &a = x[u * RR + g * 2 * HALF + i];
+                a = as_u(reduce_sym_f64(as_d(a), as_d(c.one_q), as_d(c.qd)));
+            }
     }
     // Inverse stages S0+R-1 .. S0.  When FOLD_SCALE (only legal for S0 == 0 and stage_base == 0) the last stage
     // multiplies by N^-1:  x = (u+v) N^-1,  y = (u-v) (inv[1] N^-1).
@@ -228,8 +254,12 @@ template <int LOGM, int S0, int R> struct Pass {
             const int h = hi(tid, u);
             if constexpr (R >= 4) stage<(R >= 4 ? 3 : 0), true, FOLD_SCALE, MODE>(x, u, h, tw, stage_base, blk, c);
             if constexpr (R >= 3) stage<(R >= 3 ? 2 : 0), true, FOLD_SCALE, MODE>(x, u, h, tw, stage_base, blk, c);
+            // wide FP64 mode: after the second and the fourth EXECUTED stage of the pass (V = R-2 and V = R-4)
+            if constexpr (MODE == NTT_F64W && R == 4) reduce_sums<(R == 4 ? 2 : 0)>(x, u, c);
             if constexpr (R >= 2) stage<(R >= 2 ? 1 : 0), true, FOLD_SCALE, MODE>(x, u, h, tw, stage_base, blk, c);
+            if constexpr (MODE == NTT_F64W && R == 3) reduce_sums<(R == 3 ? 1 : 0)>(x, u, c);
             stage<0, true, FOLD_SCALE, MODE>(x, u, h, tw, stage_base, blk, c);
+            if constexpr (MODE == NTT_F64W && (R == 2 || R == 4) && !FOLD_SCALE) reduce_sums<0>(x, u, c);
             // FP64 mode: register 0 of the butterfly took the sum branch in every stage (up to 2^R times the input bound);
             // every other register is a sum of at most 2^(R-1) products (<= 6q).  Reduce that one register.
             if constexpr (MODE == NTT_F64 && !FOLD_SCALE) x[u * RR] = as_u(reduce_sym_f64(as_d(x[u * RR]), as_d(c.one_q), as_d(c.qd)));
@@ -253,7 +283,7 @@ template <int LOGM, int P> struct FullPassAt {  // P-th radix-16 pass after the 
 template <int LOGM, int MODE>
 __device__ __forceinline__ void block_ntt_forward(u64 (&x)[16], u64 *sm, int tid, const ShoupW *__restrict__ tw, int stage_base, int blk, const NttConsts &c) {
     using S = NttShape<LOGM>;
-    if constexpr (MODE == NTT_F64) {
+    if constexpr (is_f64(MODE)) {
 #pragma unroll
         for (int r = 0; r < 16; ++r) x[r] = as_u(u64_to_f64(x[r]));
     }
@@ -263,26 +293,26 @@ __device__ __forceinline__ void block_ntt_forward(u64 (&x)[16], u64 *sm, int tid
     if constexpr (S::NFULL >= 1) {
         using P0 = typename FullPassAt<LOGM, 0>::type;
         P0::load_smem(x, sm, tid);
-        P0::template forward<MODE>(x, tid, tw, stage_base, blk, c);
+        P0::template forward<MODE, true>(x, tid, tw, stage_base, blk, c);
         if constexpr (S::NFULL > 1) { P0::store_smem(x, sm, tid); __syncthreads(); }
     }
     if constexpr (S::NFULL >= 2) {
         using P1 = typename FullPassAt<LOGM, 1>::type;
         P1::load_smem(x, sm, tid);
-        P1::template forward<MODE>(x, tid, tw, stage_base, blk, c);
+        P1::template forward<MODE, true>(x, tid, tw, stage_base, blk, c);
         if constexpr (S::NFULL > 2) { P1::store_smem(x, sm, tid); __syncthreads(); }
     }
     if constexpr (S::NFULL >= 3) {
         using P2 = typename FullPassAt<LOGM, 2>::type;
         P2::load_smem(x, sm, tid);
-        P2::template forward<MODE>(x, tid, tw, stage_base, blk, c);
+        P2::template forward<MODE, true>(x, tid, tw, stage_base, blk, c);
     }
 }
 template <int MODE> __device__ __forceinline__ u64 forward_canon(u64 v, const NttConsts &c) {
     if constexpr (MODE == NTT_CLASSIC) {   // [0,4q) -> [0,q)
         v = v >= c.two_q ? v - c.two_q : v;
         return v >= c.q ? v - c.q : v;
-    } else if constexpr (MODE == NTT_F64) {   // signed double -> [-q/2, q/2] -> (+q, as an integer) -> [0,q)
+    } else if constexpr (is_f64(MODE)) {   // signed double -> [-q/2, q/2] -> (+q, as an integer) -> [0,q)
         const double qd = as_d(c.qd);
         return csub(f64_to_u64_biased(reduce_sym_f64(as_d(v), as_d(c.one_q), qd), __dadd_rn(qd, kTwo52)), c.q);
     } else {
@@ -293,6 +323,7 @@ template <int MODE> __device__ __forceinline__ u64 forward_canon(u64 v, const Nt
 // input, e.g. a Shoup product): identity except in FP64 mode, where |v| <= 15.25 q is shifted by 16 q.
 template <int MODE> __device__ __forceinline__ u64 forward_lazy(u64 v, const NttConsts &c) {
     if constexpr (MODE == NTT_F64) return f64_to_u64_biased(as_d(v), __fma_rn(16.0, as_d(c.qd), kTwo52));
+    else if constexpr (MODE == NTT_F64W) return f64_to_u64_biased(as_d(v), __fma_rn(4.0, as_d(c.qd), kTwo52));   // |v| <= 4q < 2^51
     else return v;
 }
 
@@ -304,6 +335,10 @@ __device__ __forceinline__ void block_ntt_inverse(u64 (&x)[16], u64 *sm, int tid
     if constexpr (MODE == NTT_F64) {
 #pragma unroll
         for (int r = 0; r < 16; ++r) x[r] = as_u(u64_to_f64(x[r]));
+    } else if constexpr (MODE == NTT_F64W) {   // centred while converting: [0,2q) -> (-q, q)
+        const double off = __dadd_rn(kTwo52, as_d(c.qd));
+#pragma unroll
+        for (int r = 0; r < 16; ++r) x[r] = as_u(__dsub_rn(as_d(x[r] | 0x4330000000000000ULL), off));
     }
     // The first executed pass starts from [0,2q): it needs no reduction even in pass mode.
     if constexpr (S::NFULL >= 3) {
@@ -328,7 +363,7 @@ __device__ __forceinline__ void block_ntt_inverse(u64 (&x)[16], u64 *sm, int tid
     }
     CoarsePass<LOGM>::load_smem(x, sm, tid);
     CoarsePass<LOGM>::template inverse<FOLD_SCALE, MODE, (S::NFULL > 0)>(x, tid, tw, stage_base, blk, c);
-    if constexpr (MODE == NTT_F64) {   // products (FOLD_SCALE: |x| <= 0.75 q) or reduced values, shifted by q: (0, 2q) as integers
+    if constexpr (is_f64(MODE)) {   // products (FOLD_SCALE: |x| <= 0.75 q) or reduced values, shifted by q: (0, 2q) as integers
         const double qd = as_d(c.qd), bias = __dadd_rn(qd, kTwo52);
 #pragma unroll
         for (int r = 0; r < 16; ++r) x[r] = f64_to_u64_biased(FOLD_SCALE ? as_d(x[r]) : reduce_sym_f64(as_d(x[r]), as_d(c.one_q), qd), bias);

@@ -591,3 +591,43 @@ def test_keygen_uniform_rejections_match_oracle(eng, oracle):
     words = raw.view(np.uint64).reshape(3, n)
     rejected = sum(int((words[j] >= np.uint64((2**64 - 1) - ((2**64 - 1) % q[j]) - 1)).sum()) for j in range(3))
     assert rejected >= 100
+
+
+@pytest.mark.parametrize("n,bits", [(4096, 45), (4096, 49), (8192, 47), (8192, 49), (16384, 49)])
+def test_wide_fp64_moduli_match_oracle(eng, oracle, n, bits):
+    """Moduli of 45..49 bits run the FP64 transforms with the tight 2^51 = 4q budget (ntt.cuh L = 4: reductions between
+    passes / every second inverse stage).  NTT both ways, encryption and decryption against the oracle, with the largest
+    primes of each width (so that 4q is as close to 2^51 as it gets) and inputs at the edges of the residue range."""
+    q = oracle.get_primes(2 * n, bits, 3)
+    assert all(x.bit_length() == bits for x in q)
+    ctx, octx = contexts(eng, oracle, n, t=1 << 20, q=q, enforce_security=False)
+    rng = np.random.default_rng(n + bits)
+    k = ctx.limbs(0)
+    data = np.stack([np.stack([rand_residues(rng, q[:k], n) for _ in range(2)]) for _ in range(3)])
+    data[0, 0, :, ::2] = np.array(q[:k], dtype=np.uint64)[:, None] - np.uint64(1)   # extreme residues
+    data[0, 1, :, :] = np.array(q[:k], dtype=np.uint64)[:, None] - np.uint64(1)
+    data[1, 0, :, :] = 0
+    ref_f = data.copy()
+    ref_i = data.copy()
+    for qi in range(3):
+        for p in range(2):
+            for j in range(k):
+                ref_f[qi, p, j] = octx.ntt(0, j, data[qi, p, j])
+                ref_i[qi, p, j] = octx.ntt(0, j, data[qi, p, j], inverse=True)
+    d = ctx.dev(data)
+    ctx.ntt_(d, level=0)
+    assert (eng.to_np(d) == ref_f).all()
+    ctx.ntt_(d, level=0, inverse=True)
+    assert (eng.to_np(d) == data).all()
+    d = ctx.dev(data)
+    ctx.ntt_(d, level=0, inverse=True)
+    assert (eng.to_np(d) == ref_i).all()
+    # encryption (forward + inverse transforms inside the fused kernels, modulus switch) and decryption (polymul)
+    osk, opk = octx.keygen()
+    seeds = np.stack([seed8(900 + i) for i in range(3)])
+    plains = rng.integers(0, 1 << 20, size=(3, 4), dtype=np.uint64)
+    ct = eng.to_np(ctx.encrypt(ctx.dev(opk), ctx.dev(seeds), ctx.dev(plains)))
+    for i in range(3):
+        assert (ct[i] == octx.encrypt(opk, plains[i], seed=seeds[i])).all(), i
+    got = eng.to_np(ctx.decrypt(ctx.dev(ct), ctx.dev(osk)))
+    assert (got[:, :4] == plains).all() and not got[:, 4:].any()

@@ -129,6 +129,14 @@ int pplp_multiply_plain_poly(pplp_ctx *ctx, size_t level, uint64_t *d_ct, int la
  * (a zero multiplier).  out may alias c0. */
 int pplp_circuit_a(pplp_ctx *ctx, size_t level, const uint64_t *d_c0, const uint64_t *d_c1, const uint64_t *d_c2, uint64_t *d_out, int layout,
                    size_t nq, const uint64_t *d_xb, const uint64_t *d_yb, const uint64_t *d_r, const uint64_t *d_s, int *d_flags, void *stream);
+/* The same evaluation for every pair (client c, server point t) — BASELINE.json config 5, the batched form of the
+ * reference's one-client-at-a-time server loop (src/server.cc:58-135 run once per accepted client against the server's
+ * own point).  d_c0/1/2: ncl ciphertexts each, in `layout` with nq = ncl; d_xb/yb/r/s: npts server points with their
+ * blinds; d_out: ncl*npts ciphertexts in `layout` with nq = ncl*npts, pair index t*ncl + c.  Bit-identical to
+ * pplp_circuit_a on the tiled inputs; reads each client's ciphertexts once.  d_flags[t] (optional, npts entries) as above. */
+int pplp_circuit_a_cross(pplp_ctx *ctx, size_t level, const uint64_t *d_c0, const uint64_t *d_c1, const uint64_t *d_c2, size_t ncl, uint64_t *d_out,
+                         int layout, size_t npts, const uint64_t *d_xb, const uint64_t *d_yb, const uint64_t *d_r, const uint64_t *d_s, int *d_flags,
+                         void *stream);
 /* Same, with HOST buffers in PPLP_LAYOUT_SEAL (what a server holds after Ciphertext::load): chunks the batch through
  * double-buffered device slabs, overlapping the copies with the kernel.  Page-locked buffers recommended.  Synchronises. */
 int pplp_circuit_a_host(pplp_ctx *ctx, size_t level, const uint64_t *h_c0, const uint64_t *h_c1, const uint64_t *h_c2, uint64_t *h_out, size_t nq,

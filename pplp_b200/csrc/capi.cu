@@ -511,6 +511,24 @@ int pplp_circuit_a(pplp_ctx *ctx, size_t level, const uint64_t *d_c0, const uint
     PPLP_CATCH
 }
 
+int pplp_circuit_a_cross(pplp_ctx *ctx, size_t level, const uint64_t *d_c0, const uint64_t *d_c1, const uint64_t *d_c2, size_t ncl, uint64_t *d_out,
+                         int layout, size_t npts, const uint64_t *d_xb, const uint64_t *d_yb, const uint64_t *d_r, const uint64_t *d_s, int *d_flags,
+                         void *stream) {
+    PPLP_TRY
+    Engine &E = dev_engine(ctx);
+    const size_t k = check_level(E, level);
+    if (ncl == 0 || npts == 0) return PPLP_OK;
+    const int ncli = to_int(ncl, "client count"), nptsi = to_int(npts, "server point count");
+    to_int(ncl * npts, "pair count");
+    cudaStream_t st = S(stream);
+    Scratch sc(circuit_a_scratch_words(E, level, nptsi) * 8, st);
+    if (d_flags) PPLP_CUDA(cudaMemsetAsync(d_flags, 0, npts * sizeof(int), st));
+    launch_circuit_a_cross(E, level, d_c0, d_c1, d_c2, make_layout(layout, E.host.n, k, 2, ncl), ncli, d_out, make_layout(layout, E.host.n, k, 2, ncl * npts),
+                           nptsi, d_xb, d_yb, d_r, d_s, sc.as<u64>(), d_flags, st);
+    return PPLP_OK;
+    PPLP_CATCH
+}
+
 int pplp_circuit_a_host(pplp_ctx *ctx, size_t level, const uint64_t *h_c0, const uint64_t *h_c1, const uint64_t *h_c2, uint64_t *h_out, size_t nq,
                         const uint64_t *h_xb, const uint64_t *h_yb, const uint64_t *h_r, const uint64_t *h_s, int *h_flags, size_t chunk) {
     PPLP_TRY

@@ -56,6 +56,10 @@ void launch_polymul(const Engine &E, const u64 *a, Layout a_lay, const u64 *b_nt
 void launch_circuit_a(const Engine &E, size_t level, const u64 *c0, const u64 *c1, const u64 *c2, u64 *out, Layout lay, int nq,
                       const u64 *xb, const u64 *yb, const u64 *r, const u64 *s, u64 *scratch /* nq*k*8 u64 */, int *flags, cudaStream_t st);
 size_t circuit_a_scratch_words(const Engine &E, size_t level, int nq);
+// every client (ncl ciphertext triples, in_lay) against npts server points; pair t*ncl + c of the output batch (out_lay)
+void launch_circuit_a_cross(const Engine &E, size_t level, const u64 *c0, const u64 *c1, const u64 *c2, Layout in_lay, int ncl, u64 *out, Layout out_lay,
+                            int npts, const u64 *xb, const u64 *yb, const u64 *r, const u64 *s, u64 *scratch /* circuit_a_scratch_words(npts) */, int *flags,
+                            cudaStream_t st);
 // a <- a +/- b (elementwise, canonical)
 void launch_add_sub(const Engine &E, size_t level, u64 *a, const u64 *b, Layout lay, int nq, int npoly, bool subtract, bool negate_b_only, cudaStream_t st);
 // c0 +/-= round(Q*m/t) for plaintext coefficients m[0..count) (same plaintext for every query when m_stride == 0)

@@ -36,7 +36,8 @@ __device__ __forceinline__ u64 dev_shoup_quotient(u64 w, u64 q) { return (u64)((
 // scratch row per (query, limb): {XB.w, XB.wq, YB.w, YB.wq, S.w, S.wq, Z, SR}
 constexpr int kScalarWords = 8;
 
-__global__ void circuit_a_prepare_kernel(const DevLevel *Lp, int nq, const u64 *xb, const u64 *yb, const u64 *r, const u64 *s, u64 *scratch, int *flags) {
+__global__ void circuit_a_prepare_kernel(const DevLevel *Lp, int nq, const u64 *xb, const u64 *yb, const u64 *r, const u64 *s, u64 *scratch, int *flags,
+                                         int f64 = 0 /* XB, YB as bits of (double(w), fl(w/q)) for the FP64-pipe products of the cross kernel */) {
     const DevLevel &L = *Lp;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nq * L.k) return;
@@ -47,8 +48,13 @@ __global__ void circuit_a_prepare_kernel(const DevLevel *Lp, int nq, const u64 *
     const u64 sr = vs * vr;               // src/server.cc:133
     u64 *o = scratch + (size_t)idx * kScalarWords;
     const u64 a = dev_lift(L, vxb, j), b = dev_lift(L, vyb, j), c = dev_lift(L, vs, j);
-    o[0] = a; o[1] = dev_shoup_quotient(a, q);
-    o[2] = b; o[3] = dev_shoup_quotient(b, q);
+    if (f64) {
+        o[0] = as_u((double)a); o[1] = as_u(__ddiv_rn((double)a, (double)q));
+        o[2] = as_u((double)b); o[3] = as_u(__ddiv_rn((double)b, (double)q));
+    } else {
+        o[0] = a; o[1] = dev_shoup_quotient(a, q);
+        o[2] = b; o[3] = dev_shoup_quotient(b, q);
+    }
     o[4] = c; o[5] = dev_shoup_quotient(c, q);
     o[6] = dev_scaled(L, z, j);
     o[7] = dev_scaled(L, sr, j);
@@ -112,6 +118,106 @@ void launch_circuit_a(const Engine &E, size_t level, const u64 *c0, const u64 *c
     const long long ctas = (long long)nq * 2 * k * segs;
     if (ctas > 0x7fffffffLL) throw std::invalid_argument("pplp: batch too large for one launch");
     circuit_a_kernel<<<(unsigned)ctas, kCaThreads, 0, st>>>(L, c0, c1, c2, out, lay, nq, n, scratch);
+    PPLP_CUDA(cudaGetLastError());
+}
+
+// ---- every client against many server points (BASELINE.json config 5) ------------------------------------------------
+// The same evaluation for the pairs (client c, server point t), t = 0..npts-1, c = 0..ncl-1: pair index t*ncl + c in the
+// output batch.  A client's three ciphertexts are the same for every point, so each thread loads its 8 coefficients of
+// c0, c1, c2 ONCE into registers and loops over the points: compulsory traffic drops from 64*k*N bytes per pair to the
+// 16*k*N-byte output write (+ 48*k*N per client, amortised over npts).  The per-point scalars of the CTA's limb are
+// staged through shared memory in tiles of kCrossTile points.
+// With the inputs resident the kernel would be bound by the integer multiplier (three Shoup products = 30 32-bit
+// multiplies per coefficient), so for moduli of at most 49 bits (F64 = true) the two products by XB and YB run on the FP64
+// pipe (modarith.cuh mulmod_f64: the client's coefficients are converted to doubles once, outside the point loop) and only
+// the product by S stays on the integer pipe: 15 FP64 + 10 integer multiplies per coefficient, both under the HBM write.
+constexpr int kCrossTile = 32;
+template <bool F64>
+__global__ void __launch_bounds__(kCaThreads) circuit_a_cross_kernel(const DevLevel *Lp, const u64 *__restrict__ c0, const u64 *__restrict__ c1,
+                                                                     const u64 *__restrict__ c2, Layout in_lay, u64 *__restrict__ out, Layout out_lay,
+                                                                     int ncl, int npts, int n, const u64 *__restrict__ scratch) {
+    __shared__ u64 sc[kCrossTile][kScalarWords];
+    const DevLevel &L = *Lp;
+    const int segs = n / kCaSeg > 0 ? n / kCaSeg : 1;
+    const int seg = blockIdx.x % segs;
+    int row = blockIdx.x / segs;
+    const int cl = row % ncl; row /= ncl;
+    const int p = row & 1;
+    const int j = row >> 1;
+    const u64 q = L.q[j].q, two_q = q << 1, four_q = q << 2;
+    const size_t ibase = cl * in_lay.sq + p * in_lay.sp + j * in_lay.sl;
+    const int first = seg * kCaSeg + 2 * threadIdx.x;
+    ulonglong2 a[kCaUnroll], b[kCaUnroll], c[kCaUnroll];
+#pragma unroll
+    for (int u = 0; u < kCaUnroll; ++u) {
+        const int i = first + u * 2 * kCaThreads;
+        if (i < n) { a[u] = ldg_stream(c0 + ibase + i); b[u] = ldg_stream(c1 + ibase + i); c[u] = ldg_stream(c2 + ibase + i); }
+    }
+    double ad[2 * kCaUnroll], bd[2 * kCaUnroll], cd[2 * kCaUnroll];
+    const double qd = (double)q;
+    const double bias = __fma_rn(4.0, qd, kTwo52);   // v = a - t1 - t2 in (-2.5q, 2.5q)  ->  v + 4q as an integer
+    if constexpr (F64) {
+#pragma unroll
+        for (int u = 0; u < kCaUnroll; ++u) {
+            ad[2 * u] = u64_to_f64(a[u].x); ad[2 * u + 1] = u64_to_f64(a[u].y);
+            bd[2 * u] = u64_to_f64(b[u].x); bd[2 * u + 1] = u64_to_f64(b[u].y);
+            cd[2 * u] = u64_to_f64(c[u].x); cd[2 * u + 1] = u64_to_f64(c[u].y);
+        }
+    }
+    for (int t0 = 0; t0 < npts; t0 += kCrossTile) {
+        __syncthreads();
+        if (threadIdx.x < kCrossTile * kScalarWords) {
+            const int t = t0 + threadIdx.x / kScalarWords;
+            if (t < npts) sc[threadIdx.x / kScalarWords][threadIdx.x % kScalarWords] = scratch[((size_t)t * L.k + j) * kScalarWords + threadIdx.x % kScalarWords];
+        }
+        __syncthreads();
+        const int tn = min(kCrossTile, npts - t0);
+        for (int tt = 0; tt < tn; ++tt) {
+            const u64 xbw = sc[tt][0], xbq = sc[tt][1], ybw = sc[tt][2], ybq = sc[tt][3], sw = sc[tt][4], sq = sc[tt][5];
+            const size_t obase = ((size_t)(t0 + tt) * ncl + cl) * out_lay.sq + p * out_lay.sp + j * out_lay.sl;
+#pragma unroll
+            for (int u = 0; u < kCaUnroll; ++u) {
+                const int i = first + u * 2 * kCaThreads;
+                if (i >= n) continue;
+                u64 vx, vy;
+                if constexpr (F64) {
+                    const double tx = __dsub_rn(__dsub_rn(ad[2 * u], mulmod_f64(bd[2 * u], as_d(xbw), as_d(xbq), qd)), mulmod_f64(cd[2 * u], as_d(ybw), as_d(ybq), qd));
+                    const double ty = __dsub_rn(__dsub_rn(ad[2 * u + 1], mulmod_f64(bd[2 * u + 1], as_d(xbw), as_d(xbq), qd)), mulmod_f64(cd[2 * u + 1], as_d(ybw), as_d(ybq), qd));
+                    vx = f64_to_u64_biased(tx, bias);
+                    vy = f64_to_u64_biased(ty, bias);
+                } else {
+                    vx = a[u].x + four_q - mul_shoup_lazy(b[u].x, xbw, xbq, q) - mul_shoup_lazy(c[u].x, ybw, ybq, q);
+                    vy = a[u].y + four_q - mul_shoup_lazy(b[u].y, xbw, xbq, q) - mul_shoup_lazy(c[u].y, ybw, ybq, q);
+                }
+                const bool head = (p == 0 && i == 0);
+                if (head) vx += sc[tt][6];
+                u64 rx = mul_shoup_lazy_nq(vx, sw, sq, 0 - q), ry = mul_shoup_lazy_nq(vy, sw, sq, 0 - q);
+                if (head) rx += sc[tt][7];
+                rx = rx >= two_q ? rx - two_q : rx;
+                ulonglong2 o;
+                o.x = csub(rx, q);
+                o.y = csub(ry, q);
+                stg_stream(out + obase + i, o);
+            }
+        }
+    }
+}
+
+void launch_circuit_a_cross(const Engine &E, size_t level, const u64 *c0, const u64 *c1, const u64 *c2, Layout in_lay, int ncl, u64 *out, Layout out_lay,
+                            int npts, const u64 *xb, const u64 *yb, const u64 *r, const u64 *s, u64 *scratch, int *flags, cudaStream_t st) {
+    E.require_device();
+    if (ncl == 0 || npts == 0) return;
+    const int k = (int)E.host.levels[level].q.size(), n = (int)E.host.n;
+    const DevLevel *L = E.d_levels + level;
+    int bits = 0;
+    for (u64 q : E.host.levels[level].q) bits = std::max(bits, hm::bitlen(q));
+    const bool f64 = bits <= 49;
+    circuit_a_prepare_kernel<<<(npts * k + 127) / 128, 128, 0, st>>>(L, npts, xb, yb, r, s, scratch, flags, f64 ? 1 : 0);
+    const int segs = n / kCaSeg > 0 ? n / kCaSeg : 1;
+    const long long ctas = (long long)ncl * 2 * k * segs;
+    if (ctas > 0x7fffffffLL) throw std::invalid_argument("pplp: batch too large for one launch");
+    if (f64) circuit_a_cross_kernel<true><<<(unsigned)ctas, kCaThreads, 0, st>>>(L, c0, c1, c2, in_lay, out, out_lay, ncl, npts, n, scratch);
+    else circuit_a_cross_kernel<false><<<(unsigned)ctas, kCaThreads, 0, st>>>(L, c0, c1, c2, in_lay, out, out_lay, ncl, npts, n, scratch);
     PPLP_CUDA(cudaGetLastError());
 }
 

@@ -212,6 +212,17 @@ class Context:
                                     _ptr(xb), _ptr(yb), _ptr(r), _ptr(s), _ptr(flags), self._st()))
         return out
 
+    def circuit_a_cross(self, c0, c1, c2, xb, yb, r, s, out=None, level=None, layout=LAYOUT_SEAL, flags=None):
+        """Every client (the ncl ciphertexts of c0/c1/c2) against every server point (the npts entries of xb/yb/r/s):
+        output batch of ncl*npts ciphertexts, pair index t*ncl + c."""
+        ncl, _ = self._dims(c0, layout)
+        npts = int(xb.numel())
+        if out is None:
+            out = self.empty(*self.ct_shape(ncl * npts, 2, level, layout))
+        check(self.L.pplp_circuit_a_cross(self.h, self.first_level if level is None else level, _ptr(c0), _ptr(c1), _ptr(c2), ncl, _ptr(out), layout,
+                                          npts, _ptr(xb), _ptr(yb), _ptr(r), _ptr(s), _ptr(flags), self._st()))
+        return out
+
     def circuit_a_host(self, c0, c1, c2, out, xb, yb, r, s, flags=None, chunk=256, level=None):
         """Host buffers (numpy arrays or pinned torch CPU tensors) in the SEAL layout; synchronous."""
         nq = c0.shape[0]

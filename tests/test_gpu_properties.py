@@ -159,3 +159,34 @@ def test_batch_encoder_square_relinearize_is_slotwise(eng, oracle, n):
     diff = vals.astype(object) - xb.astype(object)
     expect = np.array([[int(v) * int(v) % t for v in row] for row in diff], dtype=np.uint64)
     assert (eng.to_np(dec) == expect).all()
+
+
+@pytest.mark.parametrize("layout_name,n", [("seal", 8192), ("limb_major", 8192), ("limb_major", 16384), ("seal", 32768)])
+def test_circuit_a_cross_equals_circuit_a_on_tiled_inputs(eng, layout_name, n):
+    """config 5's kernel (every client against every server point, client ciphertexts read once) is bit-identical to the
+    per-query kernel on the tiled inputs, in both layouts, including the transparent-ciphertext flags."""
+    import torch
+    # 37 points: more than one scalar tile (32) and a ragged last tile.  N=16384 (49-bit primes) still takes the FP64
+    # products, N=32768 (55-bit) the all-integer variant.
+    ncl, npts = (5, 37) if n <= 16384 else (2, 33)
+    ctx = eng.Context(n, t=T56, device=0)
+    layout = eng.LAYOUT_SEAL if layout_name == "seal" else eng.LAYOUT_LIMB_MAJOR
+    rng = np.random.default_rng(55)
+    k = ctx.k
+    q = ctx.q[:k]
+    cts = []
+    for _ in range(3):
+        a = np.stack([np.stack([np.stack([rng.integers(0, qi, n, dtype=np.uint64) for qi in q]) for _ in range(2)]) for _ in range(ncl)])   # [ncl][2][k][n]
+        cts.append(a)
+    xb = rng.integers(1, 1 << 27, npts, dtype=np.uint64); yb = rng.integers(1, 1 << 27, npts, dtype=np.uint64)
+    r = rng.integers(0, 1 << 32, npts, dtype=np.uint64); s = rng.integers(1, 1 << 32, npts, dtype=np.uint64)
+    s[3] = 0   # a zero multiplier: SEAL would throw "transparent"; the batch flags the point
+    to_layout = (lambda a: a) if layout == eng.LAYOUT_SEAL else (lambda a: np.ascontiguousarray(a.transpose(2, 1, 0, 3)))
+    d = [ctx.dev(to_layout(a)) for a in cts]
+    flags = torch.zeros(npts, dtype=torch.int32, device=ctx.device)
+    got = eng.to_np(ctx.circuit_a_cross(d[0], d[1], d[2], ctx.dev(xb), ctx.dev(yb), ctx.dev(r), ctx.dev(s), layout=layout, flags=flags))
+    tiled = [ctx.dev(to_layout(np.tile(a, (npts, 1, 1, 1)))) for a in cts]          # pair t*ncl + c  <-  client c
+    rep = lambda v: ctx.dev(np.repeat(v, ncl))
+    ref = eng.to_np(ctx.circuit_a(tiled[0], tiled[1], tiled[2], rep(xb), rep(yb), rep(r), rep(s), layout=layout))
+    assert got.shape == ref.shape and (got == ref).all()
+    assert flags.cpu().tolist() == [1 if t == 3 else 0 for t in range(npts)]

@@ -132,13 +132,21 @@ void launch_circuit_a(const Engine &E, size_t level, const u64 *c0, const u64 *c
 // pipe (modarith.cuh mulmod_f64: the client's coefficients are converted to doubles once, outside the point loop) and only
 // the product by S stays on the integer pipe: 15 FP64 + 10 integer multiplies per coefficient, both under the HBM write.
 constexpr int kCrossTile = 32;
+#ifndef PPLP_CROSS_UNROLL
+#define PPLP_CROSS_UNROLL 4
+#endif
+#ifndef PPLP_CROSS_MINB
+#define PPLP_CROSS_MINB 3
+#endif
+constexpr int kCrossUnroll = PPLP_CROSS_UNROLL;              // 16-byte accesses per stream per thread
+constexpr int kCrossSeg = kCaThreads * 2 * kCrossUnroll;     // coefficients per CTA
 template <bool F64>
-__global__ void __launch_bounds__(kCaThreads) circuit_a_cross_kernel(const DevLevel *Lp, const u64 *__restrict__ c0, const u64 *__restrict__ c1,
+__global__ void __launch_bounds__(kCaThreads, PPLP_CROSS_MINB) circuit_a_cross_kernel(const DevLevel *Lp, const u64 *__restrict__ c0, const u64 *__restrict__ c1,
                                                                      const u64 *__restrict__ c2, Layout in_lay, u64 *__restrict__ out, Layout out_lay,
                                                                      int ncl, int npts, int n, const u64 *__restrict__ scratch) {
     __shared__ u64 sc[kCrossTile][kScalarWords];
     const DevLevel &L = *Lp;
-    const int segs = n / kCaSeg > 0 ? n / kCaSeg : 1;
+    const int segs = n / kCrossSeg > 0 ? n / kCrossSeg : 1;
     const int seg = blockIdx.x % segs;
     int row = blockIdx.x / segs;
     const int cl = row % ncl; row /= ncl;
@@ -146,19 +154,19 @@ __global__ void __launch_bounds__(kCaThreads) circuit_a_cross_kernel(const DevLe
     const int j = row >> 1;
     const u64 q = L.q[j].q, two_q = q << 1, four_q = q << 2;
     const size_t ibase = cl * in_lay.sq + p * in_lay.sp + j * in_lay.sl;
-    const int first = seg * kCaSeg + 2 * threadIdx.x;
-    ulonglong2 a[kCaUnroll], b[kCaUnroll], c[kCaUnroll];
+    const int first = seg * kCrossSeg + 2 * threadIdx.x;
+    ulonglong2 a[kCrossUnroll], b[kCrossUnroll], c[kCrossUnroll];
 #pragma unroll
-    for (int u = 0; u < kCaUnroll; ++u) {
+    for (int u = 0; u < kCrossUnroll; ++u) {
         const int i = first + u * 2 * kCaThreads;
         if (i < n) { a[u] = ldg_stream(c0 + ibase + i); b[u] = ldg_stream(c1 + ibase + i); c[u] = ldg_stream(c2 + ibase + i); }
     }
-    double ad[2 * kCaUnroll], bd[2 * kCaUnroll], cd[2 * kCaUnroll];
+    double ad[2 * kCrossUnroll], bd[2 * kCrossUnroll], cd[2 * kCrossUnroll];
     const double qd = (double)q;
     const double bias = __fma_rn(4.0, qd, kTwo52);   // v = a - t1 - t2 in (-2.5q, 2.5q)  ->  v + 4q as an integer
     if constexpr (F64) {
 #pragma unroll
-        for (int u = 0; u < kCaUnroll; ++u) {
+        for (int u = 0; u < kCrossUnroll; ++u) {
             ad[2 * u] = u64_to_f64(a[u].x); ad[2 * u + 1] = u64_to_f64(a[u].y);
             bd[2 * u] = u64_to_f64(b[u].x); bd[2 * u + 1] = u64_to_f64(b[u].y);
             cd[2 * u] = u64_to_f64(c[u].x); cd[2 * u + 1] = u64_to_f64(c[u].y);
@@ -176,7 +184,7 @@ __global__ void __launch_bounds__(kCaThreads) circuit_a_cross_kernel(const DevLe
             const u64 xbw = sc[tt][0], xbq = sc[tt][1], ybw = sc[tt][2], ybq = sc[tt][3], sw = sc[tt][4], sq = sc[tt][5];
             const size_t obase = ((size_t)(t0 + tt) * ncl + cl) * out_lay.sq + p * out_lay.sp + j * out_lay.sl;
 #pragma unroll
-            for (int u = 0; u < kCaUnroll; ++u) {
+            for (int u = 0; u < kCrossUnroll; ++u) {
                 const int i = first + u * 2 * kCaThreads;
                 if (i >= n) continue;
                 u64 vx, vy;
@@ -213,7 +221,7 @@ void launch_circuit_a_cross(const Engine &E, size_t level, const u64 *c0, const 
     for (u64 q : E.host.levels[level].q) bits = std::max(bits, hm::bitlen(q));
     const bool f64 = bits <= 49;
     circuit_a_prepare_kernel<<<(npts * k + 127) / 128, 128, 0, st>>>(L, npts, xb, yb, r, s, scratch, flags, f64 ? 1 : 0);
-    const int segs = n / kCaSeg > 0 ? n / kCaSeg : 1;
+    const int segs = n / kCrossSeg > 0 ? n / kCrossSeg : 1;
     const long long ctas = (long long)ncl * 2 * k * segs;
     if (ctas > 0x7fffffffLL) throw std::invalid_argument("pplp: batch too large for one launch");
     if (f64) circuit_a_cross_kernel<true><<<(unsigned)ctas, kCaThreads, 0, st>>>(L, c0, c1, c2, in_lay, out, out_lay, ncl, npts, n, scratch);

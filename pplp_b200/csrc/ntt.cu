@@ -99,19 +99,22 @@ __global__ void __launch_bounds__(NttShape<LOGM>::T, (LOGM <= 13 ? PPLP_NTT_MIN_
 }
 
 // ---- 32 coefficients per thread, FP64 pipe (ntt32.cuh): the stand-alone transforms for moduli <= 44 bits, N = 2048..8192 ----
-template <int LOGM>
+// DENSE: the batch is limb-major and contiguous, so row r starts at data + r*M.  Worth a specialisation: the general
+// address (a sum of three runtime strides) costs 10 % — kept as a sum it is re-derived at every use and its components
+// stay live through the transform (ptxas then sinks the twiddle loads next to their uses); hidden behind an empty asm it
+// becomes a per-thread register pair instead of a uniform one.  Both were measured on the lab harness (ntt32_lab.cu).
+template <int LOGM, bool DENSE>
 __global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T) ntt32_forward_kernel(const NttArgs a) {
     using S = Ntt32Shape<LOGM>;
     extern __shared__ __align__(16) u64 sm[];
     const int tid = threadIdx.x;
-    int qi, p, j;
-    decode_row(blockIdx.x, a.nq, a.npoly, qi, p, j);
+    int qi = 0, p = 0, j;
+    if constexpr (DENSE) j = blockIdx.x / a.stage_base;   // DENSE launches pass rows per limb here
+    else decode_row(blockIdx.x, a.nq, a.npoly, qi, p, j);
     const DevMod &md = a.mods[a.map.mod_id[j]];
     const Ntt32Consts c = ntt32_consts(md, false);
-    u64 *ptr = a.data + qi * a.lay.sq + p * a.lay.sp + j * a.lay.sl;
-    // Opaque to the optimiser: otherwise the row address is re-derived from its components at every use, the components
-    // stay live through the transform, and the register scheduler sinks the twiddle loads next to their uses.
-    asm volatile("" : "+l"(ptr));
+    u64 *ptr = DENSE ? a.data + (size_t)blockIdx.x * S::M : a.data + qi * a.lay.sq + p * a.lay.sp + j * a.lay.sl;
+    if constexpr (!DENSE) asm volatile("" : "+l"(ptr));
     u64 x[32];
 #pragma unroll
     for (int e = 0; e < 32; ++e) x[e] = ptr[e * S::T + tid];
@@ -120,16 +123,17 @@ __global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T
     for (int e = 0; e < 32; ++e) x[e] = ntt32_canon(x[e], c, md.m.q);
     ntt32_store_row(x, sm, tid, ptr);
 }
-template <int LOGM>
+template <int LOGM, bool DENSE>
 __global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T) ntt32_inverse_kernel(const NttArgs a) {
     using S = Ntt32Shape<LOGM>;
     extern __shared__ __align__(16) u64 sm[];
     const int tid = threadIdx.x;
-    int qi, p, j;
-    decode_row(blockIdx.x, a.nq, a.npoly, qi, p, j);
+    int qi = 0, p = 0, j;
+    if constexpr (DENSE) j = blockIdx.x / a.stage_base;
+    else decode_row(blockIdx.x, a.nq, a.npoly, qi, p, j);
     const DevMod &md = a.mods[a.map.mod_id[j]];
     const Ntt32Consts c = ntt32_consts(md, true);
-    u64 *ptr = a.data + qi * a.lay.sq + p * a.lay.sp + j * a.lay.sl;
+    u64 *ptr = DENSE ? a.data + (size_t)blockIdx.x * S::M : a.data + qi * a.lay.sq + p * a.lay.sp + j * a.lay.sl;
     u64 x[32];
     ntt32_load_row(x, sm, tid, ptr);
     ntt32_inverse<LOGM>(x, sm, tid, c);
@@ -235,15 +239,24 @@ template <int LOGM, int L> static void run_block_ntt(const NttArgs &a, int rows,
         ntt_forward_kernel<LOGM, L><<<grid, NttShape<LOGM>::T, bytes, st>>>(a);
     }
 }
-template <int LOGM> static void run_ntt32(const NttArgs &a, int rows, bool inverse, cudaStream_t st) {
+template <int LOGM, bool DENSE> static void run_ntt32_d(const NttArgs &a, int rows, bool inverse, cudaStream_t st) {
     const int bytes = Ntt32Shape<LOGM>::SMEM_WORDS * 8;
     if (inverse) {
-        allow_smem(ntt32_inverse_kernel<LOGM>, bytes);
-        ntt32_inverse_kernel<LOGM><<<rows, Ntt32Shape<LOGM>::T, bytes, st>>>(a);
+        allow_smem(ntt32_inverse_kernel<LOGM, DENSE>, bytes);
+        ntt32_inverse_kernel<LOGM, DENSE><<<rows, Ntt32Shape<LOGM>::T, bytes, st>>>(a);
     } else {
-        allow_smem(ntt32_forward_kernel<LOGM>, bytes);
-        ntt32_forward_kernel<LOGM><<<rows, Ntt32Shape<LOGM>::T, bytes, st>>>(a);
+        allow_smem(ntt32_forward_kernel<LOGM, DENSE>, bytes);
+        ntt32_forward_kernel<LOGM, DENSE><<<rows, Ntt32Shape<LOGM>::T, bytes, st>>>(a);
     }
+}
+template <int LOGM> static void run_ntt32(const NttArgs &a, int rows, bool inverse, cudaStream_t st) {
+    const size_t m = Ntt32Shape<LOGM>::M;   // row (qi, p, j) = block (j*npoly + p)*nq + qi: contiguous when the strides say so
+    const bool dense = (a.nq == 1 || a.lay.sq == m) && (a.npoly == 1 || a.lay.sp == (size_t)a.nq * m) && (a.map.nlimbs == 1 || a.lay.sl == (size_t)a.npoly * a.nq * m);
+    if (dense) {
+        NttArgs d = a;
+        d.stage_base = a.nq * a.npoly;   // rows per limb (the ntt32 kernels have no use for stage_base: they run whole transforms only)
+        run_ntt32_d<LOGM, true>(d, rows, inverse, st);
+    } else run_ntt32_d<LOGM, false>(a, rows, inverse, st);
 }
 template <int LOGM> static void run_block_ntt_l(int level, const NttArgs &a, int rows, bool inverse, cudaStream_t st) {
     if constexpr (LOGM >= 11 && LOGM <= 13) {

@@ -75,6 +75,31 @@ __global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T
     for (int e = 0; e < 32; ++e) ptr[e * S::T + tid] = csub(x[e], md.q);
 }
 
+// scheduling experiment: the engine addresses a row as base + qi*sq + p*sp + j*sl (runtime strides)
+struct LabLayout { size_t sq, sp, sl; };
+template <int LOGM, int PTR>
+__global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T) inv_strided_kernel(u64 *data, const LabMod *mods, LabLayout lay, int nq, int npoly) {
+    using S = Ntt32Shape<LOGM>;
+    extern __shared__ __align__(16) u64 sm[];
+    const int tid = threadIdx.x;
+    int row = blockIdx.x;
+    const int qi = row % nq; row /= nq;
+    const int p = row % npoly;
+    const int j = row / npoly;
+    const LabMod &md = mods[j];
+    const Ntt32Consts c = md.i;
+    u64 *ptr = data + qi * lay.sq + p * lay.sp + j * lay.sl;
+    if (PTR == 2) asm volatile("" : "+l"(ptr));
+    u64 x[32];
+    ntt32_load_row(x, sm, tid, ptr);
+    if (PTR == 3) asm volatile("" : "+l"(ptr));
+    ntt32_inverse<LOGM>(x, sm, tid, c);
+    const u64 q = md.q;
+    if (PTR == 4) asm volatile("" : "+l"(ptr));
+#pragma unroll
+    for (int e = 0; e < 32; ++e) ptr[e * S::T + tid] = csub(x[e], q);
+}
+
 static u64 dbits(double d) { u64 b; memcpy(&b, &d, 8); return b; }
 template <class T> T *upload(const std::vector<T> &v) { T *d; CK(cudaMalloc(&d, v.size() * sizeof(T))); CK(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice)); return d; }
 
@@ -189,6 +214,23 @@ template <int LOGM> void run(int rows) {
             if (rep >= 2 && ms < best) best = ms;
         }
         printf("N=%d pf=%d %s io-variant %d: %.4f ms  %.1f GB/s\n", n, pf, k < 2 ? "forward" : "inverse", k & 1, best, 16.0 * n * rows / (best * 1e-3) / 1e9);
+    }
+    if (LOGM == 13) {
+        const LabLayout lay{(size_t)n, (size_t)rpm * n, (size_t)rpm * n};
+        for (int v = 1; v <= 4; ++v) {
+            float best = 1e9;
+            for (int rep = 0; rep < 6; ++rep) {
+                cudaEventRecord(a);
+                if (v == 1) { CK(cudaFuncSetAttribute(inv_strided_kernel<13, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)); inv_strided_kernel<13, 1><<<rows, S::T, bytes>>>(d, d_mods, lay, rpm, 1); }
+                if (v == 2) { CK(cudaFuncSetAttribute(inv_strided_kernel<13, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)); inv_strided_kernel<13, 2><<<rows, S::T, bytes>>>(d, d_mods, lay, rpm, 1); }
+                if (v == 3) { CK(cudaFuncSetAttribute(inv_strided_kernel<13, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)); inv_strided_kernel<13, 3><<<rows, S::T, bytes>>>(d, d_mods, lay, rpm, 1); }
+                if (v == 4) { CK(cudaFuncSetAttribute(inv_strided_kernel<13, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)); inv_strided_kernel<13, 4><<<rows, S::T, bytes>>>(d, d_mods, lay, rpm, 1); }
+                cudaEventRecord(b); cudaEventSynchronize(b);
+                float ms; cudaEventElapsedTime(&ms, a, b);
+                if (rep >= 2 && ms < best) best = ms;
+            }
+            printf("N=%d inverse strided-pointer variant %d: %.4f ms  %.1f GB/s\n", n, v, best, 16.0 * n * rows / (best * 1e-3) / 1e9);
+        }
     }
     CK(cudaGetLastError());
     cudaFree(d);

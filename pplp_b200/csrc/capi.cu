@@ -174,6 +174,7 @@ void Engine::upload_tables(int dev) {
         m.one_d = 0;
         m.fine_fwd = m.fine_inv = m.fine_fwd_d = m.fine_inv_d = nullptr;
         m.fine32_fwd_d = m.fine32_inv_d = nullptr;
+        m.nc32_fwd = m.nc32_inv = Ntt32Consts{0.0, 0.0, ShoupW{0, 0}, ShoupW{0, 0}, nullptr, nullptr};
         const int logn = host.logn;
         auto fine = [&](const std::vector<ShoupW> &tab) -> const ShoupW * {   // thread-interleaved last four stages
             if (logn < 4) return nullptr;
@@ -209,6 +210,8 @@ void Engine::upload_tables(int dev) {
                 };
                 m.fine32_fwd_d = fine32(fd);
                 m.fine32_inv_d = fine32(id);
+                m.nc32_fwd = Ntt32Consts{(double)T.q, 1.0 / (double)T.q, m.n_inv_d, m.inv1_n_inv_d, m.fwd_d, m.fine32_fwd_d};
+                m.nc32_inv = Ntt32Consts{(double)T.q, 1.0 / (double)T.q, m.n_inv_d, m.inv1_n_inv_d, m.inv_d, m.fine32_inv_d};
             }
         }
     }

@@ -7,6 +7,14 @@ namespace pplp {
 constexpr int kMaxLimbs = 24;   // q limbs at key level (<=16 for BFVDefault up to N=32768) or |Bsk| (<= k+2)
 constexpr int kMaxMods = 48;    // q primes + BEHZ auxiliary primes with NTT tables
 
+// What a 32-per-thread FP64 transform (ntt32.cuh) needs about its modulus, in one contiguous block.
+struct Ntt32Consts {
+    double q, qinv;                 // double(q), fl(1/q)
+    ShoupW n_inv, inv1_n_inv;       // bits of (double w, fl(w/q))
+    const ShoupW *tw;               // natural table (bits of doubles): fwd_d or inv_d
+    const ShoupW *fine;             // thread-interleaved last five stages: entry ((2^v - 1 + j) * T + t) = tw[2^(LOGM-5+v) + (t << v) + j]
+};
+
 // One NTT-capable modulus.  fwd[m+g] = psi^bitrev(m+g) is the twiddle of group g in the stage with m groups
 // (Cooley–Tukey, bit-reversed output: the function SEAL's ntt_negacyclic_harvey computes); inv[m+g] = fwd[m+g]^-1.
 struct DevMod {
@@ -28,6 +36,7 @@ struct DevMod {
     // ntt32.cuh (32 coefficients per thread, N = 2048..8192): the last FIVE stages thread-interleaved,
     // entry ((2^v - 1 + j) * N/32 + t) = twiddle of stage logN-5+v, group (t << v) + j; bits of (double(w), fl(w/q)); else null
     const ShoupW *fine32_fwd_d, *fine32_inv_d;
+    Ntt32Consts nc32_fwd, nc32_inv;
 };
 
 // How a batch of polynomials lies in HBM.  Element (query qi, poly p, limb j, coeff n) is at

@@ -38,21 +38,8 @@ template <int LOGM> struct Ntt32Shape {
 };
 __device__ __forceinline__ int slot32(int i) { return i + (i >> 5); }
 
-struct Ntt32Consts {
-    double q, qinv;                 // double(q), fl(1/q)
-    ShoupW n_inv, inv1_n_inv;       // bits of (double w, fl(w/q))
-    const ShoupW *tw;               // natural table (bits of doubles): fwd_d or inv_d
-    const ShoupW *fine;             // thread-interleaved last five stages: entry ((2^v - 1 + j) * T + t) = tw[2^(LOGM-5+v) + (t << v) + j]
-};
-
-__device__ __forceinline__ Ntt32Consts ntt32_consts(const DevMod &md, bool inverse) {
-    Ntt32Consts c;
-    c.q = (double)md.m.q; c.qinv = as_d(md.one_d);
-    c.n_inv = md.n_inv_d; c.inv1_n_inv = md.inv1_n_inv_d;
-    c.tw = inverse ? md.inv_d : md.fwd_d;
-    c.fine = inverse ? md.fine32_inv_d : md.fine32_fwd_d;
-    return c;
-}
+// per-modulus constants are prepared on the host (DevMod::nc32_fwd / nc32_inv) so that a kernel loads them in one go
+__device__ __forceinline__ Ntt32Consts ntt32_consts(const DevMod &md, bool inverse) { return inverse ? md.nc32_inv : md.nc32_fwd; }
 // Global <-> register staging through the warp's own 1024 words (coalesced 256-byte accesses on the global side):
 // registers in the "contiguous" layout x[e] = row[32 tid + e].
 __device__ __forceinline__ void ntt32_store_row(const u64 (&x)[32], u64 *sm, int tid, u64 *row) {

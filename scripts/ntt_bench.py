@@ -27,14 +27,16 @@ for n in a.n:
     for inv in (False, True):
         for _ in range(3):
             ctx.ntt_(data, level=level, inverse=inv, layout=engine.LAYOUT_LIMB_MAJOR)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(a.reps):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.reps + 1)]
+        ev[0].record()
+        for i in range(a.reps):
             ctx.ntt_(data, level=level, inverse=inv, layout=engine.LAYOUT_LIMB_MAJOR)
-        e1.record()
+            ev[i + 1].record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / a.reps
+        ms = ev[0].elapsed_time(ev[-1]) / a.reps                                  # mean over the back-to-back launches (reported)
+        best = min(ev[i].elapsed_time(ev[i + 1]) for i in range(a.reps))          # fastest single launch
         out["intt_gbs" if inv else "ntt_gbs"] = round(16 * n * rows * k / (ms * 1e-3) / 1e9, 1)
         out["intt_ms" if inv else "ntt_ms"] = round(ms, 4)
+        out["intt_best_gbs" if inv else "ntt_best_gbs"] = round(16 * n * rows * k / (best * 1e-3) / 1e9, 1)
     res.append(out)
     print(json.dumps(out), flush=True)

@@ -20,39 +20,76 @@
 //                          still in registers (Shoup products with precomputed key quotients, lazily in [0,2q)), then
 //                          runs the two inverse transforms — the NTT-form digits never touch HBM
 //   relin_moddown_kernel   divide by the special prime with rounding and add into (c0, c1)
+#include <type_traits>
 #include "engine.hpp"
 #include "ntt.cuh"
 
 namespace pplp {
 
 // ---- BEHZ: base extension ------------------------------------------------------------------------------------------
-// in: [nq][2][k][n] (layout `lay`), out: [nq][2][nb][n] contiguous.  grid.y = query*2 + poly.
-__global__ void __launch_bounds__(256) behz_extend_kernel(const DevLevel *Lp, const u64 *__restrict__ in, Layout lay, u64 *__restrict__ out) {
+// in: [nq][2][k][n] (layout `lay`), out: [nq][2][nb][n] contiguous; also copies the q residues into xq [nq][2][k][n]
+// (the operand of the q-base transform).  grid.y = query*2 + poly.
+// K / NBSK are compile-time (0 = take them from the level at run time): with fixed trip counts the per-coefficient
+// vectors z[] live in registers instead of local memory, and each thread carries kBehzIlp coefficients so that the
+// base-conversion constants are fetched once per thread and the 128-bit accumulate chains of different coefficients overlap.
+// coefficients per thread: two while the per-coefficient state (k 128-bit accumulators + k residues) fits the register file
+__host__ __device__ constexpr int behz_ilp(int K) { return (K >= 1 && K <= 4) ? 2 : 1; }
+#ifndef BEHZ_MINB
+#define BEHZ_MINB 3   // CTAs per SM the base-conversion kernels are compiled for (85 registers): the constants are re-read from L1 rather than hoisted
+#endif
+template <int K, int NBSK>
+__global__ void __launch_bounds__(256, BEHZ_MINB) behz_extend_kernel(const DevLevel *Lp, const u64 *__restrict__ in, Layout lay, u64 *__restrict__ out, u64 *__restrict__ xq) {
     const DevLevel &L = *Lp;
-    const int k = L.k, nb = L.nBsk, n = L.n;
+    constexpr int kBehzIlp = behz_ilp(K);
+    const int k = K ? K : L.k, nb = NBSK ? NBSK : L.nBsk, n = L.n;
+    constexpr int ZK = K ? K : kMaxLimbs;
     const int qi = blockIdx.y >> 1, p = blockIdx.y & 1;
     const u64 *src = in + qi * lay.sq + p * lay.sp;
     u64 *dst = out + ((size_t)qi * 2 + p) * nb * n;
+    u64 *cpy = xq + ((size_t)qi * 2 + p) * k * n;
     const u64 mt_mask = L.m_tilde - 1, mt_half = L.m_tilde >> 1;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        u64 z[kMaxLimbs];
-        u64 acc_mt = 0;
-#pragma unroll 4
-        for (int j = 0; j < k; ++j) {
+    for (int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * kBehzIlp; i0 < n; i0 += gridDim.x * blockDim.x * kBehzIlp) {
+        u64 z[kBehzIlp][ZK];
+        u64 r[kBehzIlp];
+#pragma unroll
+        for (int c = 0; c < kBehzIlp; ++c) r[c] = 0;
+#pragma unroll
+        for (int j = 0; j < ZK; ++j) {
+            if (j >= k) break;
             const u64 q = L.q[j].q;
-            const u64 tmp = mul_shoup(src[j * lay.sl + i], L.mtilde_mod_q[j], q);   // x * m_tilde mod q_j
-            z[j] = mul_shoup(tmp, L.inv_punct[j], q);
-            acc_mt += z[j] * L.punct_mod_mtilde[j];                                  // mod 2^32 survives the wrap mod 2^64
+            const ShoupW mt = L.mtilde_mod_q[j], ip = L.inv_punct[j];
+            const u64 pm = L.punct_mod_mtilde[j];
+#pragma unroll
+            for (int c = 0; c < kBehzIlp; ++c) {
+                const u64 x = src[j * lay.sl + i0 + c];
+                cpy[(size_t)j * n + i0 + c] = x;
+                z[c][j] = mul_shoup(mul_shoup(x, mt, q), ip, q);                 // (x * m_tilde) * (Q/q_j)^-1 mod q_j
+                r[c] += z[c][j] * pm;                                            // mod 2^32 survives the wrap mod 2^64
+            }
         }
-        const u64 r = ((acc_mt & mt_mask) * L.neg_inv_q_mod_mtilde) & mt_mask;       // sm_mrq: r = -x q^-1 mod m_tilde
+#pragma unroll
+        for (int c = 0; c < kBehzIlp; ++c) r[c] = ((r[c] & mt_mask) * L.neg_inv_q_mod_mtilde) & mt_mask;   // sm_mrq: r = -x q^-1 mod m_tilde
+#pragma unroll 1
         for (int b = 0; b < nb; ++b) {
-            const Mod &mp = L.bsk[b];
-            U128 acc{0, 0};
-            for (int j = 0; j < k; ++j) mac128(acc, z[j], L.punct_mod_bsk[b][j]);
-            const u64 conv = barrett128(acc.lo, acc.hi, mp);
-            const u64 rc = r >= mt_half ? r + (mp.q - L.m_tilde) : r;                // centred representative of r
-            const u64 v = add_mod(mul_shoup(rc, L.q_mod_bsk[b], mp.q), conv, mp.q);
-            dst[(size_t)b * n + i] = mul_shoup(v, L.inv_mtilde_mod_bsk[b], mp.q);
+            const Mod mp = L.bsk[b];
+            const ShoupW qm = L.q_mod_bsk[b], im = L.inv_mtilde_mod_bsk[b];
+            U128 acc[kBehzIlp];
+#pragma unroll
+            for (int c = 0; c < kBehzIlp; ++c) acc[c] = U128{0, 0};
+#pragma unroll
+            for (int j = 0; j < ZK; ++j) {
+                if (j >= k) break;
+                const u64 w = L.punct_mod_bsk[b][j];
+#pragma unroll
+                for (int c = 0; c < kBehzIlp; ++c) mac128(acc[c], z[c][j], w);
+            }
+#pragma unroll
+            for (int c = 0; c < kBehzIlp; ++c) {
+                const u64 conv = barrett128(acc[c].lo, acc[c].hi, mp);
+                const u64 rc = r[c] >= mt_half ? r[c] + (mp.q - L.m_tilde) : r[c];   // centred representative of r
+                const u64 v = add_mod(mul_shoup(rc, qm, mp.q), conv, mp.q);
+                dst[(size_t)b * n + i0 + c] = mul_shoup(v, im, mp.q);
+            }
         }
     }
 }
@@ -76,55 +113,123 @@ __global__ void __launch_bounds__(256) tensor_kernel(const DevMod *mods, RowMap 
 
 // ---- BEHZ: *t, floor, Shenoy–Kumaresan ------------------------------------------------------------------------------
 // dq: [nq][3][k][n], db: [nq][3][nb][n] (coefficient form, canonical) -> out (layout `lay`, 3 polys).  grid.y = query*3 + poly.
-__global__ void __launch_bounds__(256) behz_floor_sk_kernel(const DevLevel *Lp, const u64 *__restrict__ dq, const u64 *__restrict__ db, u64 *__restrict__ out, Layout lay) {
+// Same compile-time-size scheme as behz_extend_kernel (K, NBSK = 0: run-time sizes, vectors in local memory).
+template <int K, int NBSK>
+__global__ void __launch_bounds__(256, BEHZ_MINB) behz_floor_sk_kernel(const DevLevel *Lp, const u64 *__restrict__ dq, const u64 *__restrict__ db, u64 *__restrict__ out, Layout lay) {
     const DevLevel &L = *Lp;
-    const int k = L.k, nb = L.nBsk, nB = L.nB, n = L.n;
+    constexpr int kBehzIlp = behz_ilp(K);
+    const int k = K ? K : L.k, nb = NBSK ? NBSK : L.nBsk, nB = nb - 1, n = L.n;
+    constexpr int ZK = K ? K : kMaxLimbs;
     const int qi = blockIdx.y / 3, p = blockIdx.y % 3;
     const u64 *sq = dq + ((size_t)qi * 3 + p) * k * n;
     const u64 *sb = db + ((size_t)qi * 3 + p) * nb * n;
     u64 *dst = out + qi * lay.sq + p * lay.sp;
-    const u64 msk = L.bsk[nB].q, msk_half = msk >> 1;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        u64 z[kMaxLimbs], fl[kMaxLimbs];
-        for (int j = 0; j < k; ++j) {
+    const Mod mmsk = L.bsk[nB];
+    const u64 msk = mmsk.q, msk_half = msk >> 1;
+    for (int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * kBehzIlp; i0 < n; i0 += gridDim.x * blockDim.x * kBehzIlp) {
+        u64 z[kBehzIlp][ZK];
+        U128 acc[kBehzIlp][ZK], am[kBehzIlp];   // sum_b z_b (B/b mod q_j) for every q_j, and the same modulo m_sk
+#pragma unroll
+        for (int c = 0; c < kBehzIlp; ++c) am[c] = U128{0, 0};
+#pragma unroll
+        for (int j = 0; j < ZK; ++j) {
+            if (j >= k) break;
             const u64 q = L.q[j].q;
-            const u64 xt = mul_shoup(sq[(size_t)j * n + i], L.t_mod_q[j], q);        // * t
-            z[j] = mul_shoup(xt, L.inv_punct[j], q);
+            const ShoupW tq = L.t_mod_q[j], ip = L.inv_punct[j];
+#pragma unroll
+            for (int c = 0; c < kBehzIlp; ++c) {
+                z[c][j] = mul_shoup(mul_shoup(sq[(size_t)j * n + i0 + c], tq, q), ip, q);   // * t, then (Q/q_j)^-1
+                acc[c][j] = U128{0, 0};
+            }
         }
-        for (int b = 0; b < nb; ++b) {                                                 // fast_floor
-            const Mod &mp = L.bsk[b];
-            U128 acc{0, 0};
-            for (int j = 0; j < k; ++j) mac128(acc, z[j], L.punct_mod_bsk[b][j]);
-            const u64 conv = barrett128(acc.lo, acc.hi, mp);
-            const u64 xb = mul_shoup(sb[(size_t)b * n + i], L.t_mod_bsk[b], mp.q);
-            fl[b] = mul_shoup(sub_mod(xb, conv, mp.q), L.inv_q_mod_bsk[b], mp.q);
+        // One auxiliary prime per iteration (rolled: its constants are live for one iteration only).  fast_floor gives
+        // fl_b = (t x_b - conv_b) Q^-1 mod b; for b in B it is consumed at once by the Shenoy-Kumaresan sums
+        // (z_b = fl_b (B/b)^-1 mod b, then z_b (B/b mod q_j) for every j and z_b (B/b mod m_sk)); the last prime is m_sk.
+        u64 fl_msk[kBehzIlp];
+#pragma unroll 1
+        for (int b = 0; b < nb; ++b) {
+            const Mod mp = L.bsk[b];
+            const ShoupW tb = L.t_mod_bsk[b], iq = L.inv_q_mod_bsk[b];
+            U128 cv[kBehzIlp];
+#pragma unroll
+            for (int c = 0; c < kBehzIlp; ++c) cv[c] = U128{0, 0};
+#pragma unroll
+            for (int j = 0; j < ZK; ++j) {
+                if (j >= k) break;
+                const u64 w = L.punct_mod_bsk[b][j];
+#pragma unroll
+                for (int c = 0; c < kBehzIlp; ++c) mac128(cv[c], z[c][j], w);
+            }
+            u64 fl[kBehzIlp];
+#pragma unroll
+            for (int c = 0; c < kBehzIlp; ++c) {
+                const u64 conv = barrett128(cv[c].lo, cv[c].hi, mp);
+                const u64 xb = mul_shoup(sb[(size_t)b * n + i0 + c], tb, mp.q);
+                fl[c] = mul_shoup(sub_mod(xb, conv, mp.q), iq, mp.q);
+            }
+            if (b == nB) {
+#pragma unroll
+                for (int c = 0; c < kBehzIlp; ++c) fl_msk[c] = fl[c];
+            } else {
+                const ShoupW ipb = L.inv_punctB[b];
+                const u64 wm = L.punctB_mod_msk[b];
+#pragma unroll
+                for (int c = 0; c < kBehzIlp; ++c) {
+                    fl[c] = mul_shoup(fl[c], ipb, mp.q);
+                    mac128(am[c], fl[c], wm);
+                }
+#pragma unroll
+                for (int j = 0; j < ZK; ++j) {
+                    if (j >= k) break;
+                    const u64 w = L.punctB_mod_q[j][b];
+#pragma unroll
+                    for (int c = 0; c < kBehzIlp; ++c) mac128(acc[c][j], fl[c], w);
+                }
+            }
         }
-        // fastbconv_sk: B -> q and B -> m_sk, alpha = (conv_msk - x_msk) B^-1 mod m_sk, centred
-        for (int b = 0; b < nB; ++b) z[b] = mul_shoup(fl[b], L.inv_punctB[b], L.bsk[b].q);
-        U128 am{0, 0};
-        for (int b = 0; b < nB; ++b) mac128(am, z[b], L.punctB_mod_msk[b]);
-        const u64 conv_msk = barrett128(am.lo, am.hi, L.bsk[nB]);
-        const u64 alpha = mul_shoup(sub_mod(conv_msk, fl[nB], msk), L.inv_B_mod_msk, msk);
-        const bool neg = alpha > msk_half;
-        const u64 a_abs = neg ? msk - alpha : alpha;
-        for (int j = 0; j < k; ++j) {
-            const Mod &mq = L.q[j];
-            U128 acc{0, 0};
-            for (int b = 0; b < nB; ++b) mac128(acc, z[b], L.punctB_mod_q[j][b]);
-            const u64 conv = barrett128(acc.lo, acc.hi, mq);
-            const u64 corr = mul_shoup(a_abs, neg ? L.B_mod_q[j] : L.neg_B_mod_q[j], mq.q);
-            dst[j * lay.sl + i] = add_mod(corr, conv, mq.q);
+        // alpha = (conv_msk - x_msk) B^-1 mod m_sk, centred; out_j = conv_j - alpha B mod q_j
+        u64 a_abs[kBehzIlp];
+        bool neg[kBehzIlp];
+#pragma unroll
+        for (int c = 0; c < kBehzIlp; ++c) {
+            const u64 conv_msk = barrett128(am[c].lo, am[c].hi, mmsk);
+            const u64 alpha = mul_shoup(sub_mod(conv_msk, fl_msk[c], msk), L.inv_B_mod_msk, msk);
+            neg[c] = alpha > msk_half;
+            a_abs[c] = neg[c] ? msk - alpha : alpha;
+        }
+#pragma unroll
+        for (int j = 0; j < ZK; ++j) {
+            if (j >= k) break;
+            const Mod mq = L.q[j];
+            const ShoupW bq = L.B_mod_q[j], nbq = L.neg_B_mod_q[j];
+#pragma unroll
+            for (int c = 0; c < kBehzIlp; ++c) {
+                const u64 conv = barrett128(acc[c][j].lo, acc[c][j].hi, mq);
+                const u64 corr = mul_shoup(a_abs[c], neg[c] ? bq : nbq, mq.q);
+                dst[j * lay.sl + i0 + c] = add_mod(corr, conv, mq.q);
+            }
         }
     }
 }
 
-__global__ void gather_ct_kernel(const u64 *__restrict__ src, Layout lay, u64 *__restrict__ dst, int npoly, int k, int n) {
-    int row = blockIdx.y;
-    const int j = row % k; row /= k;
-    const int p = row % npoly, qi = row / npoly;
-    const u64 *s = src + qi * lay.sq + p * lay.sp + j * lay.sl;
-    u64 *d = dst + (((size_t)qi * npoly + p) * k + j) * n;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) d[i] = s[i];
+// compile-time (k, |Bsk|) for the common sizes (|Bsk| is k + 1 or k + 2), run-time sizes otherwise
+template <int K, class F> static void behz_dispatch_nb(int k, int nb, F f) {
+    if (nb == K + 1) f(std::integral_constant<int, K>{}, std::integral_constant<int, K + 1>{});
+    else if (nb == K + 2) f(std::integral_constant<int, K>{}, std::integral_constant<int, K + 2>{});
+    else f(std::integral_constant<int, 0>{}, std::integral_constant<int, 0>{});
+}
+template <class F> static void behz_dispatch(int k, int nb, F f) {
+    switch (k) {
+    case 1: behz_dispatch_nb<1>(k, nb, f); break;
+    case 2: behz_dispatch_nb<2>(k, nb, f); break;
+    case 3: behz_dispatch_nb<3>(k, nb, f); break;
+    case 4: behz_dispatch_nb<4>(k, nb, f); break;
+    case 5: behz_dispatch_nb<5>(k, nb, f); break;
+    case 6: behz_dispatch_nb<6>(k, nb, f); break;
+    case 7: behz_dispatch_nb<7>(k, nb, f); break;
+    case 8: behz_dispatch_nb<8>(k, nb, f); break;
+    default: f(std::integral_constant<int, 0>{}, std::integral_constant<int, 0>{});
+    }
 }
 
 size_t multiply_tmp_words(const Engine &E, size_t level, int nq, bool square) {
@@ -147,10 +252,11 @@ void launch_multiply(const Engine &E, size_t level, const u64 *a, const u64 *b, 
     u64 *bq = square ? aq : ab + wb, *bb = square ? ab : bq + wq;
     u64 *dq = (square ? ab + wb : bb + wb), *db = dq + (size_t)nq * 3 * k * n;
     const Layout ql{(size_t)2 * k * n, (size_t)k * n, (size_t)n}, bl{(size_t)2 * nb * n, (size_t)nb * n, (size_t)n};
-    dim3 ge((n + 255) / 256, nq * 2), gg((n + 1023) / 1024, nq * 2 * k);
     auto extend = [&](const u64 *src, u64 *xq, u64 *xb) {
-        gather_ct_kernel<<<gg, 256, 0, st>>>(src, in_lay, xq, 2, k, n);
-        behz_extend_kernel<<<ge, 256, 0, st>>>(L, src, in_lay, xb);
+        behz_dispatch(k, nb, [&](auto kc, auto nc) {
+            const int gx = (n / behz_ilp(decltype(kc)::value) + 255) / 256;
+            behz_extend_kernel<decltype(kc)::value, decltype(nc)::value><<<dim3(gx, nq * 2), 256, 0, st>>>(L, src, in_lay, xb, xq);
+        });
         launch_ntt(E, xq, ql, nq, 2, qm, false, st);
         launch_ntt(E, xb, bl, nq, 2, bm, false, st);
     };
@@ -160,7 +266,10 @@ void launch_multiply(const Engine &E, size_t level, const u64 *a, const u64 *b, 
     tensor_kernel<<<dim3((n + 1023) / 1024, nq * nb), 256, 0, st>>>(E.d_mods, bm, ab, bb, db, n);
     launch_ntt(E, dq, Layout{(size_t)3 * k * n, (size_t)k * n, (size_t)n}, nq, 3, qm, true, st);
     launch_ntt(E, db, Layout{(size_t)3 * nb * n, (size_t)nb * n, (size_t)n}, nq, 3, bm, true, st);
-    behz_floor_sk_kernel<<<dim3((n + 255) / 256, nq * 3), 256, 0, st>>>(L, dq, db, out, out_lay);
+    behz_dispatch(k, nb, [&](auto kc, auto nc) {
+        const int gx = (n / behz_ilp(decltype(kc)::value) + 255) / 256;
+        behz_floor_sk_kernel<decltype(kc)::value, decltype(nc)::value><<<dim3(gx, nq * 3), 256, 0, st>>>(L, dq, db, out, out_lay);
+    });
     PPLP_CUDA(cudaGetLastError());
 }
 

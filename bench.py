@@ -419,6 +419,32 @@ def run_extras(engine, ctx, torch, osk, opk):
         ex["ntt_note"] = f"16*N bytes per limb transform, {rows_q * k} rows of N={N} per launch"
     except Exception as e:
         ex["ntt_gbs"] = {"error": str(e)[:200]}
+    try:   # BASELINE.json config 5 in small: every resident client against a tile of server points (pplp_circuit_a_cross)
+        ncl, npts, k = 512, 16, ctx.k
+        cts = []
+        for _ in range(3):
+            c = ctx.empty(k, 2, ncl, N)
+            for j in range(k):
+                c[j].random_(0, ctx.q[j])
+            cts.append(c)
+        rng = np.random.default_rng(55)
+        par = [ctx.dev(rng.integers(1, 1 << 27, npts, dtype=np.uint64)) for _ in range(2)] + [ctx.dev(rng.integers(1, 1 << 32, npts, dtype=np.uint64)) for _ in range(2)]
+        out = ctx.empty(k, 2, ncl * npts, N)
+        for _ in range(2):
+            ctx.circuit_a_cross(cts[0], cts[1], cts[2], par[0], par[1], par[2], par[3], out=out, layout=engine.LAYOUT_LIMB_MAJOR)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        reps = 5
+        for _ in range(reps):
+            ctx.circuit_a_cross(cts[0], cts[1], cts[2], par[0], par[1], par[2], par[3], out=out, layout=engine.LAYOUT_LIMB_MAJOR)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / reps
+        ex["config5_cross"] = {"value": ncl * npts / (ms * 1e-3), "unit": "client-point pairs/s", "clients": ncl, "points_per_launch": npts,
+                               "hbm_write_gbs": ncl * npts * 16 * k * N / (ms * 1e-3) / 1e9,
+                               "what": "pplp_circuit_a_cross: client ciphertexts read once per launch, 16*k*N bytes written per pair"}
+    except Exception as e:
+        ex["config5_cross"] = {"error": str(e)[:200]}
     return ex
 
 

@@ -48,16 +48,19 @@ __global__ void circuit_a_prepare_kernel(const DevLevel *Lp, int nq, const u64 *
     const u64 sr = vs * vr;               // src/server.cc:133
     u64 *o = scratch + (size_t)idx * kScalarWords;
     const u64 a = dev_lift(L, vxb, j), b = dev_lift(L, vyb, j), c = dev_lift(L, vs, j);
-    if (f64) {
+    if (f64) {   // everything as bits of doubles: (w, fl(w/q)) pairs, Z, SR
         o[0] = as_u((double)a); o[1] = as_u(__ddiv_rn((double)a, (double)q));
         o[2] = as_u((double)b); o[3] = as_u(__ddiv_rn((double)b, (double)q));
+        o[4] = as_u((double)c); o[5] = as_u(__ddiv_rn((double)c, (double)q));
+        o[6] = as_u((double)dev_scaled(L, z, j));
+        o[7] = as_u((double)dev_scaled(L, sr, j));
     } else {
         o[0] = a; o[1] = dev_shoup_quotient(a, q);
         o[2] = b; o[3] = dev_shoup_quotient(b, q);
+        o[4] = c; o[5] = dev_shoup_quotient(c, q);
+        o[6] = dev_scaled(L, z, j);
+        o[7] = dev_scaled(L, sr, j);
     }
-    o[4] = c; o[5] = dev_shoup_quotient(c, q);
-    o[6] = dev_scaled(L, z, j);
-    o[7] = dev_scaled(L, sr, j);
     // SEAL throws logic_error("result ciphertext is transparent") when a multiplier plaintext is zero; a batch flags it.
     if (flags && j == 0 && (vxb == 0 || vyb == 0 || vs == 0)) atomicOr(&flags[qi], 1);   // caller zeroes flags
 }
@@ -128,9 +131,10 @@ void launch_circuit_a(const Engine &E, size_t level, const u64 *c0, const u64 *c
 // 16*k*N-byte output write (+ 48*k*N per client, amortised over npts).  The per-point scalars of the CTA's limb are
 // staged through shared memory in tiles of kCrossTile points.
 // With the inputs resident the kernel would be bound by the integer multiplier (three Shoup products = 30 32-bit
-// multiplies per coefficient), so for moduli of at most 49 bits (F64 = true) the two products by XB and YB run on the FP64
-// pipe (modarith.cuh mulmod_f64: the client's coefficients are converted to doubles once, outside the point loop) and only
-// the product by S stays on the integer pipe: 15 FP64 + 10 integer multiplies per coefficient, both under the HBM write.
+// multiplies per coefficient), so for moduli of at most 49 bits (F64 = true) all three products run on the FP64 pipe
+// (modarith.cuh mulmod_f64: the client's coefficients are converted to doubles once, outside the point loop; the last
+// product lands in (-q/2, q/2), one biased add and one conditional subtraction make it canonical): 21 FP64 instructions
+// per coefficient and almost no integer work.
 constexpr int kCrossTile = 32;
 #ifndef PPLP_CROSS_UNROLL
 #define PPLP_CROSS_UNROLL 4
@@ -163,7 +167,7 @@ __global__ void __launch_bounds__(kCaThreads, PPLP_CROSS_MINB) circuit_a_cross_k
     }
     double ad[2 * kCrossUnroll], bd[2 * kCrossUnroll], cd[2 * kCrossUnroll];
     const double qd = (double)q;
-    const double bias = __fma_rn(4.0, qd, kTwo52);   // v = a - t1 - t2 in (-2.5q, 2.5q)  ->  v + 4q as an integer
+    const double bias = __dadd_rn(qd, kTwo52);       // a product in (-q, q)  ->  + q as an integer in (0, 2q)
     if constexpr (F64) {
 #pragma unroll
         for (int u = 0; u < kCrossUnroll; ++u) {
@@ -187,24 +191,27 @@ __global__ void __launch_bounds__(kCaThreads, PPLP_CROSS_MINB) circuit_a_cross_k
             for (int u = 0; u < kCrossUnroll; ++u) {
                 const int i = first + u * 2 * kCaThreads;
                 if (i >= n) continue;
-                u64 vx, vy;
-                if constexpr (F64) {
-                    const double tx = __dsub_rn(__dsub_rn(ad[2 * u], mulmod_f64(bd[2 * u], as_d(xbw), as_d(xbq), qd)), mulmod_f64(cd[2 * u], as_d(ybw), as_d(ybq), qd));
-                    const double ty = __dsub_rn(__dsub_rn(ad[2 * u + 1], mulmod_f64(bd[2 * u + 1], as_d(xbw), as_d(xbq), qd)), mulmod_f64(cd[2 * u + 1], as_d(ybw), as_d(ybq), qd));
-                    vx = f64_to_u64_biased(tx, bias);
-                    vy = f64_to_u64_biased(ty, bias);
-                } else {
-                    vx = a[u].x + four_q - mul_shoup_lazy(b[u].x, xbw, xbq, q) - mul_shoup_lazy(c[u].x, ybw, ybq, q);
-                    vy = a[u].y + four_q - mul_shoup_lazy(b[u].y, xbw, xbq, q) - mul_shoup_lazy(c[u].y, ybw, ybq, q);
-                }
                 const bool head = (p == 0 && i == 0);
-                if (head) vx += sc[tt][6];
-                u64 rx = mul_shoup_lazy_nq(vx, sw, sq, 0 - q), ry = mul_shoup_lazy_nq(vy, sw, sq, 0 - q);
-                if (head) rx += sc[tt][7];
-                rx = rx >= two_q ? rx - two_q : rx;
                 ulonglong2 o;
-                o.x = csub(rx, q);
-                o.y = csub(ry, q);
+                if constexpr (F64) {
+                    double tx = __dsub_rn(__dsub_rn(ad[2 * u], mulmod_f64(bd[2 * u], as_d(xbw), as_d(xbq), qd)), mulmod_f64(cd[2 * u], as_d(ybw), as_d(ybq), qd));
+                    const double ty = __dsub_rn(__dsub_rn(ad[2 * u + 1], mulmod_f64(bd[2 * u + 1], as_d(xbw), as_d(xbq), qd)), mulmod_f64(cd[2 * u + 1], as_d(ybw), as_d(ybq), qd));
+                    if (head) tx = __dadd_rn(tx, as_d(sc[tt][6]));                       // |tx| < 3.5 q
+                    double rx = mulmod_f64(tx, as_d(sw), as_d(sq), qd);                  // |.| <= q/2 + eps
+                    const double ry = mulmod_f64(ty, as_d(sw), as_d(sq), qd);
+                    if (head) rx = reduce_sym_f64(__dadd_rn(rx, as_d(sc[tt][7])), 1.0 / qd, qd);
+                    o.x = csub(f64_to_u64_biased(rx, bias), q);
+                    o.y = csub(f64_to_u64_biased(ry, bias), q);
+                } else {
+                    u64 vx = a[u].x + four_q - mul_shoup_lazy(b[u].x, xbw, xbq, q) - mul_shoup_lazy(c[u].x, ybw, ybq, q);
+                    u64 vy = a[u].y + four_q - mul_shoup_lazy(b[u].y, xbw, xbq, q) - mul_shoup_lazy(c[u].y, ybw, ybq, q);
+                    if (head) vx += sc[tt][6];
+                    u64 rx = mul_shoup_lazy_nq(vx, sw, sq, 0 - q), ry = mul_shoup_lazy_nq(vy, sw, sq, 0 - q);
+                    if (head) rx += sc[tt][7];
+                    rx = rx >= two_q ? rx - two_q : rx;
+                    o.x = csub(rx, q);
+                    o.y = csub(ry, q);
+                }
                 stg_stream(out + obase + i, o);
             }
         }

@@ -25,6 +25,18 @@ import time
 
 import numpy as np
 
+# The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to fd 1 when the
+# first communicator comes up), so everything but the result line is sent to stderr: fd 1 is pointed at fd 2 for the
+# whole run and the line is written to a saved duplicate of the original stdout.
+_RESULT_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_RESULT_FD, (json.dumps(line) + "\n").encode())
+
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -168,7 +180,7 @@ def run_reference(args):
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -353,7 +365,7 @@ def run_b200(args):
                                 "sample": f"{sample} queries/step x 3 steps, SEAL-4.1-equivalent CPU restatement (oracle/), {threads} host threads"}
     if extras:
         line["extras"] = extras
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

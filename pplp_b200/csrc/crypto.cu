@@ -11,10 +11,15 @@
 //   sample_encrypt_kernel  u <- ternary (libstdc++ uniform_int_distribution<u64>(0,2) over 32-bit draws, i.e.
 //                          Lemire's method: only a zero draw is rejected), e0, e1 <- centred binomial (6 bytes each);
 //                          stream order u, e0, e1 as in encrypt_zero_asymmetric
-//   encrypt_limb_kernel    per (ciphertext, limb): U = NTT(u); for p in {0,1}: T_p = INTT(U (.) pk_p) + e_p.
-//                          One forward transform feeds both inverse transforms; nothing NTT-form touches HBM.
-//   modswitch_kernel       divide_and_round_q_last (drop the special prime) fused with the scaling-variant plaintext
-//                          addition c0 += round(Q m / t): the only cross-limb step.
+//   enc32_forward_kernel / enc_forward_kernel, enc_inverse_kernel<SPECIAL | DATA>
+//                          the split pipeline (K > 1, N <= 16384; see "split encryption pipeline" below): U = NTT(u) per
+//                          limb; T_p = INTT(U (.) pk_p) + e_p for the special prime; the same for every data limb with
+//                          divide_and_round_q_last and the plaintext addition c0 += round(Q m / t) in the epilogue,
+//                          so the key-level intermediate never reaches HBM
+//   encrypt_limb_kernel + modswitch_kernel / copy_addplain_kernel
+//                          the single-kernel form (K == 1, and the pieces of N = 32768)
+// Key generation (samplers on the device): uniform_bulk/fixup_kernel ([SEAL] sample_poly_uniform with its in-order
+// replacement of rejected words), cbd_at_kernel, pk_combine.
 #include <cstdlib>
 #include "blake2.cuh"
 #include "engine.hpp"

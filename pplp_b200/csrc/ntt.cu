@@ -2,7 +2,9 @@
 //
 // Kernels (one CTA = one RNS-limb polynomial of one query; grid = rows of the batch, limb-major so that CTAs that
 // share a twiddle table are co-resident and the table stays in L2):
-//   ntt_forward_kernel<LOGM,L>   global -> regs (coalesced) -> radix-16 passes -> smem -> coalesced stores
+//   ntt32_forward/inverse_kernel<LOGM,DENSE>  moduli <= 44 bits, N = 2048..8192: 32 coefficients per thread on the FP64
+//                                pipe, one CTA barrier (ntt32.cuh) — the stand-alone transforms of the headline degree
+//   ntt_forward_kernel<LOGM,L>   every other case: global -> regs (coalesced) -> radix-16 passes -> smem -> coalesced stores
 //   ntt_inverse_kernel<LOGM,L>   the mirror image, N^-1 folded into the last stage
 //   polymul_kernel<LOGM,L>       out = INTT(NTT(a) (.) b) [+ c]: the dyadic product happens in registers between the
 //                                two transforms (fine layout of the forward == fine layout of the inverse), so the

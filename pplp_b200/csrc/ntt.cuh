@@ -7,9 +7,10 @@
 // and the north-star square / relinearise / generic multiply_plain paths.
 //
 // How (B200).  One CTA owns one polynomial of M = 2^LOGM coefficients.  Each thread keeps 16 coefficients in
-// registers and runs radix-16 passes (4 butterfly stages each, 32 independent Shoup butterflies per thread per
-// pass).  The kernels are bound by the integer pipes, not HBM (a 64-bit Shoup product is ten 32-bit multiplies), so
-// the design minimises instructions per butterfly:
+// registers and runs radix-16 passes (4 butterfly stages each, 32 independent butterflies per thread per pass).
+// Moduli of at most 49 bits run their butterflies on the FP64 pipe (lazy levels 3 and 4 below; modarith.cuh mulmod_f64:
+// exact integers in doubles, 8 instructions per butterfly).  Wider moduli use the integer pipes, where a 64-bit Shoup
+// product is ten 32-bit multiplies and the design minimises instructions per butterfly:
 //   * twiddles are (w, w' = floor(w 2^64/q)) pairs fetched with one 128-bit read-only load from the L2-resident table;
 //   * Shoup's product accepts ANY 64-bit input and returns a value in [0,2q), so when the modulus leaves head-room in
 //     the 64-bit word the butterflies run WITHOUT per-stage conditional subtractions ("free" mode): forward values

@@ -20,6 +20,7 @@
 // Between passes the CTA transposes through shared memory (padded by one word per 16 so the stride-G accesses of every
 // pass are bank-conflict-free).  A pass is in place: a thread writes the slots it read, so one __syncthreads per pass.
 #pragma once
+#include <cstddef>
 #include "devstructs.h"
 
 namespace pplp {
@@ -126,15 +127,17 @@ __device__ __forceinline__ ShoupW ld_twiddle(const ShoupW *p) {
 struct NttConsts {          // per-modulus scalars a transform needs besides the twiddle table
     u64 q, two_q, one_q;    // one_q = floor(2^64 / q)   (L = 3: bits of fl(1/q))
     u64 qd;                 // L = 3: bits of double(q)
-    ShoupW n_inv, inv1_n_inv;
+    const ShoupW *scale;    // {N^-1, inv[1] N^-1} of the modulus: fetched where the last inverse stage needs them, not held in registers
     const ShoupW *fine_fwd, *fine_inv;   // thread-interleaved twiddles of the last four stages (see Pass::stage)
 };
 template <int L> __device__ __forceinline__ NttConsts ntt_consts(const DevMod &md) {
     NttConsts c;
     c.q = md.m.q; c.two_q = md.m.q << 1;
     c.qd = as_u((double)md.m.q);
-    if constexpr (L >= 3) { c.one_q = md.one_d; c.n_inv = md.n_inv_d; c.inv1_n_inv = md.inv1_n_inv_d; c.fine_fwd = md.fine_fwd_d; c.fine_inv = md.fine_inv_d; }
-    else { c.one_q = md.one_q; c.n_inv = md.n_inv; c.inv1_n_inv = md.inv1_n_inv; c.fine_fwd = md.fine_fwd; c.fine_inv = md.fine_inv; }
+    static_assert(offsetof(DevMod, inv1_n_inv) == offsetof(DevMod, n_inv) + sizeof(ShoupW) && offsetof(DevMod, inv1_n_inv_d) == offsetof(DevMod, n_inv_d) + sizeof(ShoupW),
+                  "the two scaling constants must be adjacent");
+    if constexpr (L >= 3) { c.one_q = md.one_d; c.scale = &md.n_inv_d; c.fine_fwd = md.fine_fwd_d; c.fine_inv = md.fine_inv_d; }
+    else { c.one_q = md.one_q; c.scale = &md.n_inv; c.fine_fwd = md.fine_fwd; c.fine_inv = md.fine_inv; }
     return c;
 }
 template <int L> __device__ __forceinline__ const ShoupW *fwd_table(const DevMod &md) { return L >= 3 ? md.fwd_d : md.fwd; }
@@ -178,17 +181,18 @@ template <int LOGM, int S0, int R> struct Pass {
         const u64 big = c.two_q << GROW;
         const u64 qm = is_f64(MODE) ? c.qd : c.q;   // what the butterflies take as "q"
         if constexpr (INVERSE && FOLD_SCALE && V == 0) {
+            const ShoupW n_inv = ld_twiddle(c.scale), inv1_n_inv = ld_twiddle(c.scale + 1);
 #pragma unroll
             for (int i = 0; i < HALF; ++i) {
                 u64 &a = x[u * RR + i], &b = x[u * RR + i + HALF];
                 if constexpr (is_f64(MODE)) {
                     const double ad = as_d(a), bd = as_d(b);
-                    a = as_u(mulmod_f64(__dadd_rn(ad, bd), as_d(c.n_inv.w), as_d(c.n_inv.wq), as_d(qm)));
-                    b = as_u(mulmod_f64(__dsub_rn(ad, bd), as_d(c.inv1_n_inv.w), as_d(c.inv1_n_inv.wq), as_d(qm)));
+                    a = as_u(mulmod_f64(__dadd_rn(ad, bd), as_d(n_inv.w), as_d(n_inv.wq), as_d(qm)));
+                    b = as_u(mulmod_f64(__dsub_rn(ad, bd), as_d(inv1_n_inv.w), as_d(inv1_n_inv.wq), as_d(qm)));
                 } else {
                     const u64 s = a + b, d = a - b + big;
-                    a = twiddle_mul<MODE>(s, c.n_inv, c.q);
-                    b = twiddle_mul<MODE>(d, c.inv1_n_inv, c.q);
+                    a = twiddle_mul<MODE>(s, n_inv, c.q);
+                    b = twiddle_mul<MODE>(d, inv1_n_inv, c.q);
                 }
             }
         } else {

@@ -8,6 +8,7 @@
 
 #include "../../include/pplp_b200.h"
 #include "bloom_host.hpp"
+#include <cstddef>
 #include "engine.hpp"
 
 using namespace pplp;
@@ -174,7 +175,7 @@ void Engine::upload_tables(int dev) {
         m.one_d = 0;
         m.fine_fwd = m.fine_inv = m.fine_fwd_d = m.fine_inv_d = nullptr;
         m.fine32_fwd_d = m.fine32_inv_d = nullptr;
-        m.nc32_fwd = m.nc32_inv = Ntt32Consts{0.0, 0.0, ShoupW{0, 0}, ShoupW{0, 0}, nullptr, nullptr};
+        m.nc32_fwd = m.nc32_inv = Ntt32Consts{0.0, 0.0, nullptr, nullptr, nullptr};
         const int logn = host.logn;
         auto fine = [&](const std::vector<ShoupW> &tab) -> const ShoupW * {   // thread-interleaved last four stages
             if (logn < 4) return nullptr;
@@ -210,12 +211,20 @@ void Engine::upload_tables(int dev) {
                 };
                 m.fine32_fwd_d = fine32(fd);
                 m.fine32_inv_d = fine32(id);
-                m.nc32_fwd = Ntt32Consts{(double)T.q, 1.0 / (double)T.q, m.n_inv_d, m.inv1_n_inv_d, m.fwd_d, m.fine32_fwd_d};
-                m.nc32_inv = Ntt32Consts{(double)T.q, 1.0 / (double)T.q, m.n_inv_d, m.inv1_n_inv_d, m.inv_d, m.fine32_inv_d};
+                m.nc32_fwd = Ntt32Consts{(double)T.q, 1.0 / (double)T.q, nullptr, m.fwd_d, m.fine32_fwd_d};   // scale: patched below
+                m.nc32_inv = Ntt32Consts{(double)T.q, 1.0 / (double)T.q, nullptr, m.inv_d, m.fine32_inv_d};
             }
         }
     }
     d_mods = upload(h_mods.data(), h_mods.size());
+    {   // the ntt32 constant blocks point at their modulus' {N^-1, inv[1] N^-1} pair inside the device copy of this very array
+        static_assert(offsetof(DevMod, inv1_n_inv_d) == offsetof(DevMod, n_inv_d) + sizeof(ShoupW), "scaling constants must be adjacent");
+        for (size_t i = 0; i < h_mods.size(); ++i) {
+            const ShoupW *dev = reinterpret_cast<const ShoupW *>(reinterpret_cast<const char *>(d_mods + i) + offsetof(DevMod, n_inv_d));
+            h_mods[i].nc32_fwd.scale = h_mods[i].nc32_inv.scale = dev;
+        }
+        PPLP_CUDA(cudaMemcpy(d_mods, h_mods.data(), h_mods.size() * sizeof(DevMod), cudaMemcpyHostToDevice));
+    }
     std::vector<DevLevel> lv(host.levels.size());
     for (size_t i = 0; i < lv.size(); ++i) lv[i] = host.levels[i].dev;
     d_levels = upload(lv.data(), lv.size());

@@ -10,7 +10,7 @@ constexpr int kMaxMods = 48;    // q primes + BEHZ auxiliary primes with NTT tab
 // What a 32-per-thread FP64 transform (ntt32.cuh) needs about its modulus, in one contiguous block.
 struct Ntt32Consts {
     double q, qinv;                 // double(q), fl(1/q)
-    ShoupW n_inv, inv1_n_inv;       // bits of (double w, fl(w/q))
+    const ShoupW *scale;            // {N^-1, inv[1] N^-1} as bits of (double w, fl(w/q)): fetched by the last inverse stage
     const ShoupW *tw;               // natural table (bits of doubles): fwd_d or inv_d
     const ShoupW *fine;             // thread-interleaved last five stages: entry ((2^v - 1 + j) * T + t) = tw[2^(LOGM-5+v) + (t << v) + j]
 };

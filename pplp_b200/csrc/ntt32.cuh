@@ -254,11 +254,12 @@ __device__ __forceinline__ void ntt32_inverse(u64 (&x)[32], u64 *sm, int tid, co
         }
     }
     const double bias = __dadd_rn(c.q, kTwo52);
+    const ShoupW n_inv = ld_tw(c.scale), inv1_n_inv = ld_tw(c.scale + 1);
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         const double ad = as_d(x[i]), bd = as_d(x[i + 16]);
-        x[i] = f64_to_u64_biased(mulmod_f64(__dadd_rn(ad, bd), as_d(c.n_inv.w), as_d(c.n_inv.wq), c.q), bias);
-        x[i + 16] = f64_to_u64_biased(mulmod_f64(__dsub_rn(ad, bd), as_d(c.inv1_n_inv.w), as_d(c.inv1_n_inv.wq), c.q), bias);
+        x[i] = f64_to_u64_biased(mulmod_f64(__dadd_rn(ad, bd), as_d(n_inv.w), as_d(n_inv.wq), c.q), bias);
+        x[i + 16] = f64_to_u64_biased(mulmod_f64(__dsub_rn(ad, bd), as_d(inv1_n_inv.w), as_d(inv1_n_inv.wq), c.q), bias);
     }
 }
 

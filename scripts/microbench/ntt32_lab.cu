@@ -145,7 +145,7 @@ template <int LOGM> void run(int rows) {
                 for (int j = 0; j < (1 << v); ++j)
                     for (int t = 0; t < S::T; ++t) fine[(size_t)((1 << v) - 1 + j) * S::T + t] = d[(size_t(1) << (LOGM - 5 + v)) + ((size_t)t << v) + j];
             c.q = (double)T.q; c.qinv = 1.0 / (double)T.q;
-            c.n_inv = pair(T.n_inv.w); c.inv1_n_inv = pair(T.inv1_n_inv.w);
+            c.scale = upload(std::vector<ShoupW>{pair(T.n_inv.w), pair(T.inv1_n_inv.w)});
             c.tw = upload(d); c.fine = upload(fine);
         };
         mods[m].q = T.q;

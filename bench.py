@@ -375,19 +375,19 @@ def run_extras(engine, ctx, torch, osk, opk):
     ex = {}
     try:
         sk, pk = ctx.dev(osk), ctx.dev(opk)
-        nq, radius = 2048, 128
+        nq, radius = 4096, 128
         rng = np.random.default_rng(99)
         r, s, w = 0x12345678, 0x9ABCDEF1, 0xBEEF
         xb = np.full(nq, 123456888, dtype=np.uint64); yb = np.full(nq, 132465777, dtype=np.uint64)
         xa = xb + rng.integers(0, 300, nq).astype(np.uint64); ya = yb + rng.integers(0, 300, nq).astype(np.uint64)
         seeds = rng.integers(0, 1 << 63, size=(nq * 3, 8), dtype=np.uint64)
         bf = engine.BloomBatch(ctx, radius, fpp=1e-4, rsw=[(r, s, w)]).build()
-        ctx.proximity_batch_host(pk, sk, xa, ya, xb, yb, seeds, bf, chunk=1024)
+        ctx.proximity_batch_host(pk, sk, xa, ya, xb, yb, seeds, bf, chunk=2048)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         reps = 3
         for _ in range(reps):
-            blind, verdict, flags = ctx.proximity_batch_host(pk, sk, xa, ya, xb, yb, seeds, bf, chunk=1024)
+            blind, verdict, flags = ctx.proximity_batch_host(pk, sk, xa, ya, xb, yb, seeds, bf, chunk=2048)
         dt = time.perf_counter() - t0
         d2 = (xa.astype(np.int64) - xb.astype(np.int64)) ** 2 + (ya.astype(np.int64) - yb.astype(np.int64)) ** 2
         expect = (np.uint64(s) * (d2.astype(np.uint64) + np.uint64(r))) & np.uint64(T - 1)

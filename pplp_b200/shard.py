@@ -25,13 +25,27 @@ def max_over_ranks(value, device="cpu"):
     return float(t.item())
 
 
-def gather_rows(local, nq, dst=0):
+def cross_shard(npts, ncl, rank, world):
+    """BASELINE.json config 5 (every client against every server point): the server points are sharded, every rank keeps
+    all `ncl` client ciphertexts.  Returns (point_lo, point_hi, pair_lo, pair_hi): the rank's points and the slice of the
+    global pair order (pair = point * ncl + client) its results occupy — contiguous, so gather_rows applies."""
+    lo, hi = shard_range(npts, rank, world)
+    return lo, hi, lo * ncl, hi * ncl
+
+
+def cross_sizes(npts, ncl, world):
+    return [s * ncl for s in shard_sizes(npts, world)]
+
+
+def gather_rows(local, nq, dst=0, sizes=None):
     """Gathers per-query rows (blinded distances, verdicts or whole result ciphertexts, first dimension = local queries)
-    from every rank to `dst` in query order.  Returns the [nq, ...] tensor on dst, None elsewhere."""
+    from every rank to `dst` in query order.  Returns the [nq, ...] tensor on dst, None elsewhere.  `sizes`: rows per
+    rank when the batch is not sharded by shard_range (e.g. cross_sizes)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return local
     world, rank = dist.get_world_size(), dist.get_rank()
-    sizes = shard_sizes(nq, world)
+    sizes = shard_sizes(nq, world) if sizes is None else list(sizes)
+    assert sum(sizes) == nq
     assert local.shape[0] == sizes[rank]
     pad = max(sizes)
     buf = torch.zeros((pad,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)

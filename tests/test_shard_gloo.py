@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from pplp_b200.shard import gather_rows, max_over_ranks, shard_range, shard_sizes
+from pplp_b200.shard import cross_shard, cross_sizes, gather_rows, max_over_ranks, shard_range, shard_sizes
 
 
 def test_shard_ranges_partition_exactly():
@@ -48,3 +48,30 @@ def _worker(rank, world, port, nq):
 def test_gather_in_query_order_over_gloo(world, nq):
     port = 29500 + (os.getpid() % 2000) + world
     mp.spawn(_worker, args=(world, port, nq), nprocs=world, join=True)
+
+
+def _cross_worker(rank, world, port, npts, ncl):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        plo, phi, lo, hi = cross_shard(npts, ncl, rank, world)
+        assert (lo, hi) == (plo * ncl, phi * ncl)
+        # the rank "evaluates" its points against all clients: result of pair (t, c) = t * 1000 + c, pair order t * ncl + c
+        t = torch.arange(plo, phi, dtype=torch.int64).repeat_interleave(ncl)
+        c = torch.arange(ncl, dtype=torch.int64).repeat(phi - plo)
+        g = gather_rows(t * 1000 + c, npts * ncl, sizes=cross_sizes(npts, ncl, world))
+        if rank == 0:
+            tt = torch.arange(npts, dtype=torch.int64).repeat_interleave(ncl)
+            cc = torch.arange(ncl, dtype=torch.int64).repeat(npts)
+            assert torch.equal(g, tt * 1000 + cc)
+        else:
+            assert g is None
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,npts,ncl", [(2, 7, 5), (3, 4, 3)])
+def test_config5_point_sharding_gathers_in_pair_order(world, npts, ncl):
+    port = 31500 + (os.getpid() % 2000) + world
+    mp.spawn(_cross_worker, args=(world, port, npts, ncl), nprocs=world, join=True)

@@ -307,9 +307,13 @@ __global__ void __launch_bounds__(NttShape<LOGM>::T, (LOGM <= 13 ? PPLP_ENC_INV_
             x[2 * c + 1] = twiddle_mul<Lazy<L>::I>(uv.y, ShoupW{k1.x, k1.y}, q);
         }
     }
-    block_ntt_inverse<LOGM, true, Lazy<L>::I>(x, sm, tid, inv_table<L>(md), 0, 0, nc);
     const signed char *e = a.noise + ((size_t)ct * 3 + 1 + p) * a.n;
     u64 *lastp = a.last + ((size_t)ct * 2 + p) * a.n;
+    if constexpr (!SPECIAL) {   // the epilogue's operands: ask L2 for them now, the transform hides the HBM round trip
+        for (int o = tid * 128; o < a.n * 8; o += NttShape<LOGM>::T * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(lastp) + o));
+        if (tid * 128 < a.n) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(e) + tid * 128));
+    }
+    block_ntt_inverse<LOGM, true, Lazy<L>::I>(x, sm, tid, inv_table<L>(md), 0, 0, nc);
     if (SPECIAL) {
         const u64 half = a.KL->half_last;
         CoarsePass<LOGM>::for_each(tid, [&](int r, int i) {

@@ -32,6 +32,8 @@ def test_empty_batches_are_no_ops(eng, ctx):
     assert L.pplp_encrypt(ctx.h, None, None, None, 1, 1, None, 0, 0, st) == 0
     assert L.pplp_decrypt(ctx.h, 1, None, 0, 0, 2, None, None, 1, 1, st) == 0
     assert L.pplp_circuit_a_host(ctx.h, 1, None, None, None, None, 0, None, None, None, None, None, 16) == 0
+    assert L.pplp_circuit_a_cross(ctx.h, 1, None, None, None, 0, None, 0, 5, None, None, None, None, None, st) == 0   # no clients
+    assert L.pplp_circuit_a_cross(ctx.h, 1, None, None, None, 5, None, 0, 0, None, None, None, None, None, st) == 0   # no server points
     assert L.pplp_multiply(ctx.h, 1, None, None, None, 0, 0, st) == 0
     assert L.pplp_relinearize(ctx.h, 1, None, None, 0, 0, None, None, st) == 0
     assert L.pplp_bloom_query(ctx.h, None, 8, None, 1, None, 1, None, None, 0, None, st) == 0
@@ -47,6 +49,12 @@ def test_argument_errors_are_codes_not_aborts(eng, ctx):
     for call, needle in [
         (lambda: L.pplp_ntt(ctx.h, 99, 0, d.data_ptr(), 0, 1, 2, 0, st), b"level out of range"),
         (lambda: L.pplp_ntt(ctx.h, 1, 7, d.data_ptr(), 0, 1, 2, 0, st), b"base must be"),
+        (lambda: L.pplp_circuit_a_cross(ctx.h, 99, d.data_ptr(), d.data_ptr(), d.data_ptr(), 1, d.data_ptr(), 0, 1, d.data_ptr(), d.data_ptr(), d.data_ptr(),
+                                        d.data_ptr(), None, st), b"level out of range"),
+        (lambda: L.pplp_circuit_a_cross(ctx.h, 1, d.data_ptr(), d.data_ptr(), d.data_ptr(), 1, d.data_ptr(), 5, 1, d.data_ptr(), d.data_ptr(), d.data_ptr(),
+                                        d.data_ptr(), None, st), b"unknown layout"),
+        (lambda: L.pplp_circuit_a_cross(ctx.h, 1, d.data_ptr(), d.data_ptr(), d.data_ptr(), 1 << 20, d.data_ptr(), 0, 1 << 20, d.data_ptr(), d.data_ptr(),
+                                        d.data_ptr(), d.data_ptr(), None, st), b"pair count"),
         (lambda: L.pplp_ntt(ctx.h, 1, 0, d.data_ptr(), 5, 1, 2, 0, st), b"unknown layout"),
         (lambda: L.pplp_decrypt(ctx.h, 1, d.data_ptr(), 0, 1, 7, d.data_ptr(), d.data_ptr(), 1, 1, st), b"not valid"),
         (lambda: L.pplp_decrypt(ctx.h, 1, d.data_ptr(), 0, 1, 2, d.data_ptr(), d.data_ptr(), 1, 0, st), b"ncoeff"),

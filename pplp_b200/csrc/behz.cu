@@ -103,6 +103,16 @@ __global__ void __launch_bounds__(256) tensor_kernel(const DevMod *mods, RowMap 
     const u64 *x0 = x + (((size_t)qi * 2 + 0) * nl + j) * n, *x1 = x + (((size_t)qi * 2 + 1) * nl + j) * n;
     const u64 *y0 = y + (((size_t)qi * 2 + 0) * nl + j) * n, *y1 = y + (((size_t)qi * 2 + 1) * nl + j) * n;
     u64 *d0 = d + (((size_t)qi * 3 + 0) * nl + j) * n, *d1 = d0 + (size_t)nl * n, *d2 = d1 + (size_t)nl * n;
+    if (x == y) {   // square: the cross term is 2 x0 x1 — the same residue as x0 x1 + x1 x0 with one product and two loads less
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            const u64 a0 = x0[i], a1 = x1[i];
+            const u64 m = mul_mod(a0, a1, mq);
+            d0[i] = mul_mod(a0, a0, mq);
+            d1[i] = add_mod(m, m, mq.q);
+            d2[i] = mul_mod(a1, a1, mq);
+        }
+        return;
+    }
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const u64 a0 = x0[i], a1 = x1[i], b0 = y0[i], b1 = y1[i];
         d0[i] = mul_mod(a0, b0, mq);

@@ -631,3 +631,52 @@ def test_wide_fp64_moduli_match_oracle(eng, oracle, n, bits):
         assert (ct[i] == octx.encrypt(opk, plains[i], seed=seeds[i])).all(), i
     got = eng.to_np(ctx.decrypt(ctx.dev(ct), ctx.dev(osk)))
     assert (got[:, :4] == plains).all() and not got[:, 4:].any()
+
+
+@pytest.mark.parametrize("n", [2048, 4096, 8192])
+def test_fp64_transforms_on_extreme_rows(eng, oracle, n):
+    """The 32-per-thread FP64 transforms (moduli <= 44 bits) on rows built to maximise intermediate magnitudes — all q-1,
+    all zero, alternating, one spike, and sign patterns that make every butterfly of the first stages add in phase — in
+    both layouts (the contiguous limb-major batch takes the DENSE kernels, the SEAL layout the strided ones)."""
+    q = oracle.bfv_default(n) if n > 2048 else oracle.get_primes(2 * n, 44, 3)
+    ctx, octx = contexts(eng, oracle, n, t=1 << 20, q=q, enforce_security=n > 2048)
+    k = ctx.limbs(0)
+    qa = np.array(q[:k], dtype=np.uint64)
+    rows = []
+    for pat in range(8):
+        r = np.zeros((k, n), dtype=np.uint64)
+        if pat == 0:
+            r[:] = (qa - np.uint64(1))[:, None]
+        elif pat == 1:
+            pass
+        elif pat == 2:
+            r[:, ::2] = (qa - np.uint64(1))[:, None]
+        elif pat == 3:
+            r[:, n // 2] = (qa - np.uint64(1))
+        elif pat == 4:
+            r[:, : n // 2] = (qa - np.uint64(1))[:, None]
+        elif pat == 5:
+            r[:] = (qa // np.uint64(2))[:, None]
+        elif pat == 6:
+            r[:, 1::2] = (qa - np.uint64(1))[:, None]
+            r[:, ::2] = 1
+        else:
+            r[:] = np.random.default_rng(n).integers(0, 2, size=(k, n), dtype=np.uint64) * (qa - np.uint64(1))[:, None]
+        rows.append(r)
+    data = np.stack(rows)[:, None]                      # [8 queries][1 poly][k][n]
+    ref_f = np.empty_like(data)
+    ref_i = np.empty_like(data)
+    for qi in range(8):
+        for j in range(k):
+            ref_f[qi, 0, j] = octx.ntt(0, j, data[qi, 0, j])
+            ref_i[qi, 0, j] = octx.ntt(0, j, data[qi, 0, j], inverse=True)
+    for layout, to_l, from_l in ((eng.LAYOUT_SEAL, lambda a: a, lambda a: a),
+                                 (eng.LAYOUT_LIMB_MAJOR, lambda a: np.ascontiguousarray(a.transpose(2, 1, 0, 3)), lambda a: a.transpose(2, 1, 0, 3))):
+        d = ctx.dev(to_l(data))
+        ctx.ntt_(d, level=0, layout=layout)
+        assert (from_l(eng.to_np(d)) == ref_f).all()
+        ctx.ntt_(d, level=0, inverse=True, layout=layout)
+        assert (from_l(eng.to_np(d)) == data).all()
+        d = ctx.dev(to_l(data))
+        ctx.ntt_(d, level=0, inverse=True, layout=layout)
+        assert (from_l(eng.to_np(d)) == ref_i).all()

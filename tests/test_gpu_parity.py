@@ -680,3 +680,22 @@ def test_fp64_transforms_on_extreme_rows(eng, oracle, n):
         d = ctx.dev(to_l(data))
         ctx.ntt_(d, level=0, inverse=True, layout=layout)
         assert (from_l(eng.to_np(d)) == ref_i).all()
+
+
+@pytest.mark.parametrize("n,nct", [(8192, 48), (4096, 32), (16384, 12)])
+def test_encrypt_many_seeds_bit_exact(eng, oracle, n, nct):
+    """A larger sample of encryptions compared bit for bit with the oracle: every ciphertext has its own PRNG stream, so
+    the sample exercises many different noise / product patterns through the FP64 transforms, the variable-operand
+    quotient of the dyadic product and the reduction-free modulus-switch epilogue."""
+    ctx, octx = contexts(eng, oracle, n)
+    osk, opk = octx.keygen()
+    rng = np.random.default_rng(4242 + n)
+    seeds = rng.integers(0, 1 << 63, size=(nct, 8), dtype=np.uint64)
+    plains = rng.integers(0, T56, size=(nct, 1), dtype=np.uint64)
+    plains[0, 0] = T56 - 1
+    plains[1, 0] = 0
+    ct = eng.to_np(ctx.encrypt(ctx.dev(opk), ctx.dev(seeds), ctx.dev(plains)))
+    for i in range(nct):
+        assert (ct[i] == octx.encrypt(opk, plains[i], seed=seeds[i])).all(), i
+    dec = eng.to_np(ctx.decrypt(ctx.dev(ct), ctx.dev(osk), ncoeff=1))
+    assert (dec[:, 0] == plains[:, 0]).all()

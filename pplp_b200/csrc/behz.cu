@@ -57,13 +57,13 @@ __global__ void __launch_bounds__(256, BEHZ_MINB) behz_extend_kernel(const DevLe
         for (int j = 0; j < ZK; ++j) {
             if (j >= k) break;
             const u64 q = L.q[j].q;
-            const ShoupW mt = L.mtilde_mod_q[j], ip = L.inv_punct[j];
+            const ShoupW mip = L.mtilde_inv_punct[j];
             const u64 pm = L.punct_mod_mtilde[j];
 #pragma unroll
             for (int c = 0; c < kBehzIlp; ++c) {
                 const u64 x = src[j * lay.sl + i0 + c];
                 cpy[(size_t)j * n + i0 + c] = x;
-                z[c][j] = mul_shoup(mul_shoup(x, mt, q), ip, q);                 // (x * m_tilde) * (Q/q_j)^-1 mod q_j
+                z[c][j] = mul_shoup(x, mip, q);                                  // x * m_tilde * (Q/q_j)^-1 mod q_j
                 r[c] += z[c][j] * pm;                                            // mod 2^32 survives the wrap mod 2^64
             }
         }
@@ -145,10 +145,10 @@ __global__ void __launch_bounds__(256, BEHZ_MINB) behz_floor_sk_kernel(const Dev
         for (int j = 0; j < ZK; ++j) {
             if (j >= k) break;
             const u64 q = L.q[j].q;
-            const ShoupW tq = L.t_mod_q[j], ip = L.inv_punct[j];
+            const ShoupW tip = L.t_inv_punct[j];
 #pragma unroll
             for (int c = 0; c < kBehzIlp; ++c) {
-                z[c][j] = mul_shoup(mul_shoup(sq[(size_t)j * n + i0 + c], tq, q), ip, q);   // * t, then (Q/q_j)^-1
+                z[c][j] = mul_shoup(sq[(size_t)j * n + i0 + c], tip, q);                    // * t (Q/q_j)^-1
                 acc[c][j] = U128{0, 0};
             }
         }

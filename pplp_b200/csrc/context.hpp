@@ -226,6 +226,8 @@ struct HostContext {
             D.t_gamma[j] = make_shoup(hm::mulm(t % p, L.gamma % p, p), p);
             D.mtilde_mod_q[j] = make_shoup(D.m_tilde % p, p);
             D.t_mod_q[j] = make_shoup(t % p, p);
+            D.mtilde_inv_punct[j] = make_shoup(hm::mulm(D.m_tilde % p, D.inv_punct[j].w, p), p);
+            D.t_inv_punct[j] = make_shoup(hm::mulm(t % p, D.inv_punct[j].w, p), p);
         }
         D.neg_inv_q_mod_t = (t - hm::inverse_or_throw(Q.mod(t), t)) % t;
         D.neg_inv_q_mod_gamma = L.gamma - hm::inverse_or_throw(Q.mod(L.gamma), L.gamma);

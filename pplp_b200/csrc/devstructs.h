@@ -74,6 +74,8 @@ struct DevLevel {
     Mod bsk[kMaxLimbs];
     u64 m_tilde;                        // 2^32
     ShoupW mtilde_mod_q[kMaxLimbs];     // m_tilde mod q_j
+    ShoupW mtilde_inv_punct[kMaxLimbs]; // m_tilde (Q/q_j)^-1 mod q_j and t (Q/q_j)^-1 mod q_j: the first two products of the
+    ShoupW t_inv_punct[kMaxLimbs];      // base conversions merged into one (same residue, one Shoup product less per limb)
     u64 punct_mod_bsk[kMaxLimbs][kMaxLimbs];   // [bsk prime][q limb]  (Q/q_j) mod p
     u64 punct_mod_mtilde[kMaxLimbs];           // (Q/q_j) mod 2^32
     u64 neg_inv_q_mod_mtilde;

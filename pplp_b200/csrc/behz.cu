@@ -155,39 +155,35 @@ __global__ void __launch_bounds__(256, BEHZ_MINB) behz_floor_sk_kernel(const Dev
         // One auxiliary prime per iteration (rolled: its constants are live for one iteration only).  fast_floor gives
         // fl_b = (t x_b - conv_b) Q^-1 mod b; for b in B it is consumed at once by the Shenoy-Kumaresan sums
         // (z_b = fl_b (B/b)^-1 mod b, then z_b (B/b mod q_j) for every j and z_b (B/b mod m_sk)); the last prime is m_sk.
+        // The constant factors Q^-1 and (B/b)^-1 are folded into the conversion matrix and into t on the host.
         u64 fl_msk[kBehzIlp];
 #pragma unroll 1
         for (int b = 0; b < nb; ++b) {
             const Mod mp = L.bsk[b];
-            const ShoupW tb = L.t_mod_bsk[b], iq = L.inv_q_mod_bsk[b];
+            const ShoupW ft = L.floor_t[b];
             U128 cv[kBehzIlp];
 #pragma unroll
             for (int c = 0; c < kBehzIlp; ++c) cv[c] = U128{0, 0};
 #pragma unroll
             for (int j = 0; j < ZK; ++j) {
                 if (j >= k) break;
-                const u64 w = L.punct_mod_bsk[b][j];
+                const u64 w = L.floor_punct[b][j];
 #pragma unroll
                 for (int c = 0; c < kBehzIlp; ++c) mac128(cv[c], z[c][j], w);
             }
-            u64 fl[kBehzIlp];
+            u64 fl[kBehzIlp];   // b in B: z_b = fl_b (B/b)^-1;  b = m_sk: fl_b itself   (constants merged, see DevLevel::floor_t)
 #pragma unroll
             for (int c = 0; c < kBehzIlp; ++c) {
                 const u64 conv = barrett128(cv[c].lo, cv[c].hi, mp);
-                const u64 xb = mul_shoup(sb[(size_t)b * n + i0 + c], tb, mp.q);
-                fl[c] = mul_shoup(sub_mod(xb, conv, mp.q), iq, mp.q);
+                fl[c] = sub_mod(mul_shoup(sb[(size_t)b * n + i0 + c], ft, mp.q), conv, mp.q);
             }
             if (b == nB) {
 #pragma unroll
                 for (int c = 0; c < kBehzIlp; ++c) fl_msk[c] = fl[c];
             } else {
-                const ShoupW ipb = L.inv_punctB[b];
                 const u64 wm = L.punctB_mod_msk[b];
 #pragma unroll
-                for (int c = 0; c < kBehzIlp; ++c) {
-                    fl[c] = mul_shoup(fl[c], ipb, mp.q);
-                    mac128(am[c], fl[c], wm);
-                }
+                for (int c = 0; c < kBehzIlp; ++c) mac128(am[c], fl[c], wm);
 #pragma unroll
                 for (int j = 0; j < ZK; ++j) {
                     if (j >= k) break;

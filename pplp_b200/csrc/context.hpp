@@ -249,6 +249,12 @@ struct HostContext {
             D.punctB_mod_msk[i] = pb.mod(L.m_sk);
             for (size_t j = 0; j < k; ++j) D.punctB_mod_q[j][i] = pb.mod(ql[j]);
         }
+        for (size_t b = 0; b < bsk.size(); ++b) {
+            const u64 p = bsk[b];
+            const u64 cb = b < nB ? hm::mulm(D.inv_q_mod_bsk[b].w, D.inv_punctB[b].w, p) : D.inv_q_mod_bsk[b].w;
+            D.floor_t[b] = make_shoup(hm::mulm(t % p, cb, p), p);
+            for (size_t j = 0; j < k; ++j) D.floor_punct[b][j] = hm::mulm(D.punct_mod_bsk[b][j], cb, p);
+        }
         D.inv_B_mod_msk = make_shoup(hm::inverse_or_throw(PB.mod(L.m_sk), L.m_sk), L.m_sk);
         for (size_t j = 0; j < k; ++j) {
             u64 p = ql[j], bm = PB.mod(p);

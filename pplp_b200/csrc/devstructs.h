@@ -84,6 +84,11 @@ struct DevLevel {
     ShoupW inv_mtilde_mod_bsk[kMaxLimbs];
     ShoupW t_mod_q[kMaxLimbs], t_mod_bsk[kMaxLimbs];
     ShoupW inv_punctB[kMaxLimbs];              // (B/b_i)^-1 mod b_i
+    // fast_floor followed by the first product of the Shenoy-Kumaresan conversion, merged per auxiliary prime b (ring
+    // identities mod b, so the residues are the ones the literal sequence gives): with c_b = Q^-1 (B/b)^-1 mod b for b in B
+    // and c_b = Q^-1 mod m_sk for the last prime,  z_b = x_b * floor_t[b] - sum_j z_j * floor_punct[b][j]  (mod b)
+    ShoupW floor_t[kMaxLimbs];                 // t c_b mod b
+    u64 floor_punct[kMaxLimbs][kMaxLimbs];     // [bsk prime][q limb]  (Q/q_j) c_b mod b
     u64 punctB_mod_q[kMaxLimbs][kMaxLimbs];    // [q limb][B prime] (B/b_i) mod q_j
     u64 punctB_mod_msk[kMaxLimbs];
     ShoupW inv_B_mod_msk;

@@ -141,28 +141,59 @@ def synth_host_batch(q, nq, seed):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+def cpu_model():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+CPU_Q_PER_THREAD = 32      # queries per thread per step (a thread sees a steady stream, not two queries)
+CPU_SAMPLE_CAP = 2048      # host memory bound: 1.5 MiB of input per query at N=8192
+
+
 def cpu_circuit_a_rate(steps, warmup, sample, threads):
-    """CPU restatement of the reference path (oracle/, 'port'): Circuit A over `sample` host-resident queries per step."""
+    """CPU restatement of the reference path (oracle/, 'port'): the seven Evaluator calls of src/server.cc:127-133 per
+    query, in place on host-resident ciphertexts (no copies, no allocation in the timed loop), Shoup products as in
+    SEAL's multiply_poly_scalar_coeffmod.  Returns all-thread and one-thread rates plus the host STREAM figure."""
+    import ctypes as C
     from tests import oracle_lib
     orc = oracle_lib.load()
     q = orc.bfv_default(N)
     octx = orc.context(N, q, T, seed=seed8(1))
     k = octx.k
-    if sample <= 0:   # calibrate: ~10 s of CPU work in total over the timed steps
-        c, xb, yb, r, s = synth_host_batch(q[:k], 16, 3)
-        t0 = time.perf_counter()
-        octx.circuit_a_batch(c[0], c[1], c[2], xb, yb, r, s, nthreads=min(threads, 16))
-        per_q_cpu = (time.perf_counter() - t0) * min(threads, 16) / 16
-        sample = int(max(threads, min(4096, 10.0 / max(per_q_cpu, 1e-6) / max(steps, 1))))
-        sample = max(threads, (sample // threads) * threads)
+    scale = max(1, (N * k) // (8192 * 4))
+    if sample <= 0:
+        sample = min(max(threads * CPU_Q_PER_THREAD // scale, threads), max(CPU_SAMPLE_CAP // scale, threads))
     c, xb, yb, r, s = synth_host_batch(q[:k], sample, 4)
-    for _ in range(warmup):
-        octx.circuit_a_batch(c[0], c[1], c[2], xb, yb, r, s, nthreads=threads)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        octx.circuit_a_batch(c[0], c[1], c[2], xb, yb, r, s, nthreads=threads)
-    dt = time.perf_counter() - t0
-    return sample * steps / dt, dt / steps, sample
+
+    def run(nsteps, nth, nq):
+        t0 = time.perf_counter()
+        for _ in range(nsteps):
+            octx.circuit_a_batch(c[0][:nq], c[1][:nq], c[2][:nq], xb[:nq], yb[:nq], r[:nq], s[:nq], nthreads=nth, inplace=True)
+        return time.perf_counter() - t0
+
+    run(max(warmup, 1), threads, sample)
+    dt = run(steps, threads, sample)
+    n1 = max(1, min(sample, CPU_Q_PER_THREAD // scale))
+    run(1, 1, n1)
+    dt1 = run(3, 1, n1)
+    info = {"threads": threads, "nproc": os.cpu_count(), "cpu_model": cpu_model(), "one_thread_value": n1 * 3 / dt1,
+            "thread_scaling": (sample * steps / dt) / (n1 * 3 / dt1), "queries_per_thread_per_step": sample / threads}
+    try:
+        f = orc.lib.orc_stream_add_gbs
+        f.restype = C.c_double
+        f.argtypes = [C.c_size_t, C.c_int, C.c_int]
+        info["host_stream_add_GBps"] = {"one_thread": f(1 << 24, 4, 1), "all_threads": f(1 << 26, 4, threads)}
+        # per query the seven calls move 3 read-modify-write passes of one ciphertext and 2 read-read-write passes
+        info["evaluator_bytes_per_query"] = 12 * 16 * k * N
+        info["evaluator_GBps"] = info["evaluator_bytes_per_query"] * sample * steps / dt / 1e9
+    except Exception as e:
+        info["host_stream_add_GBps"] = {"error": str(e)[:100]}
+    return sample * steps / dt, dt / steps, sample, info
 
 
 def run_reference(args):
@@ -170,13 +201,14 @@ def run_reference(args):
     if rank != 0:
         return
     threads = host_threads()
-    rate, per_step, sample = cpu_circuit_a_rate(args.steps, args.warmup, args.cpu_sample, threads)
+    rate, per_step, sample, info = cpu_circuit_a_rate(args.steps, args.warmup, args.cpu_sample, threads)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "queries_per_step": sample, "poly_modulus_degree": N, "limbs": LIMBS, "plain_modulus": "2^56"},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{sample} queries/step x {args.steps} steps, SEAL-4.1-equivalent CPU restatement (oracle/), {threads} host threads"},
+                         "sample": f"{sample} queries/step x {args.steps} steps in place on host-resident ciphertexts, SEAL-4.1-equivalent CPU "
+                                   f"restatement (oracle/), {threads} host threads", **info},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -360,9 +392,10 @@ def run_b200(args):
     }
     if world == 1:
         threads = host_threads()
-        rate, per_step, sample = cpu_circuit_a_rate(3, 1, args.cpu_sample, threads)
+        rate, per_step, sample, info = cpu_circuit_a_rate(5, 1, args.cpu_sample, threads)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": f"{sample} queries/step x 3 steps, SEAL-4.1-equivalent CPU restatement (oracle/), {threads} host threads"}
+                                "sample": f"{sample} queries/step x 5 steps in place on host-resident ciphertexts, SEAL-4.1-equivalent CPU "
+                                          f"restatement (oracle/), {threads} host threads", **info}
     if extras:
         line["extras"] = extras
     emit(line)

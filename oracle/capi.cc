@@ -373,7 +373,7 @@ int orc_protocol_batch(void *c, const u64 *pk_in, const u64 *sk_in, size_t nq, c
     ORC_CATCH
 }
 // Circuit A alone over nq independent (c0,c1,c2) triples resident in host memory, threaded (d_homoCalc).
-int orc_circuit_a_batch(void *c, size_t nq, u64 *c0 /* [nq][2][k][n] in/out */, const u64 *c1, const u64 *c2, const u64 *xb, const u64 *yb,
+int orc_circuit_a_batch(void *c, size_t nq, u64 *c0 /* [nq][2][k][n] in/out */, u64 *c1 /* clobbered */, u64 *c2 /* clobbered */, const u64 *xb, const u64 *yb,
                         const u64 *r, const u64 *s, int nthreads) {
     ORC_TRY
     auto *ctx = (Context *)c; const Level &L = ctx->first_level();
@@ -384,9 +384,11 @@ int orc_circuit_a_batch(void *c, size_t nq, u64 *c0 /* [nq][2][k][n] in/out */, 
             for (;;) {
                 size_t q = next.fetch_add(1);
                 if (q >= nq) break;
-                Ciphertext a = wrap_ct(*ctx, L, c0 + q * per, 2), b = wrap_ct(*ctx, L, c1 + q * per, 2), d = wrap_ct(*ctx, L, c2 + q * per, 2);
+                // in place on the resident batch, as SEAL's Evaluator works on the Ciphertext objects the server holds
+                // (src/server.cc:127-133 clobbers c1 and c2 as well): no copies, no allocation per query
+                Ciphertext a, b, d;
+                a.borrow(L, ctx->parms.n, 2, c0 + q * per); b.borrow(L, ctx->parms.n, 2, c1 + q * per); d.borrow(L, ctx->parms.n, 2, c2 + q * per);
                 circuit_a(*ctx, a, b, d, xb[q], yb[q], r[q], s[q]);
-                std::copy(a.d.begin(), a.d.end(), c0 + q * per);
             }
         } catch (...) { failed = 1; }
     };
@@ -397,6 +399,25 @@ int orc_circuit_a_batch(void *c, size_t nq, u64 *c0 /* [nq][2][k][n] in/out */, 
     if (failed) throw std::logic_error("a query failed");
     return 0;
     ORC_CATCH
+}
+
+// STREAM-style "add" over host memory (a[i] += b[i], 24 bytes of traffic per word) on nthreads threads: the ceiling the
+// element-wise evaluator passes run against, reported next to the CPU baseline so a flat thread-scaling curve can be read.
+double orc_stream_add_gbs(size_t words, int reps, int nthreads) {
+    std::vector<u64> a(words, 1), b(words, 2);
+    auto body = [&](int i) {
+        size_t lo = words / nthreads * i, hi = (i == nthreads - 1) ? words : words / nthreads * (i + 1);
+        for (int r = 0; r < reps; ++r) for (size_t k = lo; k < hi; ++k) a[k] += b[k];
+    };
+    body(0);   // first touch
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> th;
+    for (int i = 1; i < nthreads; ++i) th.emplace_back(body, i);
+    body(0);
+    for (auto &t : th) t.join();
+    double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    volatile u64 sink = a[words / 2]; (void)sink;
+    return 24.0 * (double)words * reps / dt / 1e9;
 }
 
 }  // extern "C"

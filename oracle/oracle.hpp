@@ -606,12 +606,20 @@ struct Ciphertext {
     u64 correction_factor = 1;
     double scale = 1.0;
     std::vector<u64> d;  // [poly][limb][n]
-    u64 *poly(size_t p) { return d.data() + p * k * n; }
-    const u64 *poly(size_t p) const { return d.data() + p * k * n; }
+    u64 *ext = nullptr;  // when set, the polynomials live in the caller's buffer (size*k*n words) and d is unused:
+                         // lets the evaluator run in place on a resident batch, as SEAL does on its own Ciphertext storage
+    u64 *data() { return ext ? ext : d.data(); }
+    const u64 *data() const { return ext ? ext : d.data(); }
+    size_t words() const { return ext ? size * k * n : d.size(); }
+    u64 *poly(size_t p) { return data() + p * k * n; }
+    const u64 *poly(size_t p) const { return data() + p * k * n; }
     void resize(const Level &L, size_t n_, size_t size_) { id = L.id; n = n_; k = L.q.size(); size = size_; d.resize(size * k * n); }
+    void borrow(const Level &L, size_t n_, size_t size_, u64 *buf) { id = L.id; n = n_; k = L.q.size(); size = size_; ext = buf; }
     bool transparent() const {
-        if (d.empty() || size < 2) return true;
-        for (size_t i = k * n; i < d.size(); ++i) if (d[i]) return false;
+        const size_t w = words();
+        if (w == 0 || size < 2) return true;
+        const u64 *p = data();
+        for (size_t i = k * n; i < w; ++i) if (p[i]) return false;
         return true;
     }
 };
@@ -922,13 +930,39 @@ inline void add_plain_inplace(const Context &ctx, Ciphertext &c, const Plaintext
 }
 inline void sub_plain_inplace(const Context &ctx, Ciphertext &c, const Plaintext &p) { add_plain_inplace(ctx, c, p, true); }
 
-// [SEAL] util/polyarithsmallmod.cpp negacyclic_multiply_poly_mono_coeffmod (scalar given per limb)
+// [SEAL] util/uintarithsmallmod.h MultiplyUIntModOperand + multiply_uint_mod: product by a constant y < q with the
+// precomputed quotient floor(y 2^64 / q) — one high product, two low products, one conditional subtraction.  Canonical
+// result, so bit-identical to mulmod(); this is the instruction mix SEAL's multiply_poly_scalar_coeffmod runs.
+struct ShoupOperand {
+    u64 operand, quotient;
+    ShoupOperand(u64 y, u64 q) : operand(y), quotient((u64)((((u128)y) << 64) / q)) {}
+};
+inline u64 mulmod_shoup(u64 x, const ShoupOperand &y, u64 q) {
+    u64 hi = (u64)(((u128)x * y.quotient) >> 64);
+    u64 r = y.operand * x - hi * q;
+    return r >= q ? r - q : r;
+}
+// [SEAL] util/polyarithsmallmod.cpp negacyclic_multiply_poly_mono_coeffmod (scalar given per limb):
+// multiply_poly_scalar_coeffmod followed by negacyclic_shift_poly_coeffmod.  Exponent 0 (the reference's constant
+// plaintexts, src/server.cc:128,129,132) needs no shift and runs in place; no allocation on that path.
 inline void negacyclic_mul_mono(const Level &L, size_t n, u64 *poly /* [k][n] */, const u64 *mono /* [k] */, size_t exponent) {
-    std::vector<u64> tmp(n);
+    if (exponent == 0) {
+        for (size_t j = 0; j < L.q.size(); ++j) {
+            const u64 q = L.q[j];
+            u64 *a = poly + j * n;
+            const ShoupOperand y(mono[j], q);
+            for (size_t i = 0; i < n; ++i) a[i] = mulmod_shoup(a[i], y, q);
+        }
+        return;
+    }
+    static thread_local std::vector<u64> tmp;
+    tmp.resize(n);
     for (size_t j = 0; j < L.q.size(); ++j) {
-        u64 q = L.q[j], *a = poly + j * n;
+        const u64 q = L.q[j];
+        u64 *a = poly + j * n;
+        const ShoupOperand y(mono[j], q);
         for (size_t i = 0; i < n; ++i) {
-            u64 v = mulmod(a[i], mono[j], q);
+            u64 v = mulmod_shoup(a[i], y, q);
             size_t raw = i + exponent, idx = raw & (n - 1);
             tmp[idx] = ((raw & n) && v) ? q - v : v;
         }
@@ -975,7 +1009,10 @@ inline void add_sub_inplace(const Context &ctx, Ciphertext &a, const Ciphertext 
     if (a.ntt_form != b.ntt_form) throw std::invalid_argument("NTT form mismatch");
     size_t n = ctx.parms.n, k = L.q.size();
     size_t mx = std::max(a.size, b.size), mn = std::min(a.size, b.size), asz = a.size;
-    a.d.resize(mx * k * n, 0); a.size = mx;
+    if (mx != a.size) {
+        if (a.ext) throw std::logic_error("oracle: a borrowed ciphertext cannot grow");
+        a.d.resize(mx * k * n, 0); a.size = mx;
+    }
     for (size_t s = 0; s < mn; ++s)
         for (size_t j = 0; j < k; ++j) {
             u64 q = L.q[j], *x = a.poly(s) + j * n; const u64 *y = b.poly(s) + j * n;

@@ -286,12 +286,19 @@ class OracleContext:
                                                _p(blind), _p(verdict, u8p), _p(ns)))
         return blind, verdict, ns
 
-    def circuit_a_batch(self, c0, c1, c2, xb, yb, r, s, nthreads=1):
-        c0 = np.ascontiguousarray(c0).copy()
+    def circuit_a_batch(self, c0, c1, c2, xb, yb, r, s, nthreads=1, inplace=False):
+        """The reference's seven Evaluator calls (src/server.cc:127-133) per query.  The C side works in place on all three
+        ciphertexts like SEAL does (c1 and c2 are clobbered); inplace=False hands it private copies, inplace=True (the timed
+        CPU baseline) hands it the caller's contiguous uint64 arrays and copies nothing."""
+        if inplace:
+            for a in (c0, c1, c2):
+                if not (isinstance(a, np.ndarray) and a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"] and a.flags["WRITEABLE"]):
+                    raise ValueError("inplace=True needs writable C-contiguous uint64 arrays")
+        else:
+            c0, c1, c2 = (np.array(a, dtype=np.uint64, order="C", copy=True) for a in (c0, c1, c2))
         arr = lambda v: np.ascontiguousarray(np.array(v, dtype=np.uint64))
         xb, yb, r, s = arr(xb), arr(yb), arr(r), arr(s)
-        self.o.check(self.L.orc_circuit_a_batch(self.hp, C.c_size_t(c0.shape[0]), _p(c0), _p(np.ascontiguousarray(c1)), _p(np.ascontiguousarray(c2)),
-                                                _p(xb), _p(yb), _p(r), _p(s), int(nthreads)))
+        self.o.check(self.L.orc_circuit_a_batch(self.hp, C.c_size_t(c0.shape[0]), _p(c0), _p(c1), _p(c2), _p(xb), _p(yb), _p(r), _p(s), int(nthreads)))
         return c0
 
 

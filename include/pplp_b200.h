@@ -78,6 +78,8 @@ int pplp_dev_memset(pplp_ctx *ctx, void *d_ptr, int value, size_t bytes, void *s
 int pplp_h2d(pplp_ctx *ctx, void *d_dst, const void *h_src, size_t bytes, void *stream);
 int pplp_d2h(pplp_ctx *ctx, void *h_dst, const void *d_src, size_t bytes, void *stream);
 int pplp_d2d(pplp_ctx *ctx, void *d_dst, const void *d_src, size_t bytes, void *stream);
+/* Waits for the stream and reports (PPLP_ELOGIC), then clears, a device-side failure raised by an asynchronous entry
+ * since the last call — today only "PRNG stream reserve exhausted" from pplp_encrypt / pplp_proximity_batch. */
 int pplp_sync(pplp_ctx *ctx, void *stream);
 int pplp_host_alloc(size_t bytes, void **out); /* page-locked */
 int pplp_host_free(void *ptr);
@@ -85,7 +87,11 @@ int pplp_host_free(void *ptr);
 /* ---- keys ---------------------------------------------------------------------------------------------------------
  * KeyGenerator(context), secret_key(), create_public_key(pk)  — src/demo.cc:81-85, src/client.cc:103-106.
  * seed = the 64-byte seed of SEAL's Blake2xbPRNG (prng_seed_type).  d_sk: [K][N], d_pk: [2][K][N], both NTT form at
- * the key level, exactly the words SEAL serialises.  Synchronises. */
+ * the key level, exactly the words SEAL serialises.  Synchronises.
+ * With d_pk != NULL the SAME seed drives the secret-key sampler and the public key's encryption of zero — what SEAL does
+ * under a fixed-seed Blake2xbPRNGFactory, and meant for reproducible parity tests only: s and the public-key error then
+ * come from one stream.  Production callers pass d_pk = NULL here and an independent seed to pplp_public_keygen (the
+ * seal/seal.h shim does). */
 int pplp_keygen(pplp_ctx *ctx, const uint64_t seed[8], uint64_t *d_sk, uint64_t *d_pk, void *stream);
 /* KeyGenerator::create_public_key for an existing secret key (its own PRNG seed).  Synchronises. */
 int pplp_public_keygen(pplp_ctx *ctx, const uint64_t seed[8], const uint64_t *d_sk, uint64_t *d_pk, void *stream);

@@ -28,7 +28,7 @@ namespace pplp {
 
 // ---- BEHZ: base extension ------------------------------------------------------------------------------------------
 // in: [nq][2][k][n] (layout `lay`), out: [nq][2][nb][n] contiguous; also copies the q residues into xq [nq][2][k][n]
-// (the operand of the q-base transform).  grid.y = query*2 + poly.
+// (the operand of the q-base transform).  grid.x = query*2 + poly.
 // K / NBSK are compile-time (0 = take them from the level at run time): with fixed trip counts the per-coefficient
 // vectors z[] live in registers instead of local memory, and each thread carries kBehzIlp coefficients so that the
 // base-conversion constants are fetched once per thread and the 128-bit accumulate chains of different coefficients overlap.
@@ -43,12 +43,12 @@ __global__ void __launch_bounds__(256, BEHZ_MINB) behz_extend_kernel(const DevLe
     constexpr int kBehzIlp = behz_ilp(K);
     const int k = K ? K : L.k, nb = NBSK ? NBSK : L.nBsk, n = L.n;
     constexpr int ZK = K ? K : kMaxLimbs;
-    const int qi = blockIdx.y >> 1, p = blockIdx.y & 1;
+    const int qi = blockIdx.x >> 1, p = blockIdx.x & 1;
     const u64 *src = in + qi * lay.sq + p * lay.sp;
     u64 *dst = out + ((size_t)qi * 2 + p) * nb * n;
     u64 *cpy = xq + ((size_t)qi * 2 + p) * k * n;
     const u64 mt_mask = L.m_tilde - 1, mt_half = L.m_tilde >> 1;
-    for (int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * kBehzIlp; i0 < n; i0 += gridDim.x * blockDim.x * kBehzIlp) {
+    for (int i0 = (blockIdx.y * blockDim.x + threadIdx.x) * kBehzIlp; i0 < n; i0 += gridDim.y * blockDim.x * kBehzIlp) {
         u64 z[kBehzIlp][ZK];
         u64 r[kBehzIlp];
 #pragma unroll
@@ -95,16 +95,16 @@ __global__ void __launch_bounds__(256, BEHZ_MINB) behz_extend_kernel(const DevLe
 }
 
 // ---- tensor product (NTT form) ------------------------------------------------------------------------------------
-// x, y: [nq][2][nl][n]; d: [nq][3][nl][n].  grid.y = query*nl + limb.
+// x, y: [nq][2][nl][n]; d: [nq][3][nl][n].  grid.x = query*nl + limb.
 __global__ void __launch_bounds__(256) tensor_kernel(const DevMod *mods, RowMap map, const u64 *__restrict__ x, const u64 *__restrict__ y, u64 *__restrict__ d, int n) {
     const int nl = map.nlimbs;
-    const int qi = blockIdx.y / nl, j = blockIdx.y % nl;
+    const int qi = blockIdx.x / nl, j = blockIdx.x % nl;
     const Mod mq = mods[map.mod_id[j]].m;
     const u64 *x0 = x + (((size_t)qi * 2 + 0) * nl + j) * n, *x1 = x + (((size_t)qi * 2 + 1) * nl + j) * n;
     const u64 *y0 = y + (((size_t)qi * 2 + 0) * nl + j) * n, *y1 = y + (((size_t)qi * 2 + 1) * nl + j) * n;
     u64 *d0 = d + (((size_t)qi * 3 + 0) * nl + j) * n, *d1 = d0 + (size_t)nl * n, *d2 = d1 + (size_t)nl * n;
     if (x == y) {   // square: the cross term is 2 x0 x1 — the same residue as x0 x1 + x1 x0 with one product and two loads less
-        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
             const u64 a0 = x0[i], a1 = x1[i];
             const u64 m = mul_mod(a0, a1, mq);
             d0[i] = mul_mod(a0, a0, mq);
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(256) tensor_kernel(const DevMod *mods, RowMap 
         }
         return;
     }
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
         const u64 a0 = x0[i], a1 = x1[i], b0 = y0[i], b1 = y1[i];
         d0[i] = mul_mod(a0, b0, mq);
         d1[i] = add_mod(mul_mod(a0, b1, mq), mul_mod(a1, b0, mq), mq.q);
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(256) tensor_kernel(const DevMod *mods, RowMap 
 }
 
 // ---- BEHZ: *t, floor, Shenoy–Kumaresan ------------------------------------------------------------------------------
-// dq: [nq][3][k][n], db: [nq][3][nb][n] (coefficient form, canonical) -> out (layout `lay`, 3 polys).  grid.y = query*3 + poly.
+// dq: [nq][3][k][n], db: [nq][3][nb][n] (coefficient form, canonical) -> out (layout `lay`, 3 polys).  grid.x = query*3 + poly.
 // Same compile-time-size scheme as behz_extend_kernel (K, NBSK = 0: run-time sizes, vectors in local memory).
 template <int K, int NBSK>
 __global__ void __launch_bounds__(256, BEHZ_MINB) behz_floor_sk_kernel(const DevLevel *Lp, const u64 *__restrict__ dq, const u64 *__restrict__ db, u64 *__restrict__ out, Layout lay) {
@@ -130,13 +130,13 @@ __global__ void __launch_bounds__(256, BEHZ_MINB) behz_floor_sk_kernel(const Dev
     constexpr int kBehzIlp = behz_ilp(K);
     const int k = K ? K : L.k, nb = NBSK ? NBSK : L.nBsk, nB = nb - 1, n = L.n;
     constexpr int ZK = K ? K : kMaxLimbs;
-    const int qi = blockIdx.y / 3, p = blockIdx.y % 3;
+    const int qi = blockIdx.x / 3, p = blockIdx.x % 3;
     const u64 *sq = dq + ((size_t)qi * 3 + p) * k * n;
     const u64 *sb = db + ((size_t)qi * 3 + p) * nb * n;
     u64 *dst = out + qi * lay.sq + p * lay.sp;
     const Mod mmsk = L.bsk[nB];
     const u64 msk = mmsk.q, msk_half = msk >> 1;
-    for (int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * kBehzIlp; i0 < n; i0 += gridDim.x * blockDim.x * kBehzIlp) {
+    for (int i0 = (blockIdx.y * blockDim.x + threadIdx.x) * kBehzIlp; i0 < n; i0 += gridDim.y * blockDim.x * kBehzIlp) {
         u64 z[kBehzIlp][ZK];
         U128 acc[kBehzIlp][ZK], am[kBehzIlp];   // sum_b z_b (B/b mod q_j) for every q_j, and the same modulo m_sk
 #pragma unroll
@@ -261,20 +261,20 @@ void launch_multiply(const Engine &E, size_t level, const u64 *a, const u64 *b, 
     auto extend = [&](const u64 *src, u64 *xq, u64 *xb) {
         behz_dispatch(k, nb, [&](auto kc, auto nc) {
             const int gx = (n / behz_ilp(decltype(kc)::value) + 255) / 256;
-            behz_extend_kernel<decltype(kc)::value, decltype(nc)::value><<<dim3(gx, nq * 2), 256, 0, st>>>(L, src, in_lay, xb, xq);
+            behz_extend_kernel<decltype(kc)::value, decltype(nc)::value><<<dim3(nq * 2, gx), 256, 0, st>>>(L, src, in_lay, xb, xq);
         });
         launch_ntt(E, xq, ql, nq, 2, qm, false, st);
         launch_ntt(E, xb, bl, nq, 2, bm, false, st);
     };
     extend(a, aq, ab);
     if (!square) extend(b, bq, bb);
-    tensor_kernel<<<dim3((n + 1023) / 1024, nq * k), 256, 0, st>>>(E.d_mods, qm, aq, bq, dq, n);
-    tensor_kernel<<<dim3((n + 1023) / 1024, nq * nb), 256, 0, st>>>(E.d_mods, bm, ab, bb, db, n);
+    tensor_kernel<<<dim3(nq * k, (n + 1023) / 1024), 256, 0, st>>>(E.d_mods, qm, aq, bq, dq, n);
+    tensor_kernel<<<dim3(nq * nb, (n + 1023) / 1024), 256, 0, st>>>(E.d_mods, bm, ab, bb, db, n);
     launch_ntt(E, dq, Layout{(size_t)3 * k * n, (size_t)k * n, (size_t)n}, nq, 3, qm, true, st);
     launch_ntt(E, db, Layout{(size_t)3 * nb * n, (size_t)nb * n, (size_t)n}, nq, 3, bm, true, st);
     behz_dispatch(k, nb, [&](auto kc, auto nc) {
         const int gx = (n / behz_ilp(decltype(kc)::value) + 255) / 256;
-        behz_floor_sk_kernel<decltype(kc)::value, decltype(nc)::value><<<dim3(gx, nq * 3), 256, 0, st>>>(L, dq, db, out, out_lay);
+        behz_floor_sk_kernel<decltype(kc)::value, decltype(nc)::value><<<dim3(nq * 3, gx), 256, 0, st>>>(L, dq, db, out, out_lay);
     });
     PPLP_CUDA(cudaGetLastError());
 }
@@ -285,11 +285,11 @@ void launch_multiply(const Engine &E, size_t level, const u64 *a, const u64 *b, 
 // the kernels' fine register layout: coefficient 16 t + r of a row sits at pair index r * (n/16) + t, so a warp's load
 // of "its r-th coefficient" is one coalesced 512-byte access.
 __global__ void shoup_quot_kernel(const DevMod *mods, const u64 *__restrict__ w, u64 *__restrict__ prepared, int K, int n) {
-    const int row = blockIdx.y;
+    const int row = blockIdx.x;
     const u64 q = mods[row % K].m.q;
     const int T = n / 16;
     ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(prepared) + (size_t)row * n;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
         const u64 v = w[(size_t)row * n + i];
         dst[(size_t)(i & 15) * T + (i >> 4)] = make_ulonglong2(v, (u64)((((unsigned __int128)v) << 64) / q));
     }
@@ -298,7 +298,7 @@ void launch_shoup_quotients(const Engine &E, const u64 *w, u64 *quot, int nrows,
     E.require_device();
     const int n = (int)E.host.n, K = (int)E.host.K();
     if (nrows == 0) return;
-    shoup_quot_kernel<<<dim3((n + 1023) / 1024, nrows), 256, 0, st>>>(E.d_mods, w, quot, K, n);
+    shoup_quot_kernel<<<dim3(nrows, (n + 1023) / 1024), 256, 0, st>>>(E.d_mods, w, quot, K, n);
     PPLP_CUDA(cudaGetLastError());
 }
 
@@ -365,20 +365,20 @@ __global__ void __launch_bounds__(NttShape<LOGM>::T) relin_limb_kernel(const Rel
 // generic (N = 32768) pieces
 __global__ void relin_reduce_kernel(const DevMod *mods, const u64 *__restrict__ c2, Layout lay, u64 *__restrict__ dst, int k, int K, int n) {
     // dst [nq][k+1][k][n]: digit J reduced modulo key limb I
-    int row = blockIdx.y;
+    int row = blockIdx.x;
     const int J = row % k; row /= k;
     const int I = row % (k + 1), qi = row / (k + 1);
     const Mod mod = mods[I == k ? K - 1 : I].m;
     const u64 *s = c2 + qi * lay.sq + 2 * lay.sp + J * lay.sl;
     u64 *d = dst + (((size_t)qi * (k + 1) + I) * k + J) * n;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) d[i] = barrett64(s[i], mod);
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) d[i] = barrett64(s[i], mod);
 }
 __global__ void relin_mac_kernel(const DevMod *mods, const u64 *__restrict__ digits, const u64 *__restrict__ rk, u64 *__restrict__ tmp, int k, int K, int n) {
-    int row = blockIdx.y;
+    int row = blockIdx.x;
     const int I = row % (k + 1), qi = row / (k + 1);
     const int key_index = I == k ? K - 1 : I;
     const Mod mod = mods[key_index].m;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
         u64 a0 = 0, a1 = 0;
         for (int J = 0; J < k; ++J) {
             const u64 x = digits[(((size_t)qi * (k + 1) + I) * k + J) * n + i];
@@ -390,21 +390,21 @@ __global__ void relin_mac_kernel(const DevMod *mods, const u64 *__restrict__ dig
     }
 }
 __global__ void relin_add_half_kernel(u64 *tmp, int k, int n, u64 P, u64 half) {
-    const int qi = blockIdx.y >> 1, c = blockIdx.y & 1;
+    const int qi = blockIdx.x >> 1, c = blockIdx.x & 1;
     u64 *t = tmp + (((size_t)qi * 2 + c) * (k + 1) + k) * n;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) t[i] = add_mod(t[i], half, P);
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) t[i] = add_mod(t[i], half, P);
 }
 
-// out_c[j] = in_c[j] + P^-1 (acc_c[j] - ((t_last_c + half) mod P - half)) mod q_j.  KL = key-level constants.  grid.y = query*2 + comp.
+// out_c[j] = in_c[j] + P^-1 (acc_c[j] - ((t_last_c + half) mod P - half)) mod q_j.  KL = key-level constants.  grid.x = query*2 + comp.
 __global__ void __launch_bounds__(256) relin_moddown_kernel(const DevLevel *KLp, const u64 *__restrict__ tmp, const u64 *__restrict__ in, Layout in_lay, u64 *__restrict__ out,
                                                             Layout out_lay, int k) {
     const DevLevel &KL = *KLp;
     const int n = KL.n;
-    const int qi = blockIdx.y >> 1, c = blockIdx.y & 1;
+    const int qi = blockIdx.x >> 1, c = blockIdx.x & 1;
     const u64 *acc = tmp + ((size_t)qi * 2 + c) * (k + 1) * n;
     const u64 *src = in + qi * in_lay.sq + c * in_lay.sp;
     u64 *dst = out + qi * out_lay.sq + c * out_lay.sp;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
         const u64 last = acc[(size_t)k * n + i];   // already (t_last + half) mod P
         for (int j = 0; j < k; ++j) {
             const Mod &mq = KL.q[j];
@@ -455,22 +455,22 @@ void launch_relinearize(const Engine &E, size_t level, const u64 *in, Layout in_
     case 14: run_relin_limb<14>(lazy, a, nq, st); break;
     case 15: {
         u64 *digits = tmp + (size_t)nq * 2 * (k + 1) * n;
-        relin_reduce_kernel<<<dim3((n + 1023) / 1024, nq * (k + 1) * k), 256, 0, st>>>(E.d_mods, in, in_lay, digits, k, K, n);
+        relin_reduce_kernel<<<dim3(nq * (k + 1) * k, (n + 1023) / 1024), 256, 0, st>>>(E.d_mods, in, in_lay, digits, k, K, n);
         for (int I = 0; I <= k; ++I) {   // rows of key limb I share a modulus
             RowMap m; m.nlimbs = 1; m.mod_id[0] = I == k ? K - 1 : I;
             launch_ntt(E, digits + (size_t)I * k * n, Layout{(size_t)(k + 1) * k * n, (size_t)n, 0}, nq, k, m, false, st);
         }
-        relin_mac_kernel<<<dim3((n + 1023) / 1024, nq * (k + 1)), 256, 0, st>>>(E.d_mods, digits, rk, tmp, k, K, n);
+        relin_mac_kernel<<<dim3(nq * (k + 1), (n + 1023) / 1024), 256, 0, st>>>(E.d_mods, digits, rk, tmp, k, K, n);
         for (int I = 0; I <= k; ++I) {
             RowMap m; m.nlimbs = 1; m.mod_id[0] = I == k ? K - 1 : I;
             launch_ntt(E, tmp + (size_t)I * n, Layout{(size_t)2 * (k + 1) * n, (size_t)(k + 1) * n, 0}, nq, 2, m, true, st);
         }
-        relin_add_half_kernel<<<dim3((n + 1023) / 1024, nq * 2), 256, 0, st>>>(tmp, k, n, P, P >> 1);
+        relin_add_half_kernel<<<dim3(nq * 2, (n + 1023) / 1024), 256, 0, st>>>(tmp, k, n, P, P >> 1);
         break;
     }
     default: throw std::invalid_argument("pplp: relinearisation supports poly_modulus_degree 1024..32768");
     }
-    relin_moddown_kernel<<<dim3((n + 255) / 256, nq * 2), 256, 0, st>>>(E.d_levels, tmp, in, in_lay, out, out_lay, k);
+    relin_moddown_kernel<<<dim3(nq * 2, (n + 255) / 256), 256, 0, st>>>(E.d_levels, tmp, in, in_lay, out, out_lay, k);
     PPLP_CUDA(cudaGetLastError());
 }
 

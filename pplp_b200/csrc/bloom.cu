@@ -53,10 +53,10 @@ __global__ void __launch_bounds__(1024) bloom_build_smem_kernel(unsigned char *_
 // large tables: grid.y = filter, table pre-zeroed
 __global__ void __launch_bounds__(256) bloom_build_global_kernel(unsigned char *__restrict__ tables, size_t stride, u64 m_bits, const u32 *__restrict__ salts, int k,
                                                                  const u64 *__restrict__ rsw, u64 count) {
-    const int f = blockIdx.y;
+    const int f = blockIdx.x;
     u32 *tab = reinterpret_cast<u32 *>(tables + (size_t)f * stride);
     const u64 r = rsw[3 * f], s = rsw[3 * f + 1], w = rsw[3 * f + 2];
-    for (u64 di = blockIdx.x * (u64)blockDim.x + threadIdx.x; di < count; di += (u64)gridDim.x * blockDim.x) {
+    for (u64 di = blockIdx.y * (u64)blockDim.x + threadIdx.x; di < count; di += (u64)gridDim.y * blockDim.x) {
         const u64 key = blind_key(s * (di + r), w);
         for (int h = 0; h < k; ++h) {
             const u64 bit = (u64)bloom_hash8(key, salts[h]) % m_bits;
@@ -119,7 +119,7 @@ void launch_bloom_build(const Engine &E, unsigned char *tables, u64 m_bits, cons
     } else {
         PPLP_CUDA(cudaMemsetAsync(tables, 0, stride * (size_t)nf, st));
         const unsigned bx = (unsigned)std::min<u64>((count + 255) / 256, (u64)E.sm_count * 16);
-        dim3 g(bx ? bx : 1, nf);
+        dim3 g(nf, bx ? bx : 1);
         bloom_build_global_kernel<<<g, 256, 0, st>>>(tables, stride, m_bits, salts, k, rsw, count);
     }
     PPLP_CUDA(cudaGetLastError());

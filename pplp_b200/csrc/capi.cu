@@ -134,13 +134,13 @@ __global__ void proximity_plain_kernel(const u64 *__restrict__ xa, const u64 *__
 }
 // BatchEncoder: values[q][count] -> slots scattered into the NTT-domain vector (zero elsewhere); and the reverse gather
 __global__ void batch_scatter_kernel(const u64 *__restrict__ values, size_t count, const uint32_t *__restrict__ slot_index, u64 *__restrict__ out, int n) {
-    const int q = blockIdx.y;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    const int q = blockIdx.x;
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x)
         out[(size_t)q * n + slot_index[i]] = (size_t)i < count ? values[(size_t)q * count + i] : 0;
 }
 __global__ void batch_gather_kernel(const u64 *__restrict__ in, const uint32_t *__restrict__ slot_index, u64 *__restrict__ values, int n) {
-    const int q = blockIdx.y;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) values[(size_t)q * n + i] = in[(size_t)q * n + slot_index[i]];
+    const int q = blockIdx.x;
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) values[(size_t)q * n + i] = in[(size_t)q * n + slot_index[i]];
 }
 __global__ void check_below_kernel(const u64 *__restrict__ v, size_t count, u64 bound, int *flag) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x)
@@ -159,6 +159,9 @@ void Engine::upload_tables(int dev) {
     cudaDeviceProp prop;
     PPLP_CUDA(cudaGetDeviceProperties(&prop, dev));
     sm_count = prop.multiProcessorCount;
+    PPLP_CUDA(cudaMalloc(&d_sticky, sizeof(int)));
+    owned.push_back(d_sticky);
+    PPLP_CUDA(cudaMemset(d_sticky, 0, sizeof(int)));
     h_mods.resize(host.tables.size());
     for (size_t i = 0; i < host.tables.size(); ++i) {
         const HostTable &T = host.tables[i];
@@ -344,10 +347,22 @@ int pplp_d2d(pplp_ctx *ctx, void *d_dst, const void *d_src, size_t bytes, void *
     return PPLP_OK;
     PPLP_CATCH
 }
+// Asynchronous entries (pplp_encrypt, pplp_proximity_batch) cannot report a device-side failure when they return: their
+// kernels raise the context's sticky flag instead, and the next synchronising call reports and clears it.
+static void check_sticky(Engine &E, cudaStream_t st) {
+    int bad = 0;
+    PPLP_CUDA(cudaMemcpyAsync(&bad, E.d_sticky, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PPLP_CUDA(cudaStreamSynchronize(st));
+    if (bad) {
+        PPLP_CUDA(cudaMemsetAsync(E.d_sticky, 0, sizeof(int), st));
+        PPLP_CUDA(cudaStreamSynchronize(st));
+        throw std::logic_error("pplp: PRNG stream reserve exhausted during encryption; ciphertexts produced since the last pplp_sync are invalid (noise zeroed)");
+    }
+}
 int pplp_sync(pplp_ctx *ctx, void *stream) {
     PPLP_TRY
-    dev_engine(ctx);
-    PPLP_CUDA(cudaStreamSynchronize(S(stream)));
+    Engine &E = dev_engine(ctx);
+    check_sticky(E, S(stream));
     return PPLP_OK;
     PPLP_CATCH
 }
@@ -406,9 +421,8 @@ int pplp_encrypt(pplp_ctx *ctx, const uint64_t *d_pk, const uint64_t *d_seeds, c
     const size_t first = E.host.first_level(), k = E.host.levels[first].q.size();
     const int nc = to_int(nct, "ciphertext count");
     cudaStream_t st = S(stream);
-    Scratch ws(encrypt_tmp_words(E, nc) * 8, st), flag(sizeof(int), st);
-    PPLP_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), st));
-    launch_encrypt(E, d_pk, d_seeds, d_plain, plain_count, plain_stride, ws.as<u64>(), d_out, make_layout(layout, E.host.n, k, 2, nct), nc, flag.as<int>(), st);
+    Scratch ws(encrypt_tmp_words(E, nc) * 8, st);
+    launch_encrypt(E, d_pk, d_seeds, d_plain, plain_count, plain_stride, ws.as<u64>(), d_out, make_layout(layout, E.host.n, k, 2, nct), nc, E.d_sticky, st);
     return PPLP_OK;
     PPLP_CATCH
 }
@@ -658,7 +672,7 @@ int pplp_batch_encode(pplp_ctx *ctx, const uint64_t *d_values, size_t count, uin
     PPLP_CUDA(cudaMemcpyAsync(&bad, flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     PPLP_CUDA(cudaStreamSynchronize(st));
     if (bad) throw std::invalid_argument("input value is larger than plain_modulus");
-    batch_scatter_kernel<<<dim3((unsigned)((n + 255) / 256), (unsigned)nq), 256, 0, st>>>(d_values, count, E.d_slot_index, d_plain, (int)n);
+    batch_scatter_kernel<<<dim3((unsigned)nq, (unsigned)((n + 255) / 256)), 256, 0, st>>>(d_values, count, E.d_slot_index, d_plain, (int)n);
     RowMap m; m.nlimbs = 1; m.mod_id[0] = E.host.plain_table_id;
     launch_ntt(E, d_plain, Layout{n, 0, 0}, to_int(nq, "plaintext count"), 1, m, true, st);
     return PPLP_OK;
@@ -675,7 +689,7 @@ int pplp_batch_decode(pplp_ctx *ctx, const uint64_t *d_plain, uint64_t *d_values
     PPLP_CUDA(cudaMemcpyAsync(tmp.p, d_plain, nq * n * 8, cudaMemcpyDeviceToDevice, st));
     RowMap m; m.nlimbs = 1; m.mod_id[0] = E.host.plain_table_id;
     launch_ntt(E, tmp.as<u64>(), Layout{n, 0, 0}, to_int(nq, "plaintext count"), 1, m, false, st);
-    batch_gather_kernel<<<dim3((unsigned)((n + 255) / 256), (unsigned)nq), 256, 0, st>>>(tmp.as<u64>(), E.d_slot_index, d_values, (int)n);
+    batch_gather_kernel<<<dim3((unsigned)nq, (unsigned)((n + 255) / 256)), 256, 0, st>>>(tmp.as<u64>(), E.d_slot_index, d_values, (int)n);
     return PPLP_OK;
     PPLP_CATCH
 }
@@ -775,15 +789,14 @@ int pplp_proximity_batch(pplp_ctx *ctx, const uint64_t *d_pk, const uint64_t *d_
     // per chunk: ciphertext q*3+i is encryption i of query q, so (c0,c1,c2) of one query are adjacent and Circuit A
     // sees three interleaved batches with query stride 3*ctw
     Scratch cts(chunk * 3 * ctw * 8, st), ws(encrypt_tmp_words(E, 3 * C) * 8, st), plain(chunk * 3 * 8, st), sc(circuit_a_scratch_words(E, level, C) * 8, st),
-        dtmp(decrypt_tmp_words(E, level, C, 2) * 8, st), rs(chunk * 2 * 8, st), err(sizeof(int), st);
-    PPLP_CUDA(cudaMemsetAsync(err.p, 0, sizeof(int), st));
+        dtmp(decrypt_tmp_words(E, level, C, 2) * 8, st), rs(chunk * 2 * 8, st);
     if (d_flags) PPLP_CUDA(cudaMemsetAsync(d_flags, 0, nq * sizeof(int), st));
     const Layout enc_lay = make_layout(PPLP_LAYOUT_SEAL, n, kk, 2, 3 * chunk);
     const Layout q_lay{3 * ctw, kk * n, n};
     for (size_t done = 0; done < nq; done += chunk) {
         const int c = (int)std::min(chunk, nq - done);
         proximity_plain_kernel<<<(c + 255) / 256, 256, 0, st>>>(d_xa + done, d_ya + done, c, E.host.t, plain.as<u64>(), d_flags ? d_flags + done : nullptr);
-        launch_encrypt(E, d_pk, d_seeds + done * 3 * 8, plain.as<u64>(), 1, 1, ws.as<u64>(), cts.as<u64>(), enc_lay, 3 * c, err.as<int>(), st);
+        launch_encrypt(E, d_pk, d_seeds + done * 3 * 8, plain.as<u64>(), 1, 1, ws.as<u64>(), cts.as<u64>(), enc_lay, 3 * c, E.d_sticky, st);
         gather_u64_kernel<<<(c + 255) / 256, 256, 0, st>>>(d_rsw, d_fidx ? d_fidx + done : nullptr, 3, 0, c, rs.as<u64>());
         gather_u64_kernel<<<(c + 255) / 256, 256, 0, st>>>(d_rsw, d_fidx ? d_fidx + done : nullptr, 3, 1, c, rs.as<u64>() + chunk);
         u64 *base = cts.as<u64>();
@@ -824,7 +837,8 @@ int pplp_proximity_batch_host(pplp_ctx *ctx, const uint64_t *d_pk, const uint64_
             if (h_flags) PPLP_CUDA(cudaMemcpyAsync(h_flags, flags.p, nq * sizeof(int), cudaMemcpyDeviceToHost, st));
         }
     }
-    PPLP_CUDA(cudaStreamSynchronize(st));
+    if (rc == PPLP_OK) check_sticky(E, st);
+    else PPLP_CUDA(cudaStreamSynchronize(st));
     return rc;
     PPLP_CATCH
 }

@@ -113,7 +113,10 @@ __global__ void __launch_bounds__(1024) sample_encrypt_kernel(const u64 *__restr
     }
     const int end_word = s_end_word;
     if (end_word < 0 || (size_t)end_word * 4 + (size_t)12 * n > (size_t)total_words * 4) {
+        // more than 1024 rejected draws: never seen with a real stream (a draw is rejected with probability 2^-32).  Raise the
+        // flag (the caller reports it at its next synchronisation) and leave defined, if useless, noise behind.
         if (tid == 0) atomicExch(errflag, 1);
+        for (int i = tid; i < 3 * n; i += 1024) u[i] = 0;
         return;
     }
     // centred binomial: 6 bytes per sample, x2 and x5 masked to 5 bits  ([SEAL] util/rlwe.cpp sample_poly_cbd)
@@ -190,11 +193,11 @@ __global__ void __launch_bounds__(256) modswitch_kernel(const DevLevel *KLp, con
     const DevLevel &KL = *KLp;
     const DevLevel &DL = *DLp;
     const int K = KL.k, k = K - 1, n = KL.n;
-    const int ct = blockIdx.y >> 1, p = blockIdx.y & 1;
+    const int ct = blockIdx.x >> 1, p = blockIdx.x & 1;
     const u64 P = KL.q[K - 1].q, half = KL.half_last;
     const u64 *src = tmp + ((size_t)ct * 2 + p) * K * n;
     u64 *dst = out + ct * lay.sq + p * lay.sp;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
         const u64 last = add_mod(src[(size_t)(K - 1) * n + i], half, P);
         const bool has_plain = (p == 0 && i < plain_count);
         const u64 m = has_plain ? plain[ct * plain_stride + i] : 0;
@@ -220,11 +223,11 @@ __global__ void __launch_bounds__(256) modswitch_kernel(const DevLevel *KLp, con
 // 16 t + r at pair index r*(n/16) + t: one constant-operand product per coefficient instead of a 128-bit Barrett), as
 // bare words for the FP64 kernels (whose quotient estimate needs no precomputation: modarith.cuh mul_f64_var).
 __global__ void prepare_key_kernel(const DevMod *mods, const u64 *__restrict__ src, u64 *__restrict__ dst, int K, int n, int f64) {
-    const int row = blockIdx.y;
+    const int row = blockIdx.x;
     const u64 q = mods[row % K].m.q;
     const int T = n / 16;
     ulonglong2 *d = reinterpret_cast<ulonglong2 *>(dst) + (size_t)row * n;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
         const u64 w = src[(size_t)row * n + i];
         if (f64) {   // FP64 kernels take the bare word (mul_f64_var): pair h of thread t at [h*T + t], like U
             dst[(size_t)row * n + (((size_t)((i & 15) >> 1) * T + (i >> 4)) << 1) + (i & 1)] = w;
@@ -375,10 +378,10 @@ __global__ void __launch_bounds__(256) copy_addplain_kernel(const DevLevel *DLp,
                                                             const u64 *__restrict__ plain, int plain_count, size_t plain_stride) {
     const DevLevel &DL = *DLp;
     const int k = DL.k, n = DL.n;
-    const int ct = blockIdx.y >> 1, p = blockIdx.y & 1;
+    const int ct = blockIdx.x >> 1, p = blockIdx.x & 1;
     const u64 *src = tmp + ((size_t)ct * 2 + p) * k * n;
     u64 *dst = out + ct * lay.sq + p * lay.sp;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
         const bool has_plain = (p == 0 && i < plain_count);
         const u64 m = has_plain ? plain[ct * plain_stride + i] : 0;
         for (int j = 0; j < k; ++j) {
@@ -391,31 +394,31 @@ __global__ void __launch_bounds__(256) copy_addplain_kernel(const DevLevel *DLp,
 
 // generic (unfused) pieces used when N does not fit one CTA (N = 32768)
 __global__ void expand_noise_kernel(const DevMod *mods, const signed char *__restrict__ noise, int which, u64 *__restrict__ out, size_t out_ct_stride, int K, int n) {
-    const int ct = blockIdx.z, j = blockIdx.y;
+    const int ct = blockIdx.x, j = blockIdx.y;
     const u64 q = mods[j].m.q;
     const signed char *src = noise + ((size_t)ct * 3 + which) * n;
     u64 *dst = out + ct * out_ct_stride + (size_t)j * n;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    for (int i = blockIdx.z * blockDim.x + threadIdx.x; i < n; i += gridDim.z * blockDim.x) {
         const int v = src[i];
         dst[i] = v < 0 ? q - (u64)(-v) : (u64)v;
     }
 }
 __global__ void mul_pk_kernel(const DevMod *mods, const u64 *__restrict__ u_ntt, const u64 *__restrict__ pk, u64 *__restrict__ tmp, int K, int n) {
-    const int ct = blockIdx.z, j = blockIdx.y;
+    const int ct = blockIdx.x, j = blockIdx.y;
     const Mod mq = mods[j].m;
     const u64 *uu = u_ntt + ((size_t)ct * K + j) * n;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    for (int i = blockIdx.z * blockDim.x + threadIdx.x; i < n; i += gridDim.z * blockDim.x) {
         const u64 v = uu[i];
         tmp[(((size_t)ct * 2 + 0) * K + j) * n + i] = mul_mod(v, pk[((size_t)0 * K + j) * n + i], mq);
         tmp[(((size_t)ct * 2 + 1) * K + j) * n + i] = mul_mod(v, pk[((size_t)1 * K + j) * n + i], mq);
     }
 }
 __global__ void add_noise_kernel(const DevMod *mods, const signed char *__restrict__ noise, u64 *__restrict__ tmp, int K, int n) {
-    const int ct = blockIdx.z >> 1, p = blockIdx.z & 1, j = blockIdx.y;
+    const int ct = blockIdx.x >> 1, p = blockIdx.x & 1, j = blockIdx.y;
     const u64 q = mods[j].m.q;
     const signed char *e = noise + ((size_t)ct * 3 + 1 + p) * n;
     u64 *dst = tmp + (((size_t)ct * 2 + p) * K + j) * n;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    for (int i = blockIdx.z * blockDim.x + threadIdx.x; i < n; i += gridDim.z * blockDim.x) {
         const int v = e[i];
         dst[i] = add_mod(dst[i], v < 0 ? q - (u64)(-v) : (u64)v, q);
     }
@@ -492,7 +495,7 @@ void launch_encrypt(const Engine &E, const u64 *pk, const u64 *seeds, const u64 
     if (K > 1 && E.host.logn <= 14) {   // split pipeline: forward, special-limb inverse, data-limb inverse + modulus switch + plaintext
         static const bool wide_ok = !(std::getenv("PPLP_ENC_WIDE") && std::getenv("PPLP_ENC_WIDE")[0] == '0');   // experiment hook
         const bool wide = wide_ok && lazy == 3 && E.host.logn >= 11 && E.host.logn <= 13;   // forward transform on the 32-per-thread FP64 schedule (ntt32.cuh)
-        prepare_key_kernel<<<dim3((n + 255) / 256, 2 * K), 256, 0, st>>>(E.d_mods, pk, extra, K, n, lazy >= 3 ? 1 : 0);
+        prepare_key_kernel<<<dim3(2 * K, (n + 255) / 256), 256, 0, st>>>(E.d_mods, pk, extra, K, n, lazy >= 3 ? 1 : 0);
         EncSplitArgs sa{noise, extra, tmp, tmp + (size_t)nct * K * n, out, out_lay, plain, (int)plain_count, plain_stride, K, n, E.d_mods, E.d_levels, E.d_levels + first};
         switch (E.host.logn) {
         case 10: run_encrypt_split<10>(lazy, sa, nct, st); break;
@@ -513,18 +516,18 @@ void launch_encrypt(const Engine &E, const u64 *pk, const u64 *seeds, const u64 
     case 14: run_encrypt_limb<14>(lazy, a, nct, st); break;
     case 15: {
         RowMap map = E.qmap(0);
-        dim3 g((n + 1023) / 1024, K, nct);
+        dim3 g(nct, K, (n + 1023) / 1024);   // batch index in grid.x: no 65535 limit
         expand_noise_kernel<<<g, 256, 0, st>>>(E.d_mods, noise, 0, extra, (size_t)K * n, K, n);
         launch_ntt(E, extra, Layout{(size_t)K * n, 0, (size_t)n}, nct, 1, map, false, st);
         mul_pk_kernel<<<g, 256, 0, st>>>(E.d_mods, extra, pk, tmp, K, n);
         launch_ntt(E, tmp, Layout{(size_t)2 * K * n, (size_t)K * n, (size_t)n}, nct, 2, map, true, st);
-        dim3 g2((n + 1023) / 1024, K, nct * 2);
+        dim3 g2(nct * 2, K, (n + 1023) / 1024);
         add_noise_kernel<<<g2, 256, 0, st>>>(E.d_mods, noise, tmp, K, n);
         break;
     }
     default: throw std::invalid_argument("pplp: encryption kernels support poly_modulus_degree 1024..32768");
     }
-    dim3 gm((n + 255) / 256, nct * 2);
+    dim3 gm(nct * 2, (n + 255) / 256);
     if (K > 1) modswitch_kernel<<<gm, 256, 0, st>>>(E.d_levels, E.d_levels + first, tmp, out, out_lay, plain, (int)plain_count, plain_stride);
     else copy_addplain_kernel<<<gm, 256, 0, st>>>(E.d_levels, tmp, out, out_lay, plain, (int)plain_count, plain_stride);
     PPLP_CUDA(cudaGetLastError());
@@ -538,10 +541,10 @@ __global__ void __launch_bounds__(256) scale_round_kernel(const DevLevel *Lp, co
     const DevLevel &L = *Lp;
     const int k = L.k;
     const size_t n = xl;
-    const int qi = blockIdx.y;
+    const int qi = blockIdx.x;
     const u64 t = L.t, gamma = L.gamma.q, gamma_half = gamma >> 1;
     const u64 *src = x + (size_t)qi * xq;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ncoeff; i += gridDim.x * blockDim.x) {
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < ncoeff; i += gridDim.y * blockDim.x) {
         U128 at{0, 0}, ag{0, 0};
         for (int j = 0; j < k; ++j) {
             const u64 q = L.q[j].q;
@@ -562,27 +565,27 @@ __global__ void __launch_bounds__(256) scale_round_kernel(const DevLevel *Lp, co
 
 // acc += NTT(c2) (.) s^2 : only for size-3 inputs (not on the reference path); unfused.
 __global__ void dot3_kernel(const DevMod *mods, const u64 *__restrict__ c1n, const u64 *__restrict__ c2n, const u64 *__restrict__ sk, u64 *__restrict__ acc, int k, int n) {
-    const int qi = blockIdx.z, j = blockIdx.y;
+    const int qi = blockIdx.x, j = blockIdx.y;
     const Mod mq = mods[j].m;
     const size_t off = ((size_t)qi * k + j) * n;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    for (int i = blockIdx.z * blockDim.x + threadIdx.x; i < n; i += gridDim.z * blockDim.x) {
         const u64 s = sk[(size_t)j * n + i];
         const u64 s2 = mul_mod(s, s, mq);
         acc[off + i] = add_mod(mul_mod(c1n[off + i], s, mq), mul_mod(c2n[off + i], s2, mq), mq.q);
     }
 }
 __global__ void gather_rows_kernel(const u64 *__restrict__ src, Layout lay, int p, u64 *__restrict__ dst, int k, int n) {
-    const int qi = blockIdx.z, j = blockIdx.y;
+    const int qi = blockIdx.x, j = blockIdx.y;
     const u64 *s = src + qi * lay.sq + p * lay.sp + j * lay.sl;
     u64 *d = dst + ((size_t)qi * k + j) * n;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) d[i] = s[i];
+    for (int i = blockIdx.z * blockDim.x + threadIdx.x; i < n; i += gridDim.z * blockDim.x) d[i] = s[i];
 }
 __global__ void add_rows_kernel(const DevMod *mods, u64 *__restrict__ acc, const u64 *__restrict__ src, Layout lay, int p, int k, int n) {
-    const int qi = blockIdx.z, j = blockIdx.y;
+    const int qi = blockIdx.x, j = blockIdx.y;
     const u64 q = mods[j].m.q;
     const u64 *s = src + qi * lay.sq + p * lay.sp + j * lay.sl;
     u64 *d = acc + ((size_t)qi * k + j) * n;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) d[i] = add_mod(d[i], s[i], q);
+    for (int i = blockIdx.z * blockDim.x + threadIdx.x; i < n; i += gridDim.z * blockDim.x) d[i] = add_mod(d[i], s[i], q);
 }
 
 // ---- constant-coefficient decryption ---------------------------------------------------------------------------------
@@ -648,7 +651,7 @@ void launch_decrypt(const Engine &E, size_t level, const u64 *ct, Layout lay, in
         launch_ntt(E, s_coef, tl, 1, 1, map, true, st);
         negacyclic_flip_kernel<<<dim3((n + 255) / 256, k), 256, 0, st>>>(E.d_mods, s_coef, sneg, n);
         coeff0_dot_kernel<<<nq * k, 256, 0, st>>>(E.d_mods, ct, lay, sneg, xout, k, n);
-        scale_round_kernel<<<dim3(1, nq), 32, 0, st>>>(E.d_levels + level, xout, (size_t)k, 1, plain_out, plain_stride, 1);
+        scale_round_kernel<<<dim3(nq, 1), 32, 0, st>>>(E.d_levels + level, xout, (size_t)k, 1, plain_out, plain_stride, 1);
         PPLP_CUDA(cudaGetLastError());
         return;
     }
@@ -658,7 +661,7 @@ void launch_decrypt(const Engine &E, size_t level, const u64 *ct, Layout lay, in
         launch_polymul(E, ct + lay.sp, a_lay, sk, Layout{0, 0, (size_t)n}, ct, c_lay, tmp, tl, nq, 1, map, st);
     } else {
         u64 *c1n = tmp + (size_t)nq * k * n, *c2n = c1n + (size_t)nq * k * n;
-        dim3 g((n + 1023) / 1024, k, nq);
+        dim3 g(nq, k, (n + 1023) / 1024);
         gather_rows_kernel<<<g, 256, 0, st>>>(ct, lay, 1, c1n, k, n);
         launch_ntt(E, c1n, tl, nq, 1, map, false, st);
         if (size == 3) {
@@ -674,7 +677,7 @@ void launch_decrypt(const Engine &E, size_t level, const u64 *ct, Layout lay, in
         launch_ntt(E, tmp, tl, nq, 1, map, true, st);
         add_rows_kernel<<<g, 256, 0, st>>>(E.d_mods, tmp, ct, lay, 0, k, n);
     }
-    dim3 gs((ncoeff + 255) / 256, nq);
+    dim3 gs(nq, (ncoeff + 255) / 256);
     scale_round_kernel<<<gs, 256, 0, st>>>(E.d_levels + level, tmp, (size_t)k * n, (size_t)n, plain_out, plain_stride, ncoeff);
     PPLP_CUDA(cudaGetLastError());
 }

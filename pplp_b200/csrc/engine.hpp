@@ -26,6 +26,7 @@ struct Engine {
     std::vector<void *> owned;       // device allocations freed with the engine
     std::vector<DevMod> h_mods;
     uint32_t *d_slot_index = nullptr;   // BatchEncoder permutation (when batching)
+    int *d_sticky = nullptr;            // device-side failure flag of asynchronous entries; reported and cleared by pplp_sync
 
     void require_device() const { if (device < 0) throw std::logic_error("pplp: context was created without a CUDA device"); }
     template <class T> T *upload(const T *src, size_t count) {

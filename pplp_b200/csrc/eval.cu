@@ -69,8 +69,11 @@ constexpr int kCaThreads = 256;
 constexpr int kCaUnroll = 4;
 constexpr int kCaSeg = kCaThreads * 2 * kCaUnroll;  // coefficients per CTA
 
-__global__ void __launch_bounds__(kCaThreads) circuit_a_kernel(const DevLevel *Lp, const u64 *__restrict__ c0, const u64 *__restrict__ c1,
-                                                               const u64 *__restrict__ c2, u64 *__restrict__ out, Layout lay, int nq, int n,
+// ALIAS: out == c0 (the in-place callers).  Then c0 is read through the coherent path (no .nc) and neither pointer is
+// declared __restrict__: a thread still reads its own words before it writes them, and now the memory model says so too.
+template <bool ALIAS>
+__global__ void __launch_bounds__(kCaThreads) circuit_a_kernel(const DevLevel *Lp, const u64 *c0, const u64 *__restrict__ c1,
+                                                               const u64 *__restrict__ c2, u64 *out, Layout lay, int nq, int n,
                                                                const u64 *__restrict__ scratch) {
     const DevLevel &L = *Lp;
     const int segs = n / kCaSeg > 0 ? n / kCaSeg : 1;
@@ -88,7 +91,7 @@ __global__ void __launch_bounds__(kCaThreads) circuit_a_kernel(const DevLevel *L
 #pragma unroll
     for (int u = 0; u < kCaUnroll; ++u) {
         const int i = first + u * 2 * kCaThreads;
-        if (i < n) { a[u] = ldg_stream(c0 + base + i); b[u] = ldg_stream(c1 + base + i); c[u] = ldg_stream(c2 + base + i); }
+        if (i < n) { a[u] = ALIAS ? ld_stream_coherent(c0 + base + i) : ldg_stream(c0 + base + i); b[u] = ldg_stream(c1 + base + i); c[u] = ldg_stream(c2 + base + i); }
     }
 #pragma unroll
     for (int u = 0; u < kCaUnroll; ++u) {
@@ -120,7 +123,8 @@ void launch_circuit_a(const Engine &E, size_t level, const u64 *c0, const u64 *c
     const int segs = n / kCaSeg > 0 ? n / kCaSeg : 1;
     const long long ctas = (long long)nq * 2 * k * segs;
     if (ctas > 0x7fffffffLL) throw std::invalid_argument("pplp: batch too large for one launch");
-    circuit_a_kernel<<<(unsigned)ctas, kCaThreads, 0, st>>>(L, c0, c1, c2, out, lay, nq, n, scratch);
+    if (out == c0) circuit_a_kernel<true><<<(unsigned)ctas, kCaThreads, 0, st>>>(L, c0, c1, c2, out, lay, nq, n, scratch);
+    else circuit_a_kernel<false><<<(unsigned)ctas, kCaThreads, 0, st>>>(L, c0, c1, c2, out, lay, nq, n, scratch);
     PPLP_CUDA(cudaGetLastError());
 }
 
@@ -239,12 +243,12 @@ void launch_circuit_a_cross(const Engine &E, size_t level, const u64 *c0, const 
 // ---- individual primitives (SEAL-facing shim; batch-of-nq views) ---------------------------------------------------
 __global__ void add_sub_kernel(const DevLevel *Lp, u64 *a, const u64 *b, Layout lay, int nq, int npoly, int n, int mode) {
     const DevLevel &L = *Lp;
-    int row = blockIdx.y;
+    int row = blockIdx.x;
     const int qi = row % nq; row /= nq;
     const int p = row % npoly, j = row / npoly;
     const u64 q = L.q[j].q;
     const size_t base = qi * lay.sq + p * lay.sp + j * lay.sl;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
         const u64 y = b[base + i];
         if (mode == 0) a[base + i] = add_mod(a[base + i], y, q);
         else if (mode == 1) a[base + i] = sub_mod(a[base + i], y, q);
@@ -255,7 +259,7 @@ void launch_add_sub(const Engine &E, size_t level, u64 *a, const u64 *b, Layout 
     E.require_device();
     const int k = (int)E.host.levels[level].q.size(), n = (int)E.host.n;
     if (nq * npoly == 0) return;
-    dim3 grid((n + 1023) / 1024, nq * npoly * k);
+    dim3 grid(nq * npoly * k, (n + 1023) / 1024);   // rows in grid.x: no 65535 limit
     add_sub_kernel<<<grid, 256, 0, st>>>(E.d_levels + level, a, b, lay, nq, npoly, n, negate_b_only ? 2 : (subtract ? 1 : 0));
     PPLP_CUDA(cudaGetLastError());
 }
@@ -286,13 +290,13 @@ void launch_add_plain(const Engine &E, size_t level, u64 *ct, Layout lay, int nq
 // out[idx] = +/- in[i] * lift(m) with idx = (i + exponent) mod N, sign flipped on wrap   (monomial multiply_plain)
 __global__ void mul_mono_kernel(const DevLevel *Lp, const u64 *in, u64 *out, Layout lay, int nq, int npoly, int n, const u64 *scalar, size_t scalar_stride, int exponent) {
     const DevLevel &L = *Lp;
-    int row = blockIdx.y;
+    int row = blockIdx.x;
     const int qi = row % nq; row /= nq;
     const int p = row % npoly, j = row / npoly;
     const Mod mq = L.q[j];
     const u64 w = dev_lift(L, scalar[qi * scalar_stride], j);
     const size_t base = qi * lay.sq + p * lay.sp + j * lay.sl;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
         const u64 v = mul_mod(in[base + i], w, mq);
         const int raw = i + exponent, dst = raw & (n - 1);
         out[base + dst] = ((raw & n) && v) ? mq.q - v : v;
@@ -303,7 +307,7 @@ void launch_mul_mono(const Engine &E, size_t level, const u64 *in, u64 *out, Lay
     const int k = (int)E.host.levels[level].q.size(), n = (int)E.host.n;
     if (nq * npoly == 0) return;
     if (in == out && exponent != 0) throw std::invalid_argument("pplp: shifted monomial multiply must be out of place");
-    dim3 grid((n + 1023) / 1024, nq * npoly * k);
+    dim3 grid(nq * npoly * k, (n + 1023) / 1024);
     mul_mono_kernel<<<grid, 256, 0, st>>>(E.d_levels + level, in, out, lay, nq, npoly, n, scalar, scalar_stride, (int)exponent);
     PPLP_CUDA(cudaGetLastError());
 }
@@ -322,19 +326,19 @@ void launch_lift_plain(const Engine &E, size_t level, const u64 *plain, size_t c
 }
 
 __global__ void dyadic_kernel(const DevMod *mods, RowMap map, u64 *a, Layout a_lay, const u64 *b, Layout b_lay, int nq, int npoly, int n) {
-    int row = blockIdx.y;
+    int row = blockIdx.x;
     const int qi = row % nq; row /= nq;
     const int p = row % npoly, j = row / npoly;
     const Mod mq = mods[map.mod_id[j]].m;
     u64 *pa = a + qi * a_lay.sq + p * a_lay.sp + j * a_lay.sl;
     const u64 *pb = b + qi * b_lay.sq + p * b_lay.sp + j * b_lay.sl;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) pa[i] = mul_mod(pa[i], pb[i], mq);
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) pa[i] = mul_mod(pa[i], pb[i], mq);
 }
 void launch_dyadic(const Engine &E, u64 *a, Layout a_lay, const u64 *b, Layout b_lay, int nq, int npoly, const RowMap &map, cudaStream_t st) {
     E.require_device();
     const int n = (int)E.host.n;
     if (nq * npoly == 0) return;
-    dim3 grid((n + 1023) / 1024, nq * npoly * map.nlimbs);
+    dim3 grid(nq * npoly * map.nlimbs, (n + 1023) / 1024);
     dyadic_kernel<<<grid, 256, 0, st>>>(E.d_mods, map, a, a_lay, b, b_lay, nq, npoly, n);
     PPLP_CUDA(cudaGetLastError());
 }

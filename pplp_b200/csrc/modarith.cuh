@@ -182,6 +182,12 @@ __device__ __forceinline__ ulonglong2 ldg_stream(const u64 *p) {
     asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p));
     return v;
 }
+// the same load through the coherent path, for a buffer the kernel also writes (in-place evaluation)
+__device__ __forceinline__ ulonglong2 ld_stream_coherent(const u64 *p) {
+    ulonglong2 v;
+    asm volatile("ld.global.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void stg_stream(u64 *p, ulonglong2 v) {
     asm volatile("st.global.L1::no_allocate.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(v.x), "l"(v.y) : "memory");
 }

@@ -147,12 +147,12 @@ __global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T
 // Streaming butterfly stage 0 for N = 2*M (gap N/2, single twiddle fwd[1]).  Output lazily < 4q (forward) / canonical (inverse).
 __global__ void ntt_stage0_forward_kernel(const NttArgs a, int half_n) {
     int qi, p, j;
-    decode_row(blockIdx.y, a.nq, a.npoly, qi, p, j);
+    decode_row(blockIdx.x, a.nq, a.npoly, qi, p, j);
     const DevMod &md = a.mods[a.map.mod_id[j]];
     const u64 q = md.m.q, two_q = q << 1;
     u64 *ptr = a.data + qi * a.lay.sq + p * a.lay.sp + j * a.lay.sl;
     const ShoupW w = ld_twiddle(md.fwd + 1);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < half_n; i += gridDim.x * blockDim.x) {
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < half_n; i += gridDim.y * blockDim.x) {
         u64 x = ptr[i], y = ptr[i + half_n];
         ct_butterfly<NTT_CLASSIC>(x, y, w, q, two_q);
         ptr[i] = x; ptr[i + half_n] = y;
@@ -160,11 +160,11 @@ __global__ void ntt_stage0_forward_kernel(const NttArgs a, int half_n) {
 }
 __global__ void ntt_stage0_inverse_kernel(const NttArgs a, int half_n) {
     int qi, p, j;
-    decode_row(blockIdx.y, a.nq, a.npoly, qi, p, j);
+    decode_row(blockIdx.x, a.nq, a.npoly, qi, p, j);
     const DevMod &md = a.mods[a.map.mod_id[j]];
     const u64 q = md.m.q, two_q = q << 1;
     u64 *ptr = a.data + qi * a.lay.sq + p * a.lay.sp + j * a.lay.sl;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < half_n; i += gridDim.x * blockDim.x) {
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < half_n; i += gridDim.y * blockDim.x) {
         u64 x = ptr[i], y = ptr[i + half_n];   // in [0,2q)
         u64 s = x + y, d = x - y + two_q;
         ptr[i] = csub(mul_shoup_lazy(s, md.n_inv.w, md.n_inv.wq, q), q);
@@ -289,7 +289,7 @@ void launch_ntt(const Engine &E, u64 *data, Layout lay, int nq, int npoly, const
     case 15: {
         // 15 stages: stage 0 streams (classic, values < 4q), then 14-stage blocks whose forward inputs are < 4q as required
         const int half_n = 1 << 14;
-        dim3 g0(32, rows);
+        dim3 g0(rows, 32);
         a.stage_base = 1;
         if (!inverse) {
             ntt_stage0_forward_kernel<<<g0, 512, 0, st>>>(a, half_n);

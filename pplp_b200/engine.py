@@ -123,6 +123,7 @@ class Context:
         return from_np(np.asarray(a), self.device)
 
     def sync(self):
+        check(self.L.pplp_sync(self.h, self._st()))   # also reports a device-side failure of an asynchronous entry
         _torch().cuda.synchronize(self.device)
 
     def ct_shape(self, nq, size=2, level=None, layout=LAYOUT_SEAL):
@@ -130,12 +131,20 @@ class Context:
         return (nq, size, k, self.n) if layout == LAYOUT_SEAL else (k, size, nq, self.n)
 
     # ---- keys ----
-    def keygen(self, seed):
+    def keygen(self, seed, pk_seed=None):
+        """sk, pk.  pk_seed=None reproduces SEAL under a fixed-seed factory (one seed for both: parity tests); pass an
+        independent pk_seed for keys whose secret and public-key error come from separate streams."""
         seed = np.asarray(seed, dtype=np.uint64)
         assert seed.size == 8
         sk = self.empty(self.K, self.n)
         pk = self.empty(2, self.K, self.n)
-        check(self.L.pplp_keygen(self.h, seed.ctypes.data, _ptr(sk), _ptr(pk), self._st()))
+        if pk_seed is None:
+            check(self.L.pplp_keygen(self.h, seed.ctypes.data, _ptr(sk), _ptr(pk), self._st()))
+        else:
+            pk_seed = np.asarray(pk_seed, dtype=np.uint64)
+            assert pk_seed.size == 8
+            check(self.L.pplp_keygen(self.h, seed.ctypes.data, _ptr(sk), None, self._st()))
+            check(self.L.pplp_public_keygen(self.h, pk_seed.ctypes.data, _ptr(sk), _ptr(pk), self._st()))
         return sk, pk
 
     def relin_keygen(self, seeds, sk):

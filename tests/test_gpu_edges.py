@@ -118,3 +118,41 @@ def test_circuit_a_at_the_largest_degree(eng, oracle):
     arr = lambda v: c.dev(np.array([v], dtype=np.uint64))
     out = c.circuit_a(c.dev(cts[0]), c.dev(cts[1]), c.dev(cts[2]), arr(xb), arr(yb), arr(r), arr(s))
     assert (eng.to_np(out)[0] == ref).all()
+
+
+def test_batches_beyond_65535_rows(eng):
+    """The unfused primitives, decrypt and encrypt at batch sizes whose row count exceeds CUDA's 65535 limit on
+    gridDim.y/z (the headline batch, nq=8192 x 2 polys x 4 limbs, is 65536 rows): rows travel in gridDim.x."""
+    import torch
+    from tests import oracle_lib
+    orc = oracle_lib.load()
+    n = 1024
+    q = [int(x) for x in orc.get_primes(2 * n, 40, 2)]          # one data prime + the special prime: k = 1, K = 2
+    ctx = eng.Context(n, q=q, t=1 << 20, device=0, enforce_security=False)
+    assert ctx.ok and ctx.k == 1
+    octx = orc.context(n, q, 1 << 20, seed=np.arange(8, dtype=np.uint64) + np.uint64(5))
+    nq = 33000                                                   # 66000 rows of (query, poly, limb)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(3)
+    a = torch.randint(0, q[0], (nq, 2, 1, n), device="cuda", generator=g)
+    b = torch.randint(0, q[0], (nq, 2, 1, n), device="cuda", generator=g)
+    qq = q[0]
+    assert torch.equal(ctx.add_(a.clone(), b), (a + b) % qq)
+    assert torch.equal(ctx.sub_(a.clone(), b), (a - b) % qq)
+    assert torch.equal(ctx.negate_(a.clone(), b), (-b) % qq)
+    sc = torch.randint(1, 1 << 19, (nq,), device="cuda", generator=g)      # below t/2: lift(m) = m; products stay below 2^63
+    assert torch.equal(ctx.multiply_plain_mono_(a.clone(), sc), (a * sc.view(nq, 1, 1, 1)) % qq)
+    # same values in the limb-major layout
+    al, bl = a.permute(2, 1, 0, 3).contiguous(), b.permute(2, 1, 0, 3).contiguous()
+    assert torch.equal(ctx.add_(al.clone(), bl, layout=eng.LAYOUT_LIMB_MAJOR), (al + bl) % qq)
+    # encrypt 70000 ciphertexts (nct*2 > 65535), decrypt them all (nq > 65535); oracle on a sample
+    osk, opk = octx.keygen()
+    nct = 70000
+    seeds = (np.arange(nct * 8, dtype=np.uint64).reshape(nct, 8) + np.uint64(11)) * np.uint64(0x9E3779B97F4A7C15)
+    plains = (np.arange(nct, dtype=np.uint64) * np.uint64(7919)) % np.uint64(1 << 20)
+    cts = ctx.encrypt(ctx.dev(opk), ctx.dev(seeds), ctx.dev(plains[:, None]))
+    for i in (0, 1, 32767, 32768, 65535, 65536, nct - 1):
+        assert (eng.to_np(cts[i]) == octx.encrypt(opk, plains[i:i + 1], seed=seeds[i])).all(), i
+    dec = eng.to_np(ctx.decrypt(cts, ctx.dev(osk), ncoeff=1))[:, 0]
+    assert (dec == plains).all()
+    ctx.sync()

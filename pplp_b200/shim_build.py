@@ -61,7 +61,25 @@ def build(force=False):
             if force or _newer(exe, [s] + hdrs):
                 _run(["g++", "-w", "-include", "cstdint", "-I", os.path.join(REF, "include"), s] + COMMON + ["-o", exe])
             built.append(exe)
+    built += build_cmake(force)
     return built
+
+
+def build_cmake(force=False):
+    """The reference's own CMakeLists.txt, UNMODIFIED, configured with -DSEAL_DIR=<repo>/cmake so that its
+    `find_package(SEAL 4.1 REQUIRED)` (CMakeLists.txt:29) resolves to cmake/SEALConfig.cmake; builds pplp, client, server,
+    tc, ts into build/cmake_ref/ (only where /root/reference and cmake exist; the binaries travel to the GPU box)."""
+    import shutil
+    out = os.path.join(ROOT, "build", "cmake_ref")
+    names = ["pplp", "client", "server", "tc", "ts"]
+    if not os.path.isfile(os.path.join(REF, "CMakeLists.txt")) or not shutil.which("cmake"):
+        return [os.path.join(out, x) for x in names if os.path.exists(os.path.join(out, x))]
+    deps = [os.path.join(ROOT, "include", "seal", "seal.h"), os.path.join(ROOT, "include", "pplp_b200.h"), os.path.join(ROOT, "cmake", "SEALConfig.cmake"),
+            os.path.join(ROOT, "cmake", "SEALConfigVersion.cmake")]
+    if force or any(_newer(os.path.join(out, x), deps) for x in names):
+        _run(["cmake", "-S", REF, "-B", out, "-DSEAL_DIR=" + os.path.join(ROOT, "cmake"), "-DCMAKE_BUILD_RPATH=" + PKG + ";$ORIGIN/../../pplp_b200"])
+        _run(["cmake", "--build", out, "-j", "8"])
+    return [os.path.join(out, x) for x in names]
 
 
 if __name__ == "__main__":

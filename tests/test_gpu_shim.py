@@ -108,6 +108,18 @@ def test_reference_demo_runs_unmodified_on_the_gpu(shim, args, expect):
         pytest.xfail("reference reads uninitialised upper bytes of r/s/w (undefined behaviour in src/demo.cc:115-118)")
 
 
+def test_reference_cmake_build_runs_on_the_gpu(shim):
+    """The same demo built by the reference's own, unmodified CMakeLists.txt with -DSEAL_DIR=<repo>/cmake
+    (find_package(SEAL 4.1 REQUIRED), CMakeLists.txt:29-35 -> cmake/SEALConfig.cmake)."""
+    exe = os.path.join(ROOT, "build", "cmake_ref", "pplp")
+    if not os.path.exists(exe):
+        pytest.skip("the CMake build exists only where /root/reference and cmake do (build container)")
+    p = subprocess.run([exe, "-x", "123456891", "-y", "132465781", "-u", "123456888", "-v", "132465777", "-r", "128"], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "Parameter validation (success): valid" in p.stdout
+    assert p.stdout.strip().splitlines()[-2] == "near", p.stdout[-600:]
+
+
 def test_reference_client_server_over_loopback(shim):
     """src/server.cc + src/client.cc, unmodified, talking over 127.0.0.1:51022 with this library under both."""
     server, client = _dropin("server"), _dropin("client")

@@ -302,7 +302,25 @@ def run_b200(args):
     total_ms = ev[0].elapsed_time(ev[-1])
     kernel_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
     clocks = sampler.stop(t0, t1)
+    # sustained leg: the same launch back to back for >= 1 s (the K-step region above is tens of milliseconds), with its own
+    # clock record, so the figure is also known in a steady thermal / power state
+    sus_n = int(max(args.steps, min(4000, 1.1e3 / max(total_ms / args.steps, 1e-3))))
+    sus_sampler = ClockSampler(local)
+    sus_sampler.start()
+    time.sleep(0.2)
+    barrier()
+    sa, sb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ts0 = time.time()
+    sa.record()
+    for _ in range(sus_n):
+        step()
+    sb.record()
+    barrier()
+    ts1 = time.time()
+    sus_ms = sa.elapsed_time(sb)
+    sus_clocks = sus_sampler.stop(ts0, ts1)
     from pplp_b200.shard import gather_rows, max_over_ranks
+    sus_ms_max = max_over_ranks(sus_ms, dev)
     total_ms_max = max_over_ranks(total_ms, dev)   # device time, max over ranks
     value = world * Q * args.steps / (total_ms_max * 1e-3)
 
@@ -367,10 +385,12 @@ def run_b200(args):
     avg_kernel_ms = float(np.mean(kernel_ms))
     achieved = bytes_per_query * Q / (avg_kernel_ms * 1e-3) / 1e9
     traffic = None
+    pipes = {}
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("circuit_a_kernel", {}).get("dram_bytes_per_query")
+            pipes = json.load(open(tp)).get("circuit_a_kernel", {})
+            traffic = pipes.get("dram_bytes_per_query")
             # ncu capture at a smaller batch (N=8192, k=4): scaled per query, and per ciphertext size, to this launch
             traffic = traffic * Q * (N * k) / (8192 * 4) if traffic else None
         except Exception:
@@ -383,12 +403,17 @@ def run_b200(args):
                    "layout": "limb-major [limb][poly][query][N]", "parallelism": f"query-sharded x{world}, no collective in the hot path",
                    "cache": f"inputs {3 * Q * per_ct * 8 / 2**30:.1f} GiB per step >> 126 MB L2 (no flush needed)"},
         "roofline": {"bound": "hbm", "kernel": "circuit_a_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_query * Q,
+                     "traffic": traffic, "traffic_source": "from profile: ncu --set full dram__bytes_read+write of this kernel (profiles/traffic.json), scaled per query",
+                     "fp64_pipe_pct": pipes.get("fp64_pipe_pct"), "int_pipe_pct": pipes.get("int_pipe_pct"), "dram_pct_of_ncu_peak": pipes.get("dram_pct"),
+                     "pipes_source": "from profile (profiles/traffic.json: sm__pipe_fp64_cycles_active / sm__pipe_fma+alu, ncu --set full)", "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_query * Q,
                      "avg_launch_ms": avg_kernel_ms, "note": "event pairs bracket each pplp_circuit_a call (scalar-prepare kernel + main kernel)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 3 * Qe * per_ct * 8 + 4 * Qe * 8, "d2h_bytes_per_step": Qe * per_ct * 8,
                 "queries_per_step": Qe, "steps": e2e_steps, "api": "pplp_circuit_a_host (pinned host ciphertexts, SEAL layout)"},
         "gpu_launches": 2 * args.steps,
         "clocks": clocks,
+        "sustained": {"value": world * Q * sus_n / (sus_ms_max * 1e-3), "unit": UNIT, "launches": sus_n, "seconds": sus_ms_max * 1e-3,
+                      "achieved_GBps_per_gpu": bytes_per_query * Q * sus_n / (sus_ms_max * 1e-3) / 1e9, "clocks": sus_clocks,
+                      "note": "same launch repeated for >= 1 s after the K timed steps"},
     }
     if world == 1:
         threads = host_threads()
@@ -433,7 +458,9 @@ def run_extras(engine, ctx, torch, osk, opk):
         orc = oracle_lib.load()
         octx = orc.context(N, ctx.q, T, seed=seed8(7))
         ob = OracleBloom(orc.lib, "orc", radius * radius, 1e-4)
+        tb0 = time.perf_counter()
         ob.insert_blinded_range(r, s, w, radius * radius)
+        set_bf_ms = (time.perf_counter() - tb0) * 1e3
         threads = host_threads()
         ns = max(threads, 2 * threads)
         t0 = time.perf_counter()
@@ -441,7 +468,8 @@ def run_extras(engine, ctx, torch, osk, opk):
         cdt = time.perf_counter() - t0
         ex["protocol_cpu"] = {"value": ns / cdt, "unit": UNIT, "cores": threads, "sample": f"{ns} queries", "kind": "port",
                               "agrees_with_gpu": bool((cb == blind[:ns]).all() and (cv == verdict[:ns]).all()),
-                              "stage_ms_per_query": {k: float(v) / ns / 1e6 for k, v in zip(["d_enc", "d_homoCalc", "d_dec", "d_bfQuery"], stage_ns)}}
+                              "stage_ms_per_query": {k: float(v) / ns / 1e6 for k, v in zip(["d_enc", "d_homoCalc", "d_dec", "d_bfQuery"], stage_ns)},
+                              "d_setBF_ms_per_filter": set_bf_ms, "d_setBF_note": f"radius {radius}: {radius * radius} keys x 13 hashes, one host core (src/server.cc:95-98)"}
     except Exception as e:   # extras never invalidate the headline
         ex["protocol_e2e"] = {"error": str(e)[:200]}
     try:
@@ -490,7 +518,144 @@ def run_extras(engine, ctx, torch, osk, opk):
                                "what": "pplp_circuit_a_cross: client ciphertexts read once per launch, 16*k*N bytes written per pair"}
     except Exception as e:
         ex["config5_cross"] = {"error": str(e)[:200]}
+    for name, fn in (("circuit_b", extra_circuit_b), ("bloom_build", extra_bloom_build), ("n16384", extra_n16384), ("config4_sweep", extra_config4)):
+        try:
+            ex[name] = fn(engine, torch)
+        except Exception as e:
+            ex[name] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+        torch.cuda.empty_cache()
     return ex
+
+
+def _event_time(torch, fn, reps, warm=2):
+    for _ in range(warm):
+        fn()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps * 1e-3
+
+
+def extra_circuit_b(engine, torch):
+    """north_star's direct form at N=8192, slot-batched with a prime t (PlainModulus::Batching(8192, 56)): per ciphertext
+    group  s * (relin((cx - px)^2) + relin((cy - py)^2) + r)  through pplp_circuit_b; N slot-wise queries per group.
+    Checked against the oracle's call-by-call evaluation on one group, timed next to the oracle on the host cores."""
+    import concurrent.futures
+    from tests import oracle_lib
+    n, t = 8192, 0xfffffffffb4001
+    ctx = engine.Context(n, t=t, device=torch.cuda.current_device())
+    k = ctx.k
+    orc = oracle_lib.load()
+    octx = orc.context(n, ctx.q, t, seed=seed8(11))
+    osk, opk = octx.keygen()
+    ork = octx.relin_keygen(osk)
+    rk = ctx.dev(ork)
+    quot = ctx.relin_prepare(rk)
+    rng = np.random.default_rng(77)
+    groups = 512
+    enc = lambda v: ctx.batch_encode(ctx.dev(np.ascontiguousarray(v)))
+    xb = rng.integers(0, 1 << 27, (groups, n), dtype=np.uint64); yb = rng.integers(0, 1 << 27, (groups, n), dtype=np.uint64)
+    rr = rng.integers(0, 1 << 16, (groups, n), dtype=np.uint64)
+    px, py, pr = enc(xb), enc(yb), enc(rr)
+    sv = ctx.dev(rng.integers(1, 8, groups, dtype=np.uint64))
+    xa, ya = 123456789, 132456888
+    pa = engine.to_np(enc(np.stack([np.full(n, xa, dtype=np.uint64), np.full(n, ya, dtype=np.uint64)])))
+    ex_, ey_ = octx.encrypt(opk, pa[0], seed=seed8(31)), octx.encrypt(opk, pa[1], seed=seed8(32))
+    cx = ctx.dev(np.broadcast_to(ex_, (groups,) + ex_.shape).copy()); cy = ctx.dev(np.broadcast_to(ey_, (groups,) + ey_.shape).copy())
+    out = ctx.empty(*ctx.ct_shape(groups, 2))
+    run = lambda: ctx.circuit_b(cx, cy, px, py, pr, sv, rk, quot, out=out, chunk=256)
+    sec = _event_time(torch, run, 4)
+    # parity + algebra on group 0
+    hp = [engine.to_np(x[0]) for x in (px, py, pr)]
+    s0 = int(engine.to_np(sv)[0])
+
+    def oracle_group(a, b, c):
+        ox = octx.eval_plain("sub_plain", ex_, a); oy = octx.eval_plain("sub_plain", ey_, b)
+        ox2 = octx.relinearize(octx.square(ox), ork); oy2 = octx.relinearize(octx.square(oy), ork)
+        return octx.eval_plain("multiply_plain", octx.eval_plain("add_plain", octx.eval_ct("add", ox2, oy2), c), [s0])
+
+    t0 = time.perf_counter()
+    od = oracle_group(*hp)
+    one = time.perf_counter() - t0
+    agrees = bool((engine.to_np(out[0]) == od).all())
+    slots = engine.to_np(ctx.batch_decode(ctx.decrypt(out[:1], ctx.dev(osk))))[0]
+    d2 = (xa - xb[0].astype(object)) ** 2 + (ya - yb[0].astype(object)) ** 2
+    algebra = bool(all(int(v) == (s0 * (int(a) + int(b))) % t for v, a, b in zip(slots[:64], d2[:64], rr[0][:64])))
+    threads = host_threads()
+    with concurrent.futures.ThreadPoolExecutor(threads) as pool:     # ctypes releases the GIL: one group per host thread
+        t0 = time.perf_counter()
+        list(pool.map(lambda i: oracle_group(*hp), range(threads)))
+        cdt = time.perf_counter() - t0
+    peak, _ = peaks()
+    bytes_group = 280 * n * 8           # SURVEY.md 8(d): planning estimate of compulsory HBM bytes per ciphertext group
+    gps = groups / sec
+    return {"groups_per_s": gps, "value": gps * n, "unit": "slot-wise queries/s", "queries_per_group": n, "groups_per_step": groups,
+            "squares_per_s": 2 * gps, "relinearizations_per_s": 2 * gps,
+            "workload": "circuitB_bfv_n8192_k4_t=Batching(8192,56)_slot_batched: sub_plain x2, square x2, relinearize x2, add, add_plain, multiply_plain(mono)",
+            "roofline": {"bound": "integer + FP64 pipes (61-bit BEHZ base on the integer multiplier); HBM shown for reference", "algorithmic_bytes_per_group": bytes_group,
+                         "achieved": bytes_group * gps / 1e9, "peak": peak, "unit": "GB/s", "frac": bytes_group * gps / 1e9 / peak},
+            "agrees_with_oracle": agrees, "slots_match_algebra": algebra,
+            "cpu_baseline": {"groups_per_s": threads / cdt, "value": threads / cdt * n, "unit": "slot-wise queries/s", "cores": threads, "kind": "port",
+                             "one_thread_seconds_per_group": one, "sample": f"{threads} groups, one per host thread (oracle/ restatement of SEAL's bfv_square + switch_key_inplace)"}}
+
+
+def extra_bloom_build(engine, torch):
+    """d_setBF (src/server.cc:83-98, include/benchmark.h): Bloom-filter construction rates, GPU vs the oracle on one host core."""
+    from tests import oracle_lib
+    from tests.oracle_lib import OracleBloom
+    ctx = engine.Context(4096, t=T, device=torch.cuda.current_device())
+    orc = oracle_lib.load()
+    res = {}
+    rng = np.random.default_rng(5)
+    for radius, nf, fpp in ((128, 2048, 1e-4), (128, 1, 1e-4), (4096, 1, 1e-4)):
+        rsw = np.stack([rng.integers(0, 1 << 32, nf, dtype=np.uint64), rng.integers(1, 1 << 32, nf, dtype=np.uint64), rng.integers(1 << 15, 1 << 16, nf, dtype=np.uint64)], axis=1)
+        bf = engine.BloomBatch(ctx, radius, fpp=fpp, rsw=rsw)
+        sec = _event_time(torch, lambda: bf.build(), 5)
+        ob = OracleBloom(orc.lib, "orc", radius * radius, fpp)
+        t0 = time.perf_counter()
+        ob.insert_blinded_range(int(rsw[0, 0]), int(rsw[0, 1]), int(rsw[0, 2]), radius * radius)
+        cpu = time.perf_counter() - t0
+        ok = bool((bf.table_bytes(0) == ob.table()).all())
+        res[f"r{radius}_x{nf}"] = {"filters": nf, "keys_per_filter": radius * radius, "hashes_per_key": bf.k, "table_bytes": bf.m_bits // 8, "gpu_ms": sec * 1e3,
+                                   "inserts_per_s": nf * radius * radius / sec, "filters_per_s": nf / sec, "d_setBF_cpu_ms_per_filter": cpu * 1e3,
+                                   "cpu_inserts_per_s_one_core": radius * radius / cpu, "table_equals_oracle": ok}
+    return res
+
+
+def extra_n16384(engine, torch):
+    """BASELINE.json configs[2]: the same Circuit A workload at N=16384 (k=8), device-resident, so that every N-GPU line carries it."""
+    n = 16384
+    ctx = engine.Context(n, t=T, device=torch.cuda.current_device())
+    k, Q = ctx.k, 1024
+    cin = [ctx.empty(*ctx.ct_shape(Q, 2, None, engine.LAYOUT_LIMB_MAJOR)) for _ in range(3)]
+    for c in cin:
+        for j in range(k):
+            c[j].random_(0, ctx.q[j])
+    out = ctx.empty(*ctx.ct_shape(Q, 2, None, engine.LAYOUT_LIMB_MAJOR))
+    par = [torch.randint(1, 1 << 27, (Q,), device=out.device) for _ in range(2)] + [torch.randint(1, 1 << 32, (Q,), device=out.device) for _ in range(2)]
+    sec = _event_time(torch, lambda: ctx.circuit_a(cin[0], cin[1], cin[2], par[0], par[1], par[2], par[3], out=out, layout=engine.LAYOUT_LIMB_MAJOR), 10, warm=3)
+    peak, _ = peaks()
+    gbs = 64 * k * n * Q / sec / 1e9
+    res = {"value": Q / sec, "unit": UNIT, "workload": f"circuitA_bfv_n{n}_k{k}_t2^56_batched", "queries_per_step": Q, "achieved_GBps": gbs, "frac_of_hbm_peak": gbs / peak}
+    del cin, out
+    rows = 2048
+    data = ctx.empty(k, 1, rows, n)
+    for j in range(k):
+        data[j].random_(0, ctx.q[j])
+    for inv in (False, True):
+        sec = _event_time(torch, lambda: ctx.ntt_(data, inverse=inv, layout=engine.LAYOUT_LIMB_MAJOR), 5)
+        res["intt_gbs" if inv else "ntt_gbs"] = 16 * n * rows * k / sec / 1e9
+    return res
+
+
+def extra_config4(engine, torch):
+    """BASELINE.json configs[3], reduced grid: NTT / INTT / relinearize / square at N = 4096..32768 x {3, 8} limbs."""
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import config4_sweep
+    return config4_sweep.sweep(limb_list=(3, 8), device=torch.cuda.current_device(), verbose=False, reps=3)
 
 
 if __name__ == "__main__":

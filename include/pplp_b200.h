@@ -159,6 +159,18 @@ int pplp_square(pplp_ctx *ctx, size_t level, const uint64_t *d_a, uint64_t *d_ou
 int pplp_relin_prepare(pplp_ctx *ctx, const uint64_t *d_rk, uint64_t *d_rk_quot, void *stream);
 int pplp_relinearize(pplp_ctx *ctx, size_t level, const uint64_t *d_in, uint64_t *d_out, int layout, size_t nq, const uint64_t *d_rk,
                      const uint64_t *d_rk_quot, void *stream);
+/* north_star's direct form of the encrypted squared distance (the reference itself runs the expanded
+ * form, src/server.cc:127-133, so there is no reference call site): per ciphertext group q
+ *     out = s * ( relin((cx - px)^2) + relin((cy - py)^2) + r )
+ * = Evaluator::sub_plain_inplace x2, square_inplace x2, relinearize_inplace x2, add_inplace, add_plain_inplace,
+ * multiply_plain_inplace (monomial blind), each following SEAL's routine, the glue fused.  d_cx, d_cy: nq size-2 ciphertexts;
+ * d_px, d_py: [nq][plain_stride] plaintext coefficients (plain_count used: 1 for constants, N for BatchEncoder output, i.e.
+ * N slot-wise queries per group); d_r: [nq][r_stride] (r_count used); d_s: [nq] scalar blinds; d_rk / d_rk_quot as for
+ * pplp_relinearize (the prepared image is required); d_flags[q] (optional) = 1 where s == 0.  `chunk` groups go through the
+ * scratch buffers at a time (0 = 256).  Inputs are not modified. */
+int pplp_circuit_b(pplp_ctx *ctx, size_t level, const uint64_t *d_cx, const uint64_t *d_cy, uint64_t *d_out, int layout, size_t nq, const uint64_t *d_px,
+                   const uint64_t *d_py, size_t plain_count, size_t plain_stride, const uint64_t *d_r, size_t r_count, size_t r_stride, const uint64_t *d_s,
+                   const uint64_t *d_rk, const uint64_t *d_rk_quot, int *d_flags, size_t chunk, void *stream);
 /* Negacyclic NTT / inverse NTT of every row (Evaluator::transform_to_ntt_inplace semantics; the microbenchmark of
  * BASELINE.json config 4).  base 0 = the level's q primes, base 1 = the level's BEHZ base Bsk. */
 int pplp_ntt(pplp_ctx *ctx, size_t level, int base, uint64_t *d_data, int layout, size_t nq, size_t npoly, int inverse, void *stream);

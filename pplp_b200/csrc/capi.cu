@@ -634,6 +634,44 @@ int pplp_relinearize(pplp_ctx *ctx, size_t level, const uint64_t *d_in, uint64_t
     PPLP_CATCH
 }
 
+// north_star's direct form, batched: out = s * ((cx - px)^2 + (cy - py)^2 + r), squares relinearised.
+int pplp_circuit_b(pplp_ctx *ctx, size_t level, const uint64_t *d_cx, const uint64_t *d_cy, uint64_t *d_out, int layout, size_t nq, const uint64_t *d_px,
+                   const uint64_t *d_py, size_t plain_count, size_t plain_stride, const uint64_t *d_r, size_t r_count, size_t r_stride, const uint64_t *d_s,
+                   const uint64_t *d_rk, const uint64_t *d_rk_quot, int *d_flags, size_t chunk, void *stream) {
+    PPLP_TRY
+    Engine &E = dev_engine(ctx);
+    const size_t k = check_level(E, level), n = E.host.n;
+    if (level == 0 && E.host.levels.size() > 1) throw std::invalid_argument("encrypted is not valid for encryption parameters");
+    if (E.host.levels.size() < 2) throw std::logic_error("keyswitching is not supported by the context");
+    if (plain_count > n || r_count > n) throw std::invalid_argument("plain is not valid for encryption parameters");
+    if (!d_rk_quot) throw std::invalid_argument("pplp: pplp_circuit_b needs the prepared key image (pplp_relin_prepare)");
+    if (nq == 0) return PPLP_OK;
+    to_int(nq, "query count");
+    if (chunk == 0) chunk = 256;
+    chunk = std::min(chunk, nq);
+    cudaStream_t st = S(stream);
+    const int C2 = to_int(2 * chunk, "chunk");
+    const size_t ctw = k * n;
+    // work buffers in SEAL layout: [x chunk | y chunk] as one batch of 2*chunk ciphertexts through square and relinearize
+    Scratch w2(2 * chunk * 2 * ctw * 8, st), w3(2 * chunk * 3 * ctw * 8, st), mws(multiply_tmp_words(E, level, C2, true) * 8, st),
+        rws(relin_tmp_words(E, level, C2) * 8, st);
+    if (d_flags) PPLP_CUDA(cudaMemsetAsync(d_flags, 0, nq * sizeof(int), st));
+    const Layout full2 = make_layout(layout, n, k, 2, nq);
+    const Layout wl2{2 * ctw, ctw, n}, wl3{3 * ctw, ctw, n};
+    for (size_t done = 0; done < nq; done += chunk) {
+        const int c = (int)std::min(chunk, nq - done);
+        const size_t off = done * full2.sq;
+        u64 *x = w2.as<u64>(), *y = x + (size_t)c * 2 * ctw;
+        launch_copy_sub_plain(E, level, d_cx + off, full2, x, wl2, c, d_px + done * plain_stride, plain_count, plain_stride, st);
+        launch_copy_sub_plain(E, level, d_cy + off, full2, y, wl2, c, d_py + done * plain_stride, plain_count, plain_stride, st);
+        launch_multiply(E, level, x, x, wl2, w3.as<u64>(), wl3, 2 * c, mws.as<u64>(), st);
+        launch_relinearize(E, level, w3.as<u64>(), wl3, x, wl2, 2 * c, d_rk, d_rk_quot, rws.as<u64>(), st);
+        launch_circuit_b_combine(E, level, x, y, wl2, d_out + off, full2, c, d_r + done * r_stride, r_count, r_stride, d_s + done, d_flags ? d_flags + done : nullptr, st);
+    }
+    return PPLP_OK;
+    PPLP_CATCH
+}
+
 int pplp_ntt(pplp_ctx *ctx, size_t level, int base, uint64_t *d_data, int layout, size_t nq, size_t npoly, int inverse, void *stream) {
     PPLP_TRY
     Engine &E = dev_engine(ctx);

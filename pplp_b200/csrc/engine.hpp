@@ -71,6 +71,11 @@ void launch_mul_mono(const Engine &E, size_t level, const u64 *in, u64 *out, Lay
 // lift plaintext coefficients into RNS rows: out[j][i] = lift(m_i) mod q_j
 void launch_lift_plain(const Engine &E, size_t level, const u64 *plain, size_t count, u64 *out /* [k][n] */, cudaStream_t st);
 void launch_dyadic(const Engine &E, u64 *a, Layout a_lay, const u64 *b, Layout b_lay, int nq, int npoly, const RowMap &map, cudaStream_t st);
+// Circuit B glue: chunk copy fused with sub_plain; add + add_plain + blind multiply fused (eval.cu)
+void launch_copy_sub_plain(const Engine &E, size_t level, const u64 *src, Layout src_lay, u64 *dst, Layout dst_lay, int nq, const u64 *plain, size_t count,
+                           size_t m_stride, cudaStream_t st);
+void launch_circuit_b_combine(const Engine &E, size_t level, const u64 *a, const u64 *b, Layout in_lay, u64 *out, Layout out_lay, int nq, const u64 *rplain,
+                              size_t count, size_t r_stride, const u64 *scalar, int *flags, cudaStream_t st);
 int launch_is_zero(const Engine &E, const u64 *p, size_t words, int *d_flag, cudaStream_t st);  // returns 1 if all zero (synchronises)
 
 // ---- crypto.cu ----

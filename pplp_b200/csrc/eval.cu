@@ -240,6 +240,62 @@ void launch_circuit_a_cross(const Engine &E, size_t level, const u64 *c0, const 
     PPLP_CUDA(cudaGetLastError());
 }
 
+// ---- Circuit B helpers (north_star's direct form: sub_plain -> square -> relinearize -> add -> add_plain -> multiply_plain) ----
+// dst (dst_lay) <- src (src_lay), then c0 -= round(Q m_i / t) for the first `count` coefficients: the strided copy of a batch
+// chunk into the work buffer fused with sub_plain_inplace ([SEAL] multiply_sub_plain_with_scaling_variant).  rows in grid.x.
+__global__ void __launch_bounds__(256) copy_sub_plain_kernel(const DevLevel *Lp, const u64 *__restrict__ src, Layout src_lay, u64 *__restrict__ dst, Layout dst_lay, int nq,
+                                                             int n, const u64 *__restrict__ plain, int count, size_t m_stride) {
+    const DevLevel &L = *Lp;
+    int row = blockIdx.x;
+    const int qi = row % nq; row /= nq;
+    const int p = row & 1, j = row >> 1;
+    const u64 q = L.q[j].q;
+    const u64 *s = src + qi * src_lay.sq + p * src_lay.sp + j * src_lay.sl;
+    u64 *d = dst + qi * dst_lay.sq + p * dst_lay.sp + j * dst_lay.sl;
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
+        u64 v = s[i];
+        if (p == 0 && i < count) v = sub_mod(v, dev_scaled(L, plain[qi * m_stride + i], j), q);
+        d[i] = v;
+    }
+}
+void launch_copy_sub_plain(const Engine &E, size_t level, const u64 *src, Layout src_lay, u64 *dst, Layout dst_lay, int nq, const u64 *plain, size_t count,
+                           size_t m_stride, cudaStream_t st) {
+    E.require_device();
+    const int k = (int)E.host.levels[level].q.size(), n = (int)E.host.n;
+    if (nq == 0) return;
+    copy_sub_plain_kernel<<<dim3(nq * 2 * k, (n + 1023) / 1024), 256, 0, st>>>(E.d_levels + level, src, src_lay, dst, dst_lay, nq, n, plain, (int)count, m_stride);
+    PPLP_CUDA(cudaGetLastError());
+}
+// out = lift(s) * (a + b + [p = 0, i < count] round(Q r_i / t))  mod q_j: add_inplace, add_plain_inplace and the monomial
+// multiply_plain_inplace of the blind in one pass (ring identities on canonical residues: the same words as the three calls).
+__global__ void __launch_bounds__(256) circuit_b_combine_kernel(const DevLevel *Lp, const u64 *__restrict__ a, const u64 *__restrict__ b, Layout in_lay, u64 *__restrict__ out,
+                                                                Layout out_lay, int nq, int n, const u64 *__restrict__ rplain, int count, size_t r_stride,
+                                                                const u64 *__restrict__ scalar, int *flags) {
+    const DevLevel &L = *Lp;
+    int row = blockIdx.x;
+    const int qi = row % nq; row /= nq;
+    const int p = row & 1, j = row >> 1;
+    const Mod mq = L.q[j];
+    const u64 sv = scalar[qi];
+    const u64 w = dev_lift(L, sv, j), wq = dev_shoup_quotient(w, mq.q);
+    if (flags && row == 0 && blockIdx.y == 0 && threadIdx.x == 0 && sv == 0) atomicOr(&flags[qi], 1);   // SEAL: "result ciphertext is transparent"
+    const size_t ib = qi * in_lay.sq + p * in_lay.sp + j * in_lay.sl, ob = qi * out_lay.sq + p * out_lay.sp + j * out_lay.sl;
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
+        u64 v = add_mod(a[ib + i], b[ib + i], mq.q);
+        if (p == 0 && i < count) v = add_mod(v, dev_scaled(L, rplain[qi * r_stride + i], j), mq.q);
+        out[ob + i] = mul_shoup(v, w, wq, mq.q);
+    }
+}
+void launch_circuit_b_combine(const Engine &E, size_t level, const u64 *a, const u64 *b, Layout in_lay, u64 *out, Layout out_lay, int nq, const u64 *rplain,
+                              size_t count, size_t r_stride, const u64 *scalar, int *flags, cudaStream_t st) {
+    E.require_device();
+    const int k = (int)E.host.levels[level].q.size(), n = (int)E.host.n;
+    if (nq == 0) return;
+    circuit_b_combine_kernel<<<dim3(nq * 2 * k, (n + 1023) / 1024), 256, 0, st>>>(E.d_levels + level, a, b, in_lay, out, out_lay, nq, n, rplain, (int)count, r_stride, scalar,
+                                                                               flags);
+    PPLP_CUDA(cudaGetLastError());
+}
+
 // ---- individual primitives (SEAL-facing shim; batch-of-nq views) ---------------------------------------------------
 __global__ void add_sub_kernel(const DevLevel *Lp, u64 *a, const u64 *b, Layout lay, int nq, int npoly, int n, int mode) {
     const DevLevel &L = *Lp;

@@ -260,6 +260,17 @@ class Context:
                                       self._st()))
         return out
 
+    def circuit_b(self, cx, cy, px, py, r, s, rk, rk_quot, out=None, level=None, layout=LAYOUT_SEAL, flags=None, chunk=0):
+        """north_star's direct form: out = s * (relin((cx - px)^2) + relin((cy - py)^2) + r).  px, py, r: [nq, count] plaintext
+        coefficients (count = 1: constants; count = N: BatchEncoder output, N slot-wise queries per group); s: [nq] blinds."""
+        nq, _ = self._dims(cx, layout)
+        if out is None:
+            out = self.empty(*self.ct_shape(nq, 2, level, layout))
+        assert px.shape == py.shape and px.shape[0] == nq and r.shape[0] == nq
+        check(self.L.pplp_circuit_b(self.h, self.first_level if level is None else level, _ptr(cx), _ptr(cy), _ptr(out), layout, nq, _ptr(px), _ptr(py),
+                                    px.shape[1], px.stride(0), _ptr(r), r.shape[1], r.stride(0), _ptr(s), _ptr(rk), _ptr(rk_quot), _ptr(flags), chunk, self._st()))
+        return out
+
     def ntt_(self, data, level=None, base=0, inverse=False, layout=LAYOUT_SEAL):
         nq, npoly = self._dims(data, layout)
         check(self.L.pplp_ntt(self.h, self.first_level if level is None else level, base, _ptr(data), layout, nq, npoly, 1 if inverse else 0, self._st()))

@@ -60,20 +60,16 @@ def timed(fn, reps):
     return a.elapsed_time(b) / reps * 1e-3
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--out", default="gpurun_out/config4.json")
-    ap.add_argument("--quick", action="store_true")
-    a = ap.parse_args()
+def sweep(ns=(4096, 8192, 16384, 32768), limb_list=(3, 4, 5, 6, 7, 8), device=0, verbose=True, reps=5):
+    """Rows of {n, limbs, ntt_gbs, intt_gbs, relin_per_s, relin_gbs, square_per_s, square_gbs}; also called by bench.py (reduced grid)."""
     rows_out = []
-    ns = [4096, 8192, 16384, 32768]
-    limb_list = [3, 8] if a.quick else [3, 4, 5, 6, 7, 8]
     for n in ns:
         for limbs in limb_list:
             q = primes_for(n, limbs)
-            ctx = engine.Context(n, q=q, t=1 << 20, device=0, enforce_security=False)
+            ctx = engine.Context(n, q=q, t=1 << 20, device=device, enforce_security=False)
             if not ctx.ok:
-                print("skip", n, limbs, ctx.error_message)
+                if verbose:
+                    print("skip", n, limbs, ctx.error_message)
                 continue
             rows = max(64, (1 << 25) // n)           # >= 256 MiB of data per launch at every N
             data = ctx.empty(limbs, 1, rows, n)
@@ -81,7 +77,7 @@ def main():
                 data[j].random_(0, q[j])
             rec = {"n": n, "limbs": limbs, "max_bits": max(x.bit_length() for x in q), "rows_per_launch": rows * limbs}
             for inv in (False, True):
-                s = timed(lambda: ctx.ntt_(data, level=0, inverse=inv, layout=engine.LAYOUT_LIMB_MAJOR), 5)
+                s = timed(lambda: ctx.ntt_(data, level=0, inverse=inv, layout=engine.LAYOUT_LIMB_MAJOR), reps)
                 rec["intt_gbs" if inv else "ntt_gbs"] = round(16 * n * rows * limbs / s / 1e9, 1)
             # relinearize / square at the data level (k = limbs - 1)
             k = ctx.k
@@ -100,11 +96,23 @@ def main():
             rec["square_per_s"] = round(nq / s, 1)
             rec["square_gbs"] = round(8 * k * n * 5 * nq / s / 1e9, 1)
             rows_out.append(rec)
-            print(json.dumps(rec), flush=True)
+            if verbose:
+                print(json.dumps(rec), flush=True)
             del data, ct3, ct2, rk, quot, ctx
             torch.cuda.empty_cache()
+    return rows_out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default="gpurun_out/config4.json")
+    ap.add_argument("--quick", action="store_true")
+    a = ap.parse_args()
+    rows_out = sweep(limb_list=(3, 8) if a.quick else (3, 4, 5, 6, 7, 8))
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
-    json.dump(rows_out, open(a.out, "w"), indent=1)
+    with open(a.out, "w") as f:
+        for r in rows_out:
+            f.write(json.dumps(r) + "\n")
 
 
 if __name__ == "__main__":

@@ -494,6 +494,45 @@ def test_circuit_b_direct_form_decrypts_to_squared_distance(eng, oracle):
     dec = eng.to_np(ctx.decrypt(d, ctx.dev(osk), ncoeff=1))[0, 0]
     d2 = (xa - xb) ** 2 + (ya - yb) ** 2
     assert int(dec) == (s * (d2 + r)) % t
+    # the fused entry point (pplp_circuit_b) gives the same ciphertext words, in both layouts, chunked or not
+    arr = lambda v: ctx.dev(np.array(v, dtype=np.uint64))
+    nq = 3
+    cx, cy = ctx.dev(np.stack([ex] * nq)), ctx.dev(np.stack([ey] * nq))
+    got = ctx.circuit_b(cx, cy, arr([[xb]] * nq), arr([[yb]] * nq), arr([[r]] * nq), arr([s] * nq), rk, quot, chunk=2)
+    assert all((eng.to_np(got)[i] == od).all() for i in range(nq))
+    lm = lambda c: c.permute(2, 1, 0, 3).contiguous()
+    got = ctx.circuit_b(lm(cx), lm(cy), arr([[xb]] * nq), arr([[yb]] * nq), arr([[r]] * nq), arr([s] * nq), rk, quot, layout=eng.LAYOUT_LIMB_MAJOR)
+    assert all((eng.to_np(got)[:, :, i].transpose(1, 0, 2) == od).all() for i in range(nq))
+
+
+def test_circuit_b_slot_batched_matches_oracle(eng, oracle):
+    """Slot-batched direct form: N server points per ciphertext group (BatchEncoder, prime t), multi-coefficient plaintexts
+    through pplp_circuit_b against the oracle's call-by-call evaluation, and slot-wise against the algebra."""
+    n = 8192
+    t = 0xfffffffffb4001
+    ctx, octx = contexts(eng, oracle, n, t=t)
+    osk, opk = octx.keygen()
+    ork = octx.relin_keygen(osk)
+    rk = ctx.dev(ork)
+    quot = ctx.relin_prepare(rk)
+    rng = np.random.default_rng(21)
+    xa, ya = 123456789, 132456888
+    xb = rng.integers(0, 1 << 27, n, dtype=np.uint64)
+    yb = rng.integers(0, 1 << 27, n, dtype=np.uint64)
+    rr = rng.integers(0, 1 << 16, n, dtype=np.uint64)
+    s = 5
+    enc = lambda v: eng.to_np(ctx.batch_encode(ctx.dev(np.asarray(v, dtype=np.uint64)[None, :])))[0]
+    pxa, pya, pxb, pyb, pr = enc(np.full(n, xa)), enc(np.full(n, ya)), enc(xb), enc(yb), enc(rr)
+    ex = octx.encrypt(opk, pxa, seed=seed8(31))
+    ey = octx.encrypt(opk, pya, seed=seed8(32))
+    ox = octx.eval_plain("sub_plain", ex, pxb); oy = octx.eval_plain("sub_plain", ey, pyb)
+    ox2 = octx.relinearize(octx.square(ox), ork); oy2 = octx.relinearize(octx.square(oy), ork)
+    od = octx.eval_plain("multiply_plain", octx.eval_plain("add_plain", octx.eval_ct("add", ox2, oy2), pr), [s])
+    got = ctx.circuit_b(ctx.dev(ex[None]), ctx.dev(ey[None]), ctx.dev(pxb[None]), ctx.dev(pyb[None]), ctx.dev(pr[None]), ctx.dev(np.array([s], dtype=np.uint64)), rk, quot)
+    assert (eng.to_np(got)[0] == od).all()
+    slots = eng.to_np(ctx.batch_decode(ctx.decrypt(got, ctx.dev(osk))))[0]
+    d2 = (xa - xb.astype(object)) ** 2 + (ya - yb.astype(object)) ** 2
+    assert [int(v) for v in slots] == [int((s * (int(a) + int(b))) % t) for a, b in zip(d2, rr)]
 
 
 def test_bloom_wire_format_matches_reference_golden(eng, oracle):

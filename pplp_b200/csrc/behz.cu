@@ -23,6 +23,7 @@
 #include <type_traits>
 #include "engine.hpp"
 #include "ntt.cuh"
+#include "ntt32.cuh"
 
 namespace pplp {
 
@@ -280,25 +281,36 @@ void launch_multiply(const Engine &E, size_t level, const u64 *a, const u64 *b, 
 }
 
 // ---- relinearisation -------------------------------------------------------------------------------------------------
+// Which relinearisation pipeline a context runs (host decision, shared by pplp_relin_prepare and pplp_relinearize):
+//   split  (N = 2048..8192, every key-level prime <= 44 bits: BFVDefault up to 8192)  relin_digits_kernel -> relin_mac_inverse_kernel
+//          on the 32-per-thread FP64 transforms (ntt32.cuh), NTT-form digits through an L2-sized scratch;
+//   fused  (everything else)  relin_limb_kernel, 16 coefficients per thread, digits never leave registers.
+bool relin_uses_split(const Engine &E) {
+    return E.host.logn >= 11 && E.host.logn <= 13 && E.max_bits(E.qmap(0)) <= 44;
+}
+
 // quot[i] = floor(w[i] * 2^64 / q_limb): Shoup quotients of key words, computed once per key.  rows of n words, limb = row % K.
-// The prepared image holds {w, quotient} pairs (one 128-bit load per key coefficient) in the thread-interleaved order of
-// the kernels' fine register layout: coefficient 16 t + r of a row sits at pair index r * (n/16) + t, so a warp's load
-// of "its r-th coefficient" is one coalesced 512-byte access.
-__global__ void shoup_quot_kernel(const DevMod *mods, const u64 *__restrict__ w, u64 *__restrict__ prepared, int K, int n) {
+// The prepared image holds {w, quotient} pairs (one 128-bit load per key coefficient).  Fused pipeline: in the
+// thread-interleaved order of its fine register layout — coefficient 16 t + r of a row sits at pair index r * (n/16) + t, so a
+// warp's load of "its r-th coefficient" is one coalesced 512-byte access.  Split pipeline: natural order (its products run
+// in the coalesced ownership), and the second word is the bit pattern of the double fl(w/q) — the FP64-assisted product
+// mul_f64_lazy takes its quotient estimate from one DFMA instead of a 64x64 high product.
+__global__ void shoup_quot_kernel(const DevMod *mods, const u64 *__restrict__ w, u64 *__restrict__ prepared, int K, int n, int split) {
     const int row = blockIdx.x;
     const u64 q = mods[row % K].m.q;
     const int T = n / 16;
     ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(prepared) + (size_t)row * n;
     for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
         const u64 v = w[(size_t)row * n + i];
-        dst[(size_t)(i & 15) * T + (i >> 4)] = make_ulonglong2(v, (u64)((((unsigned __int128)v) << 64) / q));
+        if (split) dst[i] = make_ulonglong2(v, as_u(__ddiv_rn((double)v, (double)q)));   // {w, fl(w/q)}: operand of mul_f64_lazy (q < 2^45)
+        else dst[(size_t)(i & 15) * T + (i >> 4)] = make_ulonglong2(v, (u64)((((unsigned __int128)v) << 64) / q));
     }
 }
 void launch_shoup_quotients(const Engine &E, const u64 *w, u64 *quot, int nrows, cudaStream_t st) {
     E.require_device();
     const int n = (int)E.host.n, K = (int)E.host.K();
     if (nrows == 0) return;
-    shoup_quot_kernel<<<dim3(nrows, (n + 1023) / 1024), 256, 0, st>>>(E.d_mods, w, quot, K, n);
+    shoup_quot_kernel<<<dim3(nrows, (n + 1023) / 1024), 256, 0, st>>>(E.d_mods, w, quot, K, n, relin_uses_split(E) ? 1 : 0);
     PPLP_CUDA(cudaGetLastError());
 }
 
@@ -362,6 +374,174 @@ __global__ void __launch_bounds__(NttShape<LOGM>::T) relin_limb_kernel(const Rel
     });
 }
 
+// ---- split pipeline (ntt32 schedule) -----------------------------------------------------------------------------------
+// Stage 1: one CTA per (ciphertext, digit J, key limb I): X = NTT_{q_I}(c2 limb J).  The residues of limb J are below q_J <
+// 4 q_I for primes of one size class (checked on the host), which is all the forward transform asks of its input, and the
+// transform is linear, so "reduce modulo q_I first" ([SEAL] switch_key_inplace) changes no output residue.  Output: some
+// representative below 32 q_I (the exact double shifted by 16 q), NTT order, to scratch [ct][I][J][n].
+struct RelinSplitArgs {
+    const u64 *c2; Layout lay;
+    u64 *digits;                    // [nq][k+1][k][n]
+    int k, K, n;
+    const DevMod *mods;
+};
+template <int LOGM>
+__global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T) relin_digits_kernel(const RelinSplitArgs a) {
+    using S = Ntt32Shape<LOGM>;
+    extern __shared__ __align__(16) u64 sm[];
+    const int tid = threadIdx.x;
+    const int kk = a.k + 1;
+    const int I = blockIdx.x % kk, J = (blockIdx.x / kk) % a.k, qi = blockIdx.x / (kk * a.k);   // the kk readers of one row are neighbours
+    const DevMod &md = a.mods[I == a.k ? a.K - 1 : I];
+    const Ntt32Consts c = ntt32_consts(md, false);
+    const u64 *row = a.c2 + qi * a.lay.sq + 2 * a.lay.sp + J * a.lay.sl;
+    u64 *dst = a.digits + (((size_t)qi * kk + I) * a.k + J) * S::M;
+    u64 x[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) x[e] = row[e * S::T + tid];
+    ntt32_forward<LOGM>(x, sm, tid, c);
+    const double bias = __fma_rn(16.0, c.q, kTwo52);   // |x| <= 14 q
+#pragma unroll
+    for (int e = 0; e < 32; ++e) x[e] = f64_to_u64_biased(as_d(x[e]), bias);
+    ntt32_store_row(x, sm, tid, dst);
+}
+// Stage 2: one CTA per (ciphertext, key limb I, component c): acc = sum_J X_J (.) key[J][c][I], then the inverse transform.
+// The products run in the coalesced ownership (every access a full line) as FP64-assisted Shoup products (modarith.cuh
+// mul_f64_lazy: quotient from one DFMA with the prepared fl(w/q), six integer multiply-adds for a w - h q; ten instructions
+// where the 128-bit accumulate + Barrett form took twenty-five — the phase is bound by instruction issue, not by L2).
+// SPECIAL = true: key limb P, output (INTT + floor(P/2)) mod P to tmp [ct][2][n].  SPECIAL = false: the data limbs, with the
+// division by P fused into the epilogue ([SEAL] switch_key_inplace tail):
+//     out_c[j] = in_c[j] + P^-1 (acc_c[j] - ((t_last_c + half) mod P - half)) mod q_j
+struct RelinMacArgs {
+    const u64 *digits;              // [nq][k+1][k][n]
+    const u64 *rkq;                 // [digit][2][K][n] {w, fl(w/q)} pairs, natural order (pplp_relin_prepare)
+    u64 *tmp;                       // [nq][2][n]  special-limb results
+    const u64 *in; Layout in_lay;   // size-3 input (c0, c1 are the addends)
+    u64 *out; Layout out_lay;
+    const DevLevel *KL;             // key-level constants (drop-last-prime)
+    int k, K, n;
+    const DevMod *mods;
+    u64 half;
+};
+// KD = number of digits at compile time (0: run-time count): with a fixed trip count all 2 KD loads of a coefficient pair
+// are issued before the first product, and two pairs are in flight per thread — the phase is latency-bound otherwise.
+template <int LOGM, bool SPECIAL, int KD>
+__global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T) relin_mac_inverse_kernel(const RelinMacArgs a) {
+    using S = Ntt32Shape<LOGM>;
+    extern __shared__ __align__(16) u64 sm[];
+    const int tid = threadIdx.x, lane = tid & 31, wbase = (tid >> 5) << 10;
+    const int kk = a.k + 1;
+    const int comp = blockIdx.x & 1;
+    const int I = SPECIAL ? a.k : (blockIdx.x >> 1) % a.k, qi = SPECIAL ? (blockIdx.x >> 1) : (blockIdx.x >> 1) / a.k;
+    const int key_index = SPECIAL ? a.K - 1 : I;
+    const DevMod &md = a.mods[key_index];
+    const u64 q = md.m.q;
+    const u64 two_q = q << 1, four_q = q << 2;
+    const u64 *X = a.digits + ((size_t)qi * kk + I) * a.k * S::M;
+    const ulonglong2 *Kp = reinterpret_cast<const ulonglong2 *>(a.rkq) + ((size_t)comp * a.K + key_index) * S::M;
+    const size_t kstride = (size_t)2 * a.K * S::M;   // pairs between consecutive digits
+    auto fold = [&](u64 v) { v = v >= four_q ? v - four_q : v; return v >= two_q ? v - two_q : v; };   // [0, 8q) -> [0, 2q)
+    __syncwarp();
+    if constexpr (KD > 0) {
+        static_assert(KD <= 4, "four lazy products stay below 8q");
+        // software pipeline: the 3 KD loads of coefficient pair e + 1 are in flight while pair e is multiplied
+        ulonglong2 xv[2][KD], k0[2][KD], k1[2][KD];
+        auto fetch = [&](int e, ulonglong2 (&xd)[KD], ulonglong2 (&kd0)[KD], ulonglong2 (&kd1)[KD]) {
+            const int idx = wbase + e * 64 + 2 * lane;      // two adjacent coefficients per thread
+#pragma unroll
+            for (int J = 0; J < KD; ++J) {
+                xd[J] = __ldg(reinterpret_cast<const ulonglong2 *>(X + (size_t)J * S::M + idx));
+                kd0[J] = __ldg(Kp + (size_t)J * kstride + idx);
+                kd1[J] = __ldg(Kp + (size_t)J * kstride + idx + 1);
+            }
+        };
+        fetch(0, xv[0], k0[0], k1[0]);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+            if (e + 1 < 16) fetch(e + 1, xv[(e + 1) & 1], k0[(e + 1) & 1], k1[(e + 1) & 1]);
+            const int idx = wbase + e * 64 + 2 * lane;
+            u64 a0 = 0, a1 = 0;
+#pragma unroll
+            for (int J = 0; J < KD; ++J) {
+                a0 += mul_f64_lazy(xv[e & 1][J].x, k0[e & 1][J].x, k0[e & 1][J].y, q);
+                a1 += mul_f64_lazy(xv[e & 1][J].y, k1[e & 1][J].x, k1[e & 1][J].y, q);
+            }
+            sm[slot32(idx)] = fold(a0);
+            sm[slot32(idx + 1)] = fold(a1);
+        }
+    } else {
+#pragma unroll 2
+        for (int e = 0; e < 32; ++e) {
+            const int idx = wbase + e * 32 + lane;
+            u64 acc = 0;
+            for (int J = 0; J < a.k; ++J) {
+                const ulonglong2 w = __ldg(Kp + (size_t)J * kstride + idx);
+                acc += mul_f64_lazy(__ldg(X + (size_t)J * S::M + idx), w.x, w.y, q);
+                if ((J & 3) == 3) acc = fold(acc);
+            }
+            sm[slot32(idx)] = fold(acc);
+        }
+    }
+    __syncwarp();
+    u64 x[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) x[e] = sm[slot32(wbase + lane * 32 + e)];
+    const Ntt32Consts c = ntt32_consts(md, true);
+    ntt32_inverse<LOGM>(x, sm, tid, c);
+    if constexpr (SPECIAL) {
+        u64 *o = a.tmp + ((size_t)qi * 2 + comp) * S::M;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) o[e * S::T + tid] = add_mod(csub(x[e], q), a.half, q);
+    } else {
+        const DevLevel &KL = *a.KL;
+        const u64 half_mod = KL.half_last_mod[I];
+        const u64 inv_w = KL.inv_last[I].w;
+        const u64 inv_c = as_u(__ddiv_rn((double)inv_w, (double)q));      // fl(P^-1 / q): operand of the FP64-assisted product
+        const u64 *last = a.tmp + ((size_t)qi * 2 + comp) * S::M;
+        const u64 *src = a.in + qi * a.in_lay.sq + comp * a.in_lay.sp + I * a.in_lay.sl;
+        u64 *dst = a.out + qi * a.out_lay.sq + comp * a.out_lay.sp + I * a.out_lay.sl;
+        // out may alias in (in-place relinearisation), so the compiler will not move a load above an earlier store: fetch
+        // the operands of eight coefficients, then compute and store them — sixteen loads in flight instead of two
+#pragma unroll
+        for (int b = 0; b < 32; b += 8) {
+            u64 lv[8], sv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { lv[u] = __ldg(last + (b + u) * S::T + tid); sv[u] = src[(b + u) * S::T + tid]; }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                // (t_last + half) mod P is below P < 4 q_j (primes of one size class, checked on the host): two conditional subtractions reduce it
+                const u64 lm = csub(csub(lv[u], two_q), q);
+                const u64 corr = sub_mod(lm, half_mod, q);
+                const u64 v = csub(mul_f64_lazy(sub_mod(csub(x[b + u], q), corr, q), inv_w, inv_c, q), q);
+                dst[(b + u) * S::T + tid] = add_mod(sv[u], v, q);
+            }
+        }
+    }
+}
+template <int LOGM, int KD> static void run_relin_split_k(const RelinSplitArgs &a, const RelinMacArgs &m, int nq, cudaStream_t st) {
+    const int bytes = Ntt32Shape<LOGM>::SMEM_WORDS * 8;
+    static bool done[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!done[dev & 63]) {
+        PPLP_CUDA(cudaFuncSetAttribute(relin_digits_kernel<LOGM>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        PPLP_CUDA(cudaFuncSetAttribute(relin_mac_inverse_kernel<LOGM, true, KD>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        PPLP_CUDA(cudaFuncSetAttribute(relin_mac_inverse_kernel<LOGM, false, KD>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        done[dev & 63] = true;
+    }
+    relin_digits_kernel<LOGM><<<nq * (a.k + 1) * a.k, Ntt32Shape<LOGM>::T, bytes, st>>>(a);
+    relin_mac_inverse_kernel<LOGM, true, KD><<<nq * 2, Ntt32Shape<LOGM>::T, bytes, st>>>(m);
+    relin_mac_inverse_kernel<LOGM, false, KD><<<nq * a.k * 2, Ntt32Shape<LOGM>::T, bytes, st>>>(m);
+}
+template <int LOGM> static void run_relin_split(const RelinSplitArgs &a, const RelinMacArgs &m, int nq, cudaStream_t st) {
+    switch (a.k) {   // BFVDefault: k = 2 (N = 4096), 4 (N = 8192); 3 = the four-prime sweep case
+    case 2: run_relin_split_k<LOGM, 2>(a, m, nq, st); break;
+    case 3: run_relin_split_k<LOGM, 3>(a, m, nq, st); break;
+    case 4: run_relin_split_k<LOGM, 4>(a, m, nq, st); break;
+    default: run_relin_split_k<LOGM, 0>(a, m, nq, st);
+    }
+}
+
 // generic (N = 32768) pieces
 __global__ void relin_reduce_kernel(const DevMod *mods, const u64 *__restrict__ c2, Layout lay, u64 *__restrict__ dst, int k, int K, int n) {
     // dst [nq][k+1][k][n]: digit J reduced modulo key limb I
@@ -415,10 +595,16 @@ __global__ void __launch_bounds__(256) relin_moddown_kernel(const DevLevel *KLp,
     }
 }
 
+// ciphertexts per pass of the split pipeline: their NTT-form digits (k (k+1) rows each) should stay in the 126 MB L2
+static int relin_split_chunk() {
+    static const int v = [] { const char *e = getenv("PPLP_RELIN_CHUNK"); const int x = e ? atoi(e) : 0; return x > 0 ? x : 64; }();
+    return v;
+}
 size_t relin_tmp_words(const Engine &E, size_t level, int nq) {
     const size_t k = E.host.levels[level].q.size(), n = E.host.n;
     size_t w = (size_t)nq * 2 * (k + 1) * n;
     if (E.host.logn == 15) w += (size_t)nq * (k + 1) * k * n;
+    else if (relin_uses_split(E)) w += (size_t)std::min(nq, relin_split_chunk()) * (k + 1) * k * n;
     return w;
 }
 
@@ -447,6 +633,25 @@ void launch_relinearize(const Engine &E, size_t level, const u64 *in, Layout in_
     u64 *tmp = ws;
     RelinArgs a{in, in_lay, rk, rkq, tmp, k, K, n, E.d_mods, P >> 1};
     const int lazy = ntt_lazy_level(E.max_bits(E.qmap(0)), E.host.logn);
+    if (relin_uses_split(E)) {
+        // the forward transform takes any input below 4 q_I: limb J's residues are below q_J, so q_J < 4 q_I for all pairs
+        u64 qmin = ~0ull, qmax = 0;
+        for (int j = 0; j < K; ++j) { qmin = std::min(qmin, E.host.q[j]); qmax = std::max(qmax, E.host.q[j]); }
+        if (qmax / 4 >= qmin) throw std::logic_error("pplp: coefficient moduli of different size classes are not supported by the split relinearisation");
+        const int chunk = relin_split_chunk();
+        u64 *digits = tmp + (size_t)nq * 2 * n;      // tmp: special-limb rows [nq][2][n]
+        for (int done = 0; done < nq; done += chunk) {
+            const int c = std::min(chunk, nq - done);
+            const u64 *cin = in + (size_t)done * in_lay.sq;
+            RelinSplitArgs sa{cin, in_lay, digits, k, K, n, E.d_mods};
+            RelinMacArgs ma{digits, rkq, tmp + (size_t)done * 2 * n, cin, in_lay, out + (size_t)done * out_lay.sq, out_lay, E.d_levels, k, K, n, E.d_mods, P >> 1};
+            if (E.host.logn == 11) run_relin_split<11>(sa, ma, c, st);
+            else if (E.host.logn == 12) run_relin_split<12>(sa, ma, c, st);
+            else run_relin_split<13>(sa, ma, c, st);
+        }
+        PPLP_CUDA(cudaGetLastError());
+        return;
+    }
     switch (E.host.logn) {
     case 10: run_relin_limb<10>(lazy, a, nq, st); break;
     case 11: run_relin_limb<11>(lazy, a, nq, st); break;

@@ -106,6 +106,7 @@ size_t multiply_tmp_words(const Engine &E, size_t level, int nq, bool square);
 void launch_relinearize(const Engine &E, size_t level, const u64 *in, Layout in_lay, u64 *out, Layout out_lay, int nq, const u64 *rk, const u64 *rkq, u64 *ws,
                         cudaStream_t st);
 size_t relin_tmp_words(const Engine &E, size_t level, int nq);
+bool relin_uses_split(const Engine &E);
 void launch_shoup_quotients(const Engine &E, const u64 *w, u64 *quot, int nrows /* rows of n words, limb = row % K */, cudaStream_t st);
 
 // ---- bloom.cu ----

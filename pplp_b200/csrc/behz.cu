@@ -292,18 +292,16 @@ bool relin_uses_split(const Engine &E) {
 // quot[i] = floor(w[i] * 2^64 / q_limb): Shoup quotients of key words, computed once per key.  rows of n words, limb = row % K.
 // The prepared image holds {w, quotient} pairs (one 128-bit load per key coefficient).  Fused pipeline: in the
 // thread-interleaved order of its fine register layout — coefficient 16 t + r of a row sits at pair index r * (n/16) + t, so a
-// warp's load of "its r-th coefficient" is one coalesced 512-byte access.  Split pipeline: natural order (its products run
-// in the coalesced ownership), and the second word is the bit pattern of the double fl(w/q) — the FP64-assisted product
-// mul_f64_lazy takes its quotient estimate from one DFMA instead of a 64x64 high product.
+// warp's load of "its r-th coefficient" is one coalesced 512-byte access.  Split pipeline: the key words as doubles, natural
+// order, 8 bytes per coefficient (the first half of the buffer): its products run on the FP64 pipe and need no quotient.
 __global__ void shoup_quot_kernel(const DevMod *mods, const u64 *__restrict__ w, u64 *__restrict__ prepared, int K, int n, int split) {
     const int row = blockIdx.x;
     const u64 q = mods[row % K].m.q;
     const int T = n / 16;
-    ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(prepared) + (size_t)row * n;
     for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
         const u64 v = w[(size_t)row * n + i];
-        if (split) dst[i] = make_ulonglong2(v, as_u(__ddiv_rn((double)v, (double)q)));   // {w, fl(w/q)}: operand of mul_f64_lazy (q < 2^45)
-        else dst[(size_t)(i & 15) * T + (i >> 4)] = make_ulonglong2(v, (u64)((((unsigned __int128)v) << 64) / q));
+        if (split) prepared[(size_t)row * n + i] = as_u((double)v);     // exact: key words are below q < 2^45
+        else reinterpret_cast<ulonglong2 *>(prepared)[(size_t)row * n + (size_t)(i & 15) * T + (i >> 4)] = make_ulonglong2(v, (u64)((((unsigned __int128)v) << 64) / q));
     }
 }
 void launch_shoup_quotients(const Engine &E, const u64 *w, u64 *quot, int nrows, cudaStream_t st) {
@@ -377,8 +375,8 @@ __global__ void __launch_bounds__(NttShape<LOGM>::T) relin_limb_kernel(const Rel
 // ---- split pipeline (ntt32 schedule) -----------------------------------------------------------------------------------
 // Stage 1: one CTA per (ciphertext, digit J, key limb I): X = NTT_{q_I}(c2 limb J).  The residues of limb J are below q_J <
 // 4 q_I for primes of one size class (checked on the host), which is all the forward transform asks of its input, and the
-// transform is linear, so "reduce modulo q_I first" ([SEAL] switch_key_inplace) changes no output residue.  Output: some
-// representative below 32 q_I (the exact double shifted by 16 q), NTT order, to scratch [ct][I][J][n].
+// transform is linear, so "reduce modulo q_I first" ([SEAL] switch_key_inplace) changes no output residue.  Output: the
+// transform's exact signed doubles (|x| <= 14 q_I, some representative of the residue), NTT order, to scratch [ct][I][J][n].
 struct RelinSplitArgs {
     const u64 *c2; Layout lay;
     u64 *digits;                    // [nq][k+1][k][n]
@@ -400,21 +398,20 @@ __global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T
 #pragma unroll
     for (int e = 0; e < 32; ++e) x[e] = row[e * S::T + tid];
     ntt32_forward<LOGM>(x, sm, tid, c);
-    const double bias = __fma_rn(16.0, c.q, kTwo52);   // |x| <= 14 q
-#pragma unroll
-    for (int e = 0; e < 32; ++e) x[e] = f64_to_u64_biased(as_d(x[e]), bias);
-    ntt32_store_row(x, sm, tid, dst);
+    ntt32_store_row(x, sm, tid, dst);   // bit patterns of the exact doubles, |x| <= 14 q: stage 2 multiplies on the FP64 pipe
 }
 // Stage 2: one CTA per (ciphertext, key limb I, component c): acc = sum_J X_J (.) key[J][c][I], then the inverse transform.
-// The products run in the coalesced ownership (every access a full line) as FP64-assisted Shoup products (modarith.cuh
-// mul_f64_lazy: quotient from one DFMA with the prepared fl(w/q), six integer multiply-adds for a w - h q; ten instructions
-// where the 128-bit accumulate + Barrett form took twenty-five — the phase is bound by instruction issue, not by L2).
+// The products run in the coalesced ownership (every access a full line) on the FP64 pipe, exact integers in doubles:
+//     h = RN(x w), l = x w - h (one FMA), c = round(h fl(1/q)), t = (h - c q) + l  ==  x w - c q  exactly, |t| <= 0.57 q
+// — six instructions and no second key word (the quotient comes from h, not from a prepared fl(w/q)): the phase streams
+// 2 k rows per CTA out of L2 and the mixed integer form needed four times the instruction issue.  Keys are read from the
+// prepared image as doubles (8 bytes per coefficient, natural order).
 // SPECIAL = true: key limb P, output (INTT + floor(P/2)) mod P to tmp [ct][2][n].  SPECIAL = false: the data limbs, with the
 // division by P fused into the epilogue ([SEAL] switch_key_inplace tail):
 //     out_c[j] = in_c[j] + P^-1 (acc_c[j] - ((t_last_c + half) mod P - half)) mod q_j
 struct RelinMacArgs {
     const u64 *digits;              // [nq][k+1][k][n]
-    const u64 *rkq;                 // [digit][2][K][n] {w, fl(w/q)} pairs, natural order (pplp_relin_prepare)
+    const u64 *rkd;                 // [digit][2][K][n] key words as doubles (pplp_relin_prepare, split form)
     u64 *tmp;                       // [nq][2][n]  special-limb results
     const u64 *in; Layout in_lay;   // size-3 input (c0, c1 are the addends)
     u64 *out; Layout out_lay;
@@ -438,48 +435,50 @@ __global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T
     const u64 q = md.m.q;
     const u64 two_q = q << 1, four_q = q << 2;
     const u64 *X = a.digits + ((size_t)qi * kk + I) * a.k * S::M;
-    const ulonglong2 *Kp = reinterpret_cast<const ulonglong2 *>(a.rkq) + ((size_t)comp * a.K + key_index) * S::M;
-    const size_t kstride = (size_t)2 * a.K * S::M;   // pairs between consecutive digits
-    auto fold = [&](u64 v) { v = v >= four_q ? v - four_q : v; return v >= two_q ? v - two_q : v; };   // [0, 8q) -> [0, 2q)
+    const u64 *Kp = a.rkd + ((size_t)comp * a.K + key_index) * S::M;
+    const size_t kstride = (size_t)2 * a.K * S::M;   // words between consecutive digits
+    const double qd = (double)q, qinv = as_d(md.one_d);
+    auto mul_key = [&](u64 xbits, u64 wbits) {       // x w - c q exactly, |.| <= 0.57 q  (|x| <= 14 q < 2^48, w < q < 2^44)
+        const double xv = as_d(xbits), w = as_d(wbits);
+        const double h = __dmul_rn(xv, w);
+        const double l = __fma_rn(xv, w, -h);
+        const double cq = __dsub_rn(__fma_rn(h, qinv, kRound52), kRound52);
+        return __dadd_rn(__fma_rn(-cq, qd, h), l);
+    };
     __syncwarp();
     if constexpr (KD > 0) {
-        static_assert(KD <= 4, "four lazy products stay below 8q");
-        // software pipeline: the 3 KD loads of coefficient pair e + 1 are in flight while pair e is multiplied
-        ulonglong2 xv[2][KD], k0[2][KD], k1[2][KD];
-        auto fetch = [&](int e, ulonglong2 (&xd)[KD], ulonglong2 (&kd0)[KD], ulonglong2 (&kd1)[KD]) {
+        // software pipeline: the 2 KD loads of coefficient pair e + 1 are in flight while pair e is multiplied
+        ulonglong2 xv[2][KD], kv[2][KD];
+        auto fetch = [&](int e, ulonglong2 (&xd)[KD], ulonglong2 (&kd)[KD]) {
             const int idx = wbase + e * 64 + 2 * lane;      // two adjacent coefficients per thread
 #pragma unroll
             for (int J = 0; J < KD; ++J) {
                 xd[J] = __ldg(reinterpret_cast<const ulonglong2 *>(X + (size_t)J * S::M + idx));
-                kd0[J] = __ldg(Kp + (size_t)J * kstride + idx);
-                kd1[J] = __ldg(Kp + (size_t)J * kstride + idx + 1);
+                kd[J] = __ldg(reinterpret_cast<const ulonglong2 *>(Kp + (size_t)J * kstride + idx));
             }
         };
-        fetch(0, xv[0], k0[0], k1[0]);
+        fetch(0, xv[0], kv[0]);
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
-            if (e + 1 < 16) fetch(e + 1, xv[(e + 1) & 1], k0[(e + 1) & 1], k1[(e + 1) & 1]);
+            if (e + 1 < 16) fetch(e + 1, xv[(e + 1) & 1], kv[(e + 1) & 1]);
             const int idx = wbase + e * 64 + 2 * lane;
-            u64 a0 = 0, a1 = 0;
+            double a0 = 0.0, a1 = 0.0;
 #pragma unroll
             for (int J = 0; J < KD; ++J) {
-                a0 += mul_f64_lazy(xv[e & 1][J].x, k0[e & 1][J].x, k0[e & 1][J].y, q);
-                a1 += mul_f64_lazy(xv[e & 1][J].y, k1[e & 1][J].x, k1[e & 1][J].y, q);
+                a0 = __dadd_rn(a0, mul_key(xv[e & 1][J].x, kv[e & 1][J].x));
+                a1 = __dadd_rn(a1, mul_key(xv[e & 1][J].y, kv[e & 1][J].y));
             }
-            sm[slot32(idx)] = fold(a0);
-            sm[slot32(idx + 1)] = fold(a1);
+            // |sum| <= 0.57 k q: back to [-q/2, q/2] for the inverse transform (its inputs must stay within 2q)
+            sm[slot32(idx)] = as_u(reduce_sym_f64(a0, qinv, qd));
+            sm[slot32(idx + 1)] = as_u(reduce_sym_f64(a1, qinv, qd));
         }
     } else {
 #pragma unroll 2
         for (int e = 0; e < 32; ++e) {
             const int idx = wbase + e * 32 + lane;
-            u64 acc = 0;
-            for (int J = 0; J < a.k; ++J) {
-                const ulonglong2 w = __ldg(Kp + (size_t)J * kstride + idx);
-                acc += mul_f64_lazy(__ldg(X + (size_t)J * S::M + idx), w.x, w.y, q);
-                if ((J & 3) == 3) acc = fold(acc);
-            }
-            sm[slot32(idx)] = fold(acc);
+            double acc = 0.0;
+            for (int J = 0; J < a.k; ++J) acc = __dadd_rn(acc, mul_key(__ldg(X + (size_t)J * S::M + idx), __ldg(Kp + (size_t)J * kstride + idx)));
+            sm[slot32(idx)] = as_u(reduce_sym_f64(acc, qinv, qd));
         }
     }
     __syncwarp();
@@ -487,11 +486,11 @@ __global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T
 #pragma unroll
     for (int e = 0; e < 32; ++e) x[e] = sm[slot32(wbase + lane * 32 + e)];
     const Ntt32Consts c = ntt32_consts(md, true);
-    ntt32_inverse<LOGM>(x, sm, tid, c);
+    ntt32_inverse<LOGM, true>(x, sm, tid, c);
     if constexpr (SPECIAL) {
         u64 *o = a.tmp + ((size_t)qi * 2 + comp) * S::M;
 #pragma unroll
-        for (int e = 0; e < 32; ++e) o[e * S::T + tid] = add_mod(csub(x[e], q), a.half, q);
+        for (int e = 0; e < 32; ++e) o[e * S::T + tid] = csub(csub(x[e] + a.half, two_q), q);
     } else {
         const DevLevel &KL = *a.KL;
         const u64 half_mod = KL.half_last_mod[I];
@@ -509,11 +508,11 @@ __global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T
             for (int u = 0; u < 8; ++u) { lv[u] = __ldg(last + (b + u) * S::T + tid); sv[u] = src[(b + u) * S::T + tid]; }
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                // (t_last + half) mod P is below P < 4 q_j (primes of one size class, checked on the host): two conditional subtractions reduce it
-                const u64 lm = csub(csub(lv[u], two_q), q);
-                const u64 corr = sub_mod(lm, half_mod, q);
-                const u64 v = csub(mul_f64_lazy(sub_mod(csub(x[b + u], q), corr, q), inv_w, inv_c, q), q);
-                dst[(b + u) * S::T + tid] = add_mod(sv[u], v, q);
+                // lazily: x in (0, 2q), (t_last + half) mod P below P < 4 q_j (primes of one size class, checked on the host), so
+                // d = x + half_mod + 4q - last is a positive representative below 7q of acc - ((t_last + half) mod P - half)
+                const u64 d = x[b + u] + half_mod + four_q - lv[u];
+                const u64 r = sv[u] + mul_f64_lazy(d, inv_w, inv_c, q);          // below 3q
+                dst[(b + u) * S::T + tid] = csub(csub(r, two_q), q);
             }
         }
     }
@@ -595,9 +594,10 @@ __global__ void __launch_bounds__(256) relin_moddown_kernel(const DevLevel *KLp,
     }
 }
 
-// ciphertexts per pass of the split pipeline: their NTT-form digits (k (k+1) rows each) should stay in the 126 MB L2
+// ciphertexts per pass of the split pipeline (bounds the digit scratch: k (k+1) rows each).  Measured: larger is faster (fewer
+// launch tails) — keeping the digits L2-resident with chunks of 32..128 cost 10-25 % (profiles/r02 notes)
 static int relin_split_chunk() {
-    static const int v = [] { const char *e = getenv("PPLP_RELIN_CHUNK"); const int x = e ? atoi(e) : 0; return x > 0 ? x : 64; }();
+    static const int v = [] { const char *e = getenv("PPLP_RELIN_CHUNK"); const int x = e ? atoi(e) : 0; return x > 0 ? x : 512; }();
     return v;
 }
 size_t relin_tmp_words(const Engine &E, size_t level, int nq) {

@@ -193,14 +193,17 @@ __device__ __forceinline__ u64 ntt32_canon(u64 v, const Ntt32Consts &c, u64 q) {
 
 // ---- inverse ----------------------------------------------------------------------------------------------------------
 // x[e] = coefficient 32*tid + e as u64 below 2q.  On return x[e] = output e*T + tid as u64 in (0, 2q), scaled by N^-1.
-template <int LOGM>
+// FROM_F64: x already holds bit patterns of doubles, |x| <= 2q (a caller that produced its operand on the FP64 pipe).
+template <int LOGM, bool FROM_F64 = false>
 __device__ __forceinline__ void ntt32_inverse(u64 (&x)[32], u64 *sm, int tid, const Ntt32Consts &c) {
     using S = Ntt32Shape<LOGM>;
     const int lane = tid & 31, warp = tid >> 5;
     u64 *twA = sm + S::TW_OFF;
     if (tid < 31) *reinterpret_cast<ulonglong2 *>(twA + 2 * tid) = __ldg(reinterpret_cast<const ulonglong2 *>(c.tw + 1 + tid));
+    if constexpr (!FROM_F64) {
 #pragma unroll
-    for (int e = 0; e < 32; ++e) x[e] = as_u(u64_to_f64(x[e]));
+        for (int e = 0; e < 32; ++e) x[e] = as_u(u64_to_f64(x[e]));
+    }
     // pass C': stages LOGM-1 .. LOGM-5
     tw_pipeline<31, PPLP_NTT32_LOOK>(
         [&](auto k) { return c.fine + (size_t)inv_row(decltype(k)::value) * S::T + tid; },

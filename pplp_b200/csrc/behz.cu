@@ -259,20 +259,38 @@ void launch_multiply(const Engine &E, size_t level, const u64 *a, const u64 *b, 
     u64 *bq = square ? aq : ab + wb, *bb = square ? ab : bq + wq;
     u64 *dq = (square ? ab + wb : bb + wb), *db = dq + (size_t)nq * 3 * k * n;
     const Layout ql{(size_t)2 * k * n, (size_t)k * n, (size_t)n}, bl{(size_t)2 * nb * n, (size_t)nb * n, (size_t)n};
+    // The q-base chain (transforms on the FP64 pipe) and the Bsk-base chain (61-bit primes: integer pipe) are independent
+    // between the base extension and the final conversion: they run on two streams so that the SMs hold CTAs of both.
+    static const bool two_streams = [] { const char *e = getenv("PPLP_BEHZ_STREAMS"); return !(e && e[0] == '1' && e[1] == 0); }();
+    cudaStream_t sq = st;
     auto extend = [&](const u64 *src, u64 *xq, u64 *xb) {
         behz_dispatch(k, nb, [&](auto kc, auto nc) {
             const int gx = (n / behz_ilp(decltype(kc)::value) + 255) / 256;
             behz_extend_kernel<decltype(kc)::value, decltype(nc)::value><<<dim3(nq * 2, gx), 256, 0, st>>>(L, src, in_lay, xb, xq);
         });
-        launch_ntt(E, xq, ql, nq, 2, qm, false, st);
-        launch_ntt(E, xb, bl, nq, 2, bm, false, st);
     };
     extend(a, aq, ab);
     if (!square) extend(b, bq, bb);
-    tensor_kernel<<<dim3(nq * k, (n + 1023) / 1024), 256, 0, st>>>(E.d_mods, qm, aq, bq, dq, n);
+    if (two_streams) {
+        E.ensure_aux();
+        sq = E.aux_stream;
+        PPLP_CUDA(cudaEventRecord(E.ev_fork, st));
+        PPLP_CUDA(cudaStreamWaitEvent(sq, E.ev_fork, 0));
+    }
+    // Bsk chain on the caller's stream
+    launch_ntt(E, ab, bl, nq, 2, bm, false, st);
+    if (!square) launch_ntt(E, bb, bl, nq, 2, bm, false, st);
     tensor_kernel<<<dim3(nq * nb, (n + 1023) / 1024), 256, 0, st>>>(E.d_mods, bm, ab, bb, db, n);
-    launch_ntt(E, dq, Layout{(size_t)3 * k * n, (size_t)k * n, (size_t)n}, nq, 3, qm, true, st);
     launch_ntt(E, db, Layout{(size_t)3 * nb * n, (size_t)nb * n, (size_t)n}, nq, 3, bm, true, st);
+    // q chain
+    launch_ntt(E, aq, ql, nq, 2, qm, false, sq);
+    if (!square) launch_ntt(E, bq, ql, nq, 2, qm, false, sq);
+    tensor_kernel<<<dim3(nq * k, (n + 1023) / 1024), 256, 0, sq>>>(E.d_mods, qm, aq, bq, dq, n);
+    launch_ntt(E, dq, Layout{(size_t)3 * k * n, (size_t)k * n, (size_t)n}, nq, 3, qm, true, sq);
+    if (two_streams) {
+        PPLP_CUDA(cudaEventRecord(E.ev_join, sq));
+        PPLP_CUDA(cudaStreamWaitEvent(st, E.ev_join, 0));
+    }
     behz_dispatch(k, nb, [&](auto kc, auto nc) {
         const int gx = (n / behz_ilp(decltype(kc)::value) + 255) / 256;
         behz_floor_sk_kernel<decltype(kc)::value, decltype(nc)::value><<<dim3(nq * 3, gx), 256, 0, st>>>(L, dq, db, out, out_lay);
@@ -597,7 +615,7 @@ __global__ void __launch_bounds__(256) relin_moddown_kernel(const DevLevel *KLp,
 // ciphertexts per pass of the split pipeline (bounds the digit scratch: k (k+1) rows each).  Measured: larger is faster (fewer
 // launch tails) — keeping the digits L2-resident with chunks of 32..128 cost 10-25 % (profiles/r02 notes)
 static int relin_split_chunk() {
-    static const int v = [] { const char *e = getenv("PPLP_RELIN_CHUNK"); const int x = e ? atoi(e) : 0; return x > 0 ? x : 512; }();
+    static const int v = [] { const char *e = getenv("PPLP_RELIN_CHUNK"); const int x = e ? atoi(e) : 0; return x > 0 ? x : 2048; }();
     return v;
 }
 size_t relin_tmp_words(const Engine &E, size_t level, int nq) {

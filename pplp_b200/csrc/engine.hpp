@@ -27,6 +27,16 @@ struct Engine {
     std::vector<DevMod> h_mods;
     uint32_t *d_slot_index = nullptr;   // BatchEncoder permutation (when batching)
     int *d_sticky = nullptr;            // device-side failure flag of asynchronous entries; reported and cleared by pplp_sync
+    // fork/join helpers: a second stream on which launch_multiply runs the q-base chain (FP64 pipe) next to the Bsk-base
+    // chain (integer pipe) of the caller's stream.  Created lazily on the engine's device.
+    mutable cudaStream_t aux_stream = nullptr;
+    mutable cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    void ensure_aux() const {
+        if (aux_stream) return;
+        PPLP_CUDA(cudaStreamCreateWithFlags(&aux_stream, cudaStreamNonBlocking));
+        PPLP_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        PPLP_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    }
 
     void require_device() const { if (device < 0) throw std::logic_error("pplp: context was created without a CUDA device"); }
     template <class T> T *upload(const T *src, size_t count) {
@@ -37,7 +47,10 @@ struct Engine {
         return d;
     }
     void upload_tables(int dev);
-    ~Engine() { for (void *p : owned) cudaFree(p); }
+    ~Engine() {
+        for (void *p : owned) cudaFree(p);
+        if (aux_stream) { cudaStreamDestroy(aux_stream); cudaEventDestroy(ev_fork); cudaEventDestroy(ev_join); }
+    }
 
     RowMap qmap(size_t level) const { RowMap m; m.nlimbs = (int)host.levels[level].q.size(); for (int j = 0; j < m.nlimbs; ++j) m.mod_id[j] = j; return m; }
     RowMap bskmap(size_t level) const { RowMap m; const DevLevel &D = host.levels[level].dev; m.nlimbs = D.nBsk; for (int j = 0; j < m.nlimbs; ++j) m.mod_id[j] = D.bsk_mod_id[j]; return m; }

@@ -168,10 +168,27 @@ __device__ __forceinline__ u64 barrett64(u64 x, const Mod &m) {
 
 // 128-bit accumulate helper for lazy inner products (key switching, base conversion).
 struct U128 { u64 lo, hi; };
+// acc += a * b over 128 bits: four 32x32 partial products folded into the accumulator words along carry chains
+// (12 instructions; the two-product form a*b, umulhi(a,b) plus a compare-based carry took 19)
 __device__ __forceinline__ void mac128(U128 &acc, u64 a, u64 b) {
-    u64 lo = a * b, hi = __umul64hi(a, b);
-    acc.lo += lo;
-    acc.hi += hi + (acc.lo < lo);
+    u32 c0 = (u32)acc.lo, c1 = (u32)(acc.lo >> 32), c2 = (u32)acc.hi, c3 = (u32)(acc.hi >> 32);
+    const u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
+    asm("mad.lo.cc.u32 %0, %4, %6, %0;\n\t"
+        "madc.hi.cc.u32 %1, %4, %6, %1;\n\t"
+        "addc.cc.u32 %2, %2, 0;\n\t"
+        "addc.u32 %3, %3, 0;\n\t"
+        "mad.lo.cc.u32 %1, %4, %7, %1;\n\t"
+        "madc.hi.cc.u32 %2, %4, %7, %2;\n\t"
+        "addc.u32 %3, %3, 0;\n\t"
+        "mad.lo.cc.u32 %1, %5, %6, %1;\n\t"
+        "madc.hi.cc.u32 %2, %5, %6, %2;\n\t"
+        "addc.u32 %3, %3, 0;\n\t"
+        "mad.lo.cc.u32 %2, %5, %7, %2;\n\t"
+        "madc.hi.u32 %3, %5, %7, %3;\n\t"
+        : "+r"(c0), "+r"(c1), "+r"(c2), "+r"(c3)
+        : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+    acc.lo = ((u64)c1 << 32) | c0;
+    acc.hi = ((u64)c3 << 32) | c2;
 }
 
 __device__ __forceinline__ u32 brev(u32 x, int bits) { return __brev(x) >> (32 - bits); }
@@ -187,6 +204,11 @@ __device__ __forceinline__ ulonglong2 ld_stream_coherent(const u64 *p) {
     ulonglong2 v;
     asm volatile("ld.global.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
     return v;
+}
+// Ask the L2 for `bytes` (a multiple of 16) at p ahead of use: one bulk prefetch (UBLKPF.L2) issued by one thread.  Used by
+// the row-per-CTA transforms to pull the row a later CTA will read out of HBM while the current rows are in the butterflies.
+__device__ __forceinline__ void prefetch_l2_bulk(const void *p, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void stg_stream(u64 *p, ulonglong2 v) {
     asm volatile("st.global.L1::no_allocate.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(v.x), "l"(v.y) : "memory");

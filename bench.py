@@ -243,6 +243,76 @@ def parity_gate(engine, ctx):
     return osk, opk
 
 
+def measure_exchange(torch, dist, ctx, engine, cin, out, xb, yb, rr, ss, Q, k, world, rank, dev, barrier):
+    """What leaves a GPU after the evaluation.  (1) default: 8 bytes per query (the decrypted blinded distance / verdict a
+    co-located client stage produces) — gathered to rank 0, negligible.  (2) result CIPHERTEXTS to rank 0 (a server that must
+    hand them to one network front end): chunks of >= 1 GiB per rank, gather of chunk i on NCCL's stream while chunk i+1 is
+    evaluated, timed as compute only / gather only / overlapped; rank 0's ingest against NVLink (900 GB/s nominal per
+    direction, 770 GB/s measured peer copy)."""
+    from pplp_b200.shard import max_over_ranks
+    per_ct = 2 * k * N * 8
+    cq = max(1, min(Q // 2, (1 << 30) // per_ct))                  # queries per chunk: 1 GiB of result ciphertexts per rank
+    nchunks = max(2, min(4, Q // cq))
+    src = [c[:, :, :cq, :].contiguous() for c in cin]              # one contiguous chunk of inputs, re-evaluated for every chunk
+    outs = [ctx.empty(*ctx.ct_shape(cq, 2, None, engine.LAYOUT_LIMB_MAJOR)) for _ in range(2)]      # double-buffered contiguous chunk results
+    recv = [[torch.empty_like(outs[0]) for _ in range(world)] for _ in range(2)] if rank == 0 else [None, None]
+    sl = lambda t, i: t[i * cq:(i + 1) * cq]
+
+    def compute(i):
+        ctx.circuit_a(src[0], src[1], src[2], sl(xb, i), sl(yb, i), sl(rr, i), sl(ss, i), out=outs[i & 1], layout=engine.LAYOUT_LIMB_MAJOR)
+
+    def gather_async(i):
+        return dist.gather(outs[i & 1], recv[i & 1] if rank == 0 else None, dst=0, async_op=True)
+
+    def run(do_compute, do_gather):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        pending = [None, None]
+        for i in range(nchunks):
+            if pending[i & 1] is not None:
+                pending[i & 1].wait()            # the buffer pair of chunk i-2 is free again
+            if do_compute:
+                compute(i)
+            if do_gather:
+                pending[i & 1] = gather_async(i)
+        for w in pending:
+            if w is not None:
+                w.wait()
+        b.record()
+        barrier()
+        return max_over_ranks(a.elapsed_time(b), dev) * 1e-3
+
+    run(True, True)                                                  # warm-up: communicators, allocations
+    t_c, t_g, t_o = run(True, False), run(False, True), run(True, True)
+    ok = True
+    if rank == 0:
+        ok = bool(torch.equal(recv[(nchunks - 1) & 1][0], outs[(nchunks - 1) & 1]))
+    # default exchange: 8 bytes per query
+    small = torch.arange(Q, dtype=torch.int64, device=dev)
+    parts = [torch.empty_like(small) for _ in range(world)] if rank == 0 else None
+    dist.gather(small, parts, dst=0)
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    dist.gather(small, parts, dst=0)
+    b.record()
+    barrier()
+    t_small = max_over_ranks(a.elapsed_time(b), dev) * 1e-3
+    if rank != 0:
+        return None
+    ingest = (world - 1) * nchunks * cq * per_ct
+    gbps = ingest / t_g / 1e9
+    return {"default_exchange": {"what": "8-byte blinded distance (or verdict) per query to rank 0", "queries_per_rank": Q, "seconds": t_small,
+                                 "queries_per_s": world * Q / t_small},
+            "ciphertext_gather": {"chunk_GiB_per_rank": cq * per_ct / 2**30, "chunks": nchunks, "ciphertexts": world * nchunks * cq,
+                                  "compute_only_s": t_c, "gather_only_s": t_g, "overlapped_s": t_o, "binds": "gather" if t_g > t_c else "compute",
+                                  "overlap_efficiency": max(t_c, t_g) / t_o, "rank0_ingest_GBps": gbps, "result_ciphertexts_per_s": world * nchunks * cq / t_o,
+                                  "nvlink_nominal_GBps": 900.0, "frac_of_nominal": gbps / 900.0, "nvlink_measured_peer_copy_GBps": 770.0, "frac": gbps / 770.0,
+                                  "ok": ok},
+            "note": "NCCL gather to rank 0 on its own stream, chunk i in flight while chunk i+1 is evaluated; the hot-path figures leave outputs on the producing GPU"}
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -327,8 +397,10 @@ def run_b200(args):
     # ---- end to end: host ciphertexts (page-locked) through the C-ABI host entry ----
     Qe = args.e2e_queries
     per_ct = 2 * k * N
-    hc = [torch.empty((Qe, 2, k, N), dtype=torch.int64).pin_memory() for _ in range(3)]
-    hout = torch.empty((Qe, 2, k, N), dtype=torch.int64).pin_memory()
+    from pplp_b200 import numa
+    numa_rep = numa.bind_to_gpu_node(local)     # pages of cudaHostAlloc land on the calling thread's node: bind first
+    hc = [numa.pinned_empty(ctx.L, (Qe, 2, k, N), torch.int64, write_combined=True) for _ in range(3)]   # H2D sources
+    hout = numa.pinned_empty(ctx.L, (Qe, 2, k, N), torch.int64)
     for t_, c in zip(hc, cin):   # fill from the device slabs (values < q_j per limb); layout SEAL on the host
         t_.copy_(c[:, :, :Qe, :].permute(2, 1, 0, 3))
     hpar = [x[:Qe].cpu().numpy().view(np.uint64).copy() for x in (xb, yb, rr, ss)]
@@ -349,26 +421,23 @@ def run_b200(args):
     ref_slice = out[:, :, :Qe, :].permute(2, 1, 0, 3).cpu()
     if not torch.equal(ref_slice, hout):
         raise SystemExit("bench: host-buffer path and resident path disagree")
+    # the host link under the same conditions: all ranks copying at once, both directions, same buffers (the ceiling of e2e)
+    link = {}
+    sA, sB = torch.cuda.Stream(), torch.cuda.Stream()
+    dtmp = [ctx.empty(Qe, 2, k, N) for _ in range(2)]
+    for name, ops in (("h2d", [(dtmp[0], hc[0], sA)]), ("d2h", [(hout, dtmp[1], sB)]), ("bidir", [(dtmp[0], hc[0], sA), (hout, dtmp[1], sB)])):
+        barrier()
+        tl0 = time.perf_counter()
+        for _ in range(4):
+            for dst_, src_, st_ in ops:
+                with torch.cuda.stream(st_):
+                    dst_.copy_(src_, non_blocking=True)
+        torch.cuda.synchronize()
+        link[name] = 4 * Qe * per_ct * 8 / max_over_ranks(time.perf_counter() - tl0, dev) / 1e9 * world
+    del dtmp
 
-    # ---- the one exchange of the design: final gather of result ciphertexts to rank 0 (outside the hot-path figure) ----
-    gather = None
-    if world > 1:
-        gq = 128
-        local_rows = out[:, :, :gq, :].permute(2, 1, 0, 3).contiguous()   # [gq][2][k][N] per rank
-        gather_rows(local_rows, gq * world)
-        barrier()
-        ga, gb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ga.record()
-        gathered = gather_rows(local_rows, gq * world)
-        gb.record()
-        barrier()
-        gms = max_over_ranks(ga.elapsed_time(gb), dev)
-        if rank == 0:
-            ingest = (world - 1) * gq * per_ct * 8
-            gather = {"result_ciphertexts_per_s": gq * world / (gms * 1e-3), "rank0_ingest_GBps": ingest / (gms * 1e-3) / 1e9,
-                      "nvlink_peak_GBps": 770.0, "frac": ingest / (gms * 1e-3) / 1e9 / 770.0, "ciphertexts": gq * world,
-                      "ok": bool(torch.equal(gathered[:gq], local_rows)),
-                      "note": "NCCL gather to rank 0, timed separately; compute figures leave outputs on the producing GPU"}
+    # ---- the one exchange of the design: results to rank 0, outside the hot-path figure ----
+    gather = measure_exchange(torch, dist, ctx, engine, cin, out, xb, yb, rr, ss, Q, k, world, rank, dev, barrier) if world > 1 else None
 
     extras = {}
     if not args.no_extras and rank == 0:
@@ -408,7 +477,11 @@ def run_b200(args):
                      "pipes_source": "from profile (profiles/traffic.json: sm__pipe_fp64_cycles_active / sm__pipe_fma+alu, ncu --set full)", "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_query * Q,
                      "avg_launch_ms": avg_kernel_ms, "note": "event pairs bracket each pplp_circuit_a call (scalar-prepare kernel + main kernel)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 3 * Qe * per_ct * 8 + 4 * Qe * 8, "d2h_bytes_per_step": Qe * per_ct * 8,
-                "queries_per_step": Qe, "steps": e2e_steps, "api": "pplp_circuit_a_host (pinned host ciphertexts, SEAL layout)"},
+                "queries_per_step": Qe, "steps": e2e_steps, "api": "pplp_circuit_a_host (pinned host ciphertexts, SEAL layout)",
+                "host_link_GBps_all_ranks": link, "link_ceiling_queries_per_s": link["bidir"] * 1e9 / (3 * per_ct * 8),
+                "numa": numa_rep,
+                "note": "pinned buffers from cudaHostAlloc after binding the rank to its GPU's NUMA node (write-combined H2D sources); "
+                        "host_link = the same buffers copied by every rank at once, so e2e / link_ceiling says how much of the host fabric the entry point uses"},
         "gpu_launches": 2 * args.steps,
         "clocks": clocks,
         "sustained": {"value": world * Q * sus_n / (sus_ms_max * 1e-3), "unit": UNIT, "launches": sus_n, "seconds": sus_ms_max * 1e-3,

@@ -82,6 +82,8 @@ int pplp_d2d(pplp_ctx *ctx, void *d_dst, const void *d_src, size_t bytes, void *
  * since the last call — today only "PRNG stream reserve exhausted" from pplp_encrypt / pplp_proximity_batch. */
 int pplp_sync(pplp_ctx *ctx, void *stream);
 int pplp_host_alloc(size_t bytes, void **out); /* page-locked */
+/* page-locked, placed on the calling thread's NUMA node; write_combined != 0 for buffers the host only writes (H2D sources) */
+int pplp_host_alloc_ex(size_t bytes, int write_combined, void **out);
 int pplp_host_free(void *ptr);
 
 /* ---- keys ---------------------------------------------------------------------------------------------------------

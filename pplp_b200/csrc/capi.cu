@@ -372,6 +372,14 @@ int pplp_host_alloc(size_t bytes, void **out) {
     return PPLP_OK;
     PPLP_CATCH
 }
+int pplp_host_alloc_ex(size_t bytes, int write_combined, void **out) {
+    PPLP_TRY
+    // cudaHostAlloc places the pages on the NUMA node of the calling thread: bind the thread to the GPU's node first
+    // (pplp_b200/numa.py).  Write-combined memory is for buffers the host only writes and the GPU reads (H2D sources).
+    PPLP_CUDA(cudaHostAlloc(out, bytes ? bytes : 8, cudaHostAllocPortable | (write_combined ? cudaHostAllocWriteCombined : 0)));
+    return PPLP_OK;
+    PPLP_CATCH
+}
 int pplp_host_free(void *ptr) {
     PPLP_TRY
     PPLP_CUDA(cudaFreeHost(ptr));

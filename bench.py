@@ -425,7 +425,8 @@ def run_b200(args):
     link = {}
     sA, sB = torch.cuda.Stream(), torch.cuda.Stream()
     dtmp = [ctx.empty(Qe, 2, k, N) for _ in range(2)]
-    for name, ops in (("h2d", [(dtmp[0], hc[0], sA)]), ("d2h", [(hout, dtmp[1], sB)]), ("bidir", [(dtmp[0], hc[0], sA), (hout, dtmp[1], sB)])):
+    mix = [(dtmp[0], hc[0], sA), (dtmp[0], hc[1], sA), (dtmp[0], hc[2], sA), (hout, dtmp[1], sB)]     # the entry point's own 3 : 1 traffic mix
+    for name, ops in (("h2d", [(dtmp[0], hc[0], sA)]), ("d2h", [(hout, dtmp[1], sB)]), ("bidir", [(dtmp[0], hc[0], sA), (hout, dtmp[1], sB)]), ("mix_3in_1out", mix)):
         barrier()
         tl0 = time.perf_counter()
         for _ in range(4):
@@ -433,7 +434,11 @@ def run_b200(args):
                 with torch.cuda.stream(st_):
                     dst_.copy_(src_, non_blocking=True)
         torch.cuda.synchronize()
-        link[name] = 4 * Qe * per_ct * 8 / max_over_ranks(time.perf_counter() - tl0, dev) / 1e9 * world
+        dtl = max_over_ranks(time.perf_counter() - tl0, dev)
+        link[name] = 4 * Qe * per_ct * 8 / dtl / 1e9 * world          # GB/s per direction (the larger one for the mix: x3)
+        if name == "mix_3in_1out":
+            link[name] *= 3
+            link_ceiling = 4 * Qe * world / dtl                          # queries/s if the entry point did nothing but these copies
     del dtmp
 
     # ---- the one exchange of the design: results to rank 0, outside the hot-path figure ----
@@ -478,7 +483,7 @@ def run_b200(args):
                      "avg_launch_ms": avg_kernel_ms, "note": "event pairs bracket each pplp_circuit_a call (scalar-prepare kernel + main kernel)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 3 * Qe * per_ct * 8 + 4 * Qe * 8, "d2h_bytes_per_step": Qe * per_ct * 8,
                 "queries_per_step": Qe, "steps": e2e_steps, "api": "pplp_circuit_a_host (pinned host ciphertexts, SEAL layout)",
-                "host_link_GBps_all_ranks": link, "link_ceiling_queries_per_s": link["bidir"] * 1e9 / (3 * per_ct * 8),
+                "host_link_GBps_all_ranks": link, "link_ceiling_queries_per_s": link_ceiling,
                 "numa": numa_rep,
                 "note": "pinned buffers from cudaHostAlloc after binding the rank to its GPU's NUMA node (write-combined H2D sources); "
                         "host_link = the same buffers copied by every rank at once, so e2e / link_ceiling says how much of the host fabric the entry point uses"},

@@ -229,6 +229,10 @@ int pplp_proximity_batch_host(pplp_ctx *ctx, const uint64_t *d_pk, const uint64_
                               const uint8_t *d_tables, uint64_t m_bits, const uint32_t *d_salts, uint32_t k, uint64_t *h_blind, uint8_t *h_verdict,
                               int *h_flags, size_t chunk);
 
+/* sample_poly_uniform of a Blake2xbPRNG(seed) over the moduli of `level`: d_out [k][N].  What Ciphertext::load needs to expand
+ * the second polynomial of a seeded (half-size) stream — SEAL ciphertext.cpp load_members / expand_seed; the reference's
+ * own streams (src/client.cc:119, public-key encryptions) are never seeded, a SEAL peer's symmetric ones are.  Synchronises. */
+int pplp_sample_uniform(pplp_ctx *ctx, size_t level, const uint64_t seed[8], uint64_t *d_out, void *stream);
 /* BLAKE2Xb PRNG stream of SEAL's default generator (tests; d_out gets nstreams*nrefill*4096 bytes) */
 int pplp_prng_stream(pplp_ctx *ctx, const uint64_t *d_seeds, size_t nstreams, size_t nrefill, uint64_t *d_out, void *stream);
 

@@ -290,10 +290,16 @@ inline std::string slurp_object(std::istream &stream) {
     std::memcpy(&total, h + 8, 8);
     if ((unsigned char)h[0] != 0x5E || (unsigned char)h[1] != 0xA1 || h[2] != 0x10 || total < 16 || total > (std::uint64_t(1) << 40))
         throw std::logic_error("loaded SEALHeader is invalid");
-    std::string obj((std::size_t)total, '\0');
-    std::memcpy(&obj[0], h, 16);
-    stream.read(&obj[16], (std::streamsize)(total - 16));
-    if (!stream) throw std::runtime_error("I/O error");
+    // The size field comes from an untrusted peer (the reference's server loads straight from the socket): never allocate more
+    // than has actually arrived — the object is read in 16 MiB pieces, so a lying header costs one piece, not a terabyte.
+    std::string obj(h, 16);
+    constexpr std::uint64_t kPiece = std::uint64_t(16) << 20;
+    while (obj.size() < total) {
+        const std::size_t want = (std::size_t)std::min<std::uint64_t>(kPiece, total - obj.size()), at = obj.size();
+        obj.resize(at + want);
+        stream.read(&obj[at], (std::streamsize)want);
+        if (!stream) throw std::runtime_error("I/O error");
+    }
     return obj;
 }
 }  // namespace detail
@@ -702,20 +708,40 @@ private:
         if (level < 0 || (key_only && !key_level_ok) || n_ != core->n || k_ != core->limbs((std::size_t)level) || size_ > 6 || (size_ != 0 && size_ < 2))
             throw std::logic_error("ciphertext data is invalid");
         level_ = (std::size_t)level;
+        // [SEAL] valcheck is_metadata_valid_for: a BFV ciphertext is in coefficient form (keys: NTT form), scale 1, correction factor 1
+        if (ntt_ != key_level_ok || scale_ != 1.0 || correction_ != 1) throw std::logic_error("ciphertext data is invalid");
         std::vector<std::uint64_t> host;
+        bool seeded = false;
         detail::read_object(m, [&](detail::Source &a) {
             const std::uint64_t count = a.pod<std::uint64_t>();
-            if (count != (std::uint64_t)size_ * k_ * n_) throw std::logic_error("ciphertext data is invalid");   // seeded (half-size) form is not on the path
+            // [SEAL] ciphertext.cpp load_members: a DynArray of exactly ONE polynomial's words is the seeded form of a size-2
+            // symmetric encryption (Serializable<Ciphertext>): c0 only, followed by the PRNG that regenerates c1
+            seeded = size_ == 2 && count == (std::uint64_t)k_ * n_;
+            if (!seeded && count != (std::uint64_t)size_ * k_ * n_) throw std::logic_error("ciphertext data is invalid");
             host.resize((std::size_t)count);
             a.raw(host.data(), host.size() * 8);
         });
-        for (std::size_t p = 0; p < size_; ++p)
+        std::uint64_t seed[8] = {0};
+        if (seeded) {   // nested UniformRandomGeneratorInfo object: u8 prng_type (1 = blake2xb, 2 = shake256), 64-byte seed
+            detail::read_object(m, [&](detail::Source &g) {
+                if (g.pod<std::uint8_t>() != 1) throw std::logic_error("prng_type is not supported (this library carries Blake2xbPRNG only)");
+                g.raw(seed, 64);
+            });
+        }
+        const std::size_t loaded_polys = seeded ? 1 : size_;
+        for (std::size_t p = 0; p < loaded_polys; ++p)
             for (std::size_t j = 0; j < k_; ++j) {
                 const std::uint64_t qj = core->prime(level_, j);
                 const std::uint64_t *row = host.data() + (p * k_ + j) * n_;
                 for (std::size_t i = 0; i < n_; ++i) if (row[i] >= qj) throw std::logic_error("ciphertext data is invalid");
             }
-        words_.upload(core, host.data(), host.size());
+        if (seeded) {   // expand_seed: c1 = sample_poly_uniform(PRNG(seed)) at this ciphertext's level, on the device
+            host.resize(size_ * k_ * n_, 0);
+            words_.upload(core, host.data(), host.size());
+            detail::check(pplp_sample_uniform(core->h, level_, seed, words_.data() + k_ * n_, nullptr));
+        } else {
+            words_.upload(core, host.data(), host.size());
+        }
     }
     void shape(const detail::CorePtr &core, std::size_t level, std::size_t size) {
         level_ = level; size_ = size; n_ = core->n; k_ = core->limbs(level); id_ = core->id(level);

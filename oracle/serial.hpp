@@ -145,7 +145,20 @@ inline void load_ciphertext_members(ByteReader &x, const Context &ctx, Ciphertex
     const Level *L = ctx.find(c.id);
     if (!L || c.n != ctx.parms.n || c.k != L->q.size() || c.size > 6) throw std::logic_error("ciphertext data is invalid");
     load_dynarray(x, c.d, c.size * c.k * c.n);
-    if (c.d.size() != c.size * c.k * c.n) throw std::logic_error("ciphertext data is invalid");  // seeded form not on the path
+    if (c.size == 2 && c.d.size() == c.k * c.n) {
+        // [SEAL] ciphertext.cpp load_members, seeded form (Serializable<Ciphertext> of a symmetric encryption): only c0 was saved,
+        // followed by a UniformRandomGeneratorInfo object {u8 prng_type (1 = blake2xb), 64-byte seed}; expand_seed regenerates
+        // c1 = sample_poly_uniform(PRNG(seed)) over this level's moduli.
+        Seed seed{};
+        load_object(x, [&](ByteReader &g) {
+            if (g.get_u8() != 1) throw std::logic_error("prng_type is not supported");
+            g.raw(seed.data(), 64);
+        });
+        c.d.resize(2 * c.k * c.n, 0);
+        Prng prng(seed);
+        sample_poly_uniform(prng, L->q, c.n, c.poly(1));
+    }
+    if (c.d.size() != c.size * c.k * c.n) throw std::logic_error("ciphertext data is invalid");
     validate_ciphertext(ctx, c, allow_key_level);
 }
 inline Ciphertext load_ciphertext(const Context &ctx, const u8 *buf, size_t len) {

@@ -889,6 +889,23 @@ int pplp_proximity_batch_host(pplp_ctx *ctx, const uint64_t *d_pk, const uint64_
     PPLP_CATCH
 }
 
+int pplp_sample_uniform(pplp_ctx *ctx, size_t level, const uint64_t seed[8], uint64_t *d_out, void *stream) {
+    PPLP_TRY
+    Engine &E = dev_engine(ctx);
+    const size_t k = check_level(E, level);
+    cudaStream_t st = S(stream);
+    Scratch ws(uniform_tmp_words(E, (int)k) * 8, st), sd(64, st), flag(sizeof(int), st);
+    PPLP_CUDA(cudaMemcpyAsync(sd.p, seed, 64, cudaMemcpyHostToDevice, st));
+    PPLP_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), st));
+    launch_sample_uniform(E, sd.as<u64>(), (int)k, d_out, ws.as<u64>(), flag.as<int>(), st);
+    int bad = 0;
+    PPLP_CUDA(cudaMemcpyAsync(&bad, flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PPLP_CUDA(cudaStreamSynchronize(st));
+    if (bad) throw std::logic_error("pplp: PRNG stream reserve exhausted while expanding a seed");
+    return PPLP_OK;
+    PPLP_CATCH
+}
+
 int pplp_prng_stream(pplp_ctx *ctx, const uint64_t *d_seeds, size_t nstreams, size_t nrefill, uint64_t *d_out, void *stream) {
     PPLP_TRY
     Engine &E = dev_engine(ctx);

@@ -826,6 +826,26 @@ void launch_symmetric_zero(const Engine &E, const u64 *d_seed, const u64 *d_sk, 
     PPLP_CUDA(cudaGetLastError());
 }
 
+// [SEAL] sample_poly_uniform with a Blake2xb PRNG of `d_seed` over the first k primes: what Ciphertext::load runs to expand the
+// second polynomial of a seeded (half-size) ciphertext stream (ciphertext.cpp expand_seed).  ws: uniform_tmp_words(k).
+size_t uniform_tmp_words(const Engine &E, int k) {
+    const size_t n = E.host.n, cap = (size_t)uniform_reject_cap(k, (int)n);
+    return ((k * n + cap) * 8 / kRefillBytes + 2) * (kRefillBytes / 8) + cap + 16;
+}
+void launch_sample_uniform(const Engine &E, const u64 *d_seed, int k, u64 *d_out, u64 *ws, int *errflag, cudaStream_t st) {
+    E.require_device();
+    const int n = (int)E.host.n;
+    const int cap = uniform_reject_cap(k, n);
+    const int nct = (int)(((size_t)k * n + cap) * 8 / kRefillBytes + 2);
+    u64 *cts = ws;
+    int *rej = reinterpret_cast<int *>(cts + (size_t)nct * (kRefillBytes / 8));
+    run_prng_stream(d_seed, 1, nct, cts, st);
+    PPLP_CUDA(cudaMemsetAsync(rej, 0, sizeof(int), st));
+    uniform_bulk_kernel<<<dim3((n + 255) / 256, k), 256, 0, st>>>(E.d_mods, cts, d_out, k, n, cap, rej, rej + 1);
+    uniform_fixup_kernel<<<1, 32, 0, st>>>(E.d_mods, cts, (size_t)nct * (kRefillBytes / 8), d_out, k, n, cap, rej, rej + 1, errflag);
+    PPLP_CUDA(cudaGetLastError());
+}
+
 // raw PRNG stream for tests and for host-driven samplers: out [nrefill*4096 bytes]
 void launch_prng_stream(const Engine &E, const u64 *d_seed, int nstreams, int nrefill, u64 *out, cudaStream_t st) {
     E.require_device();

@@ -106,6 +106,9 @@ size_t decrypt_tmp_words(const Engine &E, size_t level, int nq, int size);
 void launch_expand_small(const Engine &E, const signed char *d_small /* [n] */, u64 *out /* [K][n] */, cudaStream_t st);
 void launch_pk_combine(const Engine &E, const u64 *a, const u64 *s, const u64 *e_ntt, u64 *c0, int digit /* -1: none */, u64 factor, cudaStream_t st);
 void launch_prng_stream(const Engine &E, const u64 *d_seed, int nstreams, int nrefill, u64 *out, cudaStream_t st);
+// uniform residues below the first k primes from the Blake2xb PRNG of d_seed (SEAL's sample_poly_uniform, rejections replayed in order)
+size_t uniform_tmp_words(const Engine &E, int k);
+void launch_sample_uniform(const Engine &E, const u64 *d_seed, int k, u64 *d_out, u64 *ws, int *errflag, cudaStream_t st);
 // key generation with the samplers on the device (seed: 8 words in device memory); ws: keygen_tmp_words()
 size_t keygen_tmp_words(const Engine &E);
 void launch_keygen_secret(const Engine &E, const u64 *d_seed, u64 *d_sk, u64 *ws, int *errflag, cudaStream_t st);

@@ -71,6 +71,29 @@ def test_shim_artifacts_equal_oracle_bytes(shim, oracle, logn):
             p2 = subprocess.run([shim, "--reload", os.path.join(d2, "in.bin"), os.path.join(d2, "out.bin"), str(logn)], capture_output=True, text=True, timeout=300)
             assert p2.returncode == 0, p2.stderr
             assert open(os.path.join(d2, "out.bin"), "rb").read() == art["c2.bin"]
+    # seeded form (SEAL's Serializable<Ciphertext> of a symmetric encryption): c0 only + the PRNG that regenerates c1.  Built by
+    # hand from c3's stream; the shim expands the seed on the device, the oracle on the host, and both must agree byte for byte.
+    full = art["c3.bin"]
+    kn8 = 8 * octx.k * n
+    seed = seed8(4242)
+    info = bytes([0x5E, 0xA1, 0x10, 4, 1, 0, 0, 0]) + (16 + 65).to_bytes(8, "little") + b"\x01" + seed.tobytes()
+    arr = bytes([0x5E, 0xA1, 0x10, 4, 1, 0, 0, 0]) + (16 + 8 + kn8).to_bytes(8, "little") + (octx.k * n).to_bytes(8, "little") + full[16 + 73 + 24: 16 + 73 + 24 + kn8]
+    body = full[16: 16 + 73] + arr + info
+    blob = full[:8] + (16 + len(body)).to_bytes(8, "little") + body
+    expect, lvl = octx.load_ct(blob)
+    assert lvl == octx.first and (expect[0] == cts[2][0]).all() and not (expect[1] == cts[2][1]).all()
+    with tempfile.TemporaryDirectory() as d3:
+        open(os.path.join(d3, "in.bin"), "wb").write(blob)
+        p3 = subprocess.run([shim, "--reload", os.path.join(d3, "in.bin"), os.path.join(d3, "out.bin"), str(logn)], capture_output=True, text=True, timeout=300)
+        assert p3.returncode == 0, p3.stderr
+        assert open(os.path.join(d3, "out.bin"), "rb").read() == octx.save_ct(expect)
+        # invalid metadata is refused as SEAL's is_metadata_valid_for does: NTT flag on a BFV ciphertext, scale != 1
+        for off, val in ((16 + 32, b"\x01"), (16 + 65, (2.0).hex().encode()[:0] + __import__("struct").pack("<d", 2.0))):
+            bad = bytearray(full)
+            bad[off: off + len(val)] = val
+            open(os.path.join(d3, "bad.bin"), "wb").write(bytes(bad))
+            p4 = subprocess.run([shim, "--reload", os.path.join(d3, "bad.bin"), os.path.join(d3, "o2.bin"), str(logn)], capture_output=True, text=True, timeout=300)
+            assert p4.returncode != 0 and "ciphertext data is invalid" in p4.stderr
     res = octx.circuit_a(cts[0], cts[1], cts[2], xb, yb, r, s)
     assert art["result.bin"] == octx.save_ct(res)
     dec = octx.decrypt(osk, res)

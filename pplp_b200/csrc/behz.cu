@@ -38,7 +38,8 @@ __host__ __device__ constexpr int behz_ilp(int K) { return (K >= 1 && K <= 4) ? 
 #ifndef BEHZ_MINB
 #define BEHZ_MINB 3   // CTAs per SM the base-conversion kernels are compiled for (85 registers): the constants are re-read from L1 rather than hoisted
 #endif
-template <int K, int NBSK>
+// SH60: every auxiliary prime has 61 bits and the conversion sums stay below 2^124 (host-checked): barrett_sh60 applies.
+template <int K, int NBSK, bool SH60>
 __global__ void __launch_bounds__(256, BEHZ_MINB) behz_extend_kernel(const DevLevel *Lp, const u64 *__restrict__ in, Layout lay, u64 *__restrict__ out, u64 *__restrict__ xq) {
     const DevLevel &L = *Lp;
     constexpr int kBehzIlp = behz_ilp(K);
@@ -73,6 +74,7 @@ __global__ void __launch_bounds__(256, BEHZ_MINB) behz_extend_kernel(const DevLe
 #pragma unroll 1
         for (int b = 0; b < nb; ++b) {
             const Mod mp = L.bsk[b];
+            const u64 mu = SH60 ? mu_sh60(mp) : 0;
             const ShoupW qm = L.q_mod_bsk[b], im = L.inv_mtilde_mod_bsk[b];
             U128 acc[kBehzIlp];
 #pragma unroll
@@ -86,7 +88,7 @@ __global__ void __launch_bounds__(256, BEHZ_MINB) behz_extend_kernel(const DevLe
             }
 #pragma unroll
             for (int c = 0; c < kBehzIlp; ++c) {
-                const u64 conv = barrett128(acc[c].lo, acc[c].hi, mp);
+                const u64 conv = SH60 ? barrett_sh60(acc[c].lo, acc[c].hi, mp.q, mu) : barrett128(acc[c].lo, acc[c].hi, mp);
                 const u64 rc = r[c] >= mt_half ? r[c] + (mp.q - L.m_tilde) : r[c];   // centred representative of r
                 const u64 v = add_mod(mul_shoup(rc, qm, mp.q), conv, mp.q);
                 dst[(size_t)b * n + i0 + c] = mul_shoup(v, im, mp.q);
@@ -97,35 +99,53 @@ __global__ void __launch_bounds__(256, BEHZ_MINB) behz_extend_kernel(const DevLe
 
 // ---- tensor product (NTT form) ------------------------------------------------------------------------------------
 // x, y: [nq][2][nl][n]; d: [nq][3][nl][n].  grid.x = query*nl + limb.
+// MODE 0: any modulus (128-bit product + general Barrett).  MODE 1: 61-bit moduli (products below 2^122: barrett_sh60).
+// MODE 2: moduli of at most 44 bits with canonical operands: FP64-assisted product (mul_f64_var, 13 instructions instead of 60).
+template <int MODE> __device__ __forceinline__ u64 tensor_mul(u64 a, u64 b, const Mod &mq, u64 aux) {
+    if constexpr (MODE == 1) { U128 p{0, 0}; mac128(p, a, b); return barrett_sh60(p.lo, p.hi, mq.q, aux); }
+    else if constexpr (MODE == 2) return csub(mul_f64_var(a, b, aux, mq.q), mq.q);
+    else return mul_mod(a, b, mq);
+}
+template <int MODE>
 __global__ void __launch_bounds__(256) tensor_kernel(const DevMod *mods, RowMap map, const u64 *__restrict__ x, const u64 *__restrict__ y, u64 *__restrict__ d, int n) {
     const int nl = map.nlimbs;
     const int qi = blockIdx.x / nl, j = blockIdx.x % nl;
-    const Mod mq = mods[map.mod_id[j]].m;
+    const DevMod &md = mods[map.mod_id[j]];
+    const Mod mq = md.m;
+    const u64 aux = MODE == 1 ? mu_sh60(mq) : (MODE == 2 ? md.one_d : 0);
     const u64 *x0 = x + (((size_t)qi * 2 + 0) * nl + j) * n, *x1 = x + (((size_t)qi * 2 + 1) * nl + j) * n;
     const u64 *y0 = y + (((size_t)qi * 2 + 0) * nl + j) * n, *y1 = y + (((size_t)qi * 2 + 1) * nl + j) * n;
     u64 *d0 = d + (((size_t)qi * 3 + 0) * nl + j) * n, *d1 = d0 + (size_t)nl * n, *d2 = d1 + (size_t)nl * n;
     if (x == y) {   // square: the cross term is 2 x0 x1 — the same residue as x0 x1 + x1 x0 with one product and two loads less
         for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
             const u64 a0 = x0[i], a1 = x1[i];
-            const u64 m = mul_mod(a0, a1, mq);
-            d0[i] = mul_mod(a0, a0, mq);
+            const u64 m = tensor_mul<MODE>(a0, a1, mq, aux);
+            d0[i] = tensor_mul<MODE>(a0, a0, mq, aux);
             d1[i] = add_mod(m, m, mq.q);
-            d2[i] = mul_mod(a1, a1, mq);
+            d2[i] = tensor_mul<MODE>(a1, a1, mq, aux);
         }
         return;
     }
     for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
         const u64 a0 = x0[i], a1 = x1[i], b0 = y0[i], b1 = y1[i];
-        d0[i] = mul_mod(a0, b0, mq);
-        d1[i] = add_mod(mul_mod(a0, b1, mq), mul_mod(a1, b0, mq), mq.q);
-        d2[i] = mul_mod(a1, b1, mq);
+        d0[i] = tensor_mul<MODE>(a0, b0, mq, aux);
+        d1[i] = add_mod(tensor_mul<MODE>(a0, b1, mq, aux), tensor_mul<MODE>(a1, b0, mq, aux), mq.q);
+        d2[i] = tensor_mul<MODE>(a1, b1, mq, aux);
     }
+}
+static void launch_tensor(const Engine &E, const RowMap &map, const u64 *x, const u64 *y, u64 *d, int nq, int n, cudaStream_t st) {
+    const dim3 grid(nq * map.nlimbs, (n + 1023) / 1024);
+    int lo = 64, hi = 0;
+    for (int j = 0; j < map.nlimbs; ++j) { const int b = hm::bitlen(E.host.tables[map.mod_id[j]].q); lo = std::min(lo, b); hi = std::max(hi, b); }
+    if (lo == 61 && hi == 61) tensor_kernel<1><<<grid, 256, 0, st>>>(E.d_mods, map, x, y, d, n);
+    else if (hi <= 44) tensor_kernel<2><<<grid, 256, 0, st>>>(E.d_mods, map, x, y, d, n);
+    else tensor_kernel<0><<<grid, 256, 0, st>>>(E.d_mods, map, x, y, d, n);
 }
 
 // ---- BEHZ: *t, floor, Shenoy–Kumaresan ------------------------------------------------------------------------------
 // dq: [nq][3][k][n], db: [nq][3][nb][n] (coefficient form, canonical) -> out (layout `lay`, 3 polys).  grid.x = query*3 + poly.
 // Same compile-time-size scheme as behz_extend_kernel (K, NBSK = 0: run-time sizes, vectors in local memory).
-template <int K, int NBSK>
+template <int K, int NBSK, bool SH60>
 __global__ void __launch_bounds__(256, BEHZ_MINB) behz_floor_sk_kernel(const DevLevel *Lp, const u64 *__restrict__ dq, const u64 *__restrict__ db, u64 *__restrict__ out, Layout lay) {
     const DevLevel &L = *Lp;
     constexpr int kBehzIlp = behz_ilp(K);
@@ -161,6 +181,7 @@ __global__ void __launch_bounds__(256, BEHZ_MINB) behz_floor_sk_kernel(const Dev
 #pragma unroll 1
         for (int b = 0; b < nb; ++b) {
             const Mod mp = L.bsk[b];
+            const u64 mu = SH60 ? mu_sh60(mp) : 0;
             const ShoupW ft = L.floor_t[b];
             U128 cv[kBehzIlp];
 #pragma unroll
@@ -175,7 +196,7 @@ __global__ void __launch_bounds__(256, BEHZ_MINB) behz_floor_sk_kernel(const Dev
             u64 fl[kBehzIlp];   // b in B: z_b = fl_b (B/b)^-1;  b = m_sk: fl_b itself   (constants merged, see DevLevel::floor_t)
 #pragma unroll
             for (int c = 0; c < kBehzIlp; ++c) {
-                const u64 conv = barrett128(cv[c].lo, cv[c].hi, mp);
+                const u64 conv = SH60 ? barrett_sh60(cv[c].lo, cv[c].hi, mp.q, mu) : barrett128(cv[c].lo, cv[c].hi, mp);
                 fl[c] = sub_mod(mul_shoup(sb[(size_t)b * n + i0 + c], ft, mp.q), conv, mp.q);
             }
             if (b == nB) {
@@ -199,7 +220,8 @@ __global__ void __launch_bounds__(256, BEHZ_MINB) behz_floor_sk_kernel(const Dev
         bool neg[kBehzIlp];
 #pragma unroll
         for (int c = 0; c < kBehzIlp; ++c) {
-            const u64 conv_msk = barrett128(am[c].lo, am[c].hi, mmsk);
+            // the m_sk sum has |B| terms of two 61-bit factors: below 2^124 for |B| <= 4
+            const u64 conv_msk = (SH60 && NBSK >= 2 && NBSK <= 5) ? barrett_sh60(am[c].lo, am[c].hi, msk, mu_sh60(mmsk)) : barrett128(am[c].lo, am[c].hi, mmsk);
             const u64 alpha = mul_shoup(sub_mod(conv_msk, fl_msk[c], msk), L.inv_B_mod_msk, msk);
             neg[c] = alpha > msk_half;
             a_abs[c] = neg[c] ? msk - alpha : alpha;
@@ -254,6 +276,17 @@ void launch_multiply(const Engine &E, size_t level, const u64 *a, const u64 *b, 
     const DevLevel *L = E.d_levels + level;
     const bool square = (a == b);
     const RowMap qm = E.qmap(level), bm = E.bskmap(level);
+    // barrett_sh60 applies when every auxiliary prime has exactly 61 bits (SEAL's choice) and the k-term conversion sums of
+    // (bits(q_j) + 61)-bit products stay below 2^124
+    bool sh60 = true;
+    for (int b2 = 0; b2 < nb; ++b2) sh60 = sh60 && hm::bitlen(HL.dev.bsk[b2].q) == 61;
+    {
+        int maxq = 0;
+        for (int j = 0; j < k; ++j) maxq = std::max(maxq, hm::bitlen(HL.q[j]));
+        int lg = 0;
+        while ((1 << lg) < k) ++lg;
+        sh60 = sh60 && (maxq + 61 + lg <= 124);
+    }
     const size_t wq = (size_t)nq * 2 * k * n, wb = (size_t)nq * 2 * nb * n;
     u64 *aq = ws, *ab = aq + wq;
     u64 *bq = square ? aq : ab + wb, *bb = square ? ab : bq + wq;
@@ -266,7 +299,8 @@ void launch_multiply(const Engine &E, size_t level, const u64 *a, const u64 *b, 
     auto extend = [&](const u64 *src, u64 *xq, u64 *xb) {
         behz_dispatch(k, nb, [&](auto kc, auto nc) {
             const int gx = (n / behz_ilp(decltype(kc)::value) + 255) / 256;
-            behz_extend_kernel<decltype(kc)::value, decltype(nc)::value><<<dim3(nq * 2, gx), 256, 0, st>>>(L, src, in_lay, xb, xq);
+            if (sh60) behz_extend_kernel<decltype(kc)::value, decltype(nc)::value, true><<<dim3(nq * 2, gx), 256, 0, st>>>(L, src, in_lay, xb, xq);
+            else behz_extend_kernel<decltype(kc)::value, decltype(nc)::value, false><<<dim3(nq * 2, gx), 256, 0, st>>>(L, src, in_lay, xb, xq);
         });
     };
     extend(a, aq, ab);
@@ -280,12 +314,12 @@ void launch_multiply(const Engine &E, size_t level, const u64 *a, const u64 *b, 
     // Bsk chain on the caller's stream
     launch_ntt(E, ab, bl, nq, 2, bm, false, st);
     if (!square) launch_ntt(E, bb, bl, nq, 2, bm, false, st);
-    tensor_kernel<<<dim3(nq * nb, (n + 1023) / 1024), 256, 0, st>>>(E.d_mods, bm, ab, bb, db, n);
+    launch_tensor(E, bm, ab, bb, db, nq, n, st);
     launch_ntt(E, db, Layout{(size_t)3 * nb * n, (size_t)nb * n, (size_t)n}, nq, 3, bm, true, st);
     // q chain
     launch_ntt(E, aq, ql, nq, 2, qm, false, sq);
     if (!square) launch_ntt(E, bq, ql, nq, 2, qm, false, sq);
-    tensor_kernel<<<dim3(nq * k, (n + 1023) / 1024), 256, 0, sq>>>(E.d_mods, qm, aq, bq, dq, n);
+    launch_tensor(E, qm, aq, bq, dq, nq, n, sq);
     launch_ntt(E, dq, Layout{(size_t)3 * k * n, (size_t)k * n, (size_t)n}, nq, 3, qm, true, sq);
     if (two_streams) {
         PPLP_CUDA(cudaEventRecord(E.ev_join, sq));
@@ -293,7 +327,8 @@ void launch_multiply(const Engine &E, size_t level, const u64 *a, const u64 *b, 
     }
     behz_dispatch(k, nb, [&](auto kc, auto nc) {
         const int gx = (n / behz_ilp(decltype(kc)::value) + 255) / 256;
-        behz_floor_sk_kernel<decltype(kc)::value, decltype(nc)::value><<<dim3(nq * 3, gx), 256, 0, st>>>(L, dq, db, out, out_lay);
+        if (sh60) behz_floor_sk_kernel<decltype(kc)::value, decltype(nc)::value, true><<<dim3(nq * 3, gx), 256, 0, st>>>(L, dq, db, out, out_lay);
+        else behz_floor_sk_kernel<decltype(kc)::value, decltype(nc)::value, false><<<dim3(nq * 3, gx), 256, 0, st>>>(L, dq, db, out, out_lay);
     });
     PPLP_CUDA(cudaGetLastError());
 }

@@ -158,6 +158,16 @@ __device__ __forceinline__ u64 barrett128(u64 lo, u64 hi, const Mod &m) {
     u64 r = lo - qhat * m.q;
     return csub(r, m.q);
 }
+// Barrett step with the modulus' own shift for 61-bit moduli (2^60 <= q < 2^61: every BEHZ auxiliary prime) and x = (hi:lo)
+// below 2^124:  x1 = x >> 60 fits 64 bits, mu = floor(2^124 / q) = floor(2^128 / q) >> 4 is below 2^64, and
+// qhat = umulhi(x1, mu) misses floor(x / q) by at most 2  =>  r = x - qhat q in [0, 3q).  One high product and one low product
+// where the general 128-bit form above needs five; q < 2^61 leaves room for 3q.
+__device__ __forceinline__ u64 mu_sh60(const Mod &m) { return (m.r_hi << 60) | (m.r_lo >> 4); }
+__device__ __forceinline__ u64 barrett_sh60(u64 lo, u64 hi, u64 q, u64 mu) {
+    const u64 x1 = (lo >> 60) | (hi << 4);
+    const u64 r = lo - __umul64hi(x1, mu) * q;
+    return csub(csub(r, q << 1), q);
+}
 __device__ __forceinline__ u64 mul_mod(u64 a, u64 b, const Mod &m) { return barrett128(a * b, __umul64hi(a, b), m); }
 // 64-bit value -> canonical residue (for cross-modulus reductions x mod q_j with x < 2^64).
 __device__ __forceinline__ u64 barrett64(u64 x, const Mod &m) {

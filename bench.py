@@ -445,8 +445,20 @@ def run_b200(args):
     gather = measure_exchange(torch, dist, ctx, engine, cin, out, xb, yb, rr, ss, Q, k, world, rank, dev, barrier) if world > 1 else None
 
     extras = {}
+    n16384 = None
+    if not args.no_extras and N == 8192:
+        # BASELINE.json configs[2] (N=16384, sharded over the ranks): every rank evaluates its shard, aggregate = sum over ranks
+        # over the slowest rank's device time — the same rule as the headline value
+        del cin, out
+        torch.cuda.empty_cache()
+        try:
+            n16384 = extra_n16384(engine, torch, world, dev, barrier, rank)
+        except Exception as e:
+            n16384 = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
     if not args.no_extras and rank == 0:
         extras = run_extras(engine, ctx, torch, osk, opk)
+    if n16384 is not None:
+        extras["n16384"] = n16384
     if gather:
         extras["gather"] = gather
 
@@ -596,7 +608,7 @@ def run_extras(engine, ctx, torch, osk, opk):
                                "what": "pplp_circuit_a_cross: client ciphertexts read once per launch, 16*k*N bytes written per pair"}
     except Exception as e:
         ex["config5_cross"] = {"error": str(e)[:200]}
-    for name, fn in (("circuit_b", extra_circuit_b), ("bloom_build", extra_bloom_build), ("n16384", extra_n16384), ("config4_sweep", extra_config4)):
+    for name, fn in (("circuit_b", extra_circuit_b), ("bloom_build", extra_bloom_build), ("config4_sweep", extra_config4)):
         try:
             ex[name] = fn(engine, torch)
         except Exception as e:
@@ -703,8 +715,10 @@ def extra_bloom_build(engine, torch):
     return res
 
 
-def extra_n16384(engine, torch):
-    """BASELINE.json configs[2]: the same Circuit A workload at N=16384 (k=8), device-resident, so that every N-GPU line carries it."""
+def extra_n16384(engine, torch, world, dev, barrier, rank):
+    """BASELINE.json configs[2]: the same Circuit A workload at N=16384 (k=8), query-sharded over all ranks (every rank runs it;
+    value = queries of all ranks / slowest rank's device time), plus this rank's NTT figures at that degree."""
+    from pplp_b200.shard import max_over_ranks
     n = 16384
     ctx = engine.Context(n, t=T, device=torch.cuda.current_device())
     k, Q = ctx.k, 1024
@@ -714,18 +728,32 @@ def extra_n16384(engine, torch):
             c[j].random_(0, ctx.q[j])
     out = ctx.empty(*ctx.ct_shape(Q, 2, None, engine.LAYOUT_LIMB_MAJOR))
     par = [torch.randint(1, 1 << 27, (Q,), device=out.device) for _ in range(2)] + [torch.randint(1, 1 << 32, (Q,), device=out.device) for _ in range(2)]
-    sec = _event_time(torch, lambda: ctx.circuit_a(cin[0], cin[1], cin[2], par[0], par[1], par[2], par[3], out=out, layout=engine.LAYOUT_LIMB_MAJOR), 10, warm=3)
+    run = lambda: ctx.circuit_a(cin[0], cin[1], cin[2], par[0], par[1], par[2], par[3], out=out, layout=engine.LAYOUT_LIMB_MAJOR)
+    for _ in range(3):
+        run()
+    reps = 20
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        run()
+    b.record()
+    barrier()
+    sec = max_over_ranks(a.elapsed_time(b), dev) * 1e-3 / reps
     peak, _ = peaks()
     gbs = 64 * k * n * Q / sec / 1e9
-    res = {"value": Q / sec, "unit": UNIT, "workload": f"circuitA_bfv_n{n}_k{k}_t2^56_batched", "queries_per_step": Q, "achieved_GBps": gbs, "frac_of_hbm_peak": gbs / peak}
+    res = {"value": world * Q / sec, "unit": UNIT, "n_gpus": world, "workload": f"circuitA_bfv_n{n}_k{k}_t2^56_batched", "queries_per_gpu_per_step": Q,
+           "achieved_GBps_per_gpu": gbs, "frac_of_hbm_peak": gbs / peak}
     del cin, out
-    rows = 2048
-    data = ctx.empty(k, 1, rows, n)
-    for j in range(k):
-        data[j].random_(0, ctx.q[j])
-    for inv in (False, True):
-        sec = _event_time(torch, lambda: ctx.ntt_(data, inverse=inv, layout=engine.LAYOUT_LIMB_MAJOR), 5)
-        res["intt_gbs" if inv else "ntt_gbs"] = 16 * n * rows * k / sec / 1e9
+    if rank == 0:
+        rows = 2048
+        data = ctx.empty(k, 1, rows, n)
+        for j in range(k):
+            data[j].random_(0, ctx.q[j])
+        for inv in (False, True):
+            s_ = _event_time(torch, lambda: ctx.ntt_(data, inverse=inv, layout=engine.LAYOUT_LIMB_MAJOR), 5)
+            res["intt_gbs" if inv else "ntt_gbs"] = 16 * n * rows * k / s_ / 1e9
+    torch.cuda.empty_cache()
     return res
 
 

@@ -64,6 +64,12 @@ void orc_blake2b_general(u8 *out, size_t outlen, const u8 *in, size_t inlen, con
 }
 void orc_blake2xb(u8 *out, size_t outlen, const u8 *in, size_t inlen, const u8 *key, size_t keylen) { blake2xb(out, outlen, in, inlen, key, keylen); }
 void orc_prng_bytes(const u64 *seed, size_t nbytes, u8 *out) { Seed s; std::copy(seed, seed + 8, s.begin()); Prng p(s); p.generate(nbytes, out); }
+// sample_poly_uniform of a fresh Blake2xbPRNG(seed) over explicit moduli q[0..k): out [k][n]  (expand_seed of a seeded ciphertext)
+void orc_sample_uniform(const u64 *seed, const u64 *q, size_t k, size_t n, u64 *out) {
+    Seed s; std::copy(seed, seed + 8, s.begin()); Prng p(s);
+    std::vector<u64> moduli(q, q + k);
+    sample_poly_uniform(p, moduli, n, out);
+}
 // samplers on a fresh PRNG (kind 0 ternary, 1 cbd, 2 uniform), key-level moduli; out [K][n]
 int orc_sample(void *c, int kind, const u64 *seed, u64 *out) {
     ORC_TRY

@@ -190,3 +190,101 @@ def test_circuit_a_cross_equals_circuit_a_on_tiled_inputs(eng, layout_name, n):
     ref = eng.to_np(ctx.circuit_a(tiled[0], tiled[1], tiled[2], rep(xb), rep(yb), rep(r), rep(s), layout=layout))
     assert got.shape == ref.shape and (got == ref).all()
     assert flags.cpu().tolist() == [1 if t == 3 else 0 for t in range(npts)]
+
+
+def test_relinearize_batch_is_layout_chunk_and_batch_invariant(eng):
+    """The split relinearisation (digits -> products + inverse with the mod-down fused) at a batch larger than its internal
+    chunk (PPLP_RELIN_CHUNK, default 2048) and in both layouts: every ciphertext's result equals the result of relinearising
+    it alone, in place equals out of place, and limb-major equals SEAL order — ciphertexts are independent."""
+    import torch
+    n = 4096                                      # k = 2: 12 KiB... 128 KiB per size-3 ciphertext; 2304 of them cross the chunk boundary
+    ctx = eng.Context(n, t=T56, device=0)
+    k = ctx.k
+    sk, pk = ctx.keygen(seed8(3))
+    rk = ctx.relin_keygen(np.stack([seed8(40 + i) for i in range(k)]), sk)
+    quot = ctx.relin_prepare(rk)
+    nq = 2304
+    ct3 = ctx.empty(nq, 3, k, n)
+    for j in range(k):
+        ct3[:, :, j].random_(0, ctx.q[j])
+    full = ctx.relinearize(ct3, rk, quot)
+    for i in (0, 1, 2047, 2048, nq - 1):          # alone == inside the batch
+        assert torch.equal(ctx.relinearize(ct3[i:i + 1].contiguous(), rk, quot)[0], full[i]), i
+    lm = ct3.permute(2, 1, 0, 3).contiguous()
+    full_lm = ctx.relinearize(lm, rk, quot, layout=eng.LAYOUT_LIMB_MAJOR)
+    assert torch.equal(full_lm.permute(2, 1, 0, 3), full)
+    assert torch.equal(ctx.relinearize(ct3, rk, None), full)      # key image rebuilt on the fly (d_rk_quot = NULL)
+
+
+def test_relinearize_preserves_the_decryption(eng):
+    """Size-independent meaning: Dec_{(1, s, s^2)}(ct3) == Dec_{(1, s)}(relin(ct3)) for real products at N=8192 (BFVDefault,
+    the split pipeline) and N=16384 (the fused kernel)."""
+    for n, nq in ((8192, 24), (16384, 4)):
+        ctx = eng.Context(n, t=0xfffffffffb4001 if n == 8192 else T56, device=0)
+        k = ctx.k
+        sk, pk = ctx.keygen(seed8(5))
+        rk = ctx.relin_keygen(np.stack([seed8(60 + i) for i in range(k)]), sk)
+        quot = ctx.relin_prepare(rk)
+        rng = np.random.default_rng(n)
+        vals = rng.integers(0, 1 << 20, size=(nq, 1), dtype=np.uint64)
+        seeds = rng.integers(0, 1 << 63, size=(nq, 8), dtype=np.uint64)
+        ct = ctx.encrypt(pk, ctx.dev(seeds), ctx.dev(vals))
+        sq = ctx.square(ct)
+        d3 = eng.to_np(ctx.decrypt(sq, sk, ncoeff=1))[:, 0]
+        d2 = eng.to_np(ctx.decrypt(ctx.relinearize(sq, rk, quot), sk, ncoeff=1))[:, 0]
+        expect = (vals[:, 0].astype(object) ** 2) % ctx.t
+        assert [int(x) for x in d3] == [int(x) for x in expect]
+        assert [int(x) for x in d2] == [int(x) for x in expect]
+
+
+def test_circuit_b_edges(eng):
+    """pplp_circuit_b: empty batch, a zero blind is flagged (SEAL: "result ciphertext is transparent"), inputs are left
+    untouched, chunking does not change the result."""
+    import torch
+    n = 8192
+    ctx = eng.Context(n, t=0xfffffffffb4001, device=0)
+    k = ctx.k
+    sk, pk = ctx.keygen(seed8(7))
+    rk = ctx.relin_keygen(np.stack([seed8(80 + i) for i in range(k)]), sk)
+    quot = ctx.relin_prepare(rk)
+    nq = 5
+    rng = np.random.default_rng(1)
+    xa, ya = rng.integers(0, 1 << 27, nq, dtype=np.uint64), rng.integers(0, 1 << 27, nq, dtype=np.uint64)
+    xb, yb = rng.integers(0, 1 << 27, nq, dtype=np.uint64), rng.integers(0, 1 << 27, nq, dtype=np.uint64)
+    r = rng.integers(0, 1 << 16, nq, dtype=np.uint64)
+    s = np.array([3, 0, 1, 2, 5], dtype=np.uint64)
+    seeds = rng.integers(0, 1 << 63, size=(2 * nq, 8), dtype=np.uint64)
+    cx = ctx.encrypt(pk, ctx.dev(seeds[:nq]), ctx.dev(xa[:, None]))
+    cy = ctx.encrypt(pk, ctx.dev(seeds[nq:]), ctx.dev(ya[:, None]))
+    cx0, cy0 = cx.clone(), cy.clone()
+    flags = torch.full((nq,), 9, dtype=torch.int32, device=ctx.device)
+    args = (ctx.dev(xb[:, None]), ctx.dev(yb[:, None]), ctx.dev(r[:, None]), ctx.dev(s), rk, quot)
+    out = ctx.circuit_b(cx, cy, *args, flags=flags, chunk=2)
+    assert torch.equal(cx, cx0) and torch.equal(cy, cy0)
+    assert flags.cpu().tolist() == [0, 1, 0, 0, 0]
+    assert torch.equal(ctx.circuit_b(cx, cy, *args, chunk=0), out)
+    dec = eng.to_np(ctx.decrypt(out, sk, ncoeff=1))[:, 0]
+    for i in range(nq):
+        d2 = (int(xa[i]) - int(xb[i])) ** 2 + (int(ya[i]) - int(yb[i])) ** 2
+        assert int(dec[i]) == (int(s[i]) * (d2 + int(r[i]))) % ctx.t
+    empty = ctx.empty(0, 2, k, n)
+    assert ctx.circuit_b(empty, empty, ctx.empty(0, 1), ctx.empty(0, 1), ctx.empty(0, 1), ctx.empty(0), rk, quot).shape[0] == 0
+
+
+def test_sample_uniform_matches_oracle(eng, oracle):
+    """pplp_sample_uniform == SEAL's sample_poly_uniform over a Blake2xbPRNG (what expands a seeded ciphertext stream), also for
+    a modulus that rejects ~3 % of the draws (rejected words are replaced in stream order)."""
+    import ctypes as C
+    from pplp_b200.capi import check
+    n = 4096
+    for wide in (False, True):
+        q = [int(x) for x in oracle.get_primes(2 * n, 60, 3)] if wide else None   # 60-bit primes reject a visible share of the draws
+        ctx = eng.Context(n, q=q, t=1 << 20, device=0, enforce_security=False)
+        octx = oracle.context(n, ctx.q, 1 << 20, seed=seed8(1))
+        seed = seed8(909)
+        out = ctx.empty(ctx.k, n)
+        check(ctx.L.pplp_sample_uniform(ctx.h, ctx.first_level, seed.ctypes.data, out.data_ptr(), ctx._st()))
+        ref = np.zeros((ctx.k, n), dtype=np.uint64)
+        oracle.lib.orc_sample_uniform(seed.ctypes.data_as(C.POINTER(C.c_uint64)), np.array(ctx.q[:ctx.k], dtype=np.uint64).ctypes.data_as(C.POINTER(C.c_uint64)),
+                                      C.c_size_t(ctx.k), C.c_size_t(n), ref.ctypes.data_as(C.POINTER(C.c_uint64)))
+        assert (eng.to_np(out) == ref).all()

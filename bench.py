@@ -398,9 +398,13 @@ def run_b200(args):
     Qe = args.e2e_queries
     per_ct = 2 * k * N
     from pplp_b200 import numa
+    affinity0 = os.sched_getaffinity(0)
     numa_rep = numa.bind_to_gpu_node(local)     # pages of cudaHostAlloc land on the calling thread's node: bind first
     hc = [numa.pinned_empty(ctx.L, (Qe, 2, k, N), torch.int64, write_combined=True) for _ in range(3)]   # H2D sources
     hout = numa.pinned_empty(ctx.L, (Qe, 2, k, N), torch.int64)
+    for t_ in hc + [hout]:
+        t_.zero_()                              # first touch while bound
+    os.sched_setaffinity(0, affinity0)          # the CPU baseline leg below counts the threads it may use
     for t_, c in zip(hc, cin):   # fill from the device slabs (values < q_j per limb); layout SEAL on the host
         t_.copy_(c[:, :, :Qe, :].permute(2, 1, 0, 3))
     hpar = [x[:Qe].cpu().numpy().view(np.uint64).copy() for x in (xb, yb, rr, ss)]

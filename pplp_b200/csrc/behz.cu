@@ -339,7 +339,12 @@ void launch_multiply(const Engine &E, size_t level, const u64 *a, const u64 *b, 
 //          on the 32-per-thread FP64 transforms (ntt32.cuh), NTT-form digits through an L2-sized scratch;
 //   fused  (everything else)  relin_limb_kernel, 16 coefficients per thread, digits never leave registers.
 bool relin_uses_split(const Engine &E) {
-    return E.host.logn >= 11 && E.host.logn <= 13 && E.max_bits(E.qmap(0)) <= 44;
+    if (!(E.host.logn >= 11 && E.host.logn <= 13 && E.max_bits(E.qmap(0)) <= 44)) return false;
+    // stage 1 feeds limb J's residues (below q_J) to the transform modulo q_I unreduced: that needs q_J < 4 q_I for every pair,
+    // and the fused mod-down wants P < 4 q_j — i.e. all key-level primes within a factor of four (BFVDefault: within two)
+    u64 qmin = ~0ull, qmax = 0;
+    for (u64 q : E.host.q) { qmin = std::min(qmin, q); qmax = std::max(qmax, q); }
+    return qmax / 4 < qmin;
 }
 
 // quot[i] = floor(w[i] * 2^64 / q_limb): Shoup quotients of key words, computed once per key.  rows of n words, limb = row % K.
@@ -687,10 +692,6 @@ void launch_relinearize(const Engine &E, size_t level, const u64 *in, Layout in_
     RelinArgs a{in, in_lay, rk, rkq, tmp, k, K, n, E.d_mods, P >> 1};
     const int lazy = ntt_lazy_level(E.max_bits(E.qmap(0)), E.host.logn);
     if (relin_uses_split(E)) {
-        // the forward transform takes any input below 4 q_I: limb J's residues are below q_J, so q_J < 4 q_I for all pairs
-        u64 qmin = ~0ull, qmax = 0;
-        for (int j = 0; j < K; ++j) { qmin = std::min(qmin, E.host.q[j]); qmax = std::max(qmax, E.host.q[j]); }
-        if (qmax / 4 >= qmin) throw std::logic_error("pplp: coefficient moduli of different size classes are not supported by the split relinearisation");
         const int chunk = relin_split_chunk();
         u64 *digits = tmp + (size_t)nq * 2 * n;      // tmp: special-limb rows [nq][2][n]
         for (int done = 0; done < nq; done += chunk) {

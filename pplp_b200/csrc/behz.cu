@@ -350,15 +350,17 @@ bool relin_uses_split(const Engine &E) {
 // quot[i] = floor(w[i] * 2^64 / q_limb): Shoup quotients of key words, computed once per key.  rows of n words, limb = row % K.
 // The prepared image holds {w, quotient} pairs (one 128-bit load per key coefficient).  Fused pipeline: in the
 // thread-interleaved order of its fine register layout — coefficient 16 t + r of a row sits at pair index r * (n/16) + t, so a
-// warp's load of "its r-th coefficient" is one coalesced 512-byte access.  Split pipeline: the key words as doubles, natural
-// order, 8 bytes per coefficient (the first half of the buffer): its products run on the FP64 pipe and need no quotient.
+// warp's load of "its r-th coefficient" is one coalesced 512-byte access.  Split pipeline: the key words as doubles, 8 bytes
+// per coefficient (the first half of the buffer), in the pair-interleaved order of the 32-per-thread transforms' register
+// layout — coefficients 32 t + 2 h, 32 t + 2 h + 1 (pair h of thread t) at 16-byte slot h * (n/32) + t — so that a warp reads
+// "pair h of each of its threads" as one coalesced 512-byte access and nothing has to pass through shared memory.
 __global__ void shoup_quot_kernel(const DevMod *mods, const u64 *__restrict__ w, u64 *__restrict__ prepared, int K, int n, int split) {
     const int row = blockIdx.x;
     const u64 q = mods[row % K].m.q;
     const int T = n / 16;
     for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
         const u64 v = w[(size_t)row * n + i];
-        if (split) prepared[(size_t)row * n + i] = as_u((double)v);     // exact: key words are below q < 2^45
+        if (split) prepared[(size_t)row * n + ((((i & 31) >> 1) * (n / 32) + (i >> 5)) << 1) + (i & 1)] = as_u((double)v);   // exact: key words are below q < 2^45
         else reinterpret_cast<ulonglong2 *>(prepared)[(size_t)row * n + (size_t)(i & 15) * T + (i >> 4)] = make_ulonglong2(v, (u64)((((unsigned __int128)v) << 64) / q));
     }
 }
@@ -456,7 +458,11 @@ __global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T
 #pragma unroll
     for (int e = 0; e < 32; ++e) x[e] = row[e * S::T + tid];
     ntt32_forward<LOGM>(x, sm, tid, c);
-    ntt32_store_row(x, sm, tid, dst);   // bit patterns of the exact doubles, |x| <= 14 q: stage 2 multiplies on the FP64 pipe
+    // bit patterns of the exact doubles (|x| <= 14 q: stage 2 multiplies on the FP64 pipe), pair-interleaved: thread t holds
+    // coefficients 32 t .. 32 t + 31 and writes pair h to 16-byte slot h T + t — coalesced without staging through shared memory
+    ulonglong2 *d2 = reinterpret_cast<ulonglong2 *>(dst) + tid;
+#pragma unroll
+    for (int h = 0; h < 16; ++h) d2[h * S::T] = make_ulonglong2(x[2 * h], x[2 * h + 1]);
 }
 // Stage 2: one CTA per (ciphertext, key limb I, component c): acc = sum_J X_J (.) key[J][c][I], then the inverse transform.
 // The products run in the coalesced ownership (every access a full line) on the FP64 pipe, exact integers in doubles:
@@ -484,7 +490,7 @@ template <int LOGM, bool SPECIAL, int KD>
 __global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T) relin_mac_inverse_kernel(const RelinMacArgs a) {
     using S = Ntt32Shape<LOGM>;
     extern __shared__ __align__(16) u64 sm[];
-    const int tid = threadIdx.x, lane = tid & 31, wbase = (tid >> 5) << 10;
+    const int tid = threadIdx.x;
     const int kk = a.k + 1;
     const int comp = blockIdx.x & 1;
     const int I = SPECIAL ? a.k : (blockIdx.x >> 1) % a.k, qi = SPECIAL ? (blockIdx.x >> 1) : (blockIdx.x >> 1) / a.k;
@@ -503,46 +509,50 @@ __global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T
         const double cq = __dsub_rn(__fma_rn(h, qinv, kRound52), kRound52);
         return __dadd_rn(__fma_rn(-cq, qd, h), l);
     };
-    __syncwarp();
+    // Products in the transforms' own register layout: pair h of thread t sits at 16-byte slot h T + t of every digit row and
+    // of every key row (see relin_digits_kernel / shoup_quot_kernel), so the sums land where the inverse transform wants them.
+    u64 x[32];
+    const ulonglong2 *X2 = reinterpret_cast<const ulonglong2 *>(X) + tid;
+    const ulonglong2 *K2 = reinterpret_cast<const ulonglong2 *>(Kp) + tid;
+    constexpr int M2 = S::M / 2;
+    const size_t kstride2 = kstride / 2;
     if constexpr (KD > 0) {
-        // software pipeline: the 2 KD loads of coefficient pair e + 1 are in flight while pair e is multiplied
+        // software pipeline: the 2 KD loads of pair h + 1 are in flight while pair h is multiplied
         ulonglong2 xv[2][KD], kv[2][KD];
-        auto fetch = [&](int e, ulonglong2 (&xd)[KD], ulonglong2 (&kd)[KD]) {
-            const int idx = wbase + e * 64 + 2 * lane;      // two adjacent coefficients per thread
+        auto fetch = [&](int h, ulonglong2 (&xd)[KD], ulonglong2 (&kd)[KD]) {
 #pragma unroll
             for (int J = 0; J < KD; ++J) {
-                xd[J] = __ldg(reinterpret_cast<const ulonglong2 *>(X + (size_t)J * S::M + idx));
-                kd[J] = __ldg(reinterpret_cast<const ulonglong2 *>(Kp + (size_t)J * kstride + idx));
+                xd[J] = __ldg(X2 + (size_t)J * M2 + h * S::T);
+                kd[J] = __ldg(K2 + (size_t)J * kstride2 + h * S::T);
             }
         };
         fetch(0, xv[0], kv[0]);
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-            if (e + 1 < 16) fetch(e + 1, xv[(e + 1) & 1], kv[(e + 1) & 1]);
-            const int idx = wbase + e * 64 + 2 * lane;
+        for (int h = 0; h < 16; ++h) {
+            if (h + 1 < 16) fetch(h + 1, xv[(h + 1) & 1], kv[(h + 1) & 1]);
             double a0 = 0.0, a1 = 0.0;
 #pragma unroll
             for (int J = 0; J < KD; ++J) {
-                a0 = __dadd_rn(a0, mul_key(xv[e & 1][J].x, kv[e & 1][J].x));
-                a1 = __dadd_rn(a1, mul_key(xv[e & 1][J].y, kv[e & 1][J].y));
+                a0 = __dadd_rn(a0, mul_key(xv[h & 1][J].x, kv[h & 1][J].x));
+                a1 = __dadd_rn(a1, mul_key(xv[h & 1][J].y, kv[h & 1][J].y));
             }
             // |sum| <= 0.57 k q: back to [-q/2, q/2] for the inverse transform (its inputs must stay within 2q)
-            sm[slot32(idx)] = as_u(reduce_sym_f64(a0, qinv, qd));
-            sm[slot32(idx + 1)] = as_u(reduce_sym_f64(a1, qinv, qd));
+            x[2 * h] = as_u(reduce_sym_f64(a0, qinv, qd));
+            x[2 * h + 1] = as_u(reduce_sym_f64(a1, qinv, qd));
         }
     } else {
-#pragma unroll 2
-        for (int e = 0; e < 32; ++e) {
-            const int idx = wbase + e * 32 + lane;
-            double acc = 0.0;
-            for (int J = 0; J < a.k; ++J) acc = __dadd_rn(acc, mul_key(__ldg(X + (size_t)J * S::M + idx), __ldg(Kp + (size_t)J * kstride + idx)));
-            sm[slot32(idx)] = as_u(reduce_sym_f64(acc, qinv, qd));
+#pragma unroll
+        for (int h = 0; h < 16; ++h) {
+            double a0 = 0.0, a1 = 0.0;
+            for (int J = 0; J < a.k; ++J) {
+                const ulonglong2 xv = __ldg(X2 + (size_t)J * M2 + h * S::T), kv = __ldg(K2 + (size_t)J * kstride2 + h * S::T);
+                a0 = __dadd_rn(a0, mul_key(xv.x, kv.x));
+                a1 = __dadd_rn(a1, mul_key(xv.y, kv.y));
+            }
+            x[2 * h] = as_u(reduce_sym_f64(a0, qinv, qd));
+            x[2 * h + 1] = as_u(reduce_sym_f64(a1, qinv, qd));
         }
     }
-    __syncwarp();
-    u64 x[32];
-#pragma unroll
-    for (int e = 0; e < 32; ++e) x[e] = sm[slot32(wbase + lane * 32 + e)];
     const Ntt32Consts c = ntt32_consts(md, true);
     ntt32_inverse<LOGM, true>(x, sm, tid, c);
     if constexpr (SPECIAL) {

@@ -203,7 +203,7 @@ void Engine::upload_tables(int dev) {
             m.n_inv_d = pair(T.n_inv.w);
             m.inv1_n_inv_d = pair(T.inv1_n_inv.w);
             m.one_d = dbits(1.0 / (double)T.q);
-            if (m.bits <= 44 && logn >= 11 && logn <= 13) {
+            if ((m.bits <= 44 && logn >= 11 && logn <= 13) || logn == 14) {   // ntt32.cuh: <= 44 bits, or the wide rule set (<= 49 bits) at N = 16384
                 auto fine32 = [&](const std::vector<ShoupW> &tab) -> const ShoupW * {
                     const size_t nt = host.n / 32;
                     std::vector<ShoupW> f(31 * nt);

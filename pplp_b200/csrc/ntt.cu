@@ -112,7 +112,8 @@ __global__ void __launch_bounds__(NttShape<LOGM>::T, (LOGM <= 13 ? PPLP_NTT_MIN_
 // address (a sum of three runtime strides) costs 10 % — kept as a sum it is re-derived at every use and its components
 // stay live through the transform (ptxas then sinks the twiddle loads next to their uses); hidden behind an empty asm it
 // becomes a per-thread register pair instead of a uniform one.  Both were measured on the lab harness (ntt32_lab.cu).
-template <int LOGM, bool DENSE>
+// WIDE: the 45..49-bit rule set of ntt32.cuh (N = 16384: 512 threads, one CTA per SM).
+template <int LOGM, bool DENSE, bool WIDE = (LOGM == 14)>
 __global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T) ntt32_forward_kernel(const NttArgs a) {
     using S = Ntt32Shape<LOGM>;
     extern __shared__ __align__(16) u64 sm[];
@@ -130,12 +131,12 @@ __global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T
     u64 x[32];
 #pragma unroll
     for (int e = 0; e < 32; ++e) x[e] = ptr[e * S::T + tid];
-    ntt32_forward<LOGM>(x, sm, tid, c);
+    ntt32_forward<LOGM, WIDE>(x, sm, tid, c);
 #pragma unroll
     for (int e = 0; e < 32; ++e) x[e] = ntt32_canon(x[e], c, md.m.q);
     ntt32_store_row(x, sm, tid, ptr);
 }
-template <int LOGM, bool DENSE>
+template <int LOGM, bool DENSE, bool WIDE = (LOGM == 14)>
 __global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T) ntt32_inverse_kernel(const NttArgs a) {
     using S = Ntt32Shape<LOGM>;
     extern __shared__ __align__(16) u64 sm[];
@@ -151,7 +152,7 @@ __global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T
     }
     u64 x[32];
     ntt32_load_row(x, sm, tid, ptr);
-    ntt32_inverse<LOGM>(x, sm, tid, c);
+    ntt32_inverse<LOGM, false, WIDE>(x, sm, tid, c);
     const u64 q = md.m.q;
 #pragma unroll
     for (int e = 0; e < 32; ++e) ptr[e * S::T + tid] = csub(x[e], q);
@@ -276,6 +277,9 @@ template <int LOGM> static void run_ntt32(const NttArgs &a, int rows, bool inver
 template <int LOGM> static void run_block_ntt_l(int level, const NttArgs &a, int rows, bool inverse, cudaStream_t st) {
     if constexpr (LOGM >= 11 && LOGM <= 13) {
         if (level == 3 && a.stage_base == 0) { run_ntt32<LOGM>(a, rows, inverse, st); return; }
+    }
+    if constexpr (LOGM == 14) {   // 32 per thread with the wide rule set: moduli of at most 49 bits, whole transforms only
+        if ((level == 3 || level == 4) && a.stage_base == 0) { run_ntt32<LOGM>(a, rows, inverse, st); return; }
     }
     if constexpr (LOGM >= 12) {
         if (level == 4) { run_block_ntt<LOGM, 4>(a, rows, inverse, st); return; }

@@ -1,4 +1,5 @@
-// pplp_b200/csrc/ntt32.cuh — the FP64-pipe negacyclic NTT with 32 coefficients per thread (moduli of at most 44 bits).
+// pplp_b200/csrc/ntt32.cuh — the FP64-pipe negacyclic NTT with 32 coefficients per thread (moduli of at most 44 bits; with the
+// WIDE rule set below also 45..49 bits: BFVDefault's 48/49-bit primes at N = 16384).
 //
 // Same function as ntt.cuh (SEAL's ntt_negacyclic_harvey / inverse_ntt_negacyclic_harvey, [SEAL] util/ntt.cpp), same
 // exact-integers-in-doubles arithmetic as its L = 3 mode (modarith.cuh mulmod_f64), different schedule.  With the
@@ -22,6 +23,16 @@
 //   inverse: sums double per stage.  After a pass of R stages fed with |x| <= X, register j of a radix-2^R group holds at
 //   most X 2^R (j = 0, the all-sums path) or 0.75 q 2^(R-1-msb(j)).  After each pass the registers whose bound would
 //   exceed 96 q inside the next pass are reduced to [-q/2, q/2] (three instructions each; one to four registers of 32).
+//
+// WIDE (45..49-bit moduli: the multiplicand budget 2^51 is only 4 q; a product is at most 0.75 q):
+//   forward: inputs canonical (|x| < q).  A pass of R <= 5 stages fed with |x| <= 1 q has multiplicands 1, 1.75, .. , 4 q and
+//            leaves 4.75 q, so passes B and C start by reducing their 32 registers to [-q/2, q/2] (+ 6 instructions per
+//            coefficient over the transform).
+//   inverse: inputs below 2q are centred to (-q, q) while converting.  Stages alternate: an "a" stage fed with |x| <= 1 q has
+//            multiplicands <= 2 q and leaves sums <= 2 q; the following "b" stage has multiplicands <= 4 q and leaves sums
+//            <= 4 q, which are reduced at once (16 registers of 32), products <= 0.75 q — so the next "a" stage is fed with
+//            |x| <= 1 q again.  The 14th stage (N^-1 folded in) is a "b" stage whose outputs are all products.
+//   tests/test_fp64_bounds.py replays both rule sets with exact rationals at the widest modulus.
 #pragma once
 #include <type_traits>
 #include "devstructs.h"
@@ -29,7 +40,7 @@
 namespace pplp {
 
 template <int LOGM> struct Ntt32Shape {
-    static_assert(LOGM >= 11 && LOGM <= 13, "32-per-thread FP64 transforms cover 2048..8192 points");
+    static_assert(LOGM >= 11 && LOGM <= 14, "32-per-thread FP64 transforms cover 2048..16384 points");
     static constexpr int M = 1 << LOGM;
     static constexpr int T = M / 32;            // threads per CTA
     static constexpr int SB = LOGM - 10;        // stages of pass B
@@ -133,7 +144,7 @@ constexpr double kGsLimit = 96.0;
 // ---- forward ----------------------------------------------------------------------------------------------------------
 // x: the block as u64 values below 4q, x[e] = coefficient e*T + tid.  On return x[e] = bits of the double holding output
 // 32*tid + e, |x| <= 14 q; ntt32_canon() brings it to [0,q).  sm: Ntt32Shape::SMEM_WORDS words.
-template <int LOGM>
+template <int LOGM, bool WIDE = false>
 __device__ __forceinline__ void ntt32_forward(u64 (&x)[32], u64 *sm, int tid, const Ntt32Consts &c) {
     using S = Ntt32Shape<LOGM>;
     const int lane = tid & 31, warp = tid >> 5;
@@ -160,6 +171,10 @@ __device__ __forceinline__ void ntt32_forward(u64 (&x)[32], u64 *sm, int tid, co
     const int wbase = warp << 10;
 #pragma unroll
     for (int e = 0; e < 32; ++e) x[e] = wsm[slot32(wbase + e * 32 + lane)];
+    if constexpr (WIDE) {   // pass A left up to 4.75 q
+#pragma unroll
+        for (int e = 0; e < 32; ++e) x[e] = as_u(reduce_sym_f64(as_d(x[e]), c.qinv, c.q));
+    }
     // pass B: stage 5 + v pairs e bit (SB - 1 - v); group = (32 warp + e) >> (SB - v)
     if constexpr (S::SB > 0) {
         using PB = PassB<S::SB>;
@@ -177,6 +192,10 @@ __device__ __forceinline__ void ntt32_forward(u64 (&x)[32], u64 *sm, int tid, co
     __syncwarp();
 #pragma unroll
     for (int e = 0; e < 32; ++e) x[e] = wsm[slot32(wbase + lane * 32 + e)];
+    if constexpr (WIDE && S::SB > 0) {   // pass B left up to 0.8 q + SB * 0.75 q
+#pragma unroll
+        for (int e = 0; e < 32; ++e) x[e] = as_u(reduce_sym_f64(as_d(x[e]), c.qinv, c.q));
+    }
     // pass C: stage LOGM - 5 + v pairs e bit (4 - v); group = (tid << v) + (e >> (5 - v))
     tw_pipeline<31, PPLP_NTT32_LOOK>(
         [&](auto k) { return c.fine + (size_t)decltype(k)::value * S::T + tid; },
@@ -194,15 +213,28 @@ __device__ __forceinline__ u64 ntt32_canon(u64 v, const Ntt32Consts &c, u64 q) {
 // ---- inverse ----------------------------------------------------------------------------------------------------------
 // x[e] = coefficient 32*tid + e as u64 below 2q.  On return x[e] = output e*T + tid as u64 in (0, 2q), scaled by N^-1.
 // FROM_F64: x already holds bit patterns of doubles, |x| <= 2q (a caller that produced its operand on the FP64 pipe).
-template <int LOGM, bool FROM_F64 = false>
+// WIDE helper: reduce the sum outputs of the stage that paired registers at distance `half` (the registers with that bit clear)
+template <int HALF> __device__ __forceinline__ void ntt32_reduce_sums(u64 (&x)[32], const Ntt32Consts &c) {
+#pragma unroll
+    for (int e = 0; e < 32; ++e)
+        if ((e & HALF) == 0) x[e] = as_u(reduce_sym_f64(as_d(x[e]), c.qinv, c.q));
+}
+template <int LOGM, bool FROM_F64 = false, bool WIDE = false>
 __device__ __forceinline__ void ntt32_inverse(u64 (&x)[32], u64 *sm, int tid, const Ntt32Consts &c) {
     using S = Ntt32Shape<LOGM>;
+    static_assert(!WIDE || S::SB == 4, "the a/b stage alternation of the WIDE rule set is laid out for 5 + 4 + 5 stages");
     const int lane = tid & 31, warp = tid >> 5;
     u64 *twA = sm + S::TW_OFF;
     if (tid < 31) *reinterpret_cast<ulonglong2 *>(twA + 2 * tid) = __ldg(reinterpret_cast<const ulonglong2 *>(c.tw + 1 + tid));
     if constexpr (!FROM_F64) {
+        if constexpr (WIDE) {   // centred while converting: [0, 2q) -> (-q, q)
+            const double off = __dadd_rn(kTwo52, c.q);
 #pragma unroll
-        for (int e = 0; e < 32; ++e) x[e] = as_u(u64_to_f64(x[e]));
+            for (int e = 0; e < 32; ++e) x[e] = as_u(__dsub_rn(as_d(x[e] | 0x4330000000000000ULL), off));
+        } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) x[e] = as_u(u64_to_f64(x[e]));
+        }
     }
     // pass C': stages LOGM-1 .. LOGM-5
     tw_pipeline<31, PPLP_NTT32_LOOK>(
@@ -211,11 +243,15 @@ __device__ __forceinline__ void ntt32_inverse(u64 (&x)[32], u64 *sm, int tid, co
             constexpr int r = inv_row(decltype(k)::value), v = row_stage(r), g = r + 1 - (1 << v), half = 16 >> v;
 #pragma unroll
             for (int i = 0; i < half; ++i) bf_gs(x[g * 2 * half + i], x[g * 2 * half + i + half], w, c.q);
+            // WIDE: global stages 1..5 are v = 4, 3, 2, 1, 0; the "b" stages are the 2nd (v = 3) and the 4th (v = 1)
+            if constexpr (WIDE && (v == 3 || v == 1) && g == (1 << v) - 1) ntt32_reduce_sums<half>(x, c);
         });
     constexpr int RNEXT = S::SB > 0 ? S::SB : 5;   // stages of the pass that follows C'
+    if constexpr (!WIDE) {
 #pragma unroll
-    for (int e = 0; e < 32; ++e)
-        if (gs_bound(e, 5, 2.0) * (1 << RNEXT) > kGsLimit) x[e] = as_u(reduce_sym_f64(as_d(x[e]), c.qinv, c.q));
+        for (int e = 0; e < 32; ++e)
+            if (gs_bound(e, 5, 2.0) * (1 << RNEXT) > kGsLimit) x[e] = as_u(reduce_sym_f64(as_d(x[e]), c.qinv, c.q));
+    }
     u64 *wsm = sm;
     const int wbase = warp << 10;
     __syncwarp();
@@ -233,11 +269,15 @@ __device__ __forceinline__ void ntt32_inverse(u64 (&x)[32], u64 *sm, int tid, co
                 constexpr int f = PB::inv_k(decltype(k)::value), v = PB::stage(f), g = PB::group(f), half = 1 << (S::SB - 1 - v);
 #pragma unroll
                 for (int i = 0; i < half; ++i) bf_gs(x[g * 2 * half + i], x[g * 2 * half + i + half], w, c.q);
+                // WIDE (SB = 4): global stages 6..9 are v = 3, 2, 1, 0; the "b" stages are the 6th (v = 3) and the 8th (v = 1)
+                if constexpr (WIDE && (v == 3 || v == 1) && g == (32 >> (S::SB - v)) - 1) ntt32_reduce_sums<half>(x, c);
             });
         // inputs of B' were bounded by 12 q (or 0.5 q where reduced); the next pass has five stages
+        if constexpr (!WIDE) {
 #pragma unroll
-        for (int e = 0; e < 32; ++e)
-            if (gs_bound(e & ((1 << S::SB) - 1), S::SB, 12.0) * 32 > kGsLimit) x[e] = as_u(reduce_sym_f64(as_d(x[e]), c.qinv, c.q));
+            for (int e = 0; e < 32; ++e)
+                if (gs_bound(e & ((1 << S::SB) - 1), S::SB, 12.0) * 32 > kGsLimit) x[e] = as_u(reduce_sym_f64(as_d(x[e]), c.qinv, c.q));
+        }
         __syncwarp();
 #pragma unroll
         for (int e = 0; e < 32; ++e) wsm[slot32(wbase + e * 32 + lane)] = x[e];
@@ -254,6 +294,10 @@ __device__ __forceinline__ void ntt32_inverse(u64 (&x)[32], u64 *sm, int tid, co
             const ShoupW w = lds_tw(twA, (1 << s) - 1 + g);
 #pragma unroll
             for (int i = 0; i < half; ++i) bf_gs(x[g * 2 * half + i], x[g * 2 * half + i + half], w, c.q);
+        }
+        if constexpr (WIDE) {   // global stages 10..13 are s = 4, 3, 2, 1: "b" stages at s = 4 and s = 2 (the folded 14th is a "b" stage too)
+            if (s == 4) ntt32_reduce_sums<1>(x, c);
+            if (s == 2) ntt32_reduce_sums<4>(x, c);
         }
     }
     const double bias = __dadd_rn(c.q, kTwo52);

@@ -176,6 +176,39 @@ def test_32_per_thread_schedule_stays_within_budget(logm):
     assert B.worst <= 96 + 1e-6                      # the margin the headers quote: 96 q of 128 q
 
 
+def test_32_per_thread_wide_schedule_stays_within_budget():
+    """ntt32.cuh WIDE rule set (N = 16384: 5 + 4 + 5 stages, moduli up to 49 bits, budget 4 q)."""
+    B = Budget(49)
+    # forward: canonical inputs; passes B and C start with a reduction of all registers
+    x = max(ct_pass([Fraction(1)] * 32, 5, B))
+    assert x <= Fraction(19, 4)
+    x = max(ct_pass([B.reduced(x)] * 16, 4, B))
+    x = max(ct_pass([B.reduced(x)] * 32, 5, B))
+    assert x * B.q < TWO53 and B.reduced(x) <= 1                 # ntt32_canon reduces, then shifts by q
+    # inverse: inputs centred to (-q, q); "a" stage, then "b" stage whose sum outputs are reduced, 14 stages, the last one folded
+    def stage(b, bit, reduce_sums, fold=False):
+        gs_stage(b, bit, B, fold=fold)
+        if reduce_sums:
+            for r in range(len(b)):
+                if not r & (1 << bit):
+                    b[r] = B.reduced(b[r])
+    b = [Fraction(1)] * 32
+    for k, bit in enumerate(range(5)):                            # C': global stages 1..5 = a b a b a
+        stage(b, bit, reduce_sums=(k % 2 == 1))
+    assert max(b) <= 2
+    g = [max(b)] * 16
+    for k, bit in enumerate(range(4)):                            # B': 6..9 = b a b a
+        stage(g, bit, reduce_sums=(k % 2 == 0))
+    assert max(g) <= 2
+    b = [max(g)] * 32
+    for k, bit in enumerate(range(5)):                            # A': 10..14 = b a b a b(folded)
+        stage(b, bit, reduce_sums=(k % 2 == 0 and k != 4), fold=(k == 4))
+    assert max(b) <= 1                                            # products, shifted by q into (0, 2q)
+    assert B.worst <= B.limit
+    # relinearisation stage 2 feeds the inverse with reduced sums of products (<= 0.57 q + ...): within the "a" stage's 1 q
+    assert B.reduced(Fraction(8)) <= 1
+
+
 def test_budget_model_rejects_a_modulus_that_is_too_wide():
     B = Budget(45)                                   # ntt32 / L = 3 are limited to 44 bits for this reason
     with pytest.raises(AssertionError):

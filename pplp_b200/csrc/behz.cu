@@ -335,11 +335,13 @@ void launch_multiply(const Engine &E, size_t level, const u64 *a, const u64 *b, 
 
 // ---- relinearisation -------------------------------------------------------------------------------------------------
 // Which relinearisation pipeline a context runs (host decision, shared by pplp_relin_prepare and pplp_relinearize):
-//   split  (N = 2048..8192, every key-level prime <= 44 bits: BFVDefault up to 8192)  relin_digits_kernel -> relin_mac_inverse_kernel
+//   split  (N = 2048..8192 with key-level primes <= 44 bits, N = 16384 with <= 49 bits: BFVDefault up to 16384)
+//          relin_digits_kernel -> relin_mac_inverse_kernel
 //          on the 32-per-thread FP64 transforms (ntt32.cuh), NTT-form digits through an L2-sized scratch;
 //   fused  (everything else)  relin_limb_kernel, 16 coefficients per thread, digits never leave registers.
 bool relin_uses_split(const Engine &E) {
-    if (!(E.host.logn >= 11 && E.host.logn <= 13 && E.max_bits(E.qmap(0)) <= 44)) return false;
+    const int bits = E.max_bits(E.qmap(0));
+    if (!((E.host.logn >= 11 && E.host.logn <= 13 && bits <= 44) || (E.host.logn == 14 && bits <= 49))) return false;
     // stage 1 feeds limb J's residues (below q_J) to the transform modulo q_I unreduced: that needs q_J < 4 q_I for every pair,
     // and the fused mod-down wants P < 4 q_j — i.e. all key-level primes within a factor of four (BFVDefault: within two)
     u64 qmin = ~0ull, qmax = 0;
@@ -443,7 +445,9 @@ struct RelinSplitArgs {
     int k, K, n;
     const DevMod *mods;
 };
-template <int LOGM>
+// WIDE (N = 16384, 45..49-bit primes, ntt32.cuh's wide rule set): the input is reduced modulo q_I while it is converted and the
+// output once more before it is stored, so that stage 2's products see |x| <= 0.8 q.
+template <int LOGM, bool WIDE = (LOGM == 14)>
 __global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T) relin_digits_kernel(const RelinSplitArgs a) {
     using S = Ntt32Shape<LOGM>;
     extern __shared__ __align__(16) u64 sm[];
@@ -457,7 +461,11 @@ __global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T
     u64 x[32];
 #pragma unroll
     for (int e = 0; e < 32; ++e) x[e] = row[e * S::T + tid];
-    ntt32_forward<LOGM>(x, sm, tid, c);
+    ntt32_forward<LOGM, WIDE, true>(x, sm, tid, c);
+    if constexpr (WIDE) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) x[e] = as_u(reduce_sym_f64(as_d(x[e]), c.qinv, c.q));
+    }
     // bit patterns of the exact doubles (|x| <= 14 q: stage 2 multiplies on the FP64 pipe), pair-interleaved: thread t holds
     // coefficients 32 t .. 32 t + 31 and writes pair h to 16-byte slot h T + t — coalesced without staging through shared memory
     ulonglong2 *d2 = reinterpret_cast<ulonglong2 *>(dst) + tid;
@@ -486,7 +494,7 @@ struct RelinMacArgs {
 };
 // KD = number of digits at compile time (0: run-time count): with a fixed trip count all 2 KD loads of a coefficient pair
 // are issued before the first product, and two pairs are in flight per thread — the phase is latency-bound otherwise.
-template <int LOGM, bool SPECIAL, int KD>
+template <int LOGM, bool SPECIAL, int KD, bool WIDE = (LOGM == 14)>
 __global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T) relin_mac_inverse_kernel(const RelinMacArgs a) {
     using S = Ntt32Shape<LOGM>;
     extern __shared__ __align__(16) u64 sm[];
@@ -517,28 +525,36 @@ __global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T
     constexpr int M2 = S::M / 2;
     const size_t kstride2 = kstride / 2;
     if constexpr (KD > 0) {
-        // software pipeline: the 2 KD loads of pair h + 1 are in flight while pair h is multiplied
-        ulonglong2 xv[2][KD], kv[2][KD];
-        auto fetch = [&](int h, ulonglong2 (&xd)[KD], ulonglong2 (&kd)[KD]) {
+        // software pipeline over (pair h, group of G <= 4 digits): the 2 G loads of the next step are in flight while this
+        // step is multiplied (G = 4 keeps the two load buffers within 64 registers when k = 8)
+        constexpr int G = KD > 4 ? 4 : KD, NG = KD / G, STEPS = 16 * NG;
+        static_assert(KD % G == 0, "digit count must be a multiple of the group size");
+        ulonglong2 xv[2][G], kv[2][G];
+        auto fetch = [&](int step, ulonglong2 (&xd)[G], ulonglong2 (&kd)[G]) {
+            const int h = step / NG, g = step % NG;
 #pragma unroll
-            for (int J = 0; J < KD; ++J) {
-                xd[J] = __ldg(X2 + (size_t)J * M2 + h * S::T);
-                kd[J] = __ldg(K2 + (size_t)J * kstride2 + h * S::T);
+            for (int J = 0; J < G; ++J) {
+                xd[J] = __ldg(X2 + (size_t)(g * G + J) * M2 + h * S::T);
+                kd[J] = __ldg(K2 + (size_t)(g * G + J) * kstride2 + h * S::T);
             }
         };
         fetch(0, xv[0], kv[0]);
+        double a0 = 0.0, a1 = 0.0;
 #pragma unroll
-        for (int h = 0; h < 16; ++h) {
-            if (h + 1 < 16) fetch(h + 1, xv[(h + 1) & 1], kv[(h + 1) & 1]);
-            double a0 = 0.0, a1 = 0.0;
+        for (int step = 0; step < STEPS; ++step) {
+            if (step + 1 < STEPS) fetch(step + 1, xv[(step + 1) & 1], kv[(step + 1) & 1]);
 #pragma unroll
-            for (int J = 0; J < KD; ++J) {
-                a0 = __dadd_rn(a0, mul_key(xv[h & 1][J].x, kv[h & 1][J].x));
-                a1 = __dadd_rn(a1, mul_key(xv[h & 1][J].y, kv[h & 1][J].y));
+            for (int J = 0; J < G; ++J) {
+                a0 = __dadd_rn(a0, mul_key(xv[step & 1][J].x, kv[step & 1][J].x));
+                a1 = __dadd_rn(a1, mul_key(xv[step & 1][J].y, kv[step & 1][J].y));
             }
-            // |sum| <= 0.57 k q: back to [-q/2, q/2] for the inverse transform (its inputs must stay within 2q)
-            x[2 * h] = as_u(reduce_sym_f64(a0, qinv, qd));
-            x[2 * h + 1] = as_u(reduce_sym_f64(a1, qinv, qd));
+            if (step % NG == NG - 1) {
+                // |sum| <= 0.75 k q: back to [-q/2, q/2] for the inverse transform (its inputs must stay within 2q; 1q when WIDE)
+                const int h = step / NG;
+                x[2 * h] = as_u(reduce_sym_f64(a0, qinv, qd));
+                x[2 * h + 1] = as_u(reduce_sym_f64(a1, qinv, qd));
+                a0 = 0.0; a1 = 0.0;
+            }
         }
     } else {
 #pragma unroll
@@ -554,7 +570,7 @@ __global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T
         }
     }
     const Ntt32Consts c = ntt32_consts(md, true);
-    ntt32_inverse<LOGM, true>(x, sm, tid, c);
+    ntt32_inverse<LOGM, true, WIDE>(x, sm, tid, c);
     if constexpr (SPECIAL) {
         u64 *o = a.tmp + ((size_t)qi * 2 + comp) * S::M;
 #pragma unroll
@@ -578,7 +594,8 @@ __global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T
             for (int u = 0; u < 8; ++u) {
                 // lazily: x in (0, 2q), (t_last + half) mod P below P < 4 q_j (primes of one size class, checked on the host), so
                 // d = x + half_mod + 4q - last is a positive representative below 7q of acc - ((t_last + half) mod P - half)
-                const u64 d = x[b + u] + half_mod + four_q - lv[u];
+                // (45..49-bit primes: 7q would leave the FP64-assisted product's 2^51 range — reduce t_last first, d below 4q)
+                const u64 d = WIDE ? x[b + u] + half_mod + q - csub(csub(lv[u], two_q), q) : x[b + u] + half_mod + four_q - lv[u];
                 const u64 r = sv[u] + mul_f64_lazy(d, inv_w, inv_c, q);          // below 3q
                 dst[(b + u) * S::T + tid] = csub(csub(r, two_q), q);
             }
@@ -605,6 +622,7 @@ template <int LOGM> static void run_relin_split(const RelinSplitArgs &a, const R
     case 2: run_relin_split_k<LOGM, 2>(a, m, nq, st); break;
     case 3: run_relin_split_k<LOGM, 3>(a, m, nq, st); break;
     case 4: run_relin_split_k<LOGM, 4>(a, m, nq, st); break;
+    case 8: run_relin_split_k<LOGM, 8>(a, m, nq, st); break;   // BFVDefault(16384)
     default: run_relin_split_k<LOGM, 0>(a, m, nq, st);
     }
 }
@@ -711,7 +729,8 @@ void launch_relinearize(const Engine &E, size_t level, const u64 *in, Layout in_
             RelinMacArgs ma{digits, rkq, tmp + (size_t)done * 2 * n, cin, in_lay, out + (size_t)done * out_lay.sq, out_lay, E.d_levels, k, K, n, E.d_mods, P >> 1};
             if (E.host.logn == 11) run_relin_split<11>(sa, ma, c, st);
             else if (E.host.logn == 12) run_relin_split<12>(sa, ma, c, st);
-            else run_relin_split<13>(sa, ma, c, st);
+            else if (E.host.logn == 13) run_relin_split<13>(sa, ma, c, st);
+            else run_relin_split<14>(sa, ma, c, st);
         }
         PPLP_CUDA(cudaGetLastError());
         return;

@@ -144,14 +144,16 @@ constexpr double kGsLimit = 96.0;
 // ---- forward ----------------------------------------------------------------------------------------------------------
 // x: the block as u64 values below 4q, x[e] = coefficient e*T + tid.  On return x[e] = bits of the double holding output
 // 32*tid + e, |x| <= 14 q; ntt32_canon() brings it to [0,q).  sm: Ntt32Shape::SMEM_WORDS words.
-template <int LOGM, bool WIDE = false>
+// REDUCE_IN (WIDE only): the inputs are residues of ANOTHER modulus of the same size class (below 2^52): bring them to
+// [-q/2, q/2] first — pass A needs |x| <= 1 q.
+template <int LOGM, bool WIDE = false, bool REDUCE_IN = false>
 __device__ __forceinline__ void ntt32_forward(u64 (&x)[32], u64 *sm, int tid, const Ntt32Consts &c) {
     using S = Ntt32Shape<LOGM>;
     const int lane = tid & 31, warp = tid >> 5;
     u64 *twA = sm + S::TW_OFF;
     if (tid < 31) *reinterpret_cast<ulonglong2 *>(twA + 2 * tid) = __ldg(reinterpret_cast<const ulonglong2 *>(c.tw + 1 + tid));
 #pragma unroll
-    for (int e = 0; e < 32; ++e) x[e] = as_u(u64_to_f64(x[e]));
+    for (int e = 0; e < 32; ++e) x[e] = as_u(WIDE && REDUCE_IN ? reduce_sym_f64(u64_to_f64(x[e]), c.qinv, c.q) : u64_to_f64(x[e]));
     __syncthreads();
     // pass A: stage s pairs e bit (4 - s); group = e >> (5 - s); twiddle tw[2^s + group]
 #pragma unroll

@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T
         const int v = nz[e * S::T + tid];
         x[e] = v < 0 ? q - 1 : (u64)v;
     }
-    ntt32_forward<LOGM>(x, sm, tid, c);
+    ntt32_forward<LOGM, (LOGM == 14)>(x, sm, tid, c);   // N = 16384: the wide rule set (inputs are canonical: 0, 1, q - 1)
     // U in the interleaving the 16-per-thread inverse kernels read (pair h of their thread t' at [h * n/16 + t']): this
     // thread's 32 coefficients are those of t' = 2 tid and 2 tid + 1, so each store covers two adjacent pairs (32 bytes).
     ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(a.U + ((size_t)ct * a.K + j) * a.n) + 2 * tid;
@@ -457,15 +457,15 @@ template <int LOGM, int L> static void run_encrypt_split_l(const EncSplitArgs &a
     enc_inverse_kernel<LOGM, L, true><<<nct * 2, T, bytes, st>>>(a);
     enc_inverse_kernel<LOGM, L, false><<<nct * 2 * (a.K - 1), T, bytes, st>>>(a);
 }
-template <int LOGM> static void run_encrypt_split32(const EncSplitArgs &a, int nct, cudaStream_t st) {
-    if constexpr (LOGM >= 11 && LOGM <= 13) {
+template <int LOGM, int L = 3> static void run_encrypt_split32(const EncSplitArgs &a, int nct, cudaStream_t st) {
+    if constexpr (LOGM >= 11 && LOGM <= 14) {
         const int bytes32 = Ntt32Shape<LOGM>::SMEM_WORDS * 8, bytes = NttShape<LOGM>::SMEM_WORDS * 8, T = NttShape<LOGM>::T;
         PPLP_CUDA(cudaFuncSetAttribute(enc32_forward_kernel<LOGM>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes32));
-        PPLP_CUDA(cudaFuncSetAttribute(enc_inverse_kernel<LOGM, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-        PPLP_CUDA(cudaFuncSetAttribute(enc_inverse_kernel<LOGM, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        PPLP_CUDA(cudaFuncSetAttribute(enc_inverse_kernel<LOGM, L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        PPLP_CUDA(cudaFuncSetAttribute(enc_inverse_kernel<LOGM, L, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         enc32_forward_kernel<LOGM><<<nct * a.K, Ntt32Shape<LOGM>::T, bytes32, st>>>(a);
-        enc_inverse_kernel<LOGM, 3, true><<<nct * 2, T, bytes, st>>>(a);
-        enc_inverse_kernel<LOGM, 3, false><<<nct * 2 * (a.K - 1), T, bytes, st>>>(a);
+        enc_inverse_kernel<LOGM, L, true><<<nct * 2, T, bytes, st>>>(a);
+        enc_inverse_kernel<LOGM, L, false><<<nct * 2 * (a.K - 1), T, bytes, st>>>(a);
     }
 }
 template <int LOGM> static void run_encrypt_split(int lazy, const EncSplitArgs &a, int nct, cudaStream_t st) {
@@ -502,7 +502,11 @@ void launch_encrypt(const Engine &E, const u64 *pk, const u64 *seeds, const u64 
         case 11: if (wide) run_encrypt_split32<11>(sa, nct, st); else run_encrypt_split<11>(lazy, sa, nct, st); break;
         case 12: if (wide) run_encrypt_split32<12>(sa, nct, st); else run_encrypt_split<12>(lazy, sa, nct, st); break;
         case 13: if (wide) run_encrypt_split32<13>(sa, nct, st); else run_encrypt_split<13>(lazy, sa, nct, st); break;
-        default: run_encrypt_split<14>(lazy, sa, nct, st); break;
+        default:
+            if (wide_ok && lazy == 3) run_encrypt_split32<14, 3>(sa, nct, st);
+            else if (wide_ok && lazy == 4) run_encrypt_split32<14, 4>(sa, nct, st);
+            else run_encrypt_split<14>(lazy, sa, nct, st);
+            break;
         }
         PPLP_CUDA(cudaGetLastError());
         return;

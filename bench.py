@@ -427,9 +427,10 @@ def run_b200(args):
         raise SystemExit("bench: host-buffer path and resident path disagree")
     # the host link under the same conditions: all ranks copying at once, both directions, same buffers (the ceiling of e2e)
     link = {}
-    sA, sB = torch.cuda.Stream(), torch.cuda.Stream()
-    dtmp = [ctx.empty(Qe, 2, k, N) for _ in range(2)]
-    mix = [(dtmp[0], hc[0], sA), (dtmp[0], hc[1], sA), (dtmp[0], hc[2], sA), (hout, dtmp[1], sB)]     # the entry point's own 3 : 1 traffic mix
+    sA, sB, sC, sD = (torch.cuda.Stream() for _ in range(4))
+    dtmp = [ctx.empty(Qe, 2, k, N) for _ in range(4)]
+    # the entry point's own 3 : 1 traffic mix, every copy on its own stream (the entry keeps three slabs in flight)
+    mix = [(dtmp[0], hc[0], sA), (dtmp[2], hc[1], sC), (dtmp[3], hc[2], sD), (hout, dtmp[1], sB)]
     for name, ops in (("h2d", [(dtmp[0], hc[0], sA)]), ("d2h", [(hout, dtmp[1], sB)]), ("bidir", [(dtmp[0], hc[0], sA), (hout, dtmp[1], sB)]), ("mix_3in_1out", mix)):
         barrier()
         tl0 = time.perf_counter()

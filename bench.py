@@ -254,31 +254,25 @@ def measure_exchange(torch, dist, ctx, engine, cin, out, xb, yb, rr, ss, Q, k, w
     cq = max(1, min(Q // 2, (1 << 30) // per_ct))                  # queries per chunk: 1 GiB of result ciphertexts per rank
     nchunks = max(2, min(4, Q // cq))
     src = [c[:, :, :cq, :].contiguous() for c in cin]              # one contiguous chunk of inputs, re-evaluated for every chunk
-    outs = [ctx.empty(*ctx.ct_shape(cq, 2, None, engine.LAYOUT_LIMB_MAJOR)) for _ in range(2)]      # double-buffered contiguous chunk results
-    recv = [[torch.empty_like(outs[0]) for _ in range(world)] for _ in range(2)] if rank == 0 else [None, None]
+    from pplp_b200.shard import ChunkedGather
+    cg = ChunkedGather(ctx.empty(*ctx.ct_shape(cq, 2, None, engine.LAYOUT_LIMB_MAJOR)))      # double-buffered contiguous chunk results
+    outs, recv = cg.bufs, cg.recv
     sl = lambda t, i: t[i * cq:(i + 1) * cq]
 
-    def compute(i):
-        ctx.circuit_a(src[0], src[1], src[2], sl(xb, i), sl(yb, i), sl(rr, i), sl(ss, i), out=outs[i & 1], layout=engine.LAYOUT_LIMB_MAJOR)
-
-    def gather_async(i):
-        return dist.gather(outs[i & 1], recv[i & 1] if rank == 0 else None, dst=0, async_op=True)
+    def compute(i, out_buf):
+        ctx.circuit_a(src[0], src[1], src[2], sl(xb, i), sl(yb, i), sl(rr, i), sl(ss, i), out=out_buf, layout=engine.LAYOUT_LIMB_MAJOR)
 
     def run(do_compute, do_gather):
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        pending = [None, None]
         for i in range(nchunks):
-            if pending[i & 1] is not None:
-                pending[i & 1].wait()            # the buffer pair of chunk i-2 is free again
+            buf = cg.buffer(i)                   # the buffer pair of chunk i-2 is free again
             if do_compute:
-                compute(i)
+                compute(i, buf)
             if do_gather:
-                pending[i & 1] = gather_async(i)
-        for w in pending:
-            if w is not None:
-                w.wait()
+                cg.submit(i)
+        cg.finish()
         b.record()
         barrier()
         return max_over_ranks(a.elapsed_time(b), dev) * 1e-3

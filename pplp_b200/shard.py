@@ -56,3 +56,41 @@ def gather_rows(local, nq, dst=0, sizes=None):
         return torch.cat([p[:s] for p, s in zip(parts, sizes)], dim=0)
     dist.gather(buf, None, dst=dst)
     return None
+
+
+class ChunkedGather:
+    """Result chunks to `dst`, double-buffered and asynchronous: chunk i's gather runs on the communication stream while the
+    caller produces chunk i+1 (end-to-end = max(compute, gather)).  Usage per chunk i:
+        buf = cg.buffer(i)       # waits until the gather that last used this buffer (chunk i-2) is done
+        ... fill buf ...
+        cg.submit(i)
+    then cg.finish().  On dst, received(i) is the list of per-rank tensors of chunk i (valid until chunk i+2 is submitted)."""
+
+    def __init__(self, like, dst=0):
+        self.dst = dst
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.bufs = [torch.empty_like(like) for _ in range(2)]
+        self.recv = [[torch.empty_like(like) for _ in range(self.world)] for _ in range(2)] if self.rank == dst else [None, None]
+        self.pending = [None, None]
+
+    def buffer(self, i):
+        if self.pending[i & 1] is not None:
+            self.pending[i & 1].wait()
+            self.pending[i & 1] = None
+        return self.bufs[i & 1]
+
+    def submit(self, i):
+        if self.world == 1:
+            self.recv[i & 1][0].copy_(self.bufs[i & 1])
+            return
+        self.pending[i & 1] = dist.gather(self.bufs[i & 1], self.recv[i & 1] if self.rank == self.dst else None, dst=self.dst, async_op=True)
+
+    def received(self, i):
+        return self.recv[i & 1]
+
+    def finish(self):
+        for k in range(2):
+            if self.pending[k] is not None:
+                self.pending[k].wait()
+                self.pending[k] = None

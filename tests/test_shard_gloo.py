@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from pplp_b200.shard import cross_shard, cross_sizes, gather_rows, max_over_ranks, shard_range, shard_sizes
+from pplp_b200.shard import ChunkedGather, cross_shard, cross_sizes, gather_rows, max_over_ranks, shard_range, shard_sizes
 
 
 def test_shard_ranges_partition_exactly():
@@ -75,3 +75,34 @@ def _cross_worker(rank, world, port, npts, ncl):
 def test_config5_point_sharding_gathers_in_pair_order(world, npts, ncl):
     port = 31500 + (os.getpid() % 2000) + world
     mp.spawn(_cross_worker, args=(world, port, npts, ncl), nprocs=world, join=True)
+
+
+def _chunk_worker(rank, world, port, nchunks):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        cg = ChunkedGather(torch.empty(64, 3, dtype=torch.int64))
+        seen = []
+        for i in range(nchunks):
+            buf = cg.buffer(i)                       # waits for chunk i-2's gather before the buffer is overwritten
+            if rank == 0 and i >= 2:
+                seen.append([t.clone() for t in cg.received(i)])   # ... so chunk i-2's data is complete here
+            buf.copy_(torch.full((64, 3), 1000 * i + rank, dtype=torch.int64))
+            cg.submit(i)
+        cg.finish()
+        if rank == 0:
+            for i in range(max(0, nchunks - 2), nchunks):
+                seen_i = cg.received(i)
+                assert all(bool((seen_i[r] == 1000 * i + r).all()) for r in range(world)), i
+            for i, parts in enumerate(seen):
+                assert all(bool((parts[r] == 1000 * i + r).all()) for r in range(world)), i
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,nchunks", [(2, 5), (3, 2)])
+def test_chunked_double_buffered_gather(world, nchunks):
+    """The exchange bench.py times: chunk i's gather in flight while chunk i+1 is produced, two buffers."""
+    port = 33500 + (os.getpid() % 2000) + world
+    mp.spawn(_chunk_worker, args=(world, port, nchunks), nprocs=world, join=True)

@@ -48,7 +48,13 @@ __global__ void circuit_a_prepare_kernel(const DevLevel *Lp, int nq, const u64 *
     const u64 sr = vs * vr;               // src/server.cc:133
     u64 *o = scratch + (size_t)idx * kScalarWords;
     const u64 a = dev_lift(L, vxb, j), b = dev_lift(L, vyb, j), c = dev_lift(L, vs, j);
-    if (f64) {   // everything as bits of doubles: (w, fl(w/q)) pairs, Z, SR
+    if (f64 == 2) {   // FP64-assisted Shoup products (mul_f64_lazy): integer word + bits of fl(w/q); Z, SR as integers
+        o[0] = a; o[1] = as_u(__ddiv_rn((double)a, (double)q));
+        o[2] = b; o[3] = as_u(__ddiv_rn((double)b, (double)q));
+        o[4] = c; o[5] = as_u(__ddiv_rn((double)c, (double)q));
+        o[6] = dev_scaled(L, z, j);
+        o[7] = dev_scaled(L, sr, j);
+    } else if (f64) {   // everything as bits of doubles: (w, fl(w/q)) pairs, Z, SR
         o[0] = as_u((double)a); o[1] = as_u(__ddiv_rn((double)a, (double)q));
         o[2] = as_u((double)b); o[3] = as_u(__ddiv_rn((double)b, (double)q));
         o[4] = as_u((double)c); o[5] = as_u(__ddiv_rn((double)c, (double)q));
@@ -71,7 +77,11 @@ constexpr int kCaSeg = kCaThreads * 2 * kCaUnroll;  // coefficients per CTA
 
 // ALIAS: out == c0 (the in-place callers).  Then c0 is read through the coherent path (no .nc) and neither pointer is
 // declared __restrict__: a thread still reads its own words before it writes them, and now the memory model says so too.
-template <bool ALIAS>
+// QF64 (moduli of at most 44 bits): the three products are FP64-assisted Shoup products (modarith.cuh mul_f64_lazy: the quotient
+// estimate is one DFMA instead of a 64x64 high product) — ten instructions each instead of eighteen.  The kernel is HBM-bound
+// either way; the shorter instruction stream lowers the power draw of a sustained run (the board sits at its 1 kW cap).
+// QF64 = 2: moduli of 45..49 bits (N = 16384): the bracket (below 6q) is brought under 4q = 2^51 by one conditional subtraction first.
+template <bool ALIAS, int QF64>
 __global__ void __launch_bounds__(kCaThreads) circuit_a_kernel(const DevLevel *Lp, const u64 *c0, const u64 *__restrict__ c1,
                                                                const u64 *__restrict__ c2, u64 *out, Layout lay, int nq, int n,
                                                                const u64 *__restrict__ scratch) {
@@ -97,11 +107,16 @@ __global__ void __launch_bounds__(kCaThreads) circuit_a_kernel(const DevLevel *L
     for (int u = 0; u < kCaUnroll; ++u) {
         const int i = first + u * 2 * kCaThreads;
         if (i >= n) continue;
-        u64 vx = a[u].x + four_q - mul_shoup_lazy(b[u].x, xbw, xbq, q) - mul_shoup_lazy(c[u].x, ybw, ybq, q);
-        u64 vy = a[u].y + four_q - mul_shoup_lazy(b[u].y, xbw, xbq, q) - mul_shoup_lazy(c[u].y, ybw, ybq, q);
+        auto mul = [&](u64 v, u64 w, u64 wq) { return QF64 ? mul_f64_lazy(v, w, wq, q) : mul_shoup_lazy(v, w, wq, q); };   // [0, 2q); v below 2^51 when QF64
+        u64 vx = a[u].x + four_q - mul(b[u].x, xbw, xbq) - mul(c[u].x, ybw, ybq);
+        u64 vy = a[u].y + four_q - mul(b[u].y, xbw, xbq) - mul(c[u].y, ybw, ybq);
         const bool head = (p == 0 && i == 0);
         if (head) vx += sc[6];
-        u64 rx = mul_shoup_lazy(vx, sw, sq, q), ry = mul_shoup_lazy(vy, sw, sq, q);
+        if constexpr (QF64 == 2) {
+            vx = vx >= four_q ? vx - four_q : vx;
+            vy = vy >= four_q ? vy - four_q : vy;
+        }
+        u64 rx = mul(vx, sw, sq), ry = mul(vy, sw, sq);
         if (head) rx += sc[7];
         rx = rx >= two_q ? rx - two_q : rx;
         ulonglong2 o;
@@ -119,12 +134,25 @@ void launch_circuit_a(const Engine &E, size_t level, const u64 *c0, const u64 *c
     if (nq == 0) return;
     const int k = (int)E.host.levels[level].q.size(), n = (int)E.host.n;
     const DevLevel *L = E.d_levels + level;
-    circuit_a_prepare_kernel<<<(nq * k + 127) / 128, 128, 0, st>>>(L, nq, xb, yb, r, s, scratch, flags);
+    int bits = 0;
+    for (u64 q : E.host.levels[level].q) bits = std::max(bits, hm::bitlen(q));
+    static const bool qf64_ok = !(std::getenv("PPLP_CIRCUIT_A_INT") && std::getenv("PPLP_CIRCUIT_A_INT")[0] == '1');   // experiment hook
+    const int qf64 = !qf64_ok ? 0 : (bits <= 44 ? 1 : (bits <= 49 ? 2 : 0));     // the multiplicands must stay below 2^51 (mul_f64_lazy's range)
+    circuit_a_prepare_kernel<<<(nq * k + 127) / 128, 128, 0, st>>>(L, nq, xb, yb, r, s, scratch, flags, qf64 ? 2 : 0);
     const int segs = n / kCaSeg > 0 ? n / kCaSeg : 1;
     const long long ctas = (long long)nq * 2 * k * segs;
     if (ctas > 0x7fffffffLL) throw std::invalid_argument("pplp: batch too large for one launch");
-    if (out == c0) circuit_a_kernel<true><<<(unsigned)ctas, kCaThreads, 0, st>>>(L, c0, c1, c2, out, lay, nq, n, scratch);
-    else circuit_a_kernel<false><<<(unsigned)ctas, kCaThreads, 0, st>>>(L, c0, c1, c2, out, lay, nq, n, scratch);
+    const bool alias = out == c0;
+    if (qf64 == 1) {
+        if (alias) circuit_a_kernel<true, 1><<<(unsigned)ctas, kCaThreads, 0, st>>>(L, c0, c1, c2, out, lay, nq, n, scratch);
+        else circuit_a_kernel<false, 1><<<(unsigned)ctas, kCaThreads, 0, st>>>(L, c0, c1, c2, out, lay, nq, n, scratch);
+    } else if (qf64 == 2) {
+        if (alias) circuit_a_kernel<true, 2><<<(unsigned)ctas, kCaThreads, 0, st>>>(L, c0, c1, c2, out, lay, nq, n, scratch);
+        else circuit_a_kernel<false, 2><<<(unsigned)ctas, kCaThreads, 0, st>>>(L, c0, c1, c2, out, lay, nq, n, scratch);
+    } else {
+        if (alias) circuit_a_kernel<true, 0><<<(unsigned)ctas, kCaThreads, 0, st>>>(L, c0, c1, c2, out, lay, nq, n, scratch);
+        else circuit_a_kernel<false, 0><<<(unsigned)ctas, kCaThreads, 0, st>>>(L, c0, c1, c2, out, lay, nq, n, scratch);
+    }
     PPLP_CUDA(cudaGetLastError());
 }
 

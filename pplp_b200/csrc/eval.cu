@@ -12,7 +12,7 @@
 // with XB_j = lift(xb) mod q_j, ..., Z_j = round(Q z/t) mod q_j, SR_j = round(Q (s r mod 2^64)/t) mod q_j.
 //
 // circuit_a_kernel is the hot kernel of the headline metric: 3 ciphertexts in, 1 out, 64*k*N bytes per query, three
-// Shoup multiplications per coefficient — HBM-bound.  128-bit streaming loads/stores (L1 no-allocate: each byte is
+// Shoup multiplications per coefficient (FP64-assisted quotients for moduli up to 49 bits) — HBM-bound.  128-bit streaming loads/stores (L1 no-allocate: each byte is
 // touched once), 4 independent 16-byte accesses per input stream in flight per thread.
 #include "engine.hpp"
 

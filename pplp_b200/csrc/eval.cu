@@ -71,8 +71,11 @@ __global__ void circuit_a_prepare_kernel(const DevLevel *Lp, int nq, const u64 *
     if (flags && j == 0 && (vxb == 0 || vyb == 0 || vs == 0)) atomicOr(&flags[qi], 1);   // caller zeroes flags
 }
 
+#ifndef PPLP_CA_UNROLL
+#define PPLP_CA_UNROLL 4   // 16-byte accesses per input stream per thread (tuning knob; 4 measured best)
+#endif
 constexpr int kCaThreads = 256;
-constexpr int kCaUnroll = 4;
+constexpr int kCaUnroll = PPLP_CA_UNROLL;
 constexpr int kCaSeg = kCaThreads * 2 * kCaUnroll;  // coefficients per CTA
 
 // ALIAS: out == c0 (the in-place callers).  Then c0 is read through the coherent path (no .nc) and neither pointer is
@@ -117,8 +120,7 @@ __global__ void __launch_bounds__(kCaThreads) circuit_a_kernel(const DevLevel *L
             vy = vy >= four_q ? vy - four_q : vy;
         }
         u64 rx = mul(vx, sw, sq), ry = mul(vy, sw, sq);
-        if (head) rx += sc[7];
-        rx = rx >= two_q ? rx - two_q : rx;
+        if (head) { rx += sc[7]; rx = rx >= two_q ? rx - two_q : rx; }   // only coefficient 0 of polynomial 0 carries the scaled plaintext
         ulonglong2 o;
         o.x = csub(rx, q);
         o.y = csub(ry, q);

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "build")
 LIB = os.path.join(PKG, "libpplp_b200.so")
-SOURCES = ["capi.cu", "ntt.cu", "eval.cu", "crypto.cu", "bloom.cu", "behz.cu"]
+SOURCES = ["capi.cu", "ntt.cu", "eval.cu", "crypto.cu", "bloom.cu", "behz.cu", "behzf.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr",

@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(256) tensor_kernel(const DevMod *mods, RowMap 
         d2[i] = tensor_mul<MODE>(a1, b1, mq, aux);
     }
 }
-static void launch_tensor(const Engine &E, const RowMap &map, const u64 *x, const u64 *y, u64 *d, int nq, int n, cudaStream_t st) {
+void launch_tensor(const Engine &E, const RowMap &map, const u64 *x, const u64 *y, u64 *d, int nq, int n, cudaStream_t st) {
     const dim3 grid(nq * map.nlimbs, (n + 1023) / 1024);
     int lo = 64, hi = 0;
     for (int j = 0; j < map.nlimbs; ++j) { const int b = hm::bitlen(E.host.tables[map.mod_id[j]].q); lo = std::min(lo, b); hi = std::max(hi, b); }
@@ -262,6 +262,7 @@ template <class F> static void behz_dispatch(int k, int nb, F f) {
 }
 
 size_t multiply_tmp_words(const Engine &E, size_t level, int nq, bool square) {
+    if (behz_uses_f64(E, level)) return multiply_f64_tmp_words(E, level, nq, square);
     const size_t k = E.host.levels[level].q.size(), nb = (size_t)E.host.levels[level].dev.nBsk, n = E.host.n;
     const size_t ext = (size_t)nq * 2 * (k + nb) * n;
     return ext * (square ? 1 : 2) + (size_t)nq * 3 * (k + nb) * n;
@@ -271,6 +272,7 @@ size_t multiply_tmp_words(const Engine &E, size_t level, int nq, bool square) {
 void launch_multiply(const Engine &E, size_t level, const u64 *a, const u64 *b, Layout in_lay, u64 *out, Layout out_lay, int nq, u64 *ws, cudaStream_t st) {
     E.require_device();
     if (nq == 0) return;
+    if (behz_uses_f64(E, level)) { launch_multiply_f64(E, level, a, b, in_lay, out, out_lay, nq, ws, st); return; }   // behzf.cu
     const HostLevel &HL = E.host.levels[level];
     const int k = (int)HL.q.size(), nb = HL.dev.nBsk, n = (int)E.host.n;
     const DevLevel *L = E.d_levels + level;

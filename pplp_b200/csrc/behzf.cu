@@ -1,0 +1,229 @@
+// pplp_b200/csrc/behzf.cu — ciphertext x ciphertext multiplication (BEHZ) over an FP64-friendly auxiliary base.
+//
+// Same function as behz.cu's launch_multiply ([SEAL] evaluator.cpp bfv_multiply / bfv_square: fastbconv_m_tilde -> sm_mrq ->
+// NTT -> tensor -> INTT -> *t -> fast_floor -> fastbconv_sk) and the same output residues, but the auxiliary base is made of
+// primes of at most 44 bits instead of SEAL's 61-bit ones (behz_f64.cuh explains why the result cannot tell), so that
+//   * every transform of the product runs on the FP64 pipe (ntt32.cuh) — the 61-bit base kept 25 of the 45 row transforms of a
+//     square on the 32-bit integer multiplier at 14 multiplies per butterfly;
+//   * the base conversions are exact-integer FP64 products (six instructions) instead of 128-bit multiply-accumulates and
+//     61-bit Barrett reductions;
+//   * q rows and auxiliary rows share one modulus size class, so one launch transforms all of them, and the tensor product is
+//     fused into the inverse transform's prologue (no NTT-form product ever touches HBM).
+// Pipeline (4 launches; the 61-bit path needs 9):
+//   behzf_extend_kernel          per coefficient: q residues -> auxiliary residues of the m~-corrected lift (canonical u64)
+//   behzf_forward_kernel         one CTA per (ct, poly, row): forward transform, output reduced to [-q/2, q/2] as doubles in the
+//                                pair-interleaved order of the transforms' register layout (q rows are read straight from the input)
+//   behzf_tensor_inverse_kernel  one CTA per (ct, row, output polynomial): d0 = x0 y0 | d1 = x0 y1 + x1 y0 | d2 = x1 y1 formed in
+//                                registers (FP64 products of two variables), then the inverse transform; canonical u64 out
+//   behzf_floor_sk_kernel        per coefficient: *t, fast_floor, Shenoy-Kumaresan back to q
+// Eligibility (host, per level): N = 2048..16384, q primes of at most 49 bits, k <= 8 (context.hpp build_behzf); everything else
+// stays on behz.cu's kernels.  PPLP_BEHZ_BASE=61 forces the 61-bit path (A/B measurements, cross-check in the GPU tests);
+// PPLP_BEHZF_FUSED=0 runs the same conversions around the stand-alone transform and tensor kernels.
+#include <type_traits>
+#include "behz_f64.cuh"
+#include "engine.hpp"
+#include "ntt32.cuh"
+
+namespace pplp {
+
+template <int K>
+__global__ void __launch_bounds__(256) behzf_extend_kernel(const __grid_constant__ bf::BehzFC<K> C, const u64 *__restrict__ in, Layout lay, u64 *__restrict__ ext,
+                                                           int copy_q) {
+    const int n = C.n, NL = K + C.nA;
+    const int qp = blockIdx.x, qi = qp >> 1, p = qp & 1;
+    const int i = blockIdx.y * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u64 *src = in + qi * lay.sq + p * lay.sp + i;
+    u64 *dst = ext + (size_t)qp * NL * n + i;
+    u64 x[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) x[j] = src[j * lay.sl];
+    if (copy_q) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) dst[(size_t)j * n] = x[j];
+    }
+    bf::extend_coeff<K>(C, x, dst + (size_t)K * n, (size_t)n);
+}
+
+template <int K>
+__global__ void __launch_bounds__(256) behzf_floor_sk_kernel(const __grid_constant__ bf::BehzFC<K> C, const u64 *__restrict__ d, u64 *__restrict__ out, Layout lay) {
+    const int n = C.n, NL = K + C.nA;
+    const int qp = blockIdx.x, qi = qp / 3, p = qp % 3;
+    const int i = blockIdx.y * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u64 *src = d + (size_t)qp * NL * n + i;
+    u64 dq[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) dq[j] = src[(size_t)j * n];
+    bf::floor_sk_coeff<K>(C, dq, src + (size_t)K * n, (size_t)n, out + qi * lay.sq + p * lay.sp + i, lay.sl);
+}
+
+struct BehzfFwdArgs {
+    const u64 *in; Layout lay;      // the input ciphertexts: source of rows l < k (unless from_ext)
+    u64 *ext;                       // [nq][2][NL][n]: rows l >= k hold the auxiliary residues; every row is overwritten with its transform
+    int k, NL, from_ext;
+    RowMap map;
+    const DevMod *mods;
+};
+template <int LOGM, bool WIDE = (LOGM == 14)>
+__global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T) behzf_forward_kernel(const BehzfFwdArgs a) {
+    using S = Ntt32Shape<LOGM>;
+    extern __shared__ __align__(16) u64 sm[];
+    const int tid = threadIdx.x;
+    const int l = blockIdx.x % a.NL, qp = blockIdx.x / a.NL;
+    const DevMod &md = a.mods[a.map.mod_id[l]];
+    const Ntt32Consts c = ntt32_consts(md, false);
+    u64 *dst = a.ext + ((size_t)qp * a.NL + l) * S::M;
+    const u64 *src = (l < a.k && !a.from_ext) ? a.in + (qp >> 1) * a.lay.sq + (qp & 1) * a.lay.sp + l * a.lay.sl : dst;
+    u64 x[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) x[e] = src[e * S::T + tid];
+    ntt32_forward<LOGM, WIDE, false>(x, sm, tid, c);
+    // |x| <= 14 q (<= 5 q under the wide rule set): to [-q/2, q/2], so that the product of two of them stays an exact FP64 product
+    ulonglong2 *d2 = reinterpret_cast<ulonglong2 *>(dst) + tid;
+#pragma unroll
+    for (int h = 0; h < 16; ++h)
+        d2[h * S::T] = make_ulonglong2(as_u(reduce_sym_f64(as_d(x[2 * h]), c.qinv, c.q)), as_u(reduce_sym_f64(as_d(x[2 * h + 1]), c.qinv, c.q)));
+}
+
+struct BehzfTensorArgs {
+    const u64 *ea, *eb;             // transformed operands [nq][2][NL][n] (pair-interleaved doubles); eb == ea squares
+    u64 *d;                         // [nq][3][NL][n] canonical, coefficient form
+    int NL;
+    RowMap map;
+    const DevMod *mods;
+};
+// a * b - c q exactly for |a|, |b| <= q/2 + eps: h = RN(a b), l = a b - h, c = round(h fl(1/q)); |result| <= 0.57 q
+__device__ __forceinline__ double mulvar_f64(double a, double b, double qinv, double q) {
+    const double h = __dmul_rn(a, b);
+    const double l = __fma_rn(a, b, -h);
+    const double c = __dsub_rn(__fma_rn(h, qinv, kRound52), kRound52);
+    return __dadd_rn(__fma_rn(-c, q, h), l);
+}
+template <int LOGM, bool WIDE = (LOGM == 14)>
+__global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T) behzf_tensor_inverse_kernel(const BehzfTensorArgs a) {
+    using S = Ntt32Shape<LOGM>;
+    extern __shared__ __align__(16) u64 sm[];
+    const int tid = threadIdx.x;
+    const int comp = blockIdx.x % 3, l = (blockIdx.x / 3) % a.NL, qi = blockIdx.x / (3 * a.NL);
+    const DevMod &md = a.mods[a.map.mod_id[l]];
+    const Ntt32Consts c = ntt32_consts(md, true);
+    const double q = c.q, qinv = c.qinv;
+    const size_t prow = (size_t)a.NL * S::M;
+    const ulonglong2 *X0 = reinterpret_cast<const ulonglong2 *>(a.ea + ((size_t)qi * 2 * a.NL + l) * S::M) + tid;
+    const ulonglong2 *Y0 = reinterpret_cast<const ulonglong2 *>(a.eb + ((size_t)qi * 2 * a.NL + l) * S::M) + tid;
+    const ulonglong2 *X1 = X0 + prow / 2, *Y1 = Y0 + prow / 2;
+    u64 x[32];
+    if (comp != 1) {
+        const ulonglong2 *P = comp == 0 ? X0 : X1, *Q = comp == 0 ? Y0 : Y1;
+#pragma unroll
+        for (int h = 0; h < 16; ++h) {
+            const ulonglong2 u = __ldg(P + h * S::T), v = __ldg(Q + h * S::T);
+            x[2 * h] = as_u(mulvar_f64(as_d(u.x), as_d(v.x), qinv, q));
+            x[2 * h + 1] = as_u(mulvar_f64(as_d(u.y), as_d(v.y), qinv, q));
+        }
+    } else if (a.ea == a.eb) {   // square: the cross term is 2 x0 x1
+#pragma unroll
+        for (int h = 0; h < 16; ++h) {
+            const ulonglong2 u = __ldg(X0 + h * S::T), v = __ldg(X1 + h * S::T);
+            const double m0 = mulvar_f64(as_d(u.x), as_d(v.x), qinv, q), m1 = mulvar_f64(as_d(u.y), as_d(v.y), qinv, q);
+            x[2 * h] = as_u(reduce_sym_f64(__dadd_rn(m0, m0), qinv, q));
+            x[2 * h + 1] = as_u(reduce_sym_f64(__dadd_rn(m1, m1), qinv, q));
+        }
+    } else {
+#pragma unroll
+        for (int h = 0; h < 16; ++h) {
+            const ulonglong2 u0 = __ldg(X0 + h * S::T), u1 = __ldg(X1 + h * S::T), v0 = __ldg(Y0 + h * S::T), v1 = __ldg(Y1 + h * S::T);
+            const double m0 = __dadd_rn(mulvar_f64(as_d(u0.x), as_d(v1.x), qinv, q), mulvar_f64(as_d(u1.x), as_d(v0.x), qinv, q));
+            const double m1 = __dadd_rn(mulvar_f64(as_d(u0.y), as_d(v1.y), qinv, q), mulvar_f64(as_d(u1.y), as_d(v0.y), qinv, q));
+            x[2 * h] = as_u(reduce_sym_f64(m0, qinv, q));
+            x[2 * h + 1] = as_u(reduce_sym_f64(m1, qinv, q));
+        }
+    }
+    ntt32_inverse<LOGM, true, WIDE>(x, sm, tid, c);
+    const u64 qu = md.m.q;
+    u64 *o = a.d + (((size_t)qi * 3 + comp) * a.NL + l) * S::M;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) o[e * S::T + tid] = csub(x[e], qu);
+}
+
+bool behz_uses_f64(const Engine &E, size_t level) {
+    static const bool force61 = [] { const char *e = getenv("PPLP_BEHZ_BASE"); return e && e[0] == '6' && e[1] == '1' && e[2] == 0; }();
+    return !force61 && E.host.levels[level].bf.ok;
+}
+size_t multiply_f64_tmp_words(const Engine &E, size_t level, int nq, bool square) {
+    const HostLevel &HL = E.host.levels[level];
+    const size_t NL = HL.q.size() + (size_t)HL.bf.nA, n = E.host.n;
+    return (size_t)nq * NL * n * (square ? 2 + 3 : 4 + 3);
+}
+
+template <int LOGM> static void run_behzf_transforms(const BehzfFwdArgs &fa, const BehzfFwdArgs *fb, const BehzfTensorArgs &ta, int nq, cudaStream_t st) {
+    const int bytes = Ntt32Shape<LOGM>::SMEM_WORDS * 8;
+    static bool done[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!done[dev & 63]) {
+        PPLP_CUDA(cudaFuncSetAttribute(behzf_forward_kernel<LOGM>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        PPLP_CUDA(cudaFuncSetAttribute(behzf_tensor_inverse_kernel<LOGM>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        done[dev & 63] = true;
+    }
+    behzf_forward_kernel<LOGM><<<nq * 2 * fa.NL, Ntt32Shape<LOGM>::T, bytes, st>>>(fa);
+    if (fb) behzf_forward_kernel<LOGM><<<nq * 2 * fa.NL, Ntt32Shape<LOGM>::T, bytes, st>>>(*fb);
+    behzf_tensor_inverse_kernel<LOGM><<<nq * 3 * fa.NL, Ntt32Shape<LOGM>::T, bytes, st>>>(ta);
+}
+
+template <int K>
+static void multiply_f64_k(const Engine &E, size_t level, const u64 *a, const u64 *b, Layout in_lay, u64 *out, Layout out_lay, int nq, u64 *ws, cudaStream_t st) {
+    const HostLevel &HL = E.host.levels[level];
+    const int n = (int)E.host.n, nA = HL.bf.nA, NL = K + nA;
+    const bool square = (a == b);
+    static const bool fused = [] { const char *e = getenv("PPLP_BEHZF_FUSED"); return !(e && e[0] == '0' && e[1] == 0); }();
+    bf::BehzFC<K> C;
+    HL.bf.fill(C, n);
+    RowMap map;
+    map.nlimbs = NL;
+    for (int j = 0; j < K; ++j) map.mod_id[j] = j;
+    for (int b2 = 0; b2 < nA; ++b2) map.mod_id[K + b2] = HL.bf.mod_id[b2];
+    const size_t we = (size_t)nq * 2 * NL * n;
+    u64 *ea = ws, *eb = square ? ea : ea + we, *d = (square ? ea : eb) + we;
+    const dim3 ge(nq * 2, (n + 255) / 256), gf(nq * 3, (n + 255) / 256);
+    behzf_extend_kernel<K><<<ge, 256, 0, st>>>(C, a, in_lay, ea, fused ? 0 : 1);
+    if (!square) behzf_extend_kernel<K><<<ge, 256, 0, st>>>(C, b, in_lay, eb, fused ? 0 : 1);
+    if (fused) {
+        BehzfFwdArgs fa{a, in_lay, ea, K, NL, 0, map, E.d_mods}, fb{b, in_lay, eb, K, NL, 0, map, E.d_mods};
+        BehzfTensorArgs ta{ea, eb, d, NL, map, E.d_mods};
+        switch (E.host.logn) {
+        case 11: run_behzf_transforms<11>(fa, square ? nullptr : &fb, ta, nq, st); break;
+        case 12: run_behzf_transforms<12>(fa, square ? nullptr : &fb, ta, nq, st); break;
+        case 13: run_behzf_transforms<13>(fa, square ? nullptr : &fb, ta, nq, st); break;
+        case 14: run_behzf_transforms<14>(fa, square ? nullptr : &fb, ta, nq, st); break;
+        default: throw std::logic_error("pplp: the FP64 auxiliary base covers poly_modulus_degree 2048..16384");
+        }
+    } else {
+        const Layout el{(size_t)2 * NL * n, (size_t)NL * n, (size_t)n};
+        launch_ntt(E, ea, el, nq, 2, map, false, st);
+        if (!square) launch_ntt(E, eb, el, nq, 2, map, false, st);
+        launch_tensor(E, map, ea, eb, d, nq, n, st);
+        launch_ntt(E, d, Layout{(size_t)3 * NL * n, (size_t)NL * n, (size_t)n}, nq, 3, map, true, st);
+    }
+    behzf_floor_sk_kernel<K><<<gf, 256, 0, st>>>(C, d, out, out_lay);
+    PPLP_CUDA(cudaGetLastError());
+}
+
+void launch_multiply_f64(const Engine &E, size_t level, const u64 *a, const u64 *b, Layout in_lay, u64 *out, Layout out_lay, int nq, u64 *ws, cudaStream_t st) {
+    E.require_device();
+    if (nq == 0) return;
+    switch (E.host.levels[level].q.size()) {
+    case 1: multiply_f64_k<1>(E, level, a, b, in_lay, out, out_lay, nq, ws, st); break;
+    case 2: multiply_f64_k<2>(E, level, a, b, in_lay, out, out_lay, nq, ws, st); break;
+    case 3: multiply_f64_k<3>(E, level, a, b, in_lay, out, out_lay, nq, ws, st); break;
+    case 4: multiply_f64_k<4>(E, level, a, b, in_lay, out, out_lay, nq, ws, st); break;
+    case 5: multiply_f64_k<5>(E, level, a, b, in_lay, out, out_lay, nq, ws, st); break;
+    case 6: multiply_f64_k<6>(E, level, a, b, in_lay, out, out_lay, nq, ws, st); break;
+    case 7: multiply_f64_k<7>(E, level, a, b, in_lay, out, out_lay, nq, ws, st); break;
+    case 8: multiply_f64_k<8>(E, level, a, b, in_lay, out, out_lay, nq, ws, st); break;
+    default: throw std::logic_error("pplp: the FP64 auxiliary base covers at most 8 data limbs");
+    }
+}
+
+}  // namespace pplp

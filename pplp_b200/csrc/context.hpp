@@ -4,12 +4,14 @@
 // /root/reference/src/demo.cc:66-76, src/client.cc:82-89, src/server.cc:73-77
 // ([SEAL] context.cpp SEALContext::validate/create_next_context_data, util/ntt.cpp NTTTables, util/rns.cpp RNSTool).
 #pragma once
+#include <algorithm>
 #include <array>
 #include <cstring>
 #include <memory>
 #include <string>
 #include <vector>
 
+#include "behz_f64.cuh"
 #include "blake2.cuh"
 #include "devstructs.h"
 #include "hostmath.hpp"
@@ -52,6 +54,30 @@ struct HostTable {            // twiddles of one modulus, in the kernel's indexi
     ShoupW n_inv, inv1_n_inv;
 };
 
+// Constants of the BEHZ conversions over the FP64-friendly auxiliary base (behz_f64.cuh): a[0..nA-2] = B', a[nA-1] = m_sk'.
+struct HostBehzF {
+    bool ok = false;                    // false: this level multiplies over SEAL's 61-bit base (behz.cu's integer kernels)
+    int nA = 0;
+    std::vector<u64> a;
+    std::vector<int> mod_id;            // ids of the auxiliary primes in HostContext::tables
+    u32 neg_inv_q_mt = 0;
+    std::vector<u32> pm;
+    std::vector<u64> q;
+    std::vector<bf::F64C> zc, tz, negB, extq, ft, bm;
+    std::vector<std::vector<bf::F64C>> ext, fp, bq;   // [b][j]
+    bf::F64C invB{0.0, 0.0};
+    template <int K> void fill(bf::BehzFC<K> &C, int n) const {
+        std::memset(&C, 0, sizeof(C));
+        C.nA = nA; C.n = n; C.neg_inv_q_mt = neg_inv_q_mt; C.invB = invB;
+        for (int j = 0; j < K; ++j) { C.pm[j] = pm[j]; C.q[j] = (double)q[j]; C.qinv[j] = 1.0 / (double)q[j]; C.zc[j] = zc[j]; C.tz[j] = tz[j]; C.negB[j] = negB[j]; }
+        for (int b = 0; b < nA; ++b) {
+            C.a[b] = (double)a[b]; C.ainv[b] = 1.0 / (double)a[b];
+            C.extq[b] = extq[b]; C.ft[b] = ft[b]; C.bm[b] = bm[b];
+            for (int j = 0; j < K; ++j) { C.ext[b][j] = ext[b][j]; C.fp[b][j] = fp[b][j]; C.bq[b][j] = bq[b][j]; }
+        }
+    }
+};
+
 struct HostLevel {
     ParmsId id;
     std::vector<u64> q;
@@ -60,6 +86,7 @@ struct HostLevel {
     DevLevel dev;             // POD image uploaded verbatim
     u64 gamma = 0, m_sk = 0;
     std::vector<u64> base_B;
+    HostBehzF bf;
 };
 
 struct HostContext {
@@ -72,7 +99,9 @@ struct HostContext {
     std::string error_name = "none", error_message = "uninitialized";
     std::vector<HostLevel> levels;           // [0] key level, [1..] data levels (== [0] only when K == 1)
     std::vector<u64> aux;                    // BEHZ primes: m_sk, gamma, B...
-    std::vector<HostTable> tables;           // ids 0..K-1 = q primes; K = m_sk; K+1+i = B_i
+    std::vector<HostTable> tables;           // ids 0..K-1 = q primes; K = m_sk; K+1+i = B_i; then t (batching); then aux44
+    std::vector<u64> aux44;                  // FP64-friendly auxiliary primes (<= 44 bits, == 1 mod 2N, none of them in q)
+    int aux44_table_base = -1;               // id in `tables` of aux44[0]
     bool batching = false;                   // t prime and == 1 mod 2N
     int plain_table_id = -1;                 // id in `tables` of the NTT mod t (BatchEncoder), when batching
     std::vector<uint32_t> slot_index;        // BatchEncoder: slot i lives at coefficient slot_index[i] of the NTT-domain vector
@@ -156,6 +185,28 @@ struct HostContext {
                 slot_index[i] = rev((pos - 1) >> 1);
                 slot_index[row | i] = rev((m - pos - 1) >> 1);
                 pos = (pos * 3) & (m - 1);
+            }
+        }
+
+        // FP64-friendly auxiliary base for ciphertext products (behz_f64.cuh): enough 44-bit primes that their product exceeds
+        // 2^32 t Q at the key level (every other level uses a prefix).  Only where the 32-per-thread FP64 transforms exist and
+        // the q residues fit the FP64 products (N = 2048..16384, q primes of at most 49 bits).
+        aux44.clear(); aux44_table_base = -1;
+        {
+            int maxq = 0;
+            for (u64 p : q) maxq = std::max(maxq, hm::bitlen(p));
+            if (logn >= 11 && logn <= 14 && maxq <= 49) {
+                const int need = 32 + hm::bitlen(t) + Q.bits();
+                std::vector<u64> cand = hm::primes_below(2 * n, 44, (size_t)need / 43 + 3 + Kk);
+                hm::Wide prod(1);
+                for (u64 p : cand) {
+                    if (std::find(q.begin(), q.end(), p) != q.end() || p == t) continue;
+                    aux44.push_back(p);
+                    prod.times(p);
+                    if (aux44.size() >= 2 && prod.bits() > need) break;
+                }
+                aux44_table_base = (int)tables.size();
+                for (u64 p : aux44) { tables.emplace_back(); build_table(tables.back(), logn, p); }
             }
         }
 
@@ -261,6 +312,60 @@ struct HostContext {
             D.B_mod_q[j] = make_shoup(bm, p);
             D.neg_B_mod_q[j] = make_shoup((p - bm) % p, p);
         }
+        build_behzf(L, Q);
+    }
+
+    // The same conversions over the 44-bit auxiliary base (see behz_f64.cuh for why the returned residues are SEAL's).
+    void build_behzf(HostLevel &L, const hm::Wide &Q) {
+        HostBehzF &F = L.bf;
+        F = HostBehzF();
+        const std::vector<u64> &ql = L.q;
+        const size_t k = ql.size();
+        if (aux44.empty() || k > 8) return;
+        const int need = 32 + hm::bitlen(t) + Q.bits();     // [SEAL] RNSTool::initialize sizes B m_sk against 2^32 t Q
+        hm::Wide prod(1);
+        size_t nA = 0;
+        while (nA < aux44.size() && (nA < 2 || prod.bits() <= need)) prod.times(aux44[nA++]);
+        if (prod.bits() <= need || nA > k + 4 || k + nA > (size_t)kMaxLimbs) return;
+        F.nA = (int)nA;
+        F.a.assign(aux44.begin(), aux44.begin() + nA);
+        for (size_t b = 0; b < nA; ++b) F.mod_id.push_back(aux44_table_base + (int)b);
+        F.q = ql;
+        auto fc = [](u64 w, u64 m) { return bf::F64C{(double)w, (double)w / (double)m}; };
+        const u64 mt = u64(1) << 32;
+        const size_t nB = nA - 1;
+        const u64 msk = F.a[nB];
+        std::vector<u64> baseB(F.a.begin(), F.a.begin() + nB);
+        hm::Wide PB = hm::Wide::product_of(baseB);
+        F.neg_inv_q_mt = (u32)((mt - hm::inverse_or_throw(Q.mod(mt), mt)) % mt);
+        F.ext.assign(nA, std::vector<bf::F64C>(k)); F.fp = F.ext; F.bq = F.ext;
+        F.extq.resize(nA); F.ft.resize(nA); F.bm.assign(nA, bf::F64C{0.0, 0.0});
+        std::vector<u64> cb(nA);
+        for (size_t b = 0; b < nA; ++b) {
+            const u64 p = F.a[b];
+            const u64 inv_mt = hm::inverse_or_throw(mt % p, p), inv_q = hm::inverse_or_throw(Q.mod(p), p);
+            F.extq[b] = fc(hm::mulm(Q.mod(p), inv_mt, p), p);
+            cb[b] = b < nB ? hm::mulm(inv_q, hm::inverse_or_throw(hm::Wide::product_of(baseB, b).mod(p), p), p) : inv_q;
+            F.ft[b] = fc(hm::mulm(t % p, cb[b], p), p);
+            if (b < nB) F.bm[b] = fc(hm::Wide::product_of(baseB, b).mod(msk), msk);
+        }
+        for (size_t j = 0; j < k; ++j) {
+            const u64 p = ql[j];
+            hm::Wide pj = hm::Wide::product_of(ql, j);
+            const u64 inv_punct = hm::inverse_or_throw(pj.mod(p), p);
+            F.pm.push_back((u32)pj.mod(mt));
+            F.zc.push_back(fc(hm::mulm(mt % p, inv_punct, p), p));
+            F.tz.push_back(fc(hm::mulm(t % p, inv_punct, p), p));
+            F.negB.push_back(fc((p - PB.mod(p)) % p, p));
+            for (size_t b = 0; b < nA; ++b) {
+                const u64 a = F.a[b], pa = pj.mod(a);
+                F.ext[b][j] = fc(hm::mulm(pa, hm::inverse_or_throw(mt % a, a), a), a);
+                F.fp[b][j] = fc((a - hm::mulm(pa, cb[b], a)) % a, a);
+                F.bq[b][j] = b < nB ? fc(hm::Wide::product_of(baseB, b).mod(p), p) : bf::F64C{0.0, 0.0};
+            }
+        }
+        F.invB = fc(hm::inverse_or_throw(PB.mod(msk), msk), msk);
+        F.ok = true;
     }
 };
 

@@ -118,6 +118,11 @@ void launch_symmetric_zero(const Engine &E, const u64 *d_seed, const u64 *d_sk, 
 // out (3 polynomials) = a * b with BEHZ scale-and-round; a == b (same pointer) squares.  ws: multiply_tmp_words().
 void launch_multiply(const Engine &E, size_t level, const u64 *a, const u64 *b, Layout in_lay, u64 *out, Layout out_lay, int nq, u64 *ws, cudaStream_t st);
 size_t multiply_tmp_words(const Engine &E, size_t level, int nq, bool square);
+void launch_tensor(const Engine &E, const RowMap &map, const u64 *x, const u64 *y, u64 *d, int nq, int n, cudaStream_t st);
+// ---- behzf.cu: the same product over the FP64-friendly auxiliary base (levels where HostLevel::bf.ok) ----
+bool behz_uses_f64(const Engine &E, size_t level);
+size_t multiply_f64_tmp_words(const Engine &E, size_t level, int nq, bool square);
+void launch_multiply_f64(const Engine &E, size_t level, const u64 *a, const u64 *b, Layout in_lay, u64 *out, Layout out_lay, int nq, u64 *ws, cudaStream_t st);
 // size-3 -> size-2 with relinearisation keys rk [digit][2][K][n] and their Shoup quotients rkq (same shape).
 void launch_relinearize(const Engine &E, size_t level, const u64 *in, Layout in_lay, u64 *out, Layout out_lay, int nq, const u64 *rk, const u64 *rkq, u64 *ws,
                         cudaStream_t st);

@@ -684,7 +684,7 @@ def extra_circuit_b(engine, torch):
     return {"groups_per_s": gps, "value": gps * n, "unit": "slot-wise queries/s", "queries_per_group": n, "groups_per_step": groups,
             "squares_per_s": 2 * gps, "relinearizations_per_s": 2 * gps,
             "workload": "circuitB_bfv_n8192_k4_t=Batching(8192,56)_slot_batched: sub_plain x2, square x2, relinearize x2, add, add_plain, multiply_plain(mono)",
-            "roofline": {"bound": "integer + FP64 pipes (61-bit BEHZ base on the integer multiplier); HBM shown for reference", "algorithmic_bytes_per_group": bytes_group,
+            "roofline": {"bound": "FP64 pipe (squares over the 44-bit auxiliary base, relinearisation: every transform and base conversion in exact FP64 products); HBM shown for reference", "algorithmic_bytes_per_group": bytes_group,
                          "achieved": bytes_group * gps / 1e9, "peak": peak, "unit": "GB/s", "frac": bytes_group * gps / 1e9 / peak},
             "agrees_with_oracle": agrees, "slots_match_algebra": algebra,
             "cpu_baseline": {"groups_per_s": threads / cdt, "value": threads / cdt * n, "unit": "slot-wise queries/s", "cores": threads, "kind": "port",

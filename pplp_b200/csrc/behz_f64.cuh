@@ -33,7 +33,7 @@ namespace bf {
 typedef uint64_t u64;
 typedef unsigned int u32;
 
-struct F64C { double w, wi; };   // an exact integer constant w below its modulus m, and fl(w / m)
+struct alignas(16) F64C { double w, wi; };   // an exact integer constant w below its modulus m, and fl(w / m)
 
 constexpr double kTwo52 = 4503599627370496.0;      // 2^52
 constexpr double kRound52 = 6755399441055744.0;    // 1.5 * 2^52
@@ -90,7 +90,7 @@ PPLP_HD double rsym(double a, double mi, double m) {
 PPLP_HD double canon(double v, double m) { return v < 0.0 ? dadd(v, m) : v; }   // (-m, m) -> [0, m)
 
 // Per-level constants for K data limbs and up to K + 4 auxiliary primes (the last one in use plays m_sk).
-template <int K> struct BehzFC {
+template <int K> struct alignas(16) BehzFC {
     static constexpr int NAMAX = K + 4;
     int nA, n;
     u32 neg_inv_q_mt;             // -Q^-1 mod 2^32
@@ -109,75 +109,110 @@ template <int K> struct BehzFC {
     F64C invB;                    // B'^-1 mod m_sk'
 };
 
-// fastbconv_m_tilde + sm_mrq for one coefficient: x[j] canonical residues -> out[b * stride] canonical residues of X mod a_b
-template <int K> PPLP_HD void extend_coeff(const BehzFC<K> &C, const u64 (&x)[K], u64 *out, size_t stride) {
-    double z[K];
-    u32 racc = 0;
 #if defined(__CUDA_ARCH__)
-#pragma unroll
+#define PPLP_UNROLL _Pragma("unroll")
+#define PPLP_NOUNROLL _Pragma("unroll 1")
+#else
+#define PPLP_UNROLL
+#define PPLP_NOUNROLL
 #endif
-    for (int j = 0; j < K; ++j) {
-        z[j] = canon(mulmod(u2d(x[j]), C.zc[j], C.q[j]), C.q[j]);
-        racc += (u32)d2u(z[j]) * C.pm[j];
+
+// NC coefficients per call: the constants of a step are fetched once and the NC dependency chains interleave.
+
+// fastbconv_m_tilde + sm_mrq: x[c][j] canonical residues -> out[c][b * stride] canonical residues of X mod a_b
+template <int K, int NC> PPLP_HD void extend_coeff(const BehzFC<K> &C, const u64 (&x)[NC][K], u64 *const (&out)[NC], size_t stride) {
+    double z[NC][K], rc[NC];
+    PPLP_UNROLL
+    for (int c = 0; c < NC; ++c) {
+        u32 racc = 0;
+        PPLP_UNROLL
+        for (int j = 0; j < K; ++j) {
+            z[c][j] = canon(mulmod(u2d(x[c][j]), C.zc[j], C.q[j]), C.q[j]);
+            racc += (u32)d2u(z[c][j]) * C.pm[j];
+        }
+        const u32 r = racc * C.neg_inv_q_mt;                                       // -(sum) Q^-1 mod 2^32
+        rc[c] = dadd(u2d((u64)r), r >= 0x80000000u ? -4294967296.0 : 0.0);          // centred representative
     }
-    const u32 r = racc * C.neg_inv_q_mt;                                   // -(sum) Q^-1 mod 2^32
-    const double rc = dadd(u2d((u64)r), r >= 0x80000000u ? -4294967296.0 : 0.0);       // centred representative
-#if defined(__CUDA_ARCH__)
-#pragma unroll 1
-#endif
+    PPLP_NOUNROLL
     for (int b = 0; b < C.nA; ++b) {
-        const double m = C.a[b];
-        double s = mulmod(rc, C.extq[b], m);
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for (int j = 0; j < K; ++j) s = dadd(s, mulmod(z[j], C.ext[b][j], m));
-        out[(size_t)b * stride] = d2u(canon(rsym(s, C.ainv[b], m), m));
+        const double m = C.a[b], mi = C.ainv[b];
+        double s[NC];
+        const F64C eq = C.extq[b];
+        PPLP_UNROLL
+        for (int c = 0; c < NC; ++c) s[c] = mulmod(rc[c], eq, m);
+        PPLP_UNROLL
+        for (int j = 0; j < K; ++j) {
+            const F64C w = C.ext[b][j];
+            PPLP_UNROLL
+            for (int c = 0; c < NC; ++c) s[c] = dadd(s[c], mulmod(z[c][j], w, m));
+        }
+        PPLP_UNROLL
+        for (int c = 0; c < NC; ++c) out[c][(size_t)b * stride] = d2u(canon(rsym(s[c], mi, m), m));
     }
 }
 
-// (*t) + fast_floor + fastbconv_sk for one coefficient: dq[j] (q residues of the product), da[b * stride_a] (auxiliary
-// residues), both canonical and in coefficient form -> out[j * stride_o] canonical
-template <int K> PPLP_HD void floor_sk_coeff(const BehzFC<K> &C, const u64 (&dq)[K], const u64 *da, size_t stride_a, u64 *out, size_t stride_o) {
-    double z[K], acc[K];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int j = 0; j < K; ++j) {
-        z[j] = canon(mulmod(u2d(dq[j]), C.tz[j], C.q[j]), C.q[j]);        // canonical: the integer sum_j z_j (Q/q_j) matters
-        acc[j] = 0.0;
+// (*t) + fast_floor + fastbconv_sk: dq[c][j] (q residues of the product), da[c][b * stride_a] (auxiliary residues), both
+// canonical and in coefficient form -> out[c][j * stride_o] canonical
+template <int K, int NC>
+PPLP_HD void floor_sk_coeff(const BehzFC<K> &C, const u64 (&dq)[NC][K], const u64 *const (&da)[NC], size_t stride_a, u64 *const (&out)[NC], size_t stride_o) {
+    double z[NC][K], acc[NC][K], am[NC], flm[NC];
+    PPLP_UNROLL
+    for (int c = 0; c < NC; ++c) {
+        PPLP_UNROLL
+        for (int j = 0; j < K; ++j) {
+            z[c][j] = canon(mulmod(u2d(dq[c][j]), C.tz[j], C.q[j]), C.q[j]);       // canonical: the integer sum_j z_j (Q/q_j) matters
+            acc[c][j] = 0.0;
+        }
+        am[c] = 0.0; flm[c] = 0.0;
     }
-    double am = 0.0, flm = 0.0;
     const int nB = C.nA - 1;
     const double msk = C.a[nB], mski = C.ainv[nB];
-#if defined(__CUDA_ARCH__)
-#pragma unroll 1
-#endif
+    u64 dnext[NC];   // the auxiliary residue of the NEXT step is fetched while this one is in the multipliers
+    PPLP_UNROLL
+    for (int c = 0; c < NC; ++c) dnext[c] = da[c][0];
+    PPLP_NOUNROLL
     for (int b = 0; b <= nB; ++b) {
-        const double m = C.a[b];
-        double f = mulmod(u2d(da[(size_t)b * stride_a]), C.ft[b], m);
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for (int j = 0; j < K; ++j) f = dadd(f, mulmod(z[j], C.fp[b][j], m));
-        f = rsym(f, C.ainv[b], m);      // b in B': y_b = fl_b (B'/a_b)^-1 (any representative serves: alpha absorbs it); b = m_sk': fl
-        if (b == nB) flm = f;
-        else {
-            am = dadd(am, mulmod(f, C.bm[b], msk));
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-            for (int j = 0; j < K; ++j) acc[j] = dadd(acc[j], mulmod(f, C.bq[b][j], C.q[j]));
+        const double m = C.a[b], mi = C.ainv[b];
+        double f[NC];
+        const F64C ft = C.ft[b];
+        u64 dcur[NC];
+        PPLP_UNROLL
+        for (int c = 0; c < NC; ++c) { dcur[c] = dnext[c]; if (b < nB) dnext[c] = da[c][(size_t)(b + 1) * stride_a]; }
+        PPLP_UNROLL
+        for (int c = 0; c < NC; ++c) f[c] = mulmod(u2d(dcur[c]), ft, m);
+        PPLP_UNROLL
+        for (int j = 0; j < K; ++j) {
+            const F64C w = C.fp[b][j];
+            PPLP_UNROLL
+            for (int c = 0; c < NC; ++c) f[c] = dadd(f[c], mulmod(z[c][j], w, m));
+        }
+        // b in B': y_b = fl_b (B'/a_b)^-1 (any representative serves: alpha absorbs it); b = m_sk': fl itself
+        PPLP_UNROLL
+        for (int c = 0; c < NC; ++c) f[c] = rsym(f[c], mi, m);
+        if (b == nB) {
+            PPLP_UNROLL
+            for (int c = 0; c < NC; ++c) flm[c] = f[c];
+        } else {
+            const F64C wm = C.bm[b];
+            PPLP_UNROLL
+            for (int c = 0; c < NC; ++c) am[c] = dadd(am[c], mulmod(f[c], wm, msk));
+            PPLP_UNROLL
+            for (int j = 0; j < K; ++j) {
+                const F64C w = C.bq[b][j];
+                PPLP_UNROLL
+                for (int c = 0; c < NC; ++c) acc[c][j] = dadd(acc[c][j], mulmod(f[c], w, C.q[j]));
+            }
         }
     }
-    // alpha = (conv_msk - fl_msk) B'^-1 mod m_sk', the small signed integer itself (|alpha| << m_sk' / 2)
-    const double alpha = mulmod(rsym(dadd(am, -flm), mski, msk), C.invB, msk);
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int j = 0; j < K; ++j) {
-        const double v = dadd(acc[j], mulmod(alpha, C.negB[j], C.q[j]));
-        out[(size_t)j * stride_o] = d2u(canon(rsym(v, C.qinv[j], C.q[j]), C.q[j]));
+    PPLP_UNROLL
+    for (int c = 0; c < NC; ++c) {
+        // alpha = (conv_msk - fl_msk) B'^-1 mod m_sk', the small signed integer itself (|alpha| << m_sk' / 2)
+        const double alpha = mulmod(rsym(dadd(am[c], -flm[c]), mski, msk), C.invB, msk);
+        PPLP_UNROLL
+        for (int j = 0; j < K; ++j) {
+            const double v = dadd(acc[c][j], mulmod(alpha, C.negB[j], C.q[j]));
+            out[c][(size_t)j * stride_o] = d2u(canon(rsym(v, C.qinv[j], C.q[j]), C.q[j]));
+        }
     }
 }
 

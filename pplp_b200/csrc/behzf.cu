@@ -26,36 +26,67 @@
 
 namespace pplp {
 
-template <int K>
-__global__ void __launch_bounds__(256) behzf_extend_kernel(const __grid_constant__ bf::BehzFC<K> C, const u64 *__restrict__ in, Layout lay, u64 *__restrict__ ext,
-                                                           int copy_q) {
-    const int n = C.n, NL = K + C.nA;
-    const int qp = blockIdx.x, qi = qp >> 1, p = qp & 1;
-    const int i = blockIdx.y * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const u64 *src = in + qi * lay.sq + p * lay.sp + i;
-    u64 *dst = ext + (size_t)qp * NL * n + i;
-    u64 x[K];
-#pragma unroll
-    for (int j = 0; j < K; ++j) x[j] = src[j * lay.sl];
-    if (copy_q) {
-#pragma unroll
-        for (int j = 0; j < K; ++j) dst[(size_t)j * n] = x[j];
-    }
-    bf::extend_coeff<K>(C, x, dst + (size_t)K * n, (size_t)n);
+// Per-coefficient kernels: kBehzfNC coefficients per thread (i and i + 256 of a 512-coefficient tile), the level's constants
+// staged once per CTA from their device copy into shared memory (one 128-bit LDS per product, shared by the coefficients; as
+// kernel parameters every product paid two uniform loads and two moves, and the kernels sat at 74 % of the issue slots).
+constexpr int kBehzfNC = 2;
+template <int K> __device__ __forceinline__ const bf::BehzFC<K> &behzf_stage_consts(const bf::BehzFC<K> *Cg, unsigned char *raw) {
+    static_assert(sizeof(bf::BehzFC<K>) % 16 == 0, "constants are copied in 16-byte pieces");
+    const uint4 *g = reinterpret_cast<const uint4 *>(Cg);
+    uint4 *s = reinterpret_cast<uint4 *>(raw);
+    for (int i = threadIdx.x; i < (int)(sizeof(bf::BehzFC<K>) / 16); i += blockDim.x) s[i] = __ldg(g + i);
+    __syncthreads();
+    return *reinterpret_cast<const bf::BehzFC<K> *>(raw);
 }
 
 template <int K>
-__global__ void __launch_bounds__(256) behzf_floor_sk_kernel(const __grid_constant__ bf::BehzFC<K> C, const u64 *__restrict__ d, u64 *__restrict__ out, Layout lay) {
-    const int n = C.n, NL = K + C.nA;
-    const int qp = blockIdx.x, qi = qp / 3, p = qp % 3;
-    const int i = blockIdx.y * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const u64 *src = d + (size_t)qp * NL * n + i;
-    u64 dq[K];
+__global__ void __launch_bounds__(256) behzf_extend_kernel(const bf::BehzFC<K> *__restrict__ Cg, const u64 *__restrict__ in, Layout lay, u64 *__restrict__ ext, int copy_q) {
+    __shared__ __align__(16) unsigned char craw[sizeof(bf::BehzFC<K>)];
+    const int qp = blockIdx.x, qi = qp >> 1, p = qp & 1;
+    const int i = blockIdx.y * (256 * kBehzfNC) + threadIdx.x;   // n is a multiple of 512
+    const u64 *src = in + qi * lay.sq + p * lay.sp + i;
+    u64 x[kBehzfNC][K];
 #pragma unroll
-    for (int j = 0; j < K; ++j) dq[j] = src[(size_t)j * n];
-    bf::floor_sk_coeff<K>(C, dq, src + (size_t)K * n, (size_t)n, out + qi * lay.sq + p * lay.sp + i, lay.sl);
+    for (int c = 0; c < kBehzfNC; ++c)
+#pragma unroll
+        for (int j = 0; j < K; ++j) x[c][j] = src[j * lay.sl + c * 256];   // in flight while the constants are staged
+    const bf::BehzFC<K> &C = behzf_stage_consts<K>(Cg, craw);
+    const int n = C.n, NL = K + C.nA;
+    u64 *dst = ext + (size_t)qp * NL * n + i;
+    u64 *o[kBehzfNC];
+#pragma unroll
+    for (int c = 0; c < kBehzfNC; ++c) o[c] = dst + (size_t)K * n + c * 256;
+    if (copy_q) {
+#pragma unroll
+        for (int c = 0; c < kBehzfNC; ++c)
+#pragma unroll
+            for (int j = 0; j < K; ++j) dst[(size_t)j * n + c * 256] = x[c][j];
+    }
+    u64 *const (&oo)[kBehzfNC] = o;
+    bf::extend_coeff<K, kBehzfNC>(C, x, oo, (size_t)n);
+}
+
+template <int K>
+__global__ void __launch_bounds__(256) behzf_floor_sk_kernel(const bf::BehzFC<K> *__restrict__ Cg, int nA, const u64 *__restrict__ d, u64 *__restrict__ out, Layout lay) {
+    __shared__ __align__(16) unsigned char craw[sizeof(bf::BehzFC<K>)];
+    const int n = (int)gridDim.y * (256 * kBehzfNC), NL = K + nA;
+    const int qp = blockIdx.x, qi = qp / 3, p = qp % 3;
+    const int i = blockIdx.y * (256 * kBehzfNC) + threadIdx.x;
+    const u64 *src = d + (size_t)qp * NL * n + i;
+    u64 dq[kBehzfNC][K];
+    const u64 *da[kBehzfNC];
+    u64 *o[kBehzfNC];
+#pragma unroll
+    for (int c = 0; c < kBehzfNC; ++c) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) dq[c][j] = src[(size_t)j * n + c * 256];
+        da[c] = src + (size_t)K * n + c * 256;
+        o[c] = out + qi * lay.sq + p * lay.sp + i + c * 256;
+    }
+    const bf::BehzFC<K> &C = behzf_stage_consts<K>(Cg, craw);   // the loads above are in flight meanwhile
+    const u64 *const (&dd)[kBehzfNC] = da;
+    u64 *const (&oo)[kBehzfNC] = o;
+    bf::floor_sk_coeff<K, kBehzfNC>(C, dq, dd, (size_t)n, oo, lay.sl);
 }
 
 struct BehzfFwdArgs {
@@ -178,15 +209,17 @@ static void multiply_f64_k(const Engine &E, size_t level, const u64 *a, const u6
     const int n = (int)E.host.n, nA = HL.bf.nA, NL = K + nA;
     const bool square = (a == b);
     static const bool fused = [] { const char *e = getenv("PPLP_BEHZF_FUSED"); return !(e && e[0] == '0' && e[1] == 0); }();
-    bf::BehzFC<K> C;
-    HL.bf.fill(C, n);
+    const bf::BehzFC<K> *C = static_cast<const bf::BehzFC<K> *>(E.behzf_consts(level, [&](std::vector<unsigned char> &img) {
+        img.resize(sizeof(bf::BehzFC<K>));
+        HL.bf.fill(*reinterpret_cast<bf::BehzFC<K> *>(img.data()), n);
+    }));
     RowMap map;
     map.nlimbs = NL;
     for (int j = 0; j < K; ++j) map.mod_id[j] = j;
     for (int b2 = 0; b2 < nA; ++b2) map.mod_id[K + b2] = HL.bf.mod_id[b2];
     const size_t we = (size_t)nq * 2 * NL * n;
     u64 *ea = ws, *eb = square ? ea : ea + we, *d = (square ? ea : eb) + we;
-    const dim3 ge(nq * 2, (n + 255) / 256), gf(nq * 3, (n + 255) / 256);
+    const dim3 ge(nq * 2, n / (256 * kBehzfNC)), gf(nq * 3, n / (256 * kBehzfNC));
     behzf_extend_kernel<K><<<ge, 256, 0, st>>>(C, a, in_lay, ea, fused ? 0 : 1);
     if (!square) behzf_extend_kernel<K><<<ge, 256, 0, st>>>(C, b, in_lay, eb, fused ? 0 : 1);
     if (fused) {
@@ -206,7 +239,7 @@ static void multiply_f64_k(const Engine &E, size_t level, const u64 *a, const u6
         launch_tensor(E, map, ea, eb, d, nq, n, st);
         launch_ntt(E, d, Layout{(size_t)3 * NL * n, (size_t)NL * n, (size_t)n}, nq, 3, map, true, st);
     }
-    behzf_floor_sk_kernel<K><<<gf, 256, 0, st>>>(C, d, out, out_lay);
+    behzf_floor_sk_kernel<K><<<gf, 256, 0, st>>>(C, nA, d, out, out_lay);
     PPLP_CUDA(cudaGetLastError());
 }
 

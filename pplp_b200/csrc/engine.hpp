@@ -38,6 +38,21 @@ struct Engine {
         PPLP_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
     }
 
+    // device copies of the per-level constant blocks of behzf.cu (bf::BehzFC<k>), uploaded on first use
+    mutable std::vector<void *> d_behzf;
+    template <class Fill> const void *behzf_consts(size_t level, Fill fill) const {
+        if (d_behzf.size() < host.levels.size()) d_behzf.resize(host.levels.size(), nullptr);
+        if (!d_behzf[level]) {
+            std::vector<unsigned char> img;
+            fill(img);
+            void *d = nullptr;
+            PPLP_CUDA(cudaMalloc(&d, img.size()));
+            PPLP_CUDA(cudaMemcpy(d, img.data(), img.size(), cudaMemcpyHostToDevice));
+            d_behzf[level] = d;
+        }
+        return d_behzf[level];
+    }
+
     void require_device() const { if (device < 0) throw std::logic_error("pplp: context was created without a CUDA device"); }
     template <class T> T *upload(const T *src, size_t count) {
         T *d = nullptr;
@@ -49,6 +64,7 @@ struct Engine {
     void upload_tables(int dev);
     ~Engine() {
         for (void *p : owned) cudaFree(p);
+        for (void *p : d_behzf) if (p) cudaFree(p);
         if (aux_stream) { cudaStreamDestroy(aux_stream); cudaEventDestroy(ev_fork); cudaEventDestroy(ev_join); }
     }
 

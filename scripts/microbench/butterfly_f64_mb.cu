@@ -26,6 +26,20 @@ template <int V> __device__ __forceinline__ void bf(double &x, double &y, double
         const double c = __dsub_rn(__fma_rn(d, wi, kM), kM);
         const double r = __fma_rn(-c, q, h);
         y = __dadd_rn(r, l);
+    } else if (V == 4) {     // quotient rounded by the conversion unit (FRND.F64) instead of the 1.5*2^52 add/subtract pair: 7 FP64 + 1 FRND
+        const double h = __dmul_rn(y, w);
+        const double l = __fma_rn(y, w, -h);
+        const double c = rint(__dmul_rn(y, wi));
+        const double r = __fma_rn(-c, q, h);
+        const double t = __dadd_rn(r, l);
+        y = __dsub_rn(x, t); x = __dadd_rn(x, t);
+    } else if (V == 5) {     // every second butterfly with the FRND quotient (mix of the two pipes)
+        const double h = __dmul_rn(y, w);
+        const double l = __fma_rn(y, w, -h);
+        const double c = ((long long)__double_as_longlong(w) & 1) ? rint(__dmul_rn(y, wi)) : __dsub_rn(__fma_rn(y, wi, kM), kM);
+        const double r = __fma_rn(-c, q, h);
+        const double t = __dadd_rn(r, l);
+        y = __dsub_rn(x, t); x = __dadd_rn(x, t);
     } else if (V == 3) {     // butterfly + a range reduction of x (what a pass boundary costs): 11 instructions
         const double h = __dmul_rn(y, w);
         const double l = __fma_rn(y, w, -h);
@@ -60,11 +74,12 @@ int main() {
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
     for (int threads = 256; threads <= 1024; threads *= 2) {
         const int blocks = 148 * 2048 / threads;   // fill every SM with 2048 threads
-        for (int v = 0; v < 4; ++v) {
+        for (int v = 0; v < 6; ++v) {
             for (int rep = 0; rep < 2; ++rep) {
                 cudaEventRecord(a);
                 if (v == 0) k<0><<<blocks, threads>>>(d, tw, q, iters); else if (v == 1) k<1><<<blocks, threads>>>(d, tw, q, iters);
-                else if (v == 2) k<2><<<blocks, threads>>>(d, tw, q, iters); else k<3><<<blocks, threads>>>(d, tw, q, iters);
+                else if (v == 2) k<2><<<blocks, threads>>>(d, tw, q, iters); else if (v == 3) k<3><<<blocks, threads>>>(d, tw, q, iters);
+                else if (v == 4) k<4><<<blocks, threads>>>(d, tw, q, iters); else k<5><<<blocks, threads>>>(d, tw, q, iters);
                 cudaEventRecord(b); cudaEventSynchronize(b);
             }
             float ms; cudaEventElapsedTime(&ms, a, b);

@@ -47,9 +47,10 @@ template <int K> int multiply_k(const HostContext &H, size_t level, const u64 *a
         ext.assign(2 * NL * n, 0);
         for (size_t p = 0; p < 2; ++p) {
             for (size_t i = 0; i < n; ++i) {
-                u64 x[K];
-                for (int j = 0; j < K; ++j) { x[j] = ct[(p * K + j) * n + i]; ext[(p * NL + j) * n + i] = x[j]; }
-                bf::extend_coeff<K>(C, x, ext.data() + (p * NL + K) * n + i, n);
+                u64 x[1][K];
+                for (int j = 0; j < K; ++j) { x[0][j] = ct[(p * K + j) * n + i]; ext[(p * NL + j) * n + i] = x[0][j]; }
+                u64 *const o[1] = {ext.data() + (p * NL + K) * n + i};
+                bf::extend_coeff<K, 1>(C, x, o, n);
             }
             for (size_t l = 0; l < NL; ++l) ntt_forward(table(l), ext.data() + (p * NL + l) * n, n);
         }
@@ -71,9 +72,11 @@ template <int K> int multiply_k(const HostContext &H, size_t level, const u64 *a
     }
     for (size_t p = 0; p < 3; ++p)
         for (size_t i = 0; i < n; ++i) {
-            u64 dq[K];
-            for (int j = 0; j < K; ++j) dq[j] = d[(p * NL + j) * n + i];
-            bf::floor_sk_coeff<K>(C, dq, d.data() + (p * NL + K) * n + i, n, out + p * K * n + i, n);
+            u64 dq[1][K];
+            for (int j = 0; j < K; ++j) dq[0][j] = d[(p * NL + j) * n + i];
+            const u64 *const da[1] = {d.data() + (p * NL + K) * n + i};
+            u64 *const o[1] = {out + p * K * n + i};
+            bf::floor_sk_coeff<K, 1>(C, dq, da, n, o, n);
         }
     return 0;
 }

@@ -1,0 +1,108 @@
+"""GPU parity of the BEHZ product over the FP64-friendly auxiliary base (pplp_b200/csrc/behzf.cu) — through the C ABI, bit-exact
+against oracle/ (SEAL's bfv_multiply over its own 61-bit base, [SEAL] evaluator.cpp bfv_multiply / util/rns.cpp):
+extreme residues, lower levels of the modulus chain, batches in both layouts, and the three pipelines of the product (FP64 base
+fused / FP64 base around the stand-alone transforms / SEAL's 61-bit base) producing the same bytes."""
+import hashlib
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from tests.test_gpu_parity import contexts, eng, rand_residues   # noqa: F401  (eng is a fixture)
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _extremes(q, n):
+    top = np.stack([np.stack([np.full(n, qj - 1, dtype=np.uint64) for qj in q]) for _ in range(2)])
+    zero = np.zeros_like(top)
+    alt = top.copy()
+    alt[:, :, ::2] = 0
+    half = np.stack([np.stack([np.full(n, qj // 2, dtype=np.uint64) for qj in q]) for _ in range(2)])
+    one = np.ones_like(top)
+    return [(top, top), (top, zero), (alt, top), (half, alt), (half, half), (one, top)]
+
+
+@pytest.mark.parametrize("n", [2048, 4096, 8192, 16384])
+def test_fp64_base_extreme_residues_match_oracle(eng, oracle, n):
+    q = None
+    if n == 2048:   # BFVDefault(2048) is one 54-bit prime (not eligible): two 40-bit primes instead
+        q = oracle.get_primes(2 * n, 40, 2)
+    ctx, octx = contexts(eng, oracle, n, q=q, enforce_security=q is None)
+    ql = octx.q[: ctx.k]
+    pairs = _extremes(ql, n)
+    a = np.stack([p[0] for p in pairs])
+    b = np.stack([p[1] for p in pairs])
+    got = eng.to_np(ctx.multiply(ctx.dev(a), ctx.dev(b)))
+    for i, (x, y) in enumerate(pairs):
+        assert (got[i] == octx.multiply(x, y)).all(), (n, i)
+    sq = eng.to_np(ctx.square(ctx.dev(a)))
+    for i, (x, _) in enumerate(pairs):
+        assert (sq[i] == octx.square(x)).all(), (n, i)
+
+
+def test_fp64_base_lower_levels_and_widest_narrow_primes(eng, oracle):
+    """Every level of a 5-prime chain (k = 4, 3, 2, 1), and a chain of the largest 44-bit primes — the very primes the auxiliary
+    base would pick, so the 'not already in q' rule is exercised."""
+    n = 4096
+    rng = np.random.default_rng(99)
+    for q in (oracle.bfv_default(8192), oracle.get_primes(2 * n, 44, 4)):
+        ctx, octx = contexts(eng, oracle, n, q=q, enforce_security=False)
+        for level in range(1, len(q)):
+            k = len(q) - level
+            a = np.stack([np.stack([rand_residues(rng, q[:k], n) for _ in range(2)]) for _ in range(2)])
+            b = np.stack([np.stack([rand_residues(rng, q[:k], n) for _ in range(2)]) for _ in range(2)])
+            got = eng.to_np(ctx.multiply(ctx.dev(a), ctx.dev(b), level=level))
+            for i in range(2):
+                assert (got[i] == octx.multiply(a[i], b[i], level)).all(), (q[0], level, i)
+
+
+def test_fp64_base_batch_and_layout_invariance(eng, oracle):
+    n = 8192
+    ctx, octx = contexts(eng, oracle, n)
+    rng = np.random.default_rng(5)
+    q = octx.q[: ctx.k]
+    nq = 37
+    a = np.stack([np.stack([rand_residues(rng, q, n) for _ in range(2)]) for _ in range(nq)])
+    whole = eng.to_np(ctx.square(ctx.dev(a)))
+    for i in (0, 17, 36):
+        assert (whole[i] == octx.square(a[i])).all()
+    single = eng.to_np(ctx.square(ctx.dev(a[17:18])))
+    assert (single[0] == whole[17]).all()
+    lm = ctx.dev(np.ascontiguousarray(a.transpose(2, 1, 0, 3)))
+    got_lm = eng.to_np(ctx.square(lm, layout=eng.LAYOUT_LIMB_MAJOR)).transpose(2, 1, 0, 3)
+    assert (got_lm == whole).all()
+
+
+_SNIPPET = r"""
+import hashlib, sys
+import numpy as np
+sys.path.insert(0, %r)
+from pplp_b200 import engine
+h = hashlib.sha256()
+for n, t in ((4096, 1 << 56), (8192, 1 << 56), (8192, 0xfffffffffb4001), (16384, 1 << 20)):
+    ctx = engine.Context(n, t=t, device=0)
+    rng = np.random.default_rng(n)
+    a = np.stack([np.stack([np.stack([rng.integers(0, qj, size=n, dtype=np.uint64) for qj in ctx.q[:ctx.k]]) for _ in range(2)]) for _ in range(3)])
+    b = np.stack([np.stack([np.stack([rng.integers(0, qj, size=n, dtype=np.uint64) for qj in ctx.q[:ctx.k]]) for _ in range(2)]) for _ in range(3)])
+    h.update(engine.to_np(ctx.multiply(ctx.dev(a), ctx.dev(b))).tobytes())
+    h.update(engine.to_np(ctx.square(ctx.dev(a))).tobytes())
+print("DIGEST", h.hexdigest())
+"""
+
+
+def test_three_product_pipelines_give_the_same_bytes():
+    """PPLP_BEHZ_BASE / PPLP_BEHZF_FUSED are read once per process, so each pipeline runs in its own interpreter."""
+    digests = {}
+    for name, env in (("fp64_fused", {}), ("fp64_unfused", {"PPLP_BEHZF_FUSED": "0"}), ("seal_61bit", {"PPLP_BEHZ_BASE": "61"})):
+        e = dict(os.environ)
+        e.pop("PPLP_BEHZ_BASE", None)
+        e.pop("PPLP_BEHZF_FUSED", None)
+        e.update(env)
+        p = subprocess.run([sys.executable, "-c", _SNIPPET % ROOT], capture_output=True, text=True, env=e, timeout=600)
+        assert p.returncode == 0, p.stdout + p.stderr
+        digests[name] = [ln for ln in p.stdout.splitlines() if ln.startswith("DIGEST")][0]
+    assert digests["fp64_fused"] == digests["fp64_unfused"] == digests["seal_61bit"], digests

@@ -11,7 +11,7 @@ import re
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 HEADER = os.path.join(ROOT, "include", "pplp_b200.h")
-LIB_PATH = os.path.join(PKG, "libpplp_b200.so")
+LIB_PATH = os.environ.get("PPLP_B200_LIB") or os.path.join(PKG, "libpplp_b200.so")   # the override is for A/B builds of experiments
 
 _SCALARS = {
     "int": C.c_int, "size_t": C.c_size_t, "uint64_t": C.c_uint64, "uint32_t": C.c_uint32, "double": C.c_double,

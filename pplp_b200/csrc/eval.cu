@@ -25,12 +25,32 @@ __device__ __forceinline__ u64 dev_lift(const DevLevel &L, u64 m, int j) {
     return m >= L.t_threshold ? add_mod(r, L.neg_t[j], L.q[j].q) : r;
 }
 // round(Q*m/t) mod q_j for ANY 64-bit m:  (m * floor(Q/t) + floor((m*(Q mod t) + floor((t+1)/2)) / t)) mod q_j
-__device__ __forceinline__ u64 dev_scaled(const DevLevel &L, u64 m, int j) {
+// floor((hi:lo) / m.q) for a quotient below 2^64 and m.q < 2^62: Barrett's estimate (short by at most 2) and two corrections —
+// a handful of wide multiplies where the compiler's 128-by-64 division is a loop of several hundred instructions
+__device__ __forceinline__ u64 div128_floor(u64 lo, u64 hi, const Mod &m) {
+    const u64 t1 = __umul64hi(lo, m.r_lo);
+    const u64 p_lo = lo * m.r_hi, p_hi = __umul64hi(lo, m.r_hi);
+    const u64 s = p_lo + t1;
+    const u64 c3 = p_hi + (s < p_lo);
+    const u64 g_lo = hi * m.r_lo, g_hi = __umul64hi(hi, m.r_lo);
+    const u64 s2 = s + g_lo;
+    const u64 c1 = g_hi + (s2 < s);
+    u64 qhat = hi * m.r_hi + c3 + c1;
+    u64 r = lo - qhat * m.q;
+    if (r >= m.q) { r -= m.q; ++qhat; }
+    if (r >= m.q) ++qhat;
+    return qhat;
+}
+// the limb-independent part of round(Q*m/t): floor((m * (Q mod t) + floor((t+1)/2)) / t)
+__device__ __forceinline__ u64 dev_scaled_fix(const DevLevel &L, u64 m) {
     const u128 numer = (u128)m * L.q_mod_t + L.t_threshold;
-    const u64 fix = (u64)(numer / L.t);
+    return div128_floor((u64)numer, (u64)(numer >> 64), L.tmod);
+}
+__device__ __forceinline__ u64 dev_scaled_limb(const DevLevel &L, u64 m, u64 fix, int j) {
     const Mod &mq = L.q[j];
     return add_mod(mul_mod(barrett64(m, mq), L.delta[j], mq), barrett64(fix, mq), mq.q);
 }
+__device__ __forceinline__ u64 dev_scaled(const DevLevel &L, u64 m, int j) { return dev_scaled_limb(L, m, dev_scaled_fix(L, m), j); }
 __device__ __forceinline__ u64 dev_shoup_quotient(u64 w, u64 q) { return (u64)(((u128)w << 64) / q); }
 
 // scratch row per (query, limb): {XB.w, XB.wq, YB.w, YB.wq, S.w, S.wq, Z, SR}
@@ -273,19 +293,22 @@ void launch_circuit_a_cross(const Engine &E, size_t level, const u64 *c0, const 
 // ---- Circuit B helpers (north_star's direct form: sub_plain -> square -> relinearize -> add -> add_plain -> multiply_plain) ----
 // dst (dst_lay) <- src (src_lay), then c0 -= round(Q m_i / t) for the first `count` coefficients: the strided copy of a batch
 // chunk into the work buffer fused with sub_plain_inplace ([SEAL] multiply_sub_plain_with_scaling_variant).  rows in grid.x.
+// One thread per coefficient, all limbs of both polynomials: the scaled plaintext's limb-independent part is computed once.
 __global__ void __launch_bounds__(256) copy_sub_plain_kernel(const DevLevel *Lp, const u64 *__restrict__ src, Layout src_lay, u64 *__restrict__ dst, Layout dst_lay, int nq,
                                                              int n, const u64 *__restrict__ plain, int count, size_t m_stride) {
     const DevLevel &L = *Lp;
-    int row = blockIdx.x;
-    const int qi = row % nq; row /= nq;
-    const int p = row & 1, j = row >> 1;
-    const u64 q = L.q[j].q;
-    const u64 *s = src + qi * src_lay.sq + p * src_lay.sp + j * src_lay.sl;
-    u64 *d = dst + qi * dst_lay.sq + p * dst_lay.sp + j * dst_lay.sl;
-    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
-        u64 v = s[i];
-        if (p == 0 && i < count) v = sub_mod(v, dev_scaled(L, plain[qi * m_stride + i], j), q);
-        d[i] = v;
+    const int qi = blockIdx.x, k = L.k;
+    const int i = blockIdx.y * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u64 *s = src + qi * src_lay.sq + i;
+    u64 *d = dst + qi * dst_lay.sq + i;
+    const bool has = i < count;
+    const u64 m = has ? plain[qi * m_stride + i] : 0;
+    const u64 fix = has ? dev_scaled_fix(L, m) : 0;
+    for (int j = 0; j < k; ++j) {
+        const u64 v0 = s[j * src_lay.sl], v1 = s[src_lay.sp + j * src_lay.sl];
+        d[j * dst_lay.sl] = has ? sub_mod(v0, dev_scaled_limb(L, m, fix, j), L.q[j].q) : v0;
+        d[dst_lay.sp + j * dst_lay.sl] = v1;
     }
 }
 void launch_copy_sub_plain(const Engine &E, size_t level, const u64 *src, Layout src_lay, u64 *dst, Layout dst_lay, int nq, const u64 *plain, size_t count,
@@ -293,7 +316,7 @@ void launch_copy_sub_plain(const Engine &E, size_t level, const u64 *src, Layout
     E.require_device();
     const int k = (int)E.host.levels[level].q.size(), n = (int)E.host.n;
     if (nq == 0) return;
-    copy_sub_plain_kernel<<<dim3(nq * 2 * k, (n + 1023) / 1024), 256, 0, st>>>(E.d_levels + level, src, src_lay, dst, dst_lay, nq, n, plain, (int)count, m_stride);
+    copy_sub_plain_kernel<<<dim3(nq, (n + 255) / 256), 256, 0, st>>>(E.d_levels + level, src, src_lay, dst, dst_lay, nq, n, plain, (int)count, m_stride);
     PPLP_CUDA(cudaGetLastError());
 }
 // out = lift(s) * (a + b + [p = 0, i < count] round(Q r_i / t))  mod q_j: add_inplace, add_plain_inplace and the monomial
@@ -302,18 +325,29 @@ __global__ void __launch_bounds__(256) circuit_b_combine_kernel(const DevLevel *
                                                                 Layout out_lay, int nq, int n, const u64 *__restrict__ rplain, int count, size_t r_stride,
                                                                 const u64 *__restrict__ scalar, int *flags) {
     const DevLevel &L = *Lp;
-    int row = blockIdx.x;
-    const int qi = row % nq; row /= nq;
-    const int p = row & 1, j = row >> 1;
-    const Mod mq = L.q[j];
+    const int qi = blockIdx.x, k = L.k;
     const u64 sv = scalar[qi];
-    const u64 w = dev_lift(L, sv, j), wq = dev_shoup_quotient(w, mq.q);
-    if (flags && row == 0 && blockIdx.y == 0 && threadIdx.x == 0 && sv == 0) atomicOr(&flags[qi], 1);   // SEAL: "result ciphertext is transparent"
-    const size_t ib = qi * in_lay.sq + p * in_lay.sp + j * in_lay.sl, ob = qi * out_lay.sq + p * out_lay.sp + j * out_lay.sl;
-    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
-        u64 v = add_mod(a[ib + i], b[ib + i], mq.q);
-        if (p == 0 && i < count) v = add_mod(v, dev_scaled(L, rplain[qi * r_stride + i], j), mq.q);
-        out[ob + i] = mul_shoup(v, w, wq, mq.q);
+    if (flags && blockIdx.y == 0 && threadIdx.x == 0 && sv == 0) atomicOr(&flags[qi], 1);   // SEAL: "result ciphertext is transparent"
+    __shared__ ShoupW sw[kMaxLimbs];   // lift(s) mod q_j and its Shoup quotient floor(w 2^64 / q_j), once per CTA
+    if ((int)threadIdx.x < k) {
+        const u64 w = dev_lift(L, sv, threadIdx.x);
+        sw[threadIdx.x] = ShoupW{w, div128_floor(0, w, L.q[threadIdx.x])};
+    }
+    __syncthreads();
+    const int i = blockIdx.y * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const size_t ib = qi * in_lay.sq + i, ob = qi * out_lay.sq + i;
+    const bool has = i < count;
+    const u64 m = has ? rplain[qi * r_stride + i] : 0;
+    const u64 fix = has ? dev_scaled_fix(L, m) : 0;
+    for (int j = 0; j < k; ++j) {
+        const Mod mq = L.q[j];
+        const ShoupW w = sw[j];
+        u64 v0 = add_mod(a[ib + j * in_lay.sl], b[ib + j * in_lay.sl], mq.q);
+        const u64 v1 = add_mod(a[ib + in_lay.sp + j * in_lay.sl], b[ib + in_lay.sp + j * in_lay.sl], mq.q);
+        if (has) v0 = add_mod(v0, dev_scaled_limb(L, m, fix, j), mq.q);
+        out[ob + j * out_lay.sl] = mul_shoup(v0, w, mq.q);
+        out[ob + out_lay.sp + j * out_lay.sl] = mul_shoup(v1, w, mq.q);
     }
 }
 void launch_circuit_b_combine(const Engine &E, size_t level, const u64 *a, const u64 *b, Layout in_lay, u64 *out, Layout out_lay, int nq, const u64 *rplain,
@@ -321,8 +355,7 @@ void launch_circuit_b_combine(const Engine &E, size_t level, const u64 *a, const
     E.require_device();
     const int k = (int)E.host.levels[level].q.size(), n = (int)E.host.n;
     if (nq == 0) return;
-    circuit_b_combine_kernel<<<dim3(nq * 2 * k, (n + 1023) / 1024), 256, 0, st>>>(E.d_levels + level, a, b, in_lay, out, out_lay, nq, n, rplain, (int)count, r_stride, scalar,
-                                                                               flags);
+    circuit_b_combine_kernel<<<dim3(nq, (n + 255) / 256), 256, 0, st>>>(E.d_levels + level, a, b, in_lay, out, out_lay, nq, n, rplain, (int)count, r_stride, scalar, flags);
     PPLP_CUDA(cudaGetLastError());
 }
 

@@ -132,7 +132,13 @@ __device__ __forceinline__ u64 f64_to_u64_biased(double v, double bias) { return
 __device__ __forceinline__ double mulmod_f64(double a, double w, double wi, double q) {
     const double h = __dmul_rn(a, w);
     const double l = __fma_rn(a, w, -h);
+#if defined(PPLP_MULMOD_FRND)
+    // experiment: the quotient rounded by the conversion unit (FRND.F64) — one FP64-pipe instruction less per product; any
+    // integer within 1/2 + eps of a w / q keeps the result exact (microbenchmark: 8.5 vs 8.0 butterflies per clock per SM)
+    const double c = rint(__dmul_rn(a, wi));
+#else
     const double c = __dsub_rn(__fma_rn(a, wi, kRound52), kRound52);
+#endif
     return __dadd_rn(__fma_rn(-c, q, h), l);
 }
 // a mod q into [-q/2 - eps, q/2 + eps] for |a| <= 2^51, qi = fl(1/q)

@@ -2,7 +2,6 @@
 against oracle/ (SEAL's bfv_multiply over its own 61-bit base, [SEAL] evaluator.cpp bfv_multiply / util/rns.cpp):
 extreme residues, lower levels of the modulus chain, batches in both layouts, and the three pipelines of the product (FP64 base
 fused / FP64 base around the stand-alone transforms / SEAL's 61-bit base) producing the same bytes."""
-import hashlib
 import os
 import subprocess
 import sys
@@ -31,7 +30,7 @@ def test_fp64_base_extreme_residues_match_oracle(eng, oracle, n):
     q = None
     if n == 2048:   # BFVDefault(2048) is one 54-bit prime (not eligible): two 40-bit primes instead
         q = oracle.get_primes(2 * n, 40, 2)
-    ctx, octx = contexts(eng, oracle, n, q=q, enforce_security=q is None)
+    ctx, octx = contexts(eng, oracle, n, t=(1 << 20) if n == 2048 else (1 << 56), q=q, enforce_security=q is None)
     ql = octx.q[: ctx.k]
     pairs = _extremes(ql, n)
     a = np.stack([p[0] for p in pairs])
@@ -50,7 +49,8 @@ def test_fp64_base_lower_levels_and_widest_narrow_primes(eng, oracle):
     n = 4096
     rng = np.random.default_rng(99)
     for q in (oracle.bfv_default(8192), oracle.get_primes(2 * n, 44, 4)):
-        ctx, octx = contexts(eng, oracle, n, q=q, enforce_security=False)
+        ctx, octx = contexts(eng, oracle, n, t=1 << 20, q=q, enforce_security=False)   # a small t: the chain reaches k = 1
+        assert ctx.num_levels == len(q)
         for level in range(1, len(q)):
             k = len(q) - level
             a = np.stack([np.stack([rand_residues(rng, q[:k], n) for _ in range(2)]) for _ in range(2)])

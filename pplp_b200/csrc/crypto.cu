@@ -229,6 +229,10 @@ __global__ void prepare_key_kernel(const DevMod *mods, const u64 *__restrict__ s
     ulonglong2 *d = reinterpret_cast<ulonglong2 *>(dst) + (size_t)row * n;
     for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
         const u64 w = src[(size_t)row * n + i];
+        if (f64 == 2) {   // 32-per-thread inverse kernels: the word as a double, pair h of THEIR thread t (coefficients 32 t + 2 h, + 1) at [h * n/32 + t]
+            dst[(size_t)row * n + (((size_t)((i & 31) >> 1) * (n / 32) + (i >> 5)) << 1) + (i & 1)] = as_u((double)w);
+            continue;
+        }
         if (f64) {   // FP64 kernels take the bare word (mul_f64_var): pair h of thread t at [h*T + t], like U
             dst[(size_t)row * n + (((size_t)((i & 15) >> 1) * T + (i >> 4)) << 1) + (i & 1)] = w;
             continue;
@@ -345,7 +349,8 @@ __global__ void __launch_bounds__(NttShape<LOGM>::T, (LOGM <= 13 ? PPLP_ENC_INV_
 // ---- the forward transform of the split pipeline on the 32-per-thread FP64 schedule (ntt32.cuh): N = 2048..8192, moduli
 // of at most 44 bits.  (The inverse kernels stay on the 16-per-thread schedule: with their load-heavy prologue and
 // epilogue, 32 warps per SM hide more latency than the leaner transform saves — measured 213 k vs 194 k queries/s.)
-template <int LOGM>
+// F64OUT: U as doubles reduced to [-q/2, q/2] in the pair order of the 32-per-thread transforms (for enc32_inverse_kernel).
+template <int LOGM, bool F64OUT = false>
 __global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T) enc32_forward_kernel(const EncSplitArgs a) {
     using S = Ntt32Shape<LOGM>;
     extern __shared__ __align__(16) u64 sm[];
@@ -365,11 +370,96 @@ __global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T
     ntt32_forward<LOGM, (LOGM == 14)>(x, sm, tid, c);   // N = 16384: the wide rule set (inputs are canonical: 0, 1, q - 1)
     // U in the interleaving the 16-per-thread inverse kernels read (pair h of their thread t' at [h * n/16 + t']): this
     // thread's 32 coefficients are those of t' = 2 tid and 2 tid + 1, so each store covers two adjacent pairs (32 bytes).
+    if constexpr (F64OUT) {
+        ulonglong2 *d2 = reinterpret_cast<ulonglong2 *>(a.U + ((size_t)ct * a.K + j) * a.n) + tid;
+#pragma unroll
+        for (int h = 0; h < 16; ++h)
+            d2[h * S::T] = make_ulonglong2(as_u(reduce_sym_f64(as_d(x[2 * h]), c.qinv, c.q)), as_u(reduce_sym_f64(as_d(x[2 * h + 1]), c.qinv, c.q)));
+        return;
+    }
     ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(a.U + ((size_t)ct * a.K + j) * a.n) + 2 * tid;
 #pragma unroll
     for (int h = 0; h < 8; ++h) {
         dst[h * 2 * S::T] = make_ulonglong2(ntt32_canon(x[2 * h], c, q), ntt32_canon(x[2 * h + 1], c, q));
         dst[h * 2 * S::T + 1] = make_ulonglong2(ntt32_canon(x[16 + 2 * h], c, q), ntt32_canon(x[16 + 2 * h + 1], c, q));
+    }
+}
+
+// The inverse half of the split pipeline on the 32-per-thread FP64 schedule (N = 2048..8192, moduli of at most 44 bits):
+// U (.) pk as exact FP64 products of two variables straight in the transform's register layout (both operands are stored in
+// its pair order, so every load is a full line and nothing is staged through shared memory), ntt32_inverse, then the same
+// epilogues as enc_inverse_kernel with the division by P as an FP64-assisted product.  One barrier per transform and no
+// spills; the 16-per-thread kernel ran at 14 M rows/s with 130 bytes of spills per thread.
+template <int LOGM, bool SPECIAL>
+__global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T) enc32_inverse_kernel(const EncSplitArgs a) {
+    using S = Ntt32Shape<LOGM>;
+    extern __shared__ __align__(16) u64 sm[];
+    const int tid = threadIdx.x;
+    const int k = a.K - 1;
+    int ct, p, j;
+    if (SPECIAL) { ct = blockIdx.x >> 1; p = blockIdx.x & 1; j = a.K - 1; }
+    else { j = blockIdx.x % k; p = (blockIdx.x / k) & 1; ct = blockIdx.x / (2 * k); }
+    const DevMod &md = a.mods[j];
+    const Ntt32Consts c = ntt32_consts(md, true);
+    const u64 q = md.m.q;
+    const ulonglong2 *U2 = reinterpret_cast<const ulonglong2 *>(a.U + ((size_t)ct * a.K + j) * a.n) + tid;
+    const ulonglong2 *P2 = reinterpret_cast<const ulonglong2 *>(a.pk + ((size_t)p * a.K + j) * a.n) + tid;
+    const signed char *e = a.noise + ((size_t)ct * 3 + 1 + p) * a.n;
+    u64 *lastp = a.last + ((size_t)ct * 2 + p) * a.n;
+    if constexpr (!SPECIAL) {   // the epilogue's operands: ask L2 for them now, the transform hides the HBM round trip
+        for (int o = tid * 128; o < a.n * 8; o += S::T * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(lastp) + o));
+        if (tid * 128 < a.n) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(e) + tid * 128));
+    }
+    u64 x[32];
+#pragma unroll
+    for (int h = 0; h < 16; ++h) {
+        const ulonglong2 u = U2[h * S::T], w = __ldg(P2 + h * S::T);
+        // |u| <= q/2, 0 <= w < q: h = RN(u w), c = round(h fl(1/q)) within 1/2 + 2^-9 of u w / q; exact, |.| <= 0.57 q
+        const double h0 = __dmul_rn(as_d(u.x), as_d(w.x)), h1 = __dmul_rn(as_d(u.y), as_d(w.y));
+        const double l0 = __fma_rn(as_d(u.x), as_d(w.x), -h0), l1 = __fma_rn(as_d(u.y), as_d(w.y), -h1);
+        const double c0 = __dsub_rn(__fma_rn(h0, c.qinv, kRound52), kRound52), c1 = __dsub_rn(__fma_rn(h1, c.qinv, kRound52), kRound52);
+        x[2 * h] = as_u(__dadd_rn(__fma_rn(-c0, c.q, h0), l0));
+        x[2 * h + 1] = as_u(__dadd_rn(__fma_rn(-c1, c.q, h1), l1));
+    }
+    ntt32_inverse<LOGM, true, false>(x, sm, tid, c);   // x[e] = coefficient e T + tid, in (0, 2q)
+    if constexpr (SPECIAL) {
+        const u64 half = a.KL->half_last;
+        // (a char pointer may alias anything, so the compiler keeps every noise load behind the previous store: fetch a batch first)
+#pragma unroll
+        for (int b = 0; b < 32; b += 16) {
+            int ev[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) ev[u] = __ldg(e + (b + u) * S::T + tid);
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                const u64 t = add_mod(csub(x[b + u], q), ev[u] < 0 ? q - (u64)(-ev[u]) : (u64)ev[u], q);
+                lastp[(b + u) * S::T + tid] = add_mod(t, half, q);
+            }
+        }
+    } else {
+        // divide-and-round by P: (T + e - ((last - P/2) mod q)) P^-1, lazily: x in (0,2q), e small and signed, last < P <= cover (a
+        // multiple of q), so the bracket is a positive representative below 6q < 2^51 — what the FP64-assisted product takes
+        const DevLevel &KL = *a.KL;
+        const u64 offset = KL.half_last_mod[j] + KL.last_cover[j] + q;
+        const u64 inv_w = KL.inv_last[j].w;
+        const u64 inv_c = as_u(__ddiv_rn((double)inv_w, (double)q));
+        u64 *dst = a.out + ct * a.lay.sq + p * a.lay.sp + j * a.lay.sl;
+#pragma unroll
+        for (int b = 0; b < 32; b += 8) {
+            u64 lv[8];
+            int ev[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { lv[u] = __ldg(lastp + (b + u) * S::T + tid); ev[u] = __ldg(e + (b + u) * S::T + tid); }   // written by the SPECIAL launch, read-only here
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const u64 t = x[b + u] + (u64)(long long)ev[u] + offset - lv[u];   // offset includes one extra q: never negative
+                dst[(b + u) * S::T + tid] = csub(mul_f64_lazy(t, inv_w, inv_c, q), q);
+            }
+        }
+        // c0 += round(Q m / t) on the (few) plaintext coefficients; every thread owns its coefficients in both loops (index = tid
+        // mod T), so this reads its own store
+        if (p == 0)
+            for (int i = tid; i < a.plain_count; i += S::T) dst[i] = add_mod(dst[i], dev_scaled_plain(*a.DL, a.plain[ct * a.plain_stride + i], j), q);
     }
 }
 
@@ -468,6 +558,17 @@ template <int LOGM, int L = 3> static void run_encrypt_split32(const EncSplitArg
         enc_inverse_kernel<LOGM, L, false><<<nct * 2 * (a.K - 1), T, bytes, st>>>(a);
     }
 }
+template <int LOGM> static void run_encrypt_split32f(const EncSplitArgs &a, int nct, cudaStream_t st) {   // both halves on the 32-per-thread schedule
+    if constexpr (LOGM >= 11 && LOGM <= 13) {
+        const int bytes = Ntt32Shape<LOGM>::SMEM_WORDS * 8, T = Ntt32Shape<LOGM>::T;
+        PPLP_CUDA(cudaFuncSetAttribute(enc32_forward_kernel<LOGM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        PPLP_CUDA(cudaFuncSetAttribute(enc32_inverse_kernel<LOGM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        PPLP_CUDA(cudaFuncSetAttribute(enc32_inverse_kernel<LOGM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        enc32_forward_kernel<LOGM, true><<<nct * a.K, T, bytes, st>>>(a);
+        enc32_inverse_kernel<LOGM, true><<<nct * 2, T, bytes, st>>>(a);
+        enc32_inverse_kernel<LOGM, false><<<nct * 2 * (a.K - 1), T, bytes, st>>>(a);
+    }
+}
 template <int LOGM> static void run_encrypt_split(int lazy, const EncSplitArgs &a, int nct, cudaStream_t st) {
     if constexpr (LOGM >= 12) {
         if (lazy == 4) { run_encrypt_split_l<LOGM, 4>(a, nct, st); return; }
@@ -495,13 +596,15 @@ void launch_encrypt(const Engine &E, const u64 *pk, const u64 *seeds, const u64 
     if (K > 1 && E.host.logn <= 14) {   // split pipeline: forward, special-limb inverse, data-limb inverse + modulus switch + plaintext
         static const bool wide_ok = !(std::getenv("PPLP_ENC_WIDE") && std::getenv("PPLP_ENC_WIDE")[0] == '0');   // experiment hook
         const bool wide = wide_ok && lazy == 3 && E.host.logn >= 11 && E.host.logn <= 13;   // forward transform on the 32-per-thread FP64 schedule (ntt32.cuh)
-        prepare_key_kernel<<<dim3(2 * K, (n + 255) / 256), 256, 0, st>>>(E.d_mods, pk, extra, K, n, lazy >= 3 ? 1 : 0);
+        static const bool inv32_ok = !(std::getenv("PPLP_ENC_INV32") && std::getenv("PPLP_ENC_INV32")[0] == '0');   // experiment hook
+        const bool inv32 = wide && inv32_ok;   // ... and the inverse transforms too (enc32_inverse_kernel)
+        prepare_key_kernel<<<dim3(2 * K, (n + 255) / 256), 256, 0, st>>>(E.d_mods, pk, extra, K, n, inv32 ? 2 : (lazy >= 3 ? 1 : 0));
         EncSplitArgs sa{noise, extra, tmp, tmp + (size_t)nct * K * n, out, out_lay, plain, (int)plain_count, plain_stride, K, n, E.d_mods, E.d_levels, E.d_levels + first};
         switch (E.host.logn) {
         case 10: run_encrypt_split<10>(lazy, sa, nct, st); break;
-        case 11: if (wide) run_encrypt_split32<11>(sa, nct, st); else run_encrypt_split<11>(lazy, sa, nct, st); break;
-        case 12: if (wide) run_encrypt_split32<12>(sa, nct, st); else run_encrypt_split<12>(lazy, sa, nct, st); break;
-        case 13: if (wide) run_encrypt_split32<13>(sa, nct, st); else run_encrypt_split<13>(lazy, sa, nct, st); break;
+        case 11: if (inv32) run_encrypt_split32f<11>(sa, nct, st); else if (wide) run_encrypt_split32<11>(sa, nct, st); else run_encrypt_split<11>(lazy, sa, nct, st); break;
+        case 12: if (inv32) run_encrypt_split32f<12>(sa, nct, st); else if (wide) run_encrypt_split32<12>(sa, nct, st); else run_encrypt_split<12>(lazy, sa, nct, st); break;
+        case 13: if (inv32) run_encrypt_split32f<13>(sa, nct, st); else if (wide) run_encrypt_split32<13>(sa, nct, st); else run_encrypt_split<13>(lazy, sa, nct, st); break;
         default:
             if (wide_ok && lazy == 3) run_encrypt_split32<14, 3>(sa, nct, st);
             else if (wide_ok && lazy == 4) run_encrypt_split32<14, 4>(sa, nct, st);

@@ -686,9 +686,31 @@ def extra_circuit_b(engine, torch):
             "workload": "circuitB_bfv_n8192_k4_t=Batching(8192,56)_slot_batched: sub_plain x2, square x2, relinearize x2, add, add_plain, multiply_plain(mono)",
             "roofline": {"bound": "FP64 pipe (squares over the 44-bit auxiliary base, relinearisation: every transform and base conversion in exact FP64 products); HBM shown for reference", "algorithmic_bytes_per_group": bytes_group,
                          "achieved": bytes_group * gps / 1e9, "peak": peak, "unit": "GB/s", "frac": bytes_group * gps / 1e9 / peak},
+            "roofline_fp64": _circuit_b_fp64_roofline(gps, n),
             "agrees_with_oracle": agrees, "slots_match_algebra": algebra,
             "cpu_baseline": {"groups_per_s": threads / cdt, "value": threads / cdt * n, "unit": "slot-wise queries/s", "cores": threads, "kind": "port",
                              "one_thread_seconds_per_group": one, "sample": f"{threads} groups, one per host thread (oracle/ restatement of SEAL's bfv_square + switch_key_inplace)"}}
+
+
+def _circuit_b_fp64_roofline(gps, n):
+    """The pipe that bounds Circuit B: FP64 instructions per coefficient index (counted from the ncu captures under
+    profiles/: square 3 200 in the 50 row transforms + 2 200 in the two base conversions, relinearisation 1 900) against
+    64 FP64 lanes per clock per SM at the maximum SM clock."""
+    per_square, per_relin = 5400, 1900
+    instr_group = (2 * per_square + 2 * per_relin) * n
+    try:
+        import torch
+        sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    except Exception:
+        sms = 148
+    try:
+        mhz = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["sm_max_mhz"])
+    except Exception:
+        mhz = 1965.0
+    peak = 64.0 * sms * mhz * 1e6            # FP64 instructions per second
+    return {"bound": "fp64_pipe", "fp64_instr_per_coefficient": {"square": per_square, "relinearize": per_relin}, "fp64_instr_per_group": instr_group,
+            "achieved": instr_group * gps / 1e12, "peak": peak / 1e12, "unit": "T FP64 instr/s", "frac": instr_group * gps / peak,
+            "source": "instruction counts from profiles/r02_circuit_b_launches.csv and the ncu --set full captures; peak = 64 lanes x SMs x max SM clock"}
 
 
 def extra_bloom_build(engine, torch):

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -40,7 +41,9 @@ struct Engine {
 
     // device copies of the per-level constant blocks of behzf.cu (bf::BehzFC<k>), uploaded on first use
     mutable std::vector<void *> d_behzf;
+    mutable std::mutex behzf_mu;
     template <class Fill> const void *behzf_consts(size_t level, Fill fill) const {
+        std::lock_guard<std::mutex> lock(behzf_mu);
         if (d_behzf.size() < host.levels.size()) d_behzf.resize(host.levels.size(), nullptr);
         if (!d_behzf[level]) {
             std::vector<unsigned char> img;

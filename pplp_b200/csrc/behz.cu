@@ -496,7 +496,13 @@ struct RelinMacArgs {
 };
 // KD = number of digits at compile time (0: run-time count): with a fixed trip count all 2 KD loads of a coefficient pair
 // are issued before the first product, and two pairs are in flight per thread — the phase is latency-bound otherwise.
-template <int LOGM, bool SPECIAL, int KD, bool WIDE = (LOGM == 14)>
+// BULK: the operand stream of the product phase comes through a ring of shared-memory slots filled by bulk asynchronous copies
+// (cp.async.bulk + mbarrier, one issuing thread) instead of per-thread 128-bit loads: the transform's staging buffer is idle
+// during this phase, a slot is one (pair index h, digit J) = the 16 T bytes of digit pairs + the 16 T bytes of key pairs every
+// thread of the CTA needs next, and eight slots keep 6 steps (48 KiB per CTA at N = 8192) in flight where the register file
+// allowed two groups of loads.
+constexpr int kRelinRing = 12, kRelinLag = 2;   // 12 slots: 96 KiB per CTA at N = 8192 (two CTAs per SM fit the 227 KiB)
+template <int LOGM, bool SPECIAL, int KD, bool BULK = false, bool WIDE = (LOGM == 14)>
 __global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T) relin_mac_inverse_kernel(const RelinMacArgs a) {
     using S = Ntt32Shape<LOGM>;
     extern __shared__ __align__(16) u64 sm[];
@@ -526,7 +532,51 @@ __global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T
     const ulonglong2 *K2 = reinterpret_cast<const ulonglong2 *>(Kp) + tid;
     constexpr int M2 = S::M / 2;
     const size_t kstride2 = kstride / 2;
-    if constexpr (KD > 0) {
+    if constexpr (KD > 0 && BULK) {
+        constexpr int SLOT = 4 * S::T, STEPS = 16 * KD;                  // words per slot: 2 T of digit pairs, 2 T of key pairs
+        __shared__ __align__(8) u64 bars[2 * kRelinRing];               // [0, R): slot filled; [R, 2R): slot drained
+        if (tid == 0) {
+            for (int i = 0; i < kRelinRing; ++i) { mbar_init(&bars[i], 1); mbar_init(&bars[kRelinRing + i], S::T / 32); }
+            mbar_fence_init();
+        }
+        __syncthreads();
+        auto issue = [&](int step) {
+            const int h = step / KD, J = step % KD, slot = step % kRelinRing;
+            u64 *dst = sm + slot * SLOT;
+            mbar_arrive_expect_tx(&bars[slot], SLOT * 8);
+            bulk_g2s(dst, X + (size_t)J * S::M + (size_t)h * 2 * S::T, 2 * S::T * 8, &bars[slot]);
+            bulk_g2s(dst + 2 * S::T, Kp + (size_t)J * kstride + (size_t)h * 2 * S::T, 2 * S::T * 8, &bars[slot]);
+        };
+        if (tid == 0) {
+#pragma unroll
+            for (int st0 = 0; st0 < (kRelinRing < STEPS ? kRelinRing : STEPS); ++st0) issue(st0);
+        }
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+        for (int step = 0; step < STEPS; ++step) {
+            const int slot = step % kRelinRing;
+            mbar_wait(&bars[slot], (step / kRelinRing) & 1);
+            const ulonglong2 xv = *reinterpret_cast<const ulonglong2 *>(sm + slot * SLOT + 2 * tid);
+            const ulonglong2 kv = *reinterpret_cast<const ulonglong2 *>(sm + slot * SLOT + 2 * S::T + 2 * tid);
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(&bars[kRelinRing + slot]);   // this warp is done with the slot
+            a0 = __dadd_rn(a0, mul_key(xv.x, kv.x));
+            a1 = __dadd_rn(a1, mul_key(xv.y, kv.y));
+            if (step % KD == KD - 1) {
+                const int h = step / KD;
+                x[2 * h] = as_u(reduce_sym_f64(a0, qinv, qd));
+                x[2 * h + 1] = as_u(reduce_sym_f64(a1, qinv, qd));
+                a0 = 0.0; a1 = 0.0;
+            }
+            // refill, two steps behind the consumers so that the issuing thread seldom finds the slot still in use
+            if (tid == 0 && step >= kRelinLag && step - kRelinLag + kRelinRing < STEPS) {
+                const int r = step - kRelinLag;
+                mbar_wait(&bars[kRelinRing + r % kRelinRing], (r / kRelinRing) & 1);
+                issue(r + kRelinRing);
+            }
+        }
+        __syncthreads();   // every thread is past its last read of the ring: the transform may use the buffer
+    } else if constexpr (KD > 0) {
         // software pipeline over (pair h, group of G <= 4 digits): the 2 G loads of the next step are in flight while this
         // step is multiplied (G = 4 keeps the two load buffers within 64 registers when k = 8)
         constexpr int G = KD > 4 ? 4 : KD, NG = KD / G, STEPS = 16 * NG;
@@ -604,20 +654,32 @@ __global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T
         }
     }
 }
-template <int LOGM, int KD> static void run_relin_split_k(const RelinSplitArgs &a, const RelinMacArgs &m, int nq, cudaStream_t st) {
+template <int LOGM, int KD, bool BULK> static void run_relin_split_kb(const RelinSplitArgs &a, const RelinMacArgs &m, int nq, cudaStream_t st) {
     const int bytes = Ntt32Shape<LOGM>::SMEM_WORDS * 8;
+    const int mac_bytes = BULK ? std::max(bytes, kRelinRing * 4 * Ntt32Shape<LOGM>::T * 8) : bytes;   // the ring outgrows the staging buffer
     static bool done[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
     if (!done[dev & 63]) {
         PPLP_CUDA(cudaFuncSetAttribute(relin_digits_kernel<LOGM>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-        PPLP_CUDA(cudaFuncSetAttribute(relin_mac_inverse_kernel<LOGM, true, KD>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-        PPLP_CUDA(cudaFuncSetAttribute(relin_mac_inverse_kernel<LOGM, false, KD>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        PPLP_CUDA(cudaFuncSetAttribute(relin_mac_inverse_kernel<LOGM, true, KD, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, mac_bytes));
+        PPLP_CUDA(cudaFuncSetAttribute(relin_mac_inverse_kernel<LOGM, false, KD, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, mac_bytes));
         done[dev & 63] = true;
     }
     relin_digits_kernel<LOGM><<<nq * (a.k + 1) * a.k, Ntt32Shape<LOGM>::T, bytes, st>>>(a);
-    relin_mac_inverse_kernel<LOGM, true, KD><<<nq * 2, Ntt32Shape<LOGM>::T, bytes, st>>>(m);
-    relin_mac_inverse_kernel<LOGM, false, KD><<<nq * a.k * 2, Ntt32Shape<LOGM>::T, bytes, st>>>(m);
+    relin_mac_inverse_kernel<LOGM, true, KD, BULK><<<nq * 2, Ntt32Shape<LOGM>::T, mac_bytes, st>>>(m);
+    relin_mac_inverse_kernel<LOGM, false, KD, BULK><<<nq * a.k * 2, Ntt32Shape<LOGM>::T, mac_bytes, st>>>(m);
+}
+template <int LOGM, int KD> static void run_relin_split_k(const RelinSplitArgs &a, const RelinMacArgs &m, int nq, cudaStream_t st) {
+    // PPLP_RELIN_BULK=1: the product phase fed by the bulk-copy ring.  Measured slower than the per-thread software pipeline at every
+    // ring depth tried (N = 8192, k = 4: 609 k relin/s with 8 slots and per-thread arrivals, 619 k with 12 slots and per-warp
+    // arrivals, against 701 k): the phase is not short of bytes in flight, and a slot per (pair, digit) costs a barrier round
+    // trip for twelve FP64 instructions of work.  Kept as an option (bit-identical; covered by the GPU tests).
+    static const bool bulk = [] { const char *e = getenv("PPLP_RELIN_BULK"); return e && e[0] == '1' && e[1] == 0; }();
+    if constexpr (KD > 0) {
+        if (bulk) { run_relin_split_kb<LOGM, KD, true>(a, m, nq, st); return; }
+    }
+    run_relin_split_kb<LOGM, KD, false>(a, m, nq, st);
 }
 template <int LOGM> static void run_relin_split(const RelinSplitArgs &a, const RelinMacArgs &m, int nq, cudaStream_t st) {
     switch (a.k) {   // BFVDefault: k = 2 (N = 4096), 4 (N = 8192); 3 = the four-prime sweep case

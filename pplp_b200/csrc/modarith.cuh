@@ -226,6 +226,32 @@ __device__ __forceinline__ ulonglong2 ld_stream_coherent(const u64 *p) {
 __device__ __forceinline__ void prefetch_l2_bulk(const void *p, unsigned bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
+// ---- bulk asynchronous copies (the TMA unit's 1-D form) and the mbarriers that track them ----------------------------
+// One thread hands the copy engine a contiguous global -> shared transfer (UBLKCP); the bytes' arrival completes a transaction
+// count on a shared-memory barrier that the consumers poll.  No register staging, no per-thread load instructions: a ring of
+// such slots keeps far more bytes in flight per SM than the register file allows (relin_mac_inverse_kernel's product phase).
+__device__ __forceinline__ u32 smem_addr(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64 *bar, u32 count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(u64 *bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(u64 *bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory"); }
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t}"
+        ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+// bytes: a multiple of 16; both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u32 bytes, u64 *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
 __device__ __forceinline__ void stg_stream(u64 *p, ulonglong2 v) {
     asm volatile("st.global.L1::no_allocate.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(v.x), "l"(v.y) : "memory");
 }

@@ -106,3 +106,35 @@ def test_three_product_pipelines_give_the_same_bytes():
         assert p.returncode == 0, p.stdout + p.stderr
         digests[name] = [ln for ln in p.stdout.splitlines() if ln.startswith("DIGEST")][0]
     assert digests["fp64_fused"] == digests["fp64_unfused"] == digests["seal_61bit"], digests
+
+
+_RELIN_SNIPPET = r"""
+import hashlib, sys
+import numpy as np
+sys.path.insert(0, %r)
+from pplp_b200 import engine
+h = hashlib.sha256()
+for n in (4096, 8192, 16384):
+    ctx = engine.Context(n, t=1 << 20, device=0)
+    k, K = ctx.k, len(ctx.q)
+    rng = np.random.default_rng(n + 1)
+    rk = np.stack([np.stack([np.stack([rng.integers(0, qj, size=n, dtype=np.uint64) for qj in ctx.q]) for _ in range(2)]) for _ in range(k)])
+    ct3 = np.stack([np.stack([np.stack([rng.integers(0, qj, size=n, dtype=np.uint64) for qj in ctx.q[:k]]) for _ in range(3)]) for _ in range(3)])
+    drk = ctx.dev(rk)
+    h.update(engine.to_np(ctx.relinearize(ctx.dev(ct3), drk, ctx.relin_prepare(drk))).tobytes())
+print("DIGEST", h.hexdigest())
+"""
+
+
+def test_relinearisation_bulk_copy_ring_gives_the_same_bytes():
+    """PPLP_RELIN_BULK=1 feeds the product phase of the split relinearisation through cp.async.bulk + mbarrier slots; same bytes
+    as the default per-thread loads (which test_relin_keygen_and_relinearize_match_oracle checks against the oracle)."""
+    digests = {}
+    for name, env in (("ldg", {}), ("bulk", {"PPLP_RELIN_BULK": "1"})):
+        e = dict(os.environ)
+        e.pop("PPLP_RELIN_BULK", None)
+        e.update(env)
+        p = subprocess.run([sys.executable, "-c", _RELIN_SNIPPET % ROOT], capture_output=True, text=True, env=e, timeout=600)
+        assert p.returncode == 0, p.stdout + p.stderr
+        digests[name] = [ln for ln in p.stdout.splitlines() if ln.startswith("DIGEST")][0]
+    assert digests["ldg"] == digests["bulk"], digests

@@ -158,6 +158,54 @@ __global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T
     for (int e = 0; e < 32; ++e) ptr[e * S::T + tid] = csub(x[e], q);
 }
 
+// N = 16384 as a cluster of two 256-thread CTAs per row (ntt32.cuh, CL): two CTAs of different rows share an SM, so one row's
+// load / exchange / store phases could overlap the other's butterflies.  blockIdx.x = 2 * row + rank.  (An experiment: see
+// ntt_cluster_enabled() below for the measurement.)
+template <bool DENSE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 2) ntt32c_forward_kernel(const NttArgs a) {
+    constexpr int LOGM = 14;
+    using S = Ntt32Shape<LOGM>;
+    extern __shared__ __align__(16) u64 sm[];
+    auto cluster = cooperative_groups::this_cluster();
+    const int rank = (int)cluster.block_rank(), ltid = threadIdx.x, tid = rank * 256 + ltid, row = blockIdx.x >> 1;
+    const Ntt32Cl cl{ltid, cluster.map_shared_rank(sm, 0), cluster.map_shared_rank(sm, 1)};
+    int qi = 0, p = 0, j;
+    if constexpr (DENSE) j = row / a.stage_base;
+    else decode_row(row, a.nq, a.npoly, qi, p, j);
+    const DevMod &md = a.mods[a.map.mod_id[j]];
+    const Ntt32Consts c = ntt32_consts(md, false);
+    u64 *ptr = DENSE ? a.data + (size_t)row * S::M : a.data + qi * a.lay.sq + p * a.lay.sp + j * a.lay.sl;
+    if constexpr (!DENSE) asm volatile("" : "+l"(ptr));
+    u64 x[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) x[e] = ptr[e * S::T + tid];
+    ntt32_forward<LOGM, true, false, true>(x, sm, tid, c, &cl);
+#pragma unroll
+    for (int e = 0; e < 32; ++e) x[e] = ntt32_canon(x[e], c, md.m.q);
+    ntt32_store_row(x, sm, tid, ptr, ltid);
+}
+template <bool DENSE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 2) ntt32c_inverse_kernel(const NttArgs a) {
+    constexpr int LOGM = 14;
+    using S = Ntt32Shape<LOGM>;
+    extern __shared__ __align__(16) u64 sm[];
+    auto cluster = cooperative_groups::this_cluster();
+    const int rank = (int)cluster.block_rank(), ltid = threadIdx.x, tid = rank * 256 + ltid, row = blockIdx.x >> 1;
+    const Ntt32Cl cl{ltid, cluster.map_shared_rank(sm, 0), cluster.map_shared_rank(sm, 1)};
+    int qi = 0, p = 0, j;
+    if constexpr (DENSE) j = row / a.stage_base;
+    else decode_row(row, a.nq, a.npoly, qi, p, j);
+    const DevMod &md = a.mods[a.map.mod_id[j]];
+    const Ntt32Consts c = ntt32_consts(md, true);
+    u64 *ptr = DENSE ? a.data + (size_t)row * S::M : a.data + qi * a.lay.sq + p * a.lay.sp + j * a.lay.sl;
+    u64 x[32];
+    ntt32_load_row(x, sm, tid, ptr, ltid);
+    ntt32_inverse<LOGM, false, true, true>(x, sm, tid, c, &cl);
+    const u64 q = md.m.q;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) ptr[e * S::T + tid] = csub(x[e], q);
+}
+
 // Streaming butterfly stage 0 for N = 2*M (gap N/2, single twiddle fwd[1]).  Output lazily < 4q (forward) / canonical (inverse).
 __global__ void ntt_stage0_forward_kernel(const NttArgs a, int half_n) {
     int qi, p, j;
@@ -255,7 +303,28 @@ template <int LOGM, int L> static void run_block_ntt(const NttArgs &a, int rows,
         ntt_forward_kernel<LOGM, L><<<grid, NttShape<LOGM>::T, bytes, st>>>(a);
     }
 }
+// PPLP_NTT_CLUSTER=1: N = 16384 as a cluster of two 256-thread CTAs per row instead of one 512-thread CTA.  Measured SLOWER
+// (2.34 / 2.43 TB/s against 2.46 / 2.53): the one-CTA-per-SM shape is not what holds N = 16384 back — the wide rule set's extra
+// reductions are — and the two cluster barriers plus the distributed-shared-memory exchange cost more than the overlap returns.
+// Bit-identical (the NTT parity tests pass with it); kept as an option.
+static bool ntt_cluster_enabled() {
+    static const bool v = [] { const char *e = getenv("PPLP_NTT_CLUSTER"); return e && e[0] == '1' && e[1] == 0; }();
+    return v;
+}
 template <int LOGM, bool DENSE> static void run_ntt32_d(const NttArgs &a, int rows, bool inverse, cudaStream_t st) {
+    if constexpr (LOGM == 14) {
+        if (ntt_cluster_enabled()) {
+            const int cbytes = Ntt32Geo<14, true>::SMEM_WORDS * 8;
+            if (inverse) {
+                allow_smem(ntt32c_inverse_kernel<DENSE>, cbytes);
+                ntt32c_inverse_kernel<DENSE><<<rows * 2, 256, cbytes, st>>>(a);
+            } else {
+                allow_smem(ntt32c_forward_kernel<DENSE>, cbytes);
+                ntt32c_forward_kernel<DENSE><<<rows * 2, 256, cbytes, st>>>(a);
+            }
+            return;
+        }
+    }
     const int bytes = Ntt32Shape<LOGM>::SMEM_WORDS * 8;
     if (inverse) {
         allow_smem(ntt32_inverse_kernel<LOGM, DENSE>, bytes);

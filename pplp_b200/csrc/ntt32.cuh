@@ -34,6 +34,7 @@
 //            |x| <= 1 q again.  The 14th stage (N^-1 folded in) is a "b" stage whose outputs are all products.
 //   tests/test_fp64_bounds.py replays both rule sets with exact rationals at the widest modulus.
 #pragma once
+#include <cooperative_groups.h>
 #include <type_traits>
 #include "devstructs.h"
 
@@ -49,27 +50,50 @@ template <int LOGM> struct Ntt32Shape {
 };
 __device__ __forceinline__ int slot32(int i) { return i + (i >> 5); }
 
+// CL ("cluster"): one row is transformed by a thread-block cluster of TWO CTAs, each with half the threads, half the points in
+// its shared memory and the same 128 registers per thread.  N = 16384 needs 512 threads x 128 registers = a whole SM's register
+// file for ONE CTA, so nothing overlaps its load, exchange and store phases; as two 256-thread CTAs (of different clusters)
+// per SM the phases of one row hide behind the butterflies of another, as they do at N <= 8192.  Only the transpose between pass
+// A and pass B crosses the CTAs: it goes through distributed shared memory (each thread writes half of its 32 values into the
+// peer's buffer) and a cluster barrier replaces __syncthreads().  tid below is always the LOGICAL thread of the row
+// (rank * T/2 + threadIdx.x under CL); shared-memory indices are local to the CTA.
+struct Ntt32Cl {
+    int ltid;          // thread index within the CTA
+    u64 *sm0, *sm1;    // the staging buffers of CTA 0 and CTA 1 of the cluster (generic pointers; one of them is `sm`)
+};
+template <int LOGM, bool CL> struct Ntt32Geo {
+    using S = Ntt32Shape<LOGM>;
+    static constexpr int TC = CL ? S::T / 2 : S::T;            // threads per CTA
+    static constexpr int MC = CL ? S::M / 2 : S::M;            // points staged per CTA
+    static constexpr int TW_OFF = MC + (MC >> 5);
+    static constexpr int SMEM_WORDS = MC + (MC >> 5) + 64;
+};
+__device__ __forceinline__ void ntt32_cluster_sync() { cooperative_groups::this_cluster().sync(); }
+__device__ __forceinline__ void ntt32_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void ntt32_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
 // per-modulus constants are prepared on the host (DevMod::nc32_fwd / nc32_inv) so that a kernel loads them in one go
 __device__ __forceinline__ Ntt32Consts ntt32_consts(const DevMod &md, bool inverse) { return inverse ? md.nc32_inv : md.nc32_fwd; }
 // Global <-> register staging through the warp's own 1024 words (coalesced 256-byte accesses on the global side):
 // registers in the "contiguous" layout x[e] = row[32 tid + e].
-__device__ __forceinline__ void ntt32_store_row(const u64 (&x)[32], u64 *sm, int tid, u64 *row) {
-    const int lane = tid & 31, wbase = (tid >> 5) << 10;
+// (ltid: the thread's index within its CTA when the row is split over a cluster — the staging words are the CTA's own)
+__device__ __forceinline__ void ntt32_store_row(const u64 (&x)[32], u64 *sm, int tid, u64 *row, int ltid = -1) {
+    const int lane = tid & 31, wbase = (tid >> 5) << 10, lbase = ((ltid < 0 ? tid : ltid) >> 5) << 10;
     __syncwarp();
 #pragma unroll
-    for (int e = 0; e < 32; ++e) sm[slot32(wbase + lane * 32 + e)] = x[e];
+    for (int e = 0; e < 32; ++e) sm[slot32(lbase + lane * 32 + e)] = x[e];
     __syncwarp();
 #pragma unroll
-    for (int e = 0; e < 32; ++e) row[wbase + e * 32 + lane] = sm[slot32(wbase + e * 32 + lane)];
+    for (int e = 0; e < 32; ++e) row[wbase + e * 32 + lane] = sm[slot32(lbase + e * 32 + lane)];
 }
-__device__ __forceinline__ void ntt32_load_row(u64 (&x)[32], u64 *sm, int tid, const u64 *row) {
-    const int lane = tid & 31, wbase = (tid >> 5) << 10;
+__device__ __forceinline__ void ntt32_load_row(u64 (&x)[32], u64 *sm, int tid, const u64 *row, int ltid = -1) {
+    const int lane = tid & 31, wbase = (tid >> 5) << 10, lbase = ((ltid < 0 ? tid : ltid) >> 5) << 10;
     __syncwarp();
 #pragma unroll
-    for (int e = 0; e < 32; ++e) sm[slot32(wbase + e * 32 + lane)] = row[wbase + e * 32 + lane];
+    for (int e = 0; e < 32; ++e) sm[slot32(lbase + e * 32 + lane)] = row[wbase + e * 32 + lane];
     __syncwarp();
 #pragma unroll
-    for (int e = 0; e < 32; ++e) x[e] = sm[slot32(wbase + lane * 32 + e)];
+    for (int e = 0; e < 32; ++e) x[e] = sm[slot32(lbase + lane * 32 + e)];
 }
 
 __device__ __forceinline__ void bf_ct(u64 &x, u64 &y, const ShoupW w, const double q) {
@@ -146,12 +170,15 @@ constexpr double kGsLimit = 96.0;
 // 32*tid + e, |x| <= 14 q; ntt32_canon() brings it to [0,q).  sm: Ntt32Shape::SMEM_WORDS words.
 // REDUCE_IN (WIDE only): the inputs are residues of ANOTHER modulus of the same size class (below 2^52): bring them to
 // [-q/2, q/2] first — pass A needs |x| <= 1 q.
-template <int LOGM, bool WIDE = false, bool REDUCE_IN = false>
-__device__ __forceinline__ void ntt32_forward(u64 (&x)[32], u64 *sm, int tid, const Ntt32Consts &c) {
+template <int LOGM, bool WIDE = false, bool REDUCE_IN = false, bool CL = false>
+__device__ __forceinline__ void ntt32_forward(u64 (&x)[32], u64 *sm, int tid, const Ntt32Consts &c, const Ntt32Cl *cl = nullptr) {
     using S = Ntt32Shape<LOGM>;
-    const int lane = tid & 31, warp = tid >> 5;
-    u64 *twA = sm + S::TW_OFF;
-    if (tid < 31) *reinterpret_cast<ulonglong2 *>(twA + 2 * tid) = __ldg(reinterpret_cast<const ulonglong2 *>(c.tw + 1 + tid));
+    using G = Ntt32Geo<LOGM, CL>;
+    const int ltid = CL ? cl->ltid : tid;
+    const int lane = tid & 31, warp = tid >> 5, lwarp = ltid >> 5;
+    u64 *twA = sm + G::TW_OFF;
+    if (ltid < 31) *reinterpret_cast<ulonglong2 *>(twA + 2 * ltid) = __ldg(reinterpret_cast<const ulonglong2 *>(c.tw + 1 + ltid));
+    if constexpr (CL) ntt32_cluster_arrive();   // "this CTA is resident and done with its buffer": waited for just before the exchange
 #pragma unroll
     for (int e = 0; e < 32; ++e) x[e] = as_u(WIDE && REDUCE_IN ? reduce_sym_f64(u64_to_f64(x[e]), c.qinv, c.q) : u64_to_f64(x[e]));
     __syncthreads();
@@ -166,11 +193,18 @@ __device__ __forceinline__ void ntt32_forward(u64 (&x)[32], u64 *sm, int tid, co
             for (int i = 0; i < half; ++i) bf_ct(x[g * 2 * half + i], x[g * 2 * half + i + half], w, c.q);
         }
     }
+    if constexpr (CL) {
+        ntt32_cluster_wait();   // the peer CTA is resident and past its own reads of the buffer (a previous transform's, if any)
 #pragma unroll
-    for (int e = 0; e < 32; ++e) sm[slot32(e * S::T + tid)] = x[e];
-    __syncthreads();
-    u64 *wsm = sm;   // the warp's 1024 points live at indices [1024 warp, 1024 warp + 1024)
-    const int wbase = warp << 10;
+        for (int e = 0; e < 32; ++e) (e < 16 ? cl->sm0 : cl->sm1)[slot32((e & 15) * S::T + tid)] = x[e];   // point e T + tid lives in CTA (e >> 4)
+        ntt32_cluster_sync();
+    } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) sm[slot32(e * S::T + tid)] = x[e];
+        __syncthreads();
+    }
+    u64 *wsm = sm;   // the warp's 1024 points live at indices [1024 warp, 1024 warp + 1024) of its CTA's buffer
+    const int wbase = lwarp << 10;
 #pragma unroll
     for (int e = 0; e < 32; ++e) x[e] = wsm[slot32(wbase + e * 32 + lane)];
     if constexpr (WIDE) {   // pass A left up to 4.75 q
@@ -221,13 +255,15 @@ template <int HALF> __device__ __forceinline__ void ntt32_reduce_sums(u64 (&x)[3
     for (int e = 0; e < 32; ++e)
         if ((e & HALF) == 0) x[e] = as_u(reduce_sym_f64(as_d(x[e]), c.qinv, c.q));
 }
-template <int LOGM, bool FROM_F64 = false, bool WIDE = false>
-__device__ __forceinline__ void ntt32_inverse(u64 (&x)[32], u64 *sm, int tid, const Ntt32Consts &c) {
+template <int LOGM, bool FROM_F64 = false, bool WIDE = false, bool CL = false>
+__device__ __forceinline__ void ntt32_inverse(u64 (&x)[32], u64 *sm, int tid, const Ntt32Consts &c, const Ntt32Cl *cl = nullptr) {
     using S = Ntt32Shape<LOGM>;
+    using G = Ntt32Geo<LOGM, CL>;
     static_assert(!WIDE || S::SB == 4, "the a/b stage alternation of the WIDE rule set is laid out for 5 + 4 + 5 stages");
-    const int lane = tid & 31, warp = tid >> 5;
-    u64 *twA = sm + S::TW_OFF;
-    if (tid < 31) *reinterpret_cast<ulonglong2 *>(twA + 2 * tid) = __ldg(reinterpret_cast<const ulonglong2 *>(c.tw + 1 + tid));
+    const int ltid = CL ? cl->ltid : tid;
+    const int lane = tid & 31, warp = tid >> 5, lwarp = ltid >> 5;
+    u64 *twA = sm + G::TW_OFF;
+    if (ltid < 31) *reinterpret_cast<ulonglong2 *>(twA + 2 * ltid) = __ldg(reinterpret_cast<const ulonglong2 *>(c.tw + 1 + ltid));
     if constexpr (!FROM_F64) {
         if constexpr (WIDE) {   // centred while converting: [0, 2q) -> (-q, q)
             const double off = __dadd_rn(kTwo52, c.q);
@@ -255,7 +291,7 @@ __device__ __forceinline__ void ntt32_inverse(u64 (&x)[32], u64 *sm, int tid, co
             if (gs_bound(e, 5, 2.0) * (1 << RNEXT) > kGsLimit) x[e] = as_u(reduce_sym_f64(as_d(x[e]), c.qinv, c.q));
     }
     u64 *wsm = sm;
-    const int wbase = warp << 10;
+    const int wbase = lwarp << 10;
     __syncwarp();
 #pragma unroll
     for (int e = 0; e < 32; ++e) wsm[slot32(wbase + lane * 32 + e)] = x[e];
@@ -284,9 +320,16 @@ __device__ __forceinline__ void ntt32_inverse(u64 (&x)[32], u64 *sm, int tid, co
 #pragma unroll
         for (int e = 0; e < 32; ++e) wsm[slot32(wbase + e * 32 + lane)] = x[e];
     }
-    __syncthreads();
+    if constexpr (CL) {
+        ntt32_cluster_sync();
 #pragma unroll
-    for (int e = 0; e < 32; ++e) x[e] = sm[slot32(e * S::T + tid)];
+        for (int e = 0; e < 32; ++e) x[e] = (e < 16 ? cl->sm0 : cl->sm1)[slot32((e & 15) * S::T + tid)];
+        ntt32_cluster_sync();   // the peer has taken its half: this CTA may reuse the buffer or exit
+    } else {
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) x[e] = sm[slot32(e * S::T + tid)];
+    }
     // pass A': stages 4 .. 1, then stage 0 with N^-1 folded in
 #pragma unroll
     for (int s = 4; s >= 1; --s) {

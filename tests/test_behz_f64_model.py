@@ -123,3 +123,37 @@ def test_fp64_base_product_extreme_residues(model, orc):
         na, got, _ = _model_multiply(model, n, q, t, level, a, b)
         assert na > 0
         assert np.array_equal(got, ctx.multiply(a, b, level))
+
+
+def test_fp64_base_product_centred_r_boundary(model, orc):
+    """sm_mrq centres r = -(sum_j z_j (Q/q_j)) Q^-1 mod 2^32 at exactly 2^31 ([SEAL] rns.cpp sm_mrq: `if (r >= m_tilde_div_2)`).
+    Random inputs hit that boundary with probability 2^-32 per coefficient, so build them: with x_1.. = 0 the sum is z_0 (Q/q_0),
+    an odd multiple of z_0, hence r = 2^31 exactly when z_0 = 2^31 mod 2^32 — and x_0 = z_0 (m~ (Q/q_0)^-1)^-1 mod q_0 produces
+    that z_0.  Neighbouring values (2^31 - 1, 2^31 + 1) ride along."""
+    n, t = 4096, 1 << 56
+    q = orc.bfv_default(8192)[:3]
+    ctx = orc.context(n, q, t)
+    assert ctx.ok, ctx.error
+    level = 1
+    k = ctx.limbs(level)
+    ql = q[:k]
+    Q = 1
+    for p in ql:
+        Q *= p
+    q0 = ql[0]
+    c0 = ((1 << 32) * pow(Q // q0, -1, q0)) % q0
+    c0_inv = pow(c0, -1, q0)
+    rng = np.random.default_rng(3)
+    a = np.zeros((2, k, n), dtype=np.uint64)
+    lows = [0x80000000, 0x7FFFFFFF, 0x80000001, 0x00000000, 0xFFFFFFFF]
+    for p in range(2):
+        for i in range(n):
+            z0 = (int(rng.integers(0, q0 >> 32)) << 32) | lows[(i + p) % len(lows)]
+            if z0 >= q0:
+                z0 -= 1 << 32
+            a[p, 0, i] = (z0 * c0_inv) % q0
+    b = _random_ct(rng, ql, n)
+    for x, y in ((a, a), (a, b), (b, a)):
+        na, got, _ = _model_multiply(model, n, q, t, level, x, y)
+        assert na > 0
+        assert np.array_equal(got, ctx.multiply(x, y, level))

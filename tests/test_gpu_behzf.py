@@ -138,3 +138,29 @@ def test_relinearisation_bulk_copy_ring_gives_the_same_bytes():
         assert p.returncode == 0, p.stdout + p.stderr
         digests[name] = [ln for ln in p.stdout.splitlines() if ln.startswith("DIGEST")][0]
     assert digests["ldg"] == digests["bulk"], digests
+
+
+def test_fp64_base_centred_r_boundary(eng, oracle):
+    """The sm_mrq centring boundary r = 2^31 (probability 2^-32 per coefficient on random data) built on purpose: see
+    tests/test_behz_f64_model.py::test_fp64_base_product_centred_r_boundary for the construction."""
+    n = 8192
+    ctx, octx = contexts(eng, oracle, n)
+    ql = octx.q[: ctx.k]
+    Q = 1
+    for p in ql:
+        Q *= p
+    q0 = ql[0]
+    c0_inv = pow(((1 << 32) * pow(Q // q0, -1, q0)) % q0, -1, q0)
+    rng = np.random.default_rng(4)
+    a = np.zeros((2, ctx.k, n), dtype=np.uint64)
+    lows = [0x80000000, 0x7FFFFFFF, 0x80000001, 0x00000000, 0xFFFFFFFF]
+    for p in range(2):
+        for i in range(n):
+            z0 = (int(rng.integers(0, q0 >> 32)) << 32) | lows[(i + p) % len(lows)]
+            if z0 >= q0:
+                z0 -= 1 << 32
+            a[p, 0, i] = (z0 * c0_inv) % q0
+    b = np.stack([rand_residues(rng, ql, n) for _ in range(2)])
+    got = eng.to_np(ctx.multiply(ctx.dev(np.stack([a, a, b])), ctx.dev(np.stack([a, b, a]))))
+    for i, (x, y) in enumerate(((a, a), (a, b), (b, a))):
+        assert (got[i] == octx.multiply(x, y)).all(), i

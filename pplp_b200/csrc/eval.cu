@@ -298,17 +298,33 @@ __global__ void __launch_bounds__(256) copy_sub_plain_kernel(const DevLevel *Lp,
                                                              int n, const u64 *__restrict__ plain, int count, size_t m_stride) {
     const DevLevel &L = *Lp;
     const int qi = blockIdx.x, k = L.k;
-    const int i = blockIdx.y * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const u64 *s = src + qi * src_lay.sq + i;
-    u64 *d = dst + qi * dst_lay.sq + i;
-    const bool has = i < count;
-    const u64 m = has ? plain[qi * m_stride + i] : 0;
-    const u64 fix = has ? dev_scaled_fix(L, m) : 0;
+    // two coefficients per thread (i and i + 256): twice the loads in flight for the same instruction stream
+    const int i0 = blockIdx.y * 512 + threadIdx.x;
+    const u64 *s = src + qi * src_lay.sq;
+    u64 *d = dst + qi * dst_lay.sq;
+    bool in[2], has[2];
+    u64 m[2], fix[2];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        const int i = i0 + c * 256;
+        in[c] = i < n;
+        has[c] = i < count && in[c];
+        m[c] = has[c] ? plain[qi * m_stride + i] : 0;
+    }
+#pragma unroll
+    for (int c = 0; c < 2; ++c) fix[c] = has[c] ? dev_scaled_fix(L, m[c]) : 0;
+#pragma unroll 2
     for (int j = 0; j < k; ++j) {
-        const u64 v0 = s[j * src_lay.sl], v1 = s[src_lay.sp + j * src_lay.sl];
-        d[j * dst_lay.sl] = has ? sub_mod(v0, dev_scaled_limb(L, m, fix, j), L.q[j].q) : v0;
-        d[dst_lay.sp + j * dst_lay.sl] = v1;
+        u64 v0[2], v1[2];
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+            if (in[c]) { v0[c] = s[j * src_lay.sl + i0 + c * 256]; v1[c] = s[src_lay.sp + j * src_lay.sl + i0 + c * 256]; }
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+            if (in[c]) {
+                d[j * dst_lay.sl + i0 + c * 256] = has[c] ? sub_mod(v0[c], dev_scaled_limb(L, m[c], fix[c], j), L.q[j].q) : v0[c];
+                d[dst_lay.sp + j * dst_lay.sl + i0 + c * 256] = v1[c];
+            }
     }
 }
 void launch_copy_sub_plain(const Engine &E, size_t level, const u64 *src, Layout src_lay, u64 *dst, Layout dst_lay, int nq, const u64 *plain, size_t count,
@@ -316,7 +332,7 @@ void launch_copy_sub_plain(const Engine &E, size_t level, const u64 *src, Layout
     E.require_device();
     const int k = (int)E.host.levels[level].q.size(), n = (int)E.host.n;
     if (nq == 0) return;
-    copy_sub_plain_kernel<<<dim3(nq, (n + 255) / 256), 256, 0, st>>>(E.d_levels + level, src, src_lay, dst, dst_lay, nq, n, plain, (int)count, m_stride);
+    copy_sub_plain_kernel<<<dim3(nq, (n + 511) / 512), 256, 0, st>>>(E.d_levels + level, src, src_lay, dst, dst_lay, nq, n, plain, (int)count, m_stride);
     PPLP_CUDA(cudaGetLastError());
 }
 // out = lift(s) * (a + b + [p = 0, i < count] round(Q r_i / t))  mod q_j: add_inplace, add_plain_inplace and the monomial
@@ -334,20 +350,40 @@ __global__ void __launch_bounds__(256) circuit_b_combine_kernel(const DevLevel *
         sw[threadIdx.x] = ShoupW{w, div128_floor(0, w, L.q[threadIdx.x])};
     }
     __syncthreads();
-    const int i = blockIdx.y * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const size_t ib = qi * in_lay.sq + i, ob = qi * out_lay.sq + i;
-    const bool has = i < count;
-    const u64 m = has ? rplain[qi * r_stride + i] : 0;
-    const u64 fix = has ? dev_scaled_fix(L, m) : 0;
+    const int i0 = blockIdx.y * 512 + threadIdx.x;   // two coefficients per thread: i0 and i0 + 256
+    const size_t ib = qi * in_lay.sq, ob = qi * out_lay.sq;
+    bool in[2], has[2];
+    u64 m[2], fix[2];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        const int i = i0 + c * 256;
+        in[c] = i < n;
+        has[c] = i < count && in[c];
+        m[c] = has[c] ? rplain[qi * r_stride + i] : 0;
+    }
+#pragma unroll
+    for (int c = 0; c < 2; ++c) fix[c] = has[c] ? dev_scaled_fix(L, m[c]) : 0;
+#pragma unroll 2
     for (int j = 0; j < k; ++j) {
         const Mod mq = L.q[j];
         const ShoupW w = sw[j];
-        u64 v0 = add_mod(a[ib + j * in_lay.sl], b[ib + j * in_lay.sl], mq.q);
-        const u64 v1 = add_mod(a[ib + in_lay.sp + j * in_lay.sl], b[ib + in_lay.sp + j * in_lay.sl], mq.q);
-        if (has) v0 = add_mod(v0, dev_scaled_limb(L, m, fix, j), mq.q);
-        out[ob + j * out_lay.sl] = mul_shoup(v0, w, mq.q);
-        out[ob + out_lay.sp + j * out_lay.sl] = mul_shoup(v1, w, mq.q);
+        u64 a0[2], a1[2], b0[2], b1[2];
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+            if (in[c]) {
+                const size_t o = ib + j * in_lay.sl + i0 + c * 256;
+                a0[c] = a[o]; b0[c] = b[o]; a1[c] = a[o + in_lay.sp]; b1[c] = b[o + in_lay.sp];
+            }
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+            if (in[c]) {
+                u64 v0 = add_mod(a0[c], b0[c], mq.q);
+                const u64 v1 = add_mod(a1[c], b1[c], mq.q);
+                if (has[c]) v0 = add_mod(v0, dev_scaled_limb(L, m[c], fix[c], j), mq.q);
+                const size_t o = ob + j * out_lay.sl + i0 + c * 256;
+                out[o] = mul_shoup(v0, w, mq.q);
+                out[o + out_lay.sp] = mul_shoup(v1, w, mq.q);
+            }
     }
 }
 void launch_circuit_b_combine(const Engine &E, size_t level, const u64 *a, const u64 *b, Layout in_lay, u64 *out, Layout out_lay, int nq, const u64 *rplain,
@@ -355,7 +391,7 @@ void launch_circuit_b_combine(const Engine &E, size_t level, const u64 *a, const
     E.require_device();
     const int k = (int)E.host.levels[level].q.size(), n = (int)E.host.n;
     if (nq == 0) return;
-    circuit_b_combine_kernel<<<dim3(nq, (n + 255) / 256), 256, 0, st>>>(E.d_levels + level, a, b, in_lay, out, out_lay, nq, n, rplain, (int)count, r_stride, scalar, flags);
+    circuit_b_combine_kernel<<<dim3(nq, (n + 511) / 512), 256, 0, st>>>(E.d_levels + level, a, b, in_lay, out, out_lay, nq, n, rplain, (int)count, r_stride, scalar, flags);
     PPLP_CUDA(cudaGetLastError());
 }
 

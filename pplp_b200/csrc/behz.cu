@@ -543,6 +543,7 @@ __global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T
         auto issue = [&](int step) {
             const int h = step / KD, J = step % KD, slot = step % kRelinRing;
             u64 *dst = sm + slot * SLOT;
+            fence_proxy_async_smem();
             mbar_arrive_expect_tx(&bars[slot], SLOT * 8);
             bulk_g2s(dst, X + (size_t)J * S::M + (size_t)h * 2 * S::T, 2 * S::T * 8, &bars[slot]);
             bulk_g2s(dst + 2 * S::T, Kp + (size_t)J * kstride + (size_t)h * 2 * S::T, 2 * S::T * 8, &bars[slot]);

@@ -117,6 +117,51 @@ __global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T
         d2[h * S::T] = make_ulonglong2(as_u(reduce_sym_f64(as_d(x[2 * h]), c.qinv, c.q)), as_u(reduce_sym_f64(as_d(x[2 * h + 1]), c.qinv, c.q)));
 }
 
+// Persistent form of behzf_forward_kernel: 2 CTAs per SM, each walking rows blockIdx.x, blockIdx.x + gridDim.x, ...  While a row is
+// in pass C (registers only) one thread starts the bulk asynchronous copy (cp.async.bulk + mbarrier) of the CTA's NEXT row into
+// the transform's staging buffer, which is idle from then on; the next iteration finds its 32 coefficients per thread in shared
+// memory instead of waiting for HBM.  ncu's source view of the one-row-per-CTA kernel puts 37 % of the warp samples on the row
+// load and the first butterflies that wait for it — yet this form is SLOWER (422 vs 382 us per 10 240 rows, FP64 pipe 62 % vs 71 %;
+// PPLP_BEHZF_PERSIST=1, bit-identical): those samples are warps of one CTA waiting while the SM's other CTA keeps the FP64 pipe
+// busy, so hiding the load buys nothing and the extra barrier, the shared-memory read of the inputs and the static row
+// assignment cost more.  Kept as the record of the experiment (the review's persistent-CTA + TMA proposal).
+template <int LOGM, bool WIDE = (LOGM == 14)>
+__global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T) behzf_forward_persistent_kernel(const BehzfFwdArgs a, int rows) {
+    using S = Ntt32Shape<LOGM>;
+    extern __shared__ __align__(16) u64 sm[];
+    __shared__ __align__(8) u64 bar;
+    const int tid = threadIdx.x;
+    auto row_src = [&](int row) -> const u64 * {
+        const int l = row % a.NL, qp = row / a.NL;
+        return (l < a.k && !a.from_ext) ? a.in + (qp >> 1) * a.lay.sq + (qp & 1) * a.lay.sp + l * a.lay.sl : a.ext + ((size_t)qp * a.NL + l) * S::M;
+    };
+    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    __syncthreads();
+    int row = blockIdx.x;
+    if (tid == 0 && row < rows) { mbar_arrive_expect_tx(&bar, S::M * 8); bulk_g2s(sm, row_src(row), S::M * 8, &bar); }
+    u32 parity = 0;
+    for (; row < rows; row += gridDim.x) {
+        const int l = row % a.NL, qp = row / a.NL;
+        const DevMod &md = a.mods[a.map.mod_id[l]];
+        const Ntt32Consts c = ntt32_consts(md, false);
+        u64 *dst = a.ext + ((size_t)qp * a.NL + l) * S::M;
+        mbar_wait(&bar, parity);
+        parity ^= 1;
+        u64 x[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) x[e] = sm[e * S::T + tid];
+        const int next = row + gridDim.x;
+        ntt32_forward<LOGM, WIDE, false, false>(x, sm, tid, c, nullptr, [&]() {
+            __syncthreads();   // every warp has taken its pass-C operands: the staging buffer is free
+            if (tid == 0 && next < rows) { fence_proxy_async_smem(); mbar_arrive_expect_tx(&bar, S::M * 8); bulk_g2s(sm, row_src(next), S::M * 8, &bar); }
+        });
+        ulonglong2 *d2 = reinterpret_cast<ulonglong2 *>(dst) + tid;
+#pragma unroll
+        for (int h = 0; h < 16; ++h)
+            d2[h * S::T] = make_ulonglong2(as_u(reduce_sym_f64(as_d(x[2 * h]), c.qinv, c.q)), as_u(reduce_sym_f64(as_d(x[2 * h + 1]), c.qinv, c.q)));
+    }
+}
+
 struct BehzfTensorArgs {
     const u64 *ea, *eb;             // transformed operands [nq][2][NL][n] (pair-interleaved doubles); eb == ea squares
     u64 *d;                         // [nq][3][NL][n] canonical, coefficient form
@@ -198,8 +243,22 @@ template <int LOGM> static void run_behzf_transforms(const BehzfFwdArgs &fa, con
         PPLP_CUDA(cudaFuncSetAttribute(behzf_tensor_inverse_kernel<LOGM>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         done[dev & 63] = true;
     }
-    behzf_forward_kernel<LOGM><<<nq * 2 * fa.NL, Ntt32Shape<LOGM>::T, bytes, st>>>(fa);
-    if (fb) behzf_forward_kernel<LOGM><<<nq * 2 * fa.NL, Ntt32Shape<LOGM>::T, bytes, st>>>(*fb);
+    static const bool persist = [] { const char *e = getenv("PPLP_BEHZF_PERSIST"); return e && e[0] == '1' && e[1] == 0; }();
+    if (persist) {
+        static bool pdone[64] = {false};
+        if (!pdone[dev & 63]) {
+            PPLP_CUDA(cudaFuncSetAttribute(behzf_forward_persistent_kernel<LOGM>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            pdone[dev & 63] = true;
+        }
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int rows = nq * 2 * fa.NL, ctas = std::min(rows, sms * (512 / Ntt32Shape<LOGM>::T));
+        behzf_forward_persistent_kernel<LOGM><<<ctas, Ntt32Shape<LOGM>::T, bytes, st>>>(fa, rows);
+        if (fb) behzf_forward_persistent_kernel<LOGM><<<ctas, Ntt32Shape<LOGM>::T, bytes, st>>>(*fb, rows);
+    } else {
+        behzf_forward_kernel<LOGM><<<nq * 2 * fa.NL, Ntt32Shape<LOGM>::T, bytes, st>>>(fa);
+        if (fb) behzf_forward_kernel<LOGM><<<nq * 2 * fa.NL, Ntt32Shape<LOGM>::T, bytes, st>>>(*fb);
+    }
     behzf_tensor_inverse_kernel<LOGM><<<nq * 3 * fa.NL, Ntt32Shape<LOGM>::T, bytes, st>>>(ta);
 }
 

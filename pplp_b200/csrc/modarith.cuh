@@ -247,6 +247,9 @@ __device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
         "WAIT_DONE:\n\t}"
         ::"r"(smem_addr(bar)), "r"(parity) : "memory");
 }
+// orders this thread's earlier generic-proxy accesses of shared memory before later asynchronous-proxy ones (a bulk copy that
+// overwrites a buffer the CTA has just used)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // bytes: a multiple of 16; both addresses 16-byte aligned
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u32 bytes, u64 *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

@@ -170,8 +170,11 @@ constexpr double kGsLimit = 96.0;
 // 32*tid + e, |x| <= 14 q; ntt32_canon() brings it to [0,q).  sm: Ntt32Shape::SMEM_WORDS words.
 // REDUCE_IN (WIDE only): the inputs are residues of ANOTHER modulus of the same size class (below 2^52): bring them to
 // [-q/2, q/2] first — pass A needs |x| <= 1 q.
-template <int LOGM, bool WIDE = false, bool REDUCE_IN = false, bool CL = false>
-__device__ __forceinline__ void ntt32_forward(u64 (&x)[32], u64 *sm, int tid, const Ntt32Consts &c, const Ntt32Cl *cl = nullptr) {
+// `staging_free()` is called right after the transform's LAST read of the shared-memory staging buffer (before pass C): a
+// persistent caller uses it to start the bulk copy of its next row into the buffer (it must synchronise the CTA itself).
+struct Ntt32NoHook { __device__ __forceinline__ void operator()() const {} };
+template <int LOGM, bool WIDE = false, bool REDUCE_IN = false, bool CL = false, class Hook = Ntt32NoHook>
+__device__ __forceinline__ void ntt32_forward(u64 (&x)[32], u64 *sm, int tid, const Ntt32Consts &c, const Ntt32Cl *cl = nullptr, Hook staging_free = Hook()) {
     using S = Ntt32Shape<LOGM>;
     using G = Ntt32Geo<LOGM, CL>;
     const int ltid = CL ? cl->ltid : tid;
@@ -228,6 +231,7 @@ __device__ __forceinline__ void ntt32_forward(u64 (&x)[32], u64 *sm, int tid, co
     __syncwarp();
 #pragma unroll
     for (int e = 0; e < 32; ++e) x[e] = wsm[slot32(wbase + lane * 32 + e)];
+    staging_free();
     if constexpr (WIDE && S::SB > 0) {   // pass B left up to 0.8 q + SB * 0.75 q
 #pragma unroll
         for (int e = 0; e < 32; ++e) x[e] = as_u(reduce_sym_f64(as_d(x[e]), c.qinv, c.q));

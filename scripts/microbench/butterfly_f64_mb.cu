@@ -88,6 +88,20 @@ int main() {
                    bfs / 148 / 1.9e9, 8 * bfs / 148 / 1.9e9);
         }
     }
+    // occupancy sweep of the full butterfly (variant 0): how many resident warps does the FP64 pipe need?  (the transforms run at
+    // 16 warps per SM: two 256-thread CTAs of 128 registers)
+    for (int per_sm = 128; per_sm <= 2048; per_sm *= 2) {
+        const int threads = per_sm < 256 ? per_sm : 256, blocks = 148 * per_sm / threads;
+        for (int rep = 0; rep < 2; ++rep) {
+            cudaEventRecord(a);
+            k<0><<<blocks, threads>>>(d, tw, q, iters);
+            cudaEventRecord(b); cudaEventSynchronize(b);
+        }
+        float ms; cudaEventElapsedTime(&ms, a, b);
+        const double bfs = (double)blocks * threads * 8 * iters / (ms * 1e-3);
+        printf("resident threads per SM %4d (%2d warps): %.2f butterflies per clk per SM @1.9GHz = %.1f FP64 instr/clk/SM\n", per_sm, per_sm / 32, bfs / 148 / 1.9e9,
+               8 * bfs / 148 / 1.9e9);
+    }
     printf("%s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
 }

@@ -23,6 +23,7 @@
 #include "behz_f64.cuh"
 #include "engine.hpp"
 #include "ntt32.cuh"
+#include "scaled.cuh"
 
 namespace pplp {
 
@@ -39,8 +40,13 @@ template <int K> __device__ __forceinline__ const bf::BehzFC<K> &behzf_stage_con
     return *reinterpret_cast<const bf::BehzFC<K> *>(raw);
 }
 
+// plain != nullptr: sub_plain_inplace fused in — c0 -= round(Q m_i / t) for the first `count` coefficients of every ciphertext
+// ([SEAL] multiply_sub_plain_with_scaling_variant) before the extension, and the q rows are written to ext as well (copy_q is
+// implied: the transforms must see the subtracted rows).  Integer work on a kernel that is bound by the FP64 pipe.
+struct BehzfSubPlain { const DevLevel *L; const u64 *plain; int count; size_t stride; };
 template <int K>
-__global__ void __launch_bounds__(256) behzf_extend_kernel(const bf::BehzFC<K> *__restrict__ Cg, const u64 *__restrict__ in, Layout lay, u64 *__restrict__ ext, int copy_q) {
+__global__ void __launch_bounds__(256) behzf_extend_kernel(const bf::BehzFC<K> *__restrict__ Cg, const u64 *__restrict__ in, Layout lay, u64 *__restrict__ ext, int copy_q,
+                                                           const BehzfSubPlain sp) {
     __shared__ __align__(16) unsigned char craw[sizeof(bf::BehzFC<K>)];
     const int qp = blockIdx.x, qi = qp >> 1, p = qp & 1;
     const int i = blockIdx.y * (256 * kBehzfNC) + threadIdx.x;   // n is a multiple of 512
@@ -50,13 +56,27 @@ __global__ void __launch_bounds__(256) behzf_extend_kernel(const bf::BehzFC<K> *
     for (int c = 0; c < kBehzfNC; ++c)
 #pragma unroll
         for (int j = 0; j < K; ++j) x[c][j] = src[j * lay.sl + c * 256];   // in flight while the constants are staged
+    const bool sub = sp.plain != nullptr && p == 0;
+    u64 pm[kBehzfNC];
+#pragma unroll
+    for (int c = 0; c < kBehzfNC; ++c) pm[c] = (sub && i + c * 256 < sp.count) ? sp.plain[qi * sp.stride + i + c * 256] : 0;
     const bf::BehzFC<K> &C = behzf_stage_consts<K>(Cg, craw);
     const int n = C.n, NL = K + C.nA;
+    if (sub) {
+        const DevLevel &L = *sp.L;
+#pragma unroll
+        for (int c = 0; c < kBehzfNC; ++c)
+            if (i + c * 256 < sp.count) {
+                const u64 fix = dev_scaled_fix(L, pm[c]);
+#pragma unroll
+                for (int j = 0; j < K; ++j) x[c][j] = sub_mod(x[c][j], dev_scaled_limb(L, pm[c], fix, j), L.q[j].q);
+            }
+    }
     u64 *dst = ext + (size_t)qp * NL * n + i;
     u64 *o[kBehzfNC];
 #pragma unroll
     for (int c = 0; c < kBehzfNC; ++c) o[c] = dst + (size_t)K * n + c * 256;
-    if (copy_q) {
+    if (copy_q || sp.plain != nullptr) {
 #pragma unroll
         for (int c = 0; c < kBehzfNC; ++c)
 #pragma unroll
@@ -262,11 +282,18 @@ template <int LOGM> static void run_behzf_transforms(const BehzfFwdArgs &fa, con
     behzf_tensor_inverse_kernel<LOGM><<<nq * 3 * fa.NL, Ntt32Shape<LOGM>::T, bytes, st>>>(ta);
 }
 
+// One operand batch of the product: nq ciphertexts at src (layout lay), optionally with a fused sub_plain.
+struct BehzfSeg { const u64 *src; Layout lay; int nq; const u64 *plain; size_t count, stride; };
+
+// a = segs[0] (|| segs[1]: the two halves of one operand batch, e.g. Circuit B's x and y chunks); b == nullptr squares a.
 template <int K>
-static void multiply_f64_k(const Engine &E, size_t level, const u64 *a, const u64 *b, Layout in_lay, u64 *out, Layout out_lay, int nq, u64 *ws, cudaStream_t st) {
+static void multiply_f64_k(const Engine &E, size_t level, const BehzfSeg *segs, int nseg, const u64 *b, Layout b_lay, u64 *out, Layout out_lay, u64 *ws, cudaStream_t st) {
     const HostLevel &HL = E.host.levels[level];
     const int n = (int)E.host.n, nA = HL.bf.nA, NL = K + nA;
-    const bool square = (a == b);
+    int nq = 0;
+    bool any_plain = false;
+    for (int s2 = 0; s2 < nseg; ++s2) { nq += segs[s2].nq; any_plain = any_plain || segs[s2].plain != nullptr; }
+    const bool square = (b == nullptr);
     static const bool fused = [] { const char *e = getenv("PPLP_BEHZF_FUSED"); return !(e && e[0] == '0' && e[1] == 0); }();
     const bf::BehzFC<K> *C = static_cast<const bf::BehzFC<K> *>(E.behzf_consts(level, [&](std::vector<unsigned char> &img) {
         img.resize(sizeof(bf::BehzFC<K>));
@@ -278,11 +305,22 @@ static void multiply_f64_k(const Engine &E, size_t level, const u64 *a, const u6
     for (int b2 = 0; b2 < nA; ++b2) map.mod_id[K + b2] = HL.bf.mod_id[b2];
     const size_t we = (size_t)nq * 2 * NL * n;
     u64 *ea = ws, *eb = square ? ea : ea + we, *d = (square ? ea : eb) + we;
-    const dim3 ge(nq * 2, n / (256 * kBehzfNC)), gf(nq * 3, n / (256 * kBehzfNC));
-    behzf_extend_kernel<K><<<ge, 256, 0, st>>>(C, a, in_lay, ea, fused ? 0 : 1);
-    if (!square) behzf_extend_kernel<K><<<ge, 256, 0, st>>>(C, b, in_lay, eb, fused ? 0 : 1);
+    const int gy = n / (256 * kBehzfNC);
+    // the q rows of an operand go through ext when they are not the caller's rows any more (fused sub_plain), when the operand comes in
+    // pieces, or on the unfused path; otherwise the forward transform reads them from the caller's buffer
+    const int a_from_ext = (!fused || any_plain || nseg > 1) ? 1 : 0;
+    int done = 0;
+    for (int s2 = 0; s2 < nseg; ++s2) {
+        const BehzfSeg &sg = segs[s2];
+        if (sg.nq == 0) continue;
+        const BehzfSubPlain sp{E.d_levels + level, sg.plain, (int)sg.count, sg.stride};
+        behzf_extend_kernel<K><<<dim3(sg.nq * 2, gy), 256, 0, st>>>(C, sg.src, sg.lay, ea + (size_t)done * 2 * NL * n, a_from_ext, sp);
+        done += sg.nq;
+    }
+    const BehzfSubPlain none{nullptr, nullptr, 0, 0};
+    if (!square) behzf_extend_kernel<K><<<dim3(nq * 2, gy), 256, 0, st>>>(C, b, b_lay, eb, fused ? 0 : 1, none);
     if (fused) {
-        BehzfFwdArgs fa{a, in_lay, ea, K, NL, 0, map, E.d_mods}, fb{b, in_lay, eb, K, NL, 0, map, E.d_mods};
+        BehzfFwdArgs fa{segs[0].src, segs[0].lay, ea, K, NL, a_from_ext, map, E.d_mods}, fb{b, b_lay, eb, K, NL, 0, map, E.d_mods};
         BehzfTensorArgs ta{ea, eb, d, NL, map, E.d_mods};
         switch (E.host.logn) {
         case 11: run_behzf_transforms<11>(fa, square ? nullptr : &fb, ta, nq, st); break;
@@ -298,24 +336,43 @@ static void multiply_f64_k(const Engine &E, size_t level, const u64 *a, const u6
         launch_tensor(E, map, ea, eb, d, nq, n, st);
         launch_ntt(E, d, Layout{(size_t)3 * NL * n, (size_t)NL * n, (size_t)n}, nq, 3, map, true, st);
     }
-    behzf_floor_sk_kernel<K><<<gf, 256, 0, st>>>(C, nA, d, out, out_lay);
+    behzf_floor_sk_kernel<K><<<dim3(nq * 3, gy), 256, 0, st>>>(C, nA, d, out, out_lay);
     PPLP_CUDA(cudaGetLastError());
+}
+
+template <class F> static void behzf_dispatch_k(size_t k, F f) {
+    switch (k) {
+    case 1: f(std::integral_constant<int, 1>{}); break;
+    case 2: f(std::integral_constant<int, 2>{}); break;
+    case 3: f(std::integral_constant<int, 3>{}); break;
+    case 4: f(std::integral_constant<int, 4>{}); break;
+    case 5: f(std::integral_constant<int, 5>{}); break;
+    case 6: f(std::integral_constant<int, 6>{}); break;
+    case 7: f(std::integral_constant<int, 7>{}); break;
+    case 8: f(std::integral_constant<int, 8>{}); break;
+    default: throw std::logic_error("pplp: the FP64 auxiliary base covers at most 8 data limbs");
+    }
 }
 
 void launch_multiply_f64(const Engine &E, size_t level, const u64 *a, const u64 *b, Layout in_lay, u64 *out, Layout out_lay, int nq, u64 *ws, cudaStream_t st) {
     E.require_device();
     if (nq == 0) return;
-    switch (E.host.levels[level].q.size()) {
-    case 1: multiply_f64_k<1>(E, level, a, b, in_lay, out, out_lay, nq, ws, st); break;
-    case 2: multiply_f64_k<2>(E, level, a, b, in_lay, out, out_lay, nq, ws, st); break;
-    case 3: multiply_f64_k<3>(E, level, a, b, in_lay, out, out_lay, nq, ws, st); break;
-    case 4: multiply_f64_k<4>(E, level, a, b, in_lay, out, out_lay, nq, ws, st); break;
-    case 5: multiply_f64_k<5>(E, level, a, b, in_lay, out, out_lay, nq, ws, st); break;
-    case 6: multiply_f64_k<6>(E, level, a, b, in_lay, out, out_lay, nq, ws, st); break;
-    case 7: multiply_f64_k<7>(E, level, a, b, in_lay, out, out_lay, nq, ws, st); break;
-    case 8: multiply_f64_k<8>(E, level, a, b, in_lay, out, out_lay, nq, ws, st); break;
-    default: throw std::logic_error("pplp: the FP64 auxiliary base covers at most 8 data limbs");
-    }
+    const BehzfSeg seg{a, in_lay, nq, nullptr, 0, 0};
+    behzf_dispatch_k(E.host.levels[level].q.size(), [&](auto kc) {
+        multiply_f64_k<decltype(kc)::value>(E, level, &seg, 1, a == b ? nullptr : b, in_lay, out, out_lay, ws, st);
+    });
+}
+
+// Circuit B's front half in one go: out[0, c) = (x - px)^2, out[c, 2c) = (y - py)^2 (size 3, layout out_lay), the sub_plain fused into
+// the base extension — no copy of the chunk, no separate sub_plain pass.  ws: multiply_f64_tmp_words(E, level, 2 c, true).
+void launch_square_sub_plain_f64(const Engine &E, size_t level, const u64 *x, const u64 *px, const u64 *y, const u64 *py, Layout in_lay, size_t count, size_t stride, int c,
+                                 u64 *out, Layout out_lay, u64 *ws, cudaStream_t st) {
+    E.require_device();
+    if (c == 0) return;
+    const BehzfSeg segs[2] = {{x, in_lay, c, px, count, stride}, {y, in_lay, c, py, count, stride}};
+    behzf_dispatch_k(E.host.levels[level].q.size(), [&](auto kc) {
+        multiply_f64_k<decltype(kc)::value>(E, level, segs, 2, nullptr, in_lay, out, out_lay, ws, st);
+    });
 }
 
 }  // namespace pplp

@@ -670,9 +670,14 @@ int pplp_circuit_b(pplp_ctx *ctx, size_t level, const uint64_t *d_cx, const uint
         const int c = (int)std::min(chunk, nq - done);
         const size_t off = done * full2.sq;
         u64 *x = w2.as<u64>(), *y = x + (size_t)c * 2 * ctw;
-        launch_copy_sub_plain(E, level, d_cx + off, full2, x, wl2, c, d_px + done * plain_stride, plain_count, plain_stride, st);
-        launch_copy_sub_plain(E, level, d_cy + off, full2, y, wl2, c, d_py + done * plain_stride, plain_count, plain_stride, st);
-        launch_multiply(E, level, x, x, wl2, w3.as<u64>(), wl3, 2 * c, mws.as<u64>(), st);
+        if (behz_uses_f64(E, level)) {   // chunk copy and sub_plain fused into the square's base extension (behzf.cu)
+            launch_square_sub_plain_f64(E, level, d_cx + off, d_px + done * plain_stride, d_cy + off, d_py + done * plain_stride, full2, plain_count, plain_stride, c,
+                                        w3.as<u64>(), wl3, mws.as<u64>(), st);
+        } else {
+            launch_copy_sub_plain(E, level, d_cx + off, full2, x, wl2, c, d_px + done * plain_stride, plain_count, plain_stride, st);
+            launch_copy_sub_plain(E, level, d_cy + off, full2, y, wl2, c, d_py + done * plain_stride, plain_count, plain_stride, st);
+            launch_multiply(E, level, x, x, wl2, w3.as<u64>(), wl3, 2 * c, mws.as<u64>(), st);
+        }
         launch_relinearize(E, level, w3.as<u64>(), wl3, x, wl2, 2 * c, d_rk, d_rk_quot, rws.as<u64>(), st);
         launch_circuit_b_combine(E, level, x, y, wl2, d_out + off, full2, c, d_r + done * r_stride, r_count, r_stride, d_s + done, d_flags ? d_flags + done : nullptr, st);
     }

@@ -142,6 +142,9 @@ void launch_tensor(const Engine &E, const RowMap &map, const u64 *x, const u64 *
 bool behz_uses_f64(const Engine &E, size_t level);
 size_t multiply_f64_tmp_words(const Engine &E, size_t level, int nq, bool square);
 void launch_multiply_f64(const Engine &E, size_t level, const u64 *a, const u64 *b, Layout in_lay, u64 *out, Layout out_lay, int nq, u64 *ws, cudaStream_t st);
+// (x - px)^2 for c ciphertexts followed by (y - py)^2 for c ciphertexts, sub_plain fused into the base extension
+void launch_square_sub_plain_f64(const Engine &E, size_t level, const u64 *x, const u64 *px, const u64 *y, const u64 *py, Layout in_lay, size_t count, size_t stride, int c,
+                                 u64 *out, Layout out_lay, u64 *ws, cudaStream_t st);
 // size-3 -> size-2 with relinearisation keys rk [digit][2][K][n] and their Shoup quotients rkq (same shape).
 void launch_relinearize(const Engine &E, size_t level, const u64 *in, Layout in_lay, u64 *out, Layout out_lay, int nq, const u64 *rk, const u64 *rkq, u64 *ws,
                         cudaStream_t st);

@@ -210,7 +210,15 @@ __global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T
     const ulonglong2 *Y0 = reinterpret_cast<const ulonglong2 *>(a.eb + ((size_t)qi * 2 * a.NL + l) * S::M) + tid;
     const ulonglong2 *X1 = X0 + prow / 2, *Y1 = Y0 + prow / 2;
     u64 x[32];
-    if (comp != 1) {
+    if (comp != 1 && a.ea == a.eb) {   // square: one operand row
+        const ulonglong2 *P = comp == 0 ? X0 : X1;
+#pragma unroll
+        for (int h = 0; h < 16; ++h) {
+            const ulonglong2 u = __ldg(P + h * S::T);
+            x[2 * h] = as_u(mulvar_f64(as_d(u.x), as_d(u.x), qinv, q));
+            x[2 * h + 1] = as_u(mulvar_f64(as_d(u.y), as_d(u.y), qinv, q));
+        }
+    } else if (comp != 1) {
         const ulonglong2 *P = comp == 0 ? X0 : X1, *Q = comp == 0 ? Y0 : Y1;
 #pragma unroll
         for (int h = 0; h < 16; ++h) {

@@ -164,3 +164,30 @@ def test_fp64_base_centred_r_boundary(eng, oracle):
     got = eng.to_np(ctx.multiply(ctx.dev(np.stack([a, a, b])), ctx.dev(np.stack([a, b, a]))))
     for i, (x, y) in enumerate(((a, a), (a, b), (b, a))):
         assert (got[i] == octx.multiply(x, y)).all(), i
+
+
+def test_fp64_base_product_writes_only_its_output(eng, oracle):
+    """The product's output lands in a window of a larger buffer filled with a sentinel: the margins on both sides and the inputs
+    are untouched (compute-sanitizer is not available on the GPU pool; this is the bounds check the C ABI can offer)."""
+    import torch
+    from pplp_b200.capi import check
+    n = 4096
+    ctx, octx = contexts(eng, oracle, n)
+    k = ctx.k
+    rng = np.random.default_rng(8)
+    q = octx.q[:k]
+    nq = 5
+    a = np.stack([np.stack([rand_residues(rng, q, n) for _ in range(2)]) for _ in range(nq)])
+    da = ctx.dev(a)
+    keep = da.clone()
+    words, margin = nq * 3 * k * n, 4096
+    sentinel = -0x0123456789ABCDEF
+    big = torch.full((words + 2 * margin,), sentinel, dtype=torch.int64, device=da.device)
+    out = big[margin:margin + words]
+    check(ctx.L.pplp_multiply(ctx.h, ctx.first_level, da.data_ptr(), da.data_ptr(), out.data_ptr(), eng.LAYOUT_SEAL, nq, None))
+    torch.cuda.synchronize()
+    assert bool((big[:margin] == sentinel).all()) and bool((big[margin + words:] == sentinel).all())
+    assert bool((da == keep).all())
+    got = eng.to_np(out.view(nq, 3, k, n))
+    for i in range(nq):
+        assert (got[i] == octx.square(a[i])).all()

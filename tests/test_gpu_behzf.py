@@ -191,3 +191,42 @@ def test_fp64_base_product_writes_only_its_output(eng, oracle):
     got = eng.to_np(out.view(nq, 3, k, n))
     for i in range(nq):
         assert (got[i] == octx.square(a[i])).all()
+
+
+_SWITCH_SNIPPET = r"""
+import hashlib, sys
+import numpy as np
+sys.path.insert(0, %r)
+from pplp_b200 import engine
+h = hashlib.sha256()
+# (a) transforms at N = 16384 (PPLP_NTT_CLUSTER), (b) squares at N = 8192 (PPLP_BEHZF_PERSIST), (c) encryptions (PPLP_ENC_INV32)
+ctx = engine.Context(16384, t=1 << 20, device=0)
+rng = np.random.default_rng(16384)
+data = np.stack([np.stack([rng.integers(0, qj, size=16384, dtype=np.uint64) for qj in ctx.q[:ctx.k]]) for _ in range(6)])[:, None]
+d = ctx.dev(np.ascontiguousarray(data))
+h.update(engine.to_np(ctx.ntt_(d.clone())).tobytes())
+h.update(engine.to_np(ctx.ntt_(d.clone(), inverse=True)).tobytes())
+ctx = engine.Context(8192, t=1 << 56, device=0)
+a = np.stack([np.stack([np.stack([rng.integers(0, qj, size=8192, dtype=np.uint64) for qj in ctx.q[:ctx.k]]) for _ in range(2)]) for _ in range(7)])
+h.update(engine.to_np(ctx.square(ctx.dev(a))).tobytes())
+sk, pk = ctx.keygen(np.arange(1, 9, dtype=np.uint64))
+seeds = rng.integers(0, 1 << 63, size=(9, 8), dtype=np.uint64)
+plain = rng.integers(0, 1 << 40, size=(9, 3), dtype=np.uint64)
+h.update(engine.to_np(ctx.encrypt(pk, ctx.dev(seeds), ctx.dev(plain))).tobytes())
+print("DIGEST", h.hexdigest())
+"""
+
+
+def test_optional_kernel_variants_give_the_same_bytes():
+    """The measured-and-kept alternatives (two-CTA cluster transforms at N = 16384, persistent forward transform with bulk-copy
+    prefetch, the 16-per-thread encryption inverse) stay bit-identical to the defaults, which the parity tests pin to the oracle."""
+    digests = {}
+    for name, env in (("default", {}), ("cluster", {"PPLP_NTT_CLUSTER": "1"}), ("persistent", {"PPLP_BEHZF_PERSIST": "1"}), ("enc16", {"PPLP_ENC_INV32": "0"})):
+        e = dict(os.environ)
+        for k in ("PPLP_NTT_CLUSTER", "PPLP_BEHZF_PERSIST", "PPLP_ENC_INV32"):
+            e.pop(k, None)
+        e.update(env)
+        p = subprocess.run([sys.executable, "-c", _SWITCH_SNIPPET % ROOT], capture_output=True, text=True, env=e, timeout=600)
+        assert p.returncode == 0, p.stdout + p.stderr
+        digests[name] = [ln for ln in p.stdout.splitlines() if ln.startswith("DIGEST")][0]
+    assert len(set(digests.values())) == 1, digests

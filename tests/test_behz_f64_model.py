@@ -157,3 +157,42 @@ def test_fp64_base_product_centred_r_boundary(model, orc):
         na, got, _ = _model_multiply(model, n, q, t, level, x, y)
         assert na > 0
         assert np.array_equal(got, ctx.multiply(x, y, level))
+
+
+def test_fp64_base_product_random_parameter_sets(model, orc):
+    """Twenty random parameter sets at N = 2048 (1..5 primes of 30..49 bits, plain moduli of 2..60 bits, every level of the chain):
+    the auxiliary base is sized from (t, Q) per level, so sweep both."""
+    n = 2048
+    rng = np.random.default_rng(20261019)
+    done = 0
+    for trial in range(40):
+        K = int(rng.integers(1, 6))
+        bits = sorted((int(b) for b in rng.integers(30, 50, size=K)), reverse=True)
+        q, used = [], {}
+        for b in bits:   # distinct primes: the i-th largest prime of each bit size
+            used[b] = used.get(b, 0) + 1
+            q.append(orc.get_primes(2 * n, b, used[b])[-1])
+        tbits = int(rng.integers(2, 61))
+        t = int(rng.integers(1 << (tbits - 1), 1 << tbits)) | 1 if tbits > 1 else 3
+        if any(p == t for p in q):
+            continue
+        ctx = orc.context(n, q, t)
+        if not ctx.ok:
+            continue
+        for level in range(ctx.first, ctx.nlevels):
+            k = ctx.limbs(level)
+            ql = q[:k]
+            a, b = _random_ct(rng, ql, n), _random_ct(rng, ql, n)
+            na, got, aux = _model_multiply(model, n, q, t, level, a, b)
+            if na == 0:
+                continue            # not eligible (e.g. more auxiliary primes than the kernels are compiled for)
+            assert na > 0, (q, t, level, na)
+            prod, Q = 1, 1
+            for p in aux:
+                prod *= p
+            for p in ql:
+                Q *= p
+            assert prod > (1 << 32) * t * Q and len(set(aux) | set(q)) == len(aux) + len(q)
+            assert np.array_equal(got, ctx.multiply(a, b, level)), (q, t, level)
+            done += 1
+    assert done >= 20

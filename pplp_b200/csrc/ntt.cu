@@ -11,7 +11,7 @@
 //                                NTT-form intermediate never touches HBM  (decrypt: c1*s + c0; multiply_plain generic)
 //   stage0 kernels               N = 32768 does not fit one CTA (256 KiB > 227 KiB smem): the first (last) butterfly stage
 //                                runs as a streaming pass over HBM and the two 16384-point halves go through the CTA kernel.
-// L is the lazy-reduction level (ntt.cuh): chosen on the host from the widest modulus among the rows of the launch.
+// L is the lazy-reduction level (ntt.cuh): chosen on the host per limb; limbs of one class form one launch (launch_ntt).
 // Algorithmic HBM bytes: 16*N per limb transform (read + write); polymul: 8*N*(2 + has_c) + b (L2-resident when broadcast).
 #include "engine.hpp"
 #include "ntt.cuh"
@@ -359,13 +359,11 @@ template <int LOGM> static void run_block_ntt_l(int level, const NttArgs &a, int
     else run_block_ntt<LOGM, 0>(a, rows, inverse, st);
 }
 
-void launch_ntt(const Engine &E, u64 *data, Layout lay, int nq, int npoly, const RowMap &map, bool inverse, cudaStream_t st) {
-    E.require_device();
+// One launch (or, at N = 32768, one launch sequence) over limbs that all run on the same arithmetic (`lazy` level).
+static void launch_ntt_class(const Engine &E, u64 *data, Layout lay, int nq, int npoly, const RowMap &map, int lazy, bool inverse, cudaStream_t st) {
     const int rows = nq * npoly * map.nlimbs;
-    if (rows == 0) return;
     NttArgs a{data, lay, nq, npoly, 0, map, E.d_mods};
     const int logn = E.host.logn;
-    const int lazy = ntt_lazy_level(E.max_bits(map), logn);
     switch (logn) {
     case 10: run_block_ntt_l<10>(lazy, a, rows, inverse, st); break;
     case 11: run_block_ntt_l<11>(lazy, a, rows, inverse, st); break;
@@ -391,6 +389,28 @@ void launch_ntt(const Engine &E, u64 *data, Layout lay, int nq, int npoly, const
     PPLP_CUDA(cudaGetLastError());
 }
 
+// The arithmetic is chosen per limb, not per batch: a chain that mixes prime widths (BFVDefault's 43/44-bit primes next to 50-bit
+// ones, say) keeps its narrow limbs on the FP64 pipe instead of dragging every row to the widest prime's integer kernel.  Limbs
+// are taken in maximal runs of one class so that each run is still one launch over a contiguous block of rows
+// (PPLP_NTT_PER_LIMB=0: one class for the whole batch, the widest prime's — the old behaviour, for A/B measurements).
+void launch_ntt(const Engine &E, u64 *data, Layout lay, int nq, int npoly, const RowMap &map, bool inverse, cudaStream_t st) {
+    E.require_device();
+    if (nq * npoly * map.nlimbs == 0) return;
+    const int logn = E.host.logn;
+    static const bool per_limb = [] { const char *e = getenv("PPLP_NTT_PER_LIMB"); return !(e && e[0] == '0' && e[1] == 0); }();
+    // N = 32768 runs a streamed stage around 14-stage blocks that start at stage 1: no FP64 schedule there, one class
+    if (!per_limb || logn == 15) { launch_ntt_class(E, data, lay, nq, npoly, map, ntt_lazy_level(E.max_bits(map), logn), inverse, st); return; }
+    for (int j0 = 0; j0 < map.nlimbs;) {
+        const int lazy = ntt_lazy_level(hm::bitlen(E.host.tables[map.mod_id[j0]].q), logn);
+        RowMap run;
+        run.nlimbs = 0;
+        int j = j0;
+        for (; j < map.nlimbs && ntt_lazy_level(hm::bitlen(E.host.tables[map.mod_id[j]].q), logn) == lazy; ++j) run.mod_id[run.nlimbs++] = map.mod_id[j];
+        launch_ntt_class(E, data + (size_t)j0 * lay.sl, lay, nq, npoly, run, lazy, inverse, st);
+        j0 = j;
+    }
+}
+
 template <int LOGM, int L> static void run_polymul(const PolymulArgs &a, int rows, cudaStream_t st) {
     const int bytes = NttShape<LOGM>::SMEM_WORDS * 8;
     allow_smem(polymul_kernel<LOGM, L>, bytes);
@@ -409,17 +429,27 @@ template <int LOGM> static void run_polymul_l(int level, const PolymulArgs &a, i
 void launch_polymul(const Engine &E, const u64 *a, Layout a_lay, const u64 *b_ntt, Layout b_lay, const u64 *c, Layout c_lay, u64 *out, Layout out_lay,
                     int nq, int npoly, const RowMap &map, cudaStream_t st) {
     E.require_device();
-    const int rows = nq * npoly * map.nlimbs;
-    if (rows == 0) return;
-    PolymulArgs pa{a, a_lay, b_ntt, b_lay, c, c_lay, out, out_lay, nq, npoly, map, E.d_mods};
-    const int lazy = ntt_lazy_level(E.max_bits(map), E.host.logn);
-    switch (E.host.logn) {
-    case 10: run_polymul_l<10>(lazy, pa, rows, st); break;
-    case 11: run_polymul_l<11>(lazy, pa, rows, st); break;
-    case 12: run_polymul_l<12>(lazy, pa, rows, st); break;
-    case 13: run_polymul_l<13>(lazy, pa, rows, st); break;
-    case 14: run_polymul_l<14>(lazy, pa, rows, st); break;
-    default: throw std::invalid_argument("pplp: fused polymul supports poly_modulus_degree 1024..16384");
+    if (nq * npoly * map.nlimbs == 0) return;
+    const int logn = E.host.logn;
+    if (logn < 10 || logn > 14) throw std::invalid_argument("pplp: fused polymul supports poly_modulus_degree 1024..16384");
+    // arithmetic per limb, in maximal runs of one class (see launch_ntt)
+    for (int j0 = 0; j0 < map.nlimbs;) {
+        const int lazy = ntt_lazy_level(hm::bitlen(E.host.tables[map.mod_id[j0]].q), logn);
+        RowMap run;
+        run.nlimbs = 0;
+        int j = j0;
+        for (; j < map.nlimbs && ntt_lazy_level(hm::bitlen(E.host.tables[map.mod_id[j]].q), logn) == lazy; ++j) run.mod_id[run.nlimbs++] = map.mod_id[j];
+        const int rows = nq * npoly * run.nlimbs;
+        PolymulArgs pa{a + (size_t)j0 * a_lay.sl, a_lay, b_ntt + (size_t)j0 * b_lay.sl, b_lay, c ? c + (size_t)j0 * c_lay.sl : nullptr, c_lay,
+                       out + (size_t)j0 * out_lay.sl, out_lay, nq, npoly, run, E.d_mods};
+        switch (logn) {
+        case 10: run_polymul_l<10>(lazy, pa, rows, st); break;
+        case 11: run_polymul_l<11>(lazy, pa, rows, st); break;
+        case 12: run_polymul_l<12>(lazy, pa, rows, st); break;
+        case 13: run_polymul_l<13>(lazy, pa, rows, st); break;
+        default: run_polymul_l<14>(lazy, pa, rows, st); break;
+        }
+        j0 = j;
     }
     PPLP_CUDA(cudaGetLastError());
 }

@@ -107,8 +107,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default="gpurun_out/config4.json")
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--n", type=int, nargs="*", default=[4096, 8192, 16384, 32768])
     a = ap.parse_args()
-    rows_out = sweep(limb_list=(3, 8) if a.quick else (3, 4, 5, 6, 7, 8))
+    rows_out = sweep(ns=tuple(a.n), limb_list=(3, 8) if a.quick else (3, 4, 5, 6, 7, 8))
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
     with open(a.out, "w") as f:
         for r in rows_out:

@@ -288,3 +288,51 @@ def test_sample_uniform_matches_oracle(eng, oracle):
         oracle.lib.orc_sample_uniform(seed.ctypes.data_as(C.POINTER(C.c_uint64)), np.array(ctx.q[:ctx.k], dtype=np.uint64).ctypes.data_as(C.POINTER(C.c_uint64)),
                                       C.c_size_t(ctx.k), C.c_size_t(n), ref.ctypes.data_as(C.POINTER(C.c_uint64)))
         assert (eng.to_np(out) == ref).all()
+
+
+@pytest.mark.parametrize("layout_name", ["seal", "limb_major"])
+def test_interleaved_prime_widths_run_per_limb_and_match_oracle(eng, oracle, layout_name):
+    """A chain that alternates prime widths (50 / 36 / 49 / 36 / 50 bits + a 37-bit special prime) is transformed in runs of one
+    arithmetic class each (launch_ntt / launch_polymul in ntt.cu: FP64 narrow, FP64 wide, integer) — every limb of the forward and
+    inverse transform, the generic multiply_plain and a decryption are compared with the oracle."""
+    n = 4096
+    d = oracle.bfv_default(n)
+    p50 = [p for p in oracle.get_primes(2 * n, 50, 2)]
+    p49 = [p for p in oracle.get_primes(2 * n, 49, 1)]
+    q = [p50[0], d[0], p49[0], d[1], p50[1], d[2]]
+    K = len(q)
+    ctx = eng.Context(n, q=q, t=T56, device=0, enforce_security=False)
+    assert ctx.ok, ctx.error_message
+    octx = oracle.context(n, q, T56, seed=seed8(5))
+    layout = eng.LAYOUT_SEAL if layout_name == "seal" else eng.LAYOUT_LIMB_MAJOR
+    import torch
+    rows = 5
+    rng = np.random.default_rng(4096)
+    host = np.stack([rng.integers(0, q[j], size=(rows, n), dtype=np.uint64) for j in range(K)])          # [K][rows][n]
+    host[1, 0, :] = q[1] - 1; host[4, 1, :] = q[4] - 1; host[2, 2, :] = 0
+    dev = ctx.dev(host.transpose(1, 0, 2)[:, None] if layout == eng.LAYOUT_SEAL else host[:, None])     # [rows][1][K][n] / [K][1][rows][n]
+    fwd = eng.to_np(ctx.ntt_(dev.clone(), level=0, layout=layout))
+    back = eng.to_np(ctx.ntt_(ctx.dev(fwd), level=0, inverse=True, layout=layout))
+    for j in range(K):
+        for r in range(rows):
+            got = fwd[r, 0, j] if layout == eng.LAYOUT_SEAL else fwd[j, 0, r]
+            assert (got == octx.ntt(0, j, host[j, r])).all(), (j, r)
+            assert ((back[r, 0, j] if layout == eng.LAYOUT_SEAL else back[j, 0, r]) == host[j, r]).all(), (j, r)
+    # generic multiply_plain (fused NTT -> product -> INTT per limb) and decryption on the same chain
+    sk, pk = ctx.keygen(seed8(5))
+    osk, opk = octx.keygen()
+    assert (eng.to_np(sk) == osk).all() and (eng.to_np(pk) == opk).all()
+    nq = 3
+    seeds = np.stack([seed8(100 + i) for i in range(nq)])
+    plain = rng.integers(0, T56, size=(nq, 4), dtype=np.uint64)
+    cts = np.stack([octx.encrypt(opk, plain[i], seed=seeds[i]) for i in range(nq)])                       # [nq][2][k][n]
+    assert (eng.to_np(ctx.encrypt(pk, ctx.dev(seeds), ctx.dev(plain))) == cts).all()
+    mult = rng.integers(0, T56, size=n, dtype=np.uint64)
+    want = np.stack([octx.eval_plain("multiply_plain", cts[i], mult) for i in range(nq)])
+    arg = ctx.dev(cts if layout == eng.LAYOUT_SEAL else cts.transpose(2, 1, 0, 3))
+    got = eng.to_np(ctx.multiply_plain_poly_(arg, ctx.dev(mult), layout=layout))
+    assert ((got if layout == eng.LAYOUT_SEAL else got.transpose(2, 1, 0, 3)) == want).all()
+    dec = eng.to_np(ctx.decrypt(ctx.dev(want), sk))
+    for i in range(nq):
+        ref = octx.decrypt(osk, want[i])
+        assert (dec[i, : len(ref)] == ref).all() and not dec[i, len(ref):].any()

@@ -107,8 +107,12 @@ __device__ __forceinline__ void bf_gs(u64 &x, u64 &y, const ShoupW w, const doub
     y = as_u(mulmod_f64(__dsub_rn(xd, yd), as_d(w.w), as_d(w.wq), q));
 }
 __device__ __forceinline__ ShoupW ld_tw(const ShoupW *p) {
+#ifdef PPLP_NTT32_ABL_TW   // lab ablation only (scripts/microbench/ntt32_lab.cu): no twiddle loads, made-up values
+    return ShoupW{0x4280000000000000ULL + (u64)(size_t)p, 0x3fe0000000000000ULL};
+#else
     const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(p));
     return ShoupW{v.x, v.y};
+#endif
 }
 __device__ __forceinline__ ShoupW lds_tw(const u64 *sm, int i) {
     const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(sm + 2 * i);
@@ -202,14 +206,18 @@ __device__ __forceinline__ void ntt32_forward(u64 (&x)[32], u64 *sm, int tid, co
         for (int e = 0; e < 32; ++e) (e < 16 ? cl->sm0 : cl->sm1)[slot32((e & 15) * S::T + tid)] = x[e];   // point e T + tid lives in CTA (e >> 4)
         ntt32_cluster_sync();
     } else {
+#ifndef PPLP_NTT32_ABL_TR   // (lab ablation: no transposes)
 #pragma unroll
         for (int e = 0; e < 32; ++e) sm[slot32(e * S::T + tid)] = x[e];
         __syncthreads();
+#endif
     }
     u64 *wsm = sm;   // the warp's 1024 points live at indices [1024 warp, 1024 warp + 1024) of its CTA's buffer
     const int wbase = lwarp << 10;
+#ifndef PPLP_NTT32_ABL_TR
 #pragma unroll
     for (int e = 0; e < 32; ++e) x[e] = wsm[slot32(wbase + e * 32 + lane)];
+#endif
     if constexpr (WIDE) {   // pass A left up to 4.75 q
 #pragma unroll
         for (int e = 0; e < 32; ++e) x[e] = as_u(reduce_sym_f64(as_d(x[e]), c.qinv, c.q));
@@ -224,13 +232,17 @@ __device__ __forceinline__ void ntt32_forward(u64 (&x)[32], u64 *sm, int tid, co
 #pragma unroll
                 for (int i = 0; i < half; ++i) bf_ct(x[g * 2 * half + i], x[g * 2 * half + i + half], w, c.q);
             });
+#ifndef PPLP_NTT32_ABL_TR
         __syncwarp();
 #pragma unroll
         for (int e = 0; e < 32; ++e) wsm[slot32(wbase + e * 32 + lane)] = x[e];
+#endif
     }
+#ifndef PPLP_NTT32_ABL_TR
     __syncwarp();
 #pragma unroll
     for (int e = 0; e < 32; ++e) x[e] = wsm[slot32(wbase + lane * 32 + e)];
+#endif
     staging_free();
     if constexpr (WIDE && S::SB > 0) {   // pass B left up to 0.8 q + SB * 0.75 q
 #pragma unroll

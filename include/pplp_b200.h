@@ -112,6 +112,11 @@ int pplp_encrypt(pplp_ctx *ctx, const uint64_t *d_pk, const uint64_t *d_seeds, c
  * the protocol reads coefficient 0). */
 int pplp_decrypt(pplp_ctx *ctx, size_t level, const uint64_t *d_ct, int layout, size_t nq, size_t size, const uint64_t *d_sk, uint64_t *d_plain,
                  size_t plain_stride, size_t ncoeff, void *stream);
+/* Decryptor::invariant_noise_budget(ct) (SEAL decryptor.cpp; the reference never calls it — a diagnostic for the north_star's
+ * square / relinearize circuits): d_budget[q] = max(0, bits(Q) - bits(|| t (c0 + c1 s + c2 s^2) mod Q ||_inf, centred) - 1) for
+ * every ciphertext of the batch (size 2 or 3), the infinity norm taken over the CRT-composed coefficients as SEAL does. */
+int pplp_noise_budget(pplp_ctx *ctx, size_t level, const uint64_t *d_ct, int layout, size_t nq, size_t size, const uint64_t *d_sk, int *d_budget,
+                      void *stream);
 
 /* ---- Evaluator ---------------------------------------------------------------------------------------------------
  * add_inplace / sub_inplace  — src/server.cc:130,131.  a <- a +/- b over npoly polynomials; negate: a <- -b. */

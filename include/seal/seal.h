@@ -949,6 +949,18 @@ public:
         std::memcpy(destination.data(), host.data(), destination.coeff_count() * 8);
     }
 
+    // SEAL decryptor.cpp invariant_noise_budget (no call site in the reference; the usual check around square / relinearize)
+    int invariant_noise_budget(const Ciphertext &encrypted) {
+        if (encrypted.size_ < 2 || !encrypted.words_.data() || encrypted.words_.core() != core_) throw std::invalid_argument("encrypted is not valid for encryption parameters");
+        if (encrypted.ntt_) throw std::invalid_argument("encrypted cannot be in NTT form");
+        if (encrypted.size_ > 3) throw std::invalid_argument("pplp_b200 measures ciphertexts of size 2 or 3");
+        detail::DeviceWords out;
+        out.resize(core_, 1);
+        detail::check(pplp_noise_budget(core_->h, encrypted.level_, encrypted.words_.data(), PPLP_LAYOUT_SEAL, 1, encrypted.size_, sk_.words_.data(),
+                                        reinterpret_cast<int *>(out.data()), nullptr));
+        return (int)(std::uint32_t)out.download()[0];
+    }
+
 private:
     detail::CorePtr core_;
     SecretKey sk_;

@@ -450,6 +450,20 @@ int pplp_decrypt(pplp_ctx *ctx, size_t level, const uint64_t *d_ct, int layout, 
     PPLP_CATCH
 }
 
+int pplp_noise_budget(pplp_ctx *ctx, size_t level, const uint64_t *d_ct, int layout, size_t nq, size_t size, const uint64_t *d_sk, int *d_budget, void *stream) {
+    PPLP_TRY
+    Engine &E = dev_engine(ctx);
+    const size_t k = check_level(E, level);
+    if (size < 2 || size > 3) throw std::invalid_argument("encrypted is not valid for encryption parameters");
+    if (nq == 0) return PPLP_OK;
+    const int nqi = to_int(nq, "query count");
+    cudaStream_t st = S(stream);
+    Scratch tmp(noise_tmp_words(E, level, nqi, (int)size) * 8, st);
+    launch_noise_budget(E, level, d_ct, make_layout(layout, E.host.n, k, size, nq), nqi, (int)size, d_sk, tmp.as<u64>(), d_budget, st);
+    return PPLP_OK;
+    PPLP_CATCH
+}
+
 // ---- evaluator ----
 static int add_sub_common(pplp_ctx *ctx, size_t level, uint64_t *d_a, const uint64_t *d_b, int layout, size_t nq, size_t npoly, int mode, void *stream) {
     PPLP_TRY

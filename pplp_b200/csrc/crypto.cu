@@ -745,23 +745,11 @@ size_t decrypt_tmp_words(const Engine &E, size_t level, int nq, int size) {
     return (size_t)nq * k * n * (generic ? 3 : 1) + 2 * k * n + 16;   // + room for the constant-coefficient path's key images
 }
 
-void launch_decrypt(const Engine &E, size_t level, const u64 *ct, Layout lay, int nq, int size, const u64 *sk, u64 *tmp, u64 *plain_out, size_t plain_stride,
-                    int ncoeff, cudaStream_t st) {
-    E.require_device();
-    if (nq == 0) return;
+// x = c0 + c1 s (+ c2 s^2) per limb, coefficient form, canonical, to tmp [nq][k][n]  ([SEAL] Decryptor::dot_product_ct_sk_array)
+static void launch_dot_ct_sk(const Engine &E, size_t level, const u64 *ct, Layout lay, int nq, int size, const u64 *sk, u64 *tmp, cudaStream_t st) {
     const int k = (int)E.host.levels[level].q.size(), n = (int)E.host.n;
     RowMap map = E.qmap(level);
     const Layout tl{(size_t)k * n, 0, (size_t)n};
-    if (size == 2 && ncoeff == 1) {
-        u64 *s_coef = tmp, *sneg = tmp + (size_t)k * n, *xout = sneg + (size_t)k * n;
-        PPLP_CUDA(cudaMemcpyAsync(s_coef, sk, (size_t)k * n * 8, cudaMemcpyDeviceToDevice, st));   // data limb j == key limb j
-        launch_ntt(E, s_coef, tl, 1, 1, map, true, st);
-        negacyclic_flip_kernel<<<dim3((n + 255) / 256, k), 256, 0, st>>>(E.d_mods, s_coef, sneg, n);
-        coeff0_dot_kernel<<<nq * k, 256, 0, st>>>(E.d_mods, ct, lay, sneg, xout, k, n);
-        scale_round_kernel<<<dim3(nq, 1), 32, 0, st>>>(E.d_levels + level, xout, (size_t)k, 1, plain_out, plain_stride, 1);
-        PPLP_CUDA(cudaGetLastError());
-        return;
-    }
     if (size == 2 && E.host.logn <= 14) {
         // x = INTT(NTT(c1) (.) s) + c0 in one kernel
         Layout a_lay = lay, c_lay = lay;
@@ -784,8 +772,109 @@ void launch_decrypt(const Engine &E, size_t level, const u64 *ct, Layout lay, in
         launch_ntt(E, tmp, tl, nq, 1, map, true, st);
         add_rows_kernel<<<g, 256, 0, st>>>(E.d_mods, tmp, ct, lay, 0, k, n);
     }
+}
+
+void launch_decrypt(const Engine &E, size_t level, const u64 *ct, Layout lay, int nq, int size, const u64 *sk, u64 *tmp, u64 *plain_out, size_t plain_stride,
+                    int ncoeff, cudaStream_t st) {
+    E.require_device();
+    if (nq == 0) return;
+    const int k = (int)E.host.levels[level].q.size(), n = (int)E.host.n;
+    RowMap map = E.qmap(level);
+    const Layout tl{(size_t)k * n, 0, (size_t)n};
+    if (size == 2 && ncoeff == 1) {
+        u64 *s_coef = tmp, *sneg = tmp + (size_t)k * n, *xout = sneg + (size_t)k * n;
+        PPLP_CUDA(cudaMemcpyAsync(s_coef, sk, (size_t)k * n * 8, cudaMemcpyDeviceToDevice, st));   // data limb j == key limb j
+        launch_ntt(E, s_coef, tl, 1, 1, map, true, st);
+        negacyclic_flip_kernel<<<dim3((n + 255) / 256, k), 256, 0, st>>>(E.d_mods, s_coef, sneg, n);
+        coeff0_dot_kernel<<<nq * k, 256, 0, st>>>(E.d_mods, ct, lay, sneg, xout, k, n);
+        scale_round_kernel<<<dim3(nq, 1), 32, 0, st>>>(E.d_levels + level, xout, (size_t)k, 1, plain_out, plain_stride, 1);
+        PPLP_CUDA(cudaGetLastError());
+        return;
+    }
+    launch_dot_ct_sk(E, level, ct, lay, nq, size, sk, tmp, st);
     dim3 gs(nq, (ncoeff + 255) / 256);
     scale_round_kernel<<<gs, 256, 0, st>>>(E.d_levels + level, tmp, (size_t)k * n, (size_t)n, plain_out, plain_stride, ncoeff);
+    PPLP_CUDA(cudaGetLastError());
+}
+
+// ---- Decryptor::invariant_noise_budget ([SEAL] decryptor.cpp) --------------------------------------------------------
+// budget = max(0, bits(Q) - bits(|| t * (c0 + c1 s + c2 s^2) mod Q ||_inf, centred) - 1).  The norm needs the integer behind the
+// residues: per coefficient  v = sum_j [x_j t (Q/q_j)^-1]_{q_j} (Q/q_j)  (below k Q), reduced modulo Q by subtraction, centred
+// against (Q+1)/2 — W = words(Q) + 1 sixty-four-bit words per thread.  big: [k][W] punctured products, then Q, then (Q+1)/2.
+constexpr int kNoiseMaxWords = 16;   // bits(Q) <= 881 at N = 32768 (14 words) + 1
+struct NoiseArgs { int k, W, n, total_bits; u64 c[kMaxLimbs]; };   // c_j = (t mod q_j) (Q/q_j)^-1 mod q_j
+__device__ __forceinline__ bool noise_geq(const u64 *a, const u64 *b, int W) {
+    for (int i = W - 1; i >= 0; --i) if (a[i] != b[i]) return a[i] > b[i];
+    return true;
+}
+__global__ void __launch_bounds__(128) noise_norm_kernel(const DevMod *mods, const u64 *__restrict__ x, const u64 *__restrict__ big, const NoiseArgs a, int *max_bits) {
+    const int qi = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const int W = a.W;
+    u64 acc[kNoiseMaxWords];
+    for (int w = 0; w < W; ++w) acc[w] = 0;
+    for (int j = 0; j < a.k; ++j) {
+        const u64 v = mul_mod(x[((size_t)qi * a.k + j) * a.n + i], a.c[j], mods[j].m);
+        const u64 *p = big + (size_t)j * W;
+        u64 carry = 0;
+        for (int w = 0; w < W; ++w) {      // acc += v * p  (p < Q/q_j, v < q_j: the running sum stays below k Q < 2^(64 W))
+            const u64 lo = v * p[w], hi = __umul64hi(v, p[w]);
+            u64 s0 = acc[w] + lo;
+            u64 c0 = s0 < lo;
+            const u64 s1 = s0 + carry;
+            c0 += s1 < carry;
+            acc[w] = s1;
+            carry = hi + c0;               // hi <= 2^64 - 2, c0 <= 2 only when lo + acc wrapped: no overflow (v p[w] + acc + carry < 2^128)
+        }
+    }
+    const u64 *Q = big + (size_t)a.k * W, *half = Q + W;
+    while (noise_geq(acc, Q, W)) {
+        u64 borrow = 0;
+        for (int w = 0; w < W; ++w) { const u64 y = Q[w], d = acc[w] - y - borrow; borrow = (acc[w] < y) || (acc[w] == y && borrow); acc[w] = d; }
+    }
+    if (noise_geq(acc, half, W)) {   // centred: Q - v
+        u64 borrow = 0;
+        for (int w = 0; w < W; ++w) { const u64 y = acc[w], d = Q[w] - y - borrow; borrow = (Q[w] < y) || (Q[w] == y && borrow); acc[w] = d; }
+    }
+    int bits = 0;
+    for (int w = W - 1; w >= 0; --w) if (acc[w]) { bits = 64 * w + 64 - __clzll((long long)acc[w]); break; }
+    bits = __reduce_max_sync(__activemask(), bits);
+    if ((threadIdx.x & 31) == 0 || __activemask() != 0xffffffffu) atomicMax(max_bits + qi, bits);
+}
+__global__ void noise_finish_kernel(int *v, int nq, int total_bits) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nq) v[q] = max(0, total_bits - v[q] - 1);
+}
+size_t noise_tmp_words(const Engine &E, size_t level, int nq, int size) {
+    const size_t k = E.host.levels[level].q.size();
+    return decrypt_tmp_words(E, level, nq, size) + (k + 2) * kNoiseMaxWords;
+}
+void launch_noise_budget(const Engine &E, size_t level, const u64 *ct, Layout lay, int nq, int size, const u64 *sk, u64 *tmp, int *budget, cudaStream_t st) {
+    E.require_device();
+    if (nq == 0) return;
+    const auto &q = E.host.levels[level].q;
+    const int k = (int)q.size(), n = (int)E.host.n;
+    hm::Wide Q = hm::Wide::product_of(q);
+    NoiseArgs a;
+    a.k = k; a.n = n; a.total_bits = Q.bits();
+    a.W = (a.total_bits + 63) / 64 + 1;
+    if (a.W > kNoiseMaxWords) throw std::invalid_argument("pplp: coefficient modulus too wide for the noise-budget kernel");
+    std::vector<u64> big((size_t)(k + 2) * a.W, 0);
+    for (int j = 0; j < k; ++j) {
+        const hm::Wide p = hm::Wide::product_of(q, (size_t)j);
+        std::copy(p.limb.begin(), p.limb.end(), big.begin() + (size_t)j * a.W);
+        a.c[j] = hm::mulm(E.host.t % q[j], hm::inverse_or_throw(p.mod(q[j]), q[j]), q[j]);
+    }
+    u64 *Qw = big.data() + (size_t)k * a.W, *half = Qw + a.W;
+    std::copy(Q.limb.begin(), Q.limb.end(), Qw);
+    for (int w = 0; w < a.W; ++w) half[w] = (Qw[w] >> 1) | (w + 1 < a.W ? Qw[w + 1] << 63 : 0);   // floor(Q/2); Q is odd, so (Q+1)/2 = that + 1
+    for (int w = 0; w < a.W; ++w) if (++half[w]) break;
+    u64 *x = tmp, *dbig = tmp + decrypt_tmp_words(E, level, nq, size);
+    PPLP_CUDA(cudaMemcpyAsync(dbig, big.data(), big.size() * 8, cudaMemcpyHostToDevice, st));   // pageable source: staged before the call returns
+    launch_dot_ct_sk(E, level, ct, lay, nq, size, sk, x, st);
+    PPLP_CUDA(cudaMemsetAsync(budget, 0, (size_t)nq * sizeof(int), st));
+    noise_norm_kernel<<<dim3((n + 127) / 128, nq), 128, 0, st>>>(E.d_mods, x, dbig, a, budget);
+    noise_finish_kernel<<<(nq + 255) / 256, 256, 0, st>>>(budget, nq, a.total_bits);
     PPLP_CUDA(cudaGetLastError());
 }
 

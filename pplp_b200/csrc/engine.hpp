@@ -121,6 +121,9 @@ int encrypt_stream_refills(int n);
 void launch_decrypt(const Engine &E, size_t level, const u64 *ct, Layout lay, int nq, int size, const u64 *sk /* [K][n] NTT */, u64 *tmp, u64 *plain_out,
                     size_t plain_stride, int ncoeff /* leading coefficients to produce per query */, cudaStream_t st);
 size_t decrypt_tmp_words(const Engine &E, size_t level, int nq, int size);
+// Decryptor::invariant_noise_budget for a batch: budget[q] = max(0, bits(Q) - bits(||t (c0 + c1 s + c2 s^2) mod Q||_inf) - 1)
+void launch_noise_budget(const Engine &E, size_t level, const u64 *ct, Layout lay, int nq, int size, const u64 *sk, u64 *tmp, int *budget, cudaStream_t st);
+size_t noise_tmp_words(const Engine &E, size_t level, int nq, int size);
 // key generation pieces (sampling is sequential rejection logic and runs on the host once per key; the transforms run here)
 void launch_expand_small(const Engine &E, const signed char *d_small /* [n] */, u64 *out /* [K][n] */, cudaStream_t st);
 void launch_pk_combine(const Engine &E, const u64 *a, const u64 *s, const u64 *e_ntt, u64 *c0, int digit /* -1: none */, u64 factor, cudaStream_t st);

@@ -174,6 +174,18 @@ class Context:
         check(self.L.pplp_decrypt(self.h, level, _ptr(ct), layout, nq, size, _ptr(sk), _ptr(out), ncoeff, ncoeff, self._st()))
         return out
 
+    def noise_budget(self, ct, sk, level=None, layout=LAYOUT_SEAL):
+        """Decryptor::invariant_noise_budget for every ciphertext of the batch -> int32 tensor [nq]."""
+        import torch
+        level = self.first_level if level is None else level
+        if layout == LAYOUT_SEAL:
+            nq, size = ct.shape[0], ct.shape[1]
+        else:
+            nq, size = ct.shape[2], ct.shape[1]
+        out = torch.empty(nq, dtype=torch.int32, device=self.device)
+        check(self.L.pplp_noise_budget(self.h, level, _ptr(ct), layout, nq, size, _ptr(sk), _ptr(out), self._st()))
+        return out
+
     # ---- evaluator ----
     def _dims(self, ct, layout):
         return (ct.shape[0], ct.shape[1]) if layout == LAYOUT_SEAL else (ct.shape[2], ct.shape[1])

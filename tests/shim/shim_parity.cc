@@ -115,6 +115,8 @@ int main(int argc, char **argv) {
         evaluator.multiply_plain_inplace(c1, Plaintext(hex(s)));
         evaluator.add_plain_inplace(c1, Plaintext(hex(s * r)));
         dump(dir, "result.bin", saved(c1));
+        std::printf("noise_budget: %d\n", decryptor.invariant_noise_budget(c1));
+        dump(dir, "budget.txt", std::to_string(decryptor.invariant_noise_budget(c1)));
         Plaintext out;
         decryptor.decrypt(c1, out);
         // constant coefficient (at N = 4096 the 72-bit q leaves no noise budget and the plaintext is a full polynomial)

@@ -738,3 +738,33 @@ def test_encrypt_many_seeds_bit_exact(eng, oracle, n, nct):
         assert (ct[i] == octx.encrypt(opk, plains[i], seed=seeds[i])).all(), i
     dec = eng.to_np(ctx.decrypt(ctx.dev(ct), ctx.dev(osk), ncoeff=1))
     assert (dec[:, 0] == plains[:, 0]).all()
+
+
+@pytest.mark.parametrize("n", [4096, 8192, 16384, 32768])
+def test_noise_budget_matches_oracle(eng, oracle, n):
+    """Decryptor::invariant_noise_budget (SEAL decryptor.cpp as restated in oracle/evalb.hpp noise_budget): fresh ciphertexts, a
+    square (size 3), its relinearisation, random residues (budget 0) and an all-zero noise polynomial, both layouts."""
+    ctx, octx = contexts(eng, oracle, n)
+    osk, opk = octx.keygen()
+    sk = ctx.dev(osk)
+    rng = np.random.default_rng(n + 17)
+    nq = 3 if n <= 8192 else 1
+    cts = np.stack([octx.encrypt(opk, rng.integers(0, 1 << 20, 2, dtype=np.uint64), seed=seed8(900 + i)) for i in range(nq)])
+    got = eng.to_np(ctx.noise_budget(ctx.dev(cts), sk), np.int32)
+    want = [octx.noise_budget(osk, cts[i]) for i in range(nq)]
+    assert got.tolist() == want and min(want) > (100 if n >= 8192 else 0), (got.tolist(), want)   # t = 2^56 leaves 9 bits at N = 4096
+    lm = ctx.dev(np.ascontiguousarray(cts.transpose(2, 1, 0, 3)))
+    assert eng.to_np(ctx.noise_budget(lm, sk, layout=eng.LAYOUT_LIMB_MAJOR), np.int32).tolist() == want
+    sq = np.stack([octx.square(cts[i]) for i in range(nq)])
+    got3 = eng.to_np(ctx.noise_budget(ctx.dev(sq), sk), np.int32).tolist()
+    assert got3 == [octx.noise_budget(osk, sq[i]) for i in range(nq)]
+    if n <= 16384:
+        ork = octx.relin_keygen(osk)
+        rl = np.stack([octx.relinearize(sq[i], ork) for i in range(nq)])
+        got2 = eng.to_np(ctx.noise_budget(ctx.dev(rl), sk), np.int32).tolist()
+        assert got2 == [octx.noise_budget(osk, rl[i]) for i in range(nq)]
+        assert all((0 < b or n == 4096) and b <= a for a, b in zip(want, got2))
+    junk = np.stack([rand_residues(rng, octx.q[: ctx.k], n) for _ in range(2)])[None]
+    assert eng.to_np(ctx.noise_budget(ctx.dev(junk), sk), np.int32).tolist() == [octx.noise_budget(osk, junk[0])]
+    zero = np.zeros_like(junk)
+    assert eng.to_np(ctx.noise_budget(ctx.dev(zero), sk), np.int32).tolist() == [octx.noise_budget(osk, zero[0])]

@@ -98,6 +98,7 @@ def test_shim_artifacts_equal_oracle_bytes(shim, oracle, logn):
     assert art["result.bin"] == octx.save_ct(res)
     dec = octx.decrypt(osk, res)
     assert int(art["blind.txt"].decode(), 16) == int(dec[0])
+    assert int(art["budget.txt"].decode()) == octx.noise_budget(osk, res)   # Decryptor::invariant_noise_budget through the shim
     if logn >= 13:
         d2 = (xa - xb) ** 2 + (ya - yb) ** 2
         assert int(dec[0]) == (s * (d2 + r)) % T56

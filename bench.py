@@ -673,6 +673,9 @@ def extra_circuit_b(engine, torch):
     slots = engine.to_np(ctx.batch_decode(ctx.decrypt(out[:1], ctx.dev(osk))))[0]
     d2 = (xa - xb[0].astype(object)) ** 2 + (ya - yb[0].astype(object)) ** 2
     algebra = bool(all(int(v) == (s0 * (int(a) + int(b))) % t for v, a, b in zip(slots[:64], d2[:64], rr[0][:64])))
+    dsk = ctx.dev(osk)
+    budget = {"fresh_input": int(ctx.noise_budget(cx[:1], dsk)[0].item()), "output_min": int(ctx.noise_budget(out, dsk).min().item()),
+              "what": "Decryptor::invariant_noise_budget in bits (pplp_noise_budget), input ciphertext and the minimum over the step's outputs"}
     threads = host_threads()
     with concurrent.futures.ThreadPoolExecutor(threads) as pool:     # ctypes releases the GIL: one group per host thread
         t0 = time.perf_counter()
@@ -687,16 +690,16 @@ def extra_circuit_b(engine, torch):
             "roofline": {"bound": "FP64 pipe (squares over the 44-bit auxiliary base, relinearisation: every transform and base conversion in exact FP64 products); HBM shown for reference", "algorithmic_bytes_per_group": bytes_group,
                          "achieved": bytes_group * gps / 1e9, "peak": peak, "unit": "GB/s", "frac": bytes_group * gps / 1e9 / peak},
             "roofline_fp64": _circuit_b_fp64_roofline(gps, n),
-            "agrees_with_oracle": agrees, "slots_match_algebra": algebra,
+            "agrees_with_oracle": agrees, "slots_match_algebra": algebra, "noise_budget_bits": budget,
             "cpu_baseline": {"groups_per_s": threads / cdt, "value": threads / cdt * n, "unit": "slot-wise queries/s", "cores": threads, "kind": "port",
                              "one_thread_seconds_per_group": one, "sample": f"{threads} groups, one per host thread (oracle/ restatement of SEAL's bfv_square + switch_key_inplace)"}}
 
 
 def _circuit_b_fp64_roofline(gps, n):
     """The pipe that bounds Circuit B: FP64 instructions per coefficient index (counted from the ncu captures under
-    profiles/: square 3 200 in the 50 row transforms + 2 200 in the two base conversions, relinearisation 1 900) against
+    profiles/r02_circuit_b_fp64_counts.csv: square 5 100, relinearisation 1 950; by hand 5 400 and 1 900) against
     64 FP64 lanes per clock per SM at the maximum SM clock."""
-    per_square, per_relin = 5400, 1900
+    per_square, per_relin = 5100, 1950   # sm__inst_executed_pipe_fp64.sum x 32 / (ciphertexts x N), profiles/r02_circuit_b_fp64_counts.csv
     instr_group = (2 * per_square + 2 * per_relin) * n
     try:
         import torch
@@ -710,7 +713,7 @@ def _circuit_b_fp64_roofline(gps, n):
     peak = 64.0 * sms * mhz * 1e6            # FP64 instructions per second
     return {"bound": "fp64_pipe", "fp64_instr_per_coefficient": {"square": per_square, "relinearize": per_relin}, "fp64_instr_per_group": instr_group,
             "achieved": instr_group * gps / 1e12, "peak": peak / 1e12, "unit": "T FP64 instr/s", "frac": instr_group * gps / peak,
-            "source": "instruction counts from profiles/r02_circuit_b_launches.csv and the ncu --set full captures; peak = 64 lanes x SMs x max SM clock"}
+            "source": "instruction counts measured with ncu (sm__inst_executed_pipe_fp64.sum, profiles/r02_circuit_b_fp64_counts.csv); peak = 64 lanes x SMs x max SM clock"}
 
 
 def extra_bloom_build(engine, torch):

@@ -446,6 +446,7 @@ struct RelinSplitArgs {
     u64 *digits;                    // [nq][k+1][k][n]
     int k, K, n;
     const DevMod *mods;
+    int prefetch_ahead = 0;         // N = 16384 (one CTA per SM): CTAs ahead whose input row the first reader of a row pulls into L2
 };
 // WIDE (N = 16384, 45..49-bit primes, ntt32.cuh's wide rule set): the input is reduced modulo q_I while it is converted and the
 // output once more before it is stored, so that stage 2's products see |x| <= 0.8 q.
@@ -460,6 +461,12 @@ __global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T
     const Ntt32Consts c = ntt32_consts(md, false);
     const u64 *row = a.c2 + qi * a.lay.sq + 2 * a.lay.sp + J * a.lay.sl;
     u64 *dst = a.digits + (((size_t)qi * kk + I) * a.k + J) * S::M;
+    if constexpr (LOGM == 14) {
+        // the kk readers of one row are neighbours: the first of them asks for the row the SM's next CTA (or a neighbour of it) will read
+        const int nr = blockIdx.x / kk + (a.prefetch_ahead + kk - 1) / kk;
+        if (tid == 0 && I == 0 && a.prefetch_ahead > 0 && nr * kk < (int)gridDim.x)
+            prefetch_l2_bulk(a.c2 + (nr / a.k) * a.lay.sq + 2 * a.lay.sp + (nr % a.k) * a.lay.sl, S::M * 8);
+    }
     u64 x[32];
 #pragma unroll
     for (int e = 0; e < 32; ++e) x[e] = row[e * S::T + tid];
@@ -791,6 +798,7 @@ void launch_relinearize(const Engine &E, size_t level, const u64 *in, Layout in_
             const int c = std::min(chunk, nq - done);
             const u64 *cin = in + (size_t)done * in_lay.sq;
             RelinSplitArgs sa{cin, in_lay, digits, k, K, n, E.d_mods};
+            if (E.host.logn == 14) sa.prefetch_ahead = ntt_prefetch_ahead();
             RelinMacArgs ma{digits, rkq, tmp + (size_t)done * 2 * n, cin, in_lay, out + (size_t)done * out_lay.sq, out_lay, E.d_levels, k, K, n, E.d_mods, P >> 1};
             if (E.host.logn == 11) run_relin_split<11>(sa, ma, c, st);
             else if (E.host.logn == 12) run_relin_split<12>(sa, ma, c, st);

@@ -115,6 +115,7 @@ struct BehzfFwdArgs {
     int k, NL, from_ext;
     RowMap map;
     const DevMod *mods;
+    int prefetch_ahead = 0;         // N = 16384 (one CTA per SM): rows ahead whose source the CTA pulls into L2 (ntt.cu ntt_prefetch_ahead)
 };
 template <int LOGM, bool WIDE = (LOGM == 14)>
 __global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T) behzf_forward_kernel(const BehzfFwdArgs a) {
@@ -126,6 +127,14 @@ __global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T
     const Ntt32Consts c = ntt32_consts(md, false);
     u64 *dst = a.ext + ((size_t)qp * a.NL + l) * S::M;
     const u64 *src = (l < a.k && !a.from_ext) ? a.in + (qp >> 1) * a.lay.sq + (qp & 1) * a.lay.sp + l * a.lay.sl : dst;
+    if constexpr (LOGM == 14) {
+        const int nb = blockIdx.x + a.prefetch_ahead;
+        if (tid == 0 && a.prefetch_ahead > 0 && nb < (int)gridDim.x) {
+            const int nl = nb % a.NL, nqp = nb / a.NL;
+            const u64 *nsrc = (nl < a.k && !a.from_ext) ? a.in + (nqp >> 1) * a.lay.sq + (nqp & 1) * a.lay.sp + nl * a.lay.sl : a.ext + ((size_t)nqp * a.NL + nl) * S::M;
+            prefetch_l2_bulk(nsrc, S::M * 8);
+        }
+    }
     u64 x[32];
 #pragma unroll
     for (int e = 0; e < 32; ++e) x[e] = src[e * S::T + tid];
@@ -329,6 +338,7 @@ static void multiply_f64_k(const Engine &E, size_t level, const BehzfSeg *segs, 
     if (!square) behzf_extend_kernel<K><<<dim3(nq * 2, gy), 256, 0, st>>>(C, b, b_lay, eb, fused ? 0 : 1, none);
     if (fused) {
         BehzfFwdArgs fa{segs[0].src, segs[0].lay, ea, K, NL, a_from_ext, map, E.d_mods}, fb{b, b_lay, eb, K, NL, 0, map, E.d_mods};
+        if (E.host.logn == 14) fa.prefetch_ahead = fb.prefetch_ahead = ntt_prefetch_ahead();
         BehzfTensorArgs ta{ea, eb, d, NL, map, E.d_mods};
         switch (E.host.logn) {
         case 11: run_behzf_transforms<11>(fa, square ? nullptr : &fb, ta, nq, st); break;

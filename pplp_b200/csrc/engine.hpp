@@ -81,6 +81,7 @@ struct Engine {
 // ---- ntt.cu ----
 // In-place transform of every (query, poly, limb) row of a batch.  `map` gives the modulus of each limb.
 void launch_ntt(const Engine &E, u64 *data, Layout lay, int nq, int npoly, const RowMap &map, bool inverse, cudaStream_t st);
+int ntt_prefetch_ahead();   // rows ahead that the N = 16384 forward transforms prefetch into L2 (SM count; 0 = off)
 // out = INTT(NTT(a) (.) b_ntt) [+ c]   row-wise; b is broadcast over queries when b_lay.sq == 0.
 void launch_polymul(const Engine &E, const u64 *a, Layout a_lay, const u64 *b_ntt, Layout b_lay, const u64 *c, Layout c_lay, u64 *out, Layout out_lay,
                     int nq, int npoly, const RowMap &map, cudaStream_t st);

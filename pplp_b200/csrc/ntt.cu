@@ -129,10 +129,10 @@ __global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T
     u64 *ptr = DENSE ? a.data + (size_t)blockIdx.x * S::M : a.data + qi * a.lay.sq + p * a.lay.sp + j * a.lay.sl;
     if constexpr (DENSE && PPLP_NTT_PREFETCH_AHEAD > 0) {
         if (tid == 0 && blockIdx.x + PPLP_NTT_PREFETCH_AHEAD < gridDim.x) prefetch_l2_bulk(ptr + (size_t)PPLP_NTT_PREFETCH_AHEAD * S::M, S::M * 8);
-    } else if constexpr (DENSE && LOGM == 14) {
-        // one 512-thread CTA per SM: nothing overlaps this CTA's strided row load, so the row its SM takes next is pulled into L2 now
-        // (one bulk prefetch, UBLKPF.L2).  N = 16384 forward: 2.46 -> 2.79 TB/s; the inverse (contiguous loads, strided stores) and the
-        // two-CTA-per-SM shapes of N <= 8192 do not move (+1 % at best), so only this kernel asks for it.
+    } else if constexpr (DENSE && LOGM >= 12) {
+        // the row this SM slot takes next is pulled into L2 now (one bulk prefetch, UBLKPF.L2).  N = 16384 (one 512-thread CTA per SM:
+        // nothing else overlaps its strided row load): forward 2.46 -> 2.79 TB/s; N = 8192 (two CTAs per SM): 3.40 -> 3.46 TB/s.  The
+        // inverse (contiguous loads, strided stores) does not move.
         if (tid == 0 && a.prefetch_ahead > 0 && blockIdx.x + a.prefetch_ahead < gridDim.x) prefetch_l2_bulk(ptr + (size_t)a.prefetch_ahead * S::M, S::M * 8);
     }
     if constexpr (!DENSE) asm volatile("" : "+l"(ptr));
@@ -348,7 +348,8 @@ template <int LOGM> static void run_ntt32(const NttArgs &a, int rows, bool inver
     if (dense) {
         NttArgs d = a;
         d.stage_base = a.nq * a.npoly;   // rows per limb (the ntt32 kernels have no use for stage_base: they run whole transforms only)
-        if (LOGM == 14 && !inverse) d.prefetch_ahead = ntt_prefetch_ahead();
+        // the row this SM slot takes next: (CTAs per SM) x (SMs) rows ahead
+        if (LOGM >= 12 && !inverse) d.prefetch_ahead = (512 / Ntt32Shape<LOGM>::T) * ntt_prefetch_ahead();
         run_ntt32_d<LOGM, true>(d, rows, inverse, st);
     } else run_ntt32_d<LOGM, false>(a, rows, inverse, st);
 }

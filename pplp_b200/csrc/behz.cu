@@ -634,7 +634,7 @@ __global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T
     if constexpr (SPECIAL) {
         u64 *o = a.tmp + ((size_t)qi * 2 + comp) * S::M;
 #pragma unroll
-        for (int e = 0; e < 32; ++e) o[e * S::T + tid] = csub(csub(x[e] + a.half, two_q), q);
+        for (int e = 0; e < 32; ++e) { const u64 qq = md.m.q; o[e * S::T + tid] = csub(csub(x[e] + a.half, qq << 1), qq); }   // stores interleaved with the last stage
     } else {
         const DevLevel &KL = *a.KL;
         const u64 half_mod = KL.half_last_mod[I];

@@ -254,10 +254,9 @@ __global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T
         }
     }
     ntt32_inverse<LOGM, true, WIDE>(x, sm, tid, c);
-    const u64 qu = md.m.q;
     u64 *o = a.d + (((size_t)qi * 3 + comp) * a.NL + l) * S::M;
 #pragma unroll
-    for (int e = 0; e < 32; ++e) o[e * S::T + tid] = csub(x[e], qu);
+    for (int e = 0; e < 32; ++e) o[e * S::T + tid] = csub(x[e], md.m.q);   // stores interleaved with the last stage (modarith.cuh)
 }
 
 bool behz_uses_f64(const Engine &E, size_t level) {

@@ -223,6 +223,13 @@ __device__ __forceinline__ ulonglong2 ld_stream_coherent(const u64 *p) {
 }
 // Ask the L2 for `bytes` (a multiple of 16) at p ahead of use: one bulk prefetch (UBLKPF.L2) issued by one thread.  Used by
 // the row-per-CTA transforms to pull the row a later CTA will read out of HBM while the current rows are in the butterflies.
+// Interleaved epilogue stores.  A transform's epilogue of the form `const u64 q = md.m.q; for e: out[e] = f(x[e], q)` is scheduled as
+// "all 32 results, then 32 stores in one burst at the very end of the CTA's life".  Re-reading the per-row constant through its
+// (possibly aliasing, as far as the compiler and ptxas know) global pointer inside the loop — `f(x[e], md.m.q)` — makes store e
+// depend on a load that cannot move above store e-1, so the stores stay interleaved with the last stage's arithmetic and drain
+// while the CTA still computes: inverse transform at N = 8192 3.13 -> 3.39 TB/s, square +3.6 %.  The load hits L1 every time.
+// (An `asm volatile` load with a memory clobber does the same but orders more than needed: 3.33 TB/s.)  Found by diffing the SASS of
+// the engine's kernel against the lab harness (scripts/microbench/ntt32_lab.cu), which happened to have the re-read.
 __device__ __forceinline__ void prefetch_l2_bulk(const void *p, unsigned bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }

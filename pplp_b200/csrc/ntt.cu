@@ -161,9 +161,9 @@ __global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T
     u64 x[32];
     ntt32_load_row(x, sm, tid, ptr);
     ntt32_inverse<LOGM, false, WIDE>(x, sm, tid, c);
-    const u64 q = md.m.q;
+    // q is re-read for every store on purpose (modarith.cuh, "interleaved epilogue stores"): the stores stay interleaved with the last stage
 #pragma unroll
-    for (int e = 0; e < 32; ++e) ptr[e * S::T + tid] = csub(x[e], q);
+    for (int e = 0; e < 32; ++e) ptr[e * S::T + tid] = csub(x[e], md.m.q);
 }
 
 // N = 16384 as a cluster of two 256-thread CTAs per row (ntt32.cuh, CL): two CTAs of different rows share an SM, so one row's

@@ -141,6 +141,62 @@ template <int LOGM, int ABL> float time_abl(u64 *d, const LabMod *d_mods, int ro
     return best;
 }
 
+// the same ablation for the inverse: bit 0 no global load (and no input staging), bit 1 no global store, bit 3 streaming hints
+template <int LOGM, int ABL>
+__global__ void __launch_bounds__(Ntt32Shape<LOGM>::T, 512 / Ntt32Shape<LOGM>::T) inv_abl_kernel(u64 *data, const LabMod *mods, int rows_per_mod) {
+    using S = Ntt32Shape<LOGM>;
+    extern __shared__ __align__(16) u64 sm[];
+    const int tid = threadIdx.x;
+    const LabMod &md = mods[blockIdx.x / rows_per_mod];
+    const Ntt32Consts c = md.i;
+    u64 *ptr = data + (size_t)blockIdx.x * S::M;
+    u64 x[32];
+    const int lane = tid & 31, wbase = (tid >> 5) << 10;
+    if (ABL & 1) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) x[e] = ((u64)(blockIdx.x * 7919u + tid * 32u + e) * 0x9E3779B1ull) & 0x3ffffffffffull;
+    } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+            u64 v;
+            if (ABL & 8) asm volatile("ld.global.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(ptr + wbase + e * 32 + lane));
+            else v = ptr[wbase + e * 32 + lane];
+            sm[slot32(wbase + e * 32 + lane)] = v;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) x[e] = sm[slot32(wbase + lane * 32 + e)];
+    }
+    ntt32_inverse<LOGM>(x, sm, tid, c);
+    if (ABL & 2) {
+        u64 acc = 0;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) acc ^= csub(x[e], md.q);
+        if (acc == 0x123456789abcdef0ull) ptr[tid] = acc;
+    } else if (ABL & 8) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) asm volatile("st.global.cs.u64 [%0], %1;" ::"l"(ptr + e * S::T + tid), "l"(csub(x[e], md.q)) : "memory");
+    } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) ptr[e * S::T + tid] = csub(x[e], md.q);
+    }
+}
+template <int LOGM, int ABL> float time_inv_abl(u64 *d, const LabMod *d_mods, int rows, int rpm) {
+    using S = Ntt32Shape<LOGM>;
+    const int bytes = S::SMEM_WORDS * 8;
+    CK(cudaFuncSetAttribute(inv_abl_kernel<LOGM, ABL>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    float best = 1e9;
+    for (int rep = 0; rep < 6; ++rep) {
+        cudaEventRecord(a);
+        inv_abl_kernel<LOGM, ABL><<<rows, S::T, bytes>>>(d, d_mods, rpm);
+        cudaEventRecord(b); cudaEventSynchronize(b);
+        float ms; cudaEventElapsedTime(&ms, a, b);
+        if (rep >= 2 && ms < best) best = ms;
+    }
+    return best;
+}
+
 // scheduling experiment: the engine addresses a row as base + qi*sq + p*sp + j*sl (runtime strides)
 struct LabLayout { size_t sq, sp, sl; };
 template <int LOGM, int PTR>
@@ -285,6 +341,10 @@ template <int LOGM> void run(int rows) {
         const float t0 = time_abl<13, 0>(d, d_mods, rows, rpm), t1 = time_abl<13, 1>(d, d_mods, rows, rpm), t2 = time_abl<13, 2>(d, d_mods, rows, rpm),
                     t3 = time_abl<13, 3>(d, d_mods, rows, rpm), t7 = time_abl<13, 7>(d, d_mods, rows, rpm), t8 = time_abl<13, 8>(d, d_mods, rows, rpm);
         printf("N=%d forward with streaming hints (ld no_allocate, st.cs): %.4f ms (%.0f GB/s)\n", n, t8, 16.0 * n * rows / 1e6 / t8);
+        const float i0 = time_inv_abl<13, 0>(d, d_mods, rows, rpm), i1 = time_inv_abl<13, 1>(d, d_mods, rows, rpm), i2 = time_inv_abl<13, 2>(d, d_mods, rows, rpm),
+                    i3 = time_inv_abl<13, 3>(d, d_mods, rows, rpm), i8 = time_inv_abl<13, 8>(d, d_mods, rows, rpm);
+        printf("N=%d inverse ablation: full %.4f ms (%.0f GB/s) | no load %.4f (%.0f) | no store %.4f (%.0f) | neither %.4f (%.0f) | streaming hints %.4f (%.0f)\n", n,
+               i0, 16.0 * n * rows / 1e6 / i0, i1, 16.0 * n * rows / 1e6 / i1, i2, 16.0 * n * rows / 1e6 / i2, i3, 16.0 * n * rows / 1e6 / i3, i8, 16.0 * n * rows / 1e6 / i8);
         const double gb = 16.0 * n * rows / 1e6;
         printf("N=%d forward ablation: full %.4f ms (%.0f GB/s) | no load %.4f (%.0f) | no store %.4f (%.0f) | neither %.4f (%.0f) | transform only %.4f (%.0f)\n", n,
                t0, gb / t0, t1, gb / t1, t2, gb / t2, t3, gb / t3, t7, gb / t7);

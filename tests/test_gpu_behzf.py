@@ -90,6 +90,13 @@ for n, t in ((4096, 1 << 56), (8192, 1 << 56), (8192, 0xfffffffffb4001), (16384,
     b = np.stack([np.stack([np.stack([rng.integers(0, qj, size=n, dtype=np.uint64) for qj in ctx.q[:ctx.k]]) for _ in range(2)]) for _ in range(3)])
     h.update(engine.to_np(ctx.multiply(ctx.dev(a), ctx.dev(b))).tobytes())
     h.update(engine.to_np(ctx.square(ctx.dev(a))).tobytes())
+# (d) a chain of mixed prime widths at N = 4096 (PPLP_NTT_PER_LIMB: one arithmetic class per limb or the widest prime's for all)
+q0 = engine.bfv_default(4096)
+ctx = engine.Context(4096, q=[q0[0], 0x3ffffffffc001, q0[1], 0x3fffffffcc001, q0[2]], t=1 << 20, device=0, enforce_security=False)
+data = np.stack([np.stack([rng.integers(0, qj, size=4096, dtype=np.uint64) for qj in ctx.q]) for _ in range(5)])[:, None]
+d = ctx.dev(np.ascontiguousarray(data))
+h.update(engine.to_np(ctx.ntt_(d.clone(), level=0)).tobytes())
+h.update(engine.to_np(ctx.ntt_(d.clone(), level=0, inverse=True)).tobytes())
 print("DIGEST", h.hexdigest())
 """
 
@@ -219,11 +226,12 @@ print("DIGEST", h.hexdigest())
 
 def test_optional_kernel_variants_give_the_same_bytes():
     """The measured-and-kept alternatives (two-CTA cluster transforms at N = 16384, persistent forward transform with bulk-copy
-    prefetch, the 16-per-thread encryption inverse) stay bit-identical to the defaults, which the parity tests pin to the oracle."""
+    prefetch, the 16-per-thread encryption inverse) and the A/B switches of the L2 row prefetch and the per-limb arithmetic class stay bit-identical to the defaults, which the parity tests pin to the oracle."""
     digests = {}
-    for name, env in (("default", {}), ("cluster", {"PPLP_NTT_CLUSTER": "1"}), ("persistent", {"PPLP_BEHZF_PERSIST": "1"}), ("enc16", {"PPLP_ENC_INV32": "0"})):
+    for name, env in (("default", {}), ("cluster", {"PPLP_NTT_CLUSTER": "1"}), ("persistent", {"PPLP_BEHZF_PERSIST": "1"}), ("enc16", {"PPLP_ENC_INV32": "0"}),
+                      ("no_prefetch", {"PPLP_NTT_PREFETCH": "0"}), ("batch_class", {"PPLP_NTT_PER_LIMB": "0"})):
         e = dict(os.environ)
-        for k in ("PPLP_NTT_CLUSTER", "PPLP_BEHZF_PERSIST", "PPLP_ENC_INV32"):
+        for k in ("PPLP_NTT_CLUSTER", "PPLP_BEHZF_PERSIST", "PPLP_ENC_INV32", "PPLP_NTT_PREFETCH", "PPLP_NTT_PER_LIMB"):
             e.pop(k, None)
         e.update(env)
         p = subprocess.run([sys.executable, "-c", _SWITCH_SNIPPET % ROOT], capture_output=True, text=True, env=e, timeout=600)
